@@ -1,0 +1,530 @@
+"""`CRBM` — the secomo.CRBM interface (reference secomo/convRBM.py:25-726) driving the sm_100a kernels.
+
+Same constructor hyper-parameters, defaults, validation errors and method names as the reference class, so code
+written against `secomo.CRBM` runs unchanged; the Theano graph is replaced by calls through the C ABI of
+libcrbm_b200.so (include/crbm_b200.h). PyTorch only provides device memory, streams and torch.distributed.
+There is no CPU fallback: anything that computes raises if no CUDA device / library is available.
+
+Differences a caller can observe (all documented in DESIGN.md):
+  * random numbers come from Philox, not MRG31k3p (same distributions; `seed=` keyword added, default clock like :155);
+  * exp() is evaluated with the group maximum subtracted, so results stay finite where the reference overflows;
+  * motif_length <= 33 and pooling <= 16 (NotImplementedError beyond), input_dims must be 4 to compute;
+  * `fit`/`motifHitProbs`/`freeEnergy` also accept a GPU-resident `PackedSequences` (2 bit/base);
+  * under torch.distributed (one process per GPU) `fit` is data-parallel: every minibatch and the persistent chain
+    are sharded across ranks and one all-reduce of the statistics vector per step keeps all replicas identical.
+"""
+import time
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .sequences import PackedSequences
+
+FANTASY_LEN = _lib.FANTASY_LEN
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class _SharedParam(object):
+    """Stand-in for a `theano.shared` variable (reference :133,149,152): get_value() / set_value() in host layout."""
+
+    def __init__(self, owner, name, shape):
+        self._owner, self.name, self._shape = owner, name, tuple(shape)
+
+    def _tensor(self):
+        return getattr(self._owner, '_t_' + self.name)
+
+    def get_value(self, borrow=False):
+        return self._tensor().detach().cpu().numpy().reshape(self._shape).copy()
+
+    def set_value(self, value, borrow=False):
+        torch = _torch()
+        value = np.asarray(value, dtype=np.float32)
+        if value.shape != self._shape:
+            raise ValueError("%s: expected shape %r, got %r" % (self.name, self._shape, value.shape))
+        self._tensor().copy_(torch.from_numpy(np.ascontiguousarray(value)).reshape(self._tensor().shape))
+
+
+class _FantasyParam(object):
+    """The persistent chain as the reference exposes it: dense (batchsize,K,1,200) float (reference :168-173)."""
+
+    def __init__(self, owner, strand):
+        self._owner, self._strand = owner, strand
+
+    def get_value(self, borrow=False):
+        o = self._owner
+        o._require_cuda()
+        torch = _torch()
+        lib = _lib.load()
+        dense = torch.empty((o._local_batch, o.num_motifs, 1, FANTASY_LEN), dtype=torch.float32, device=o._device)
+        _lib.check(lib.crbm_hidden_bits_to_dense(_lib.ptr(o._t_fantasy[self._strand]), o._local_batch, o.num_motifs,
+                                                 _lib.ptr(dense), _lib.stream_handle()), 'bits_to_dense')
+        return dense.cpu().numpy()
+
+    def set_value(self, value, borrow=False):
+        o = self._owner
+        o._require_cuda()
+        torch = _torch()
+        lib = _lib.load()
+        value = np.ascontiguousarray(value, dtype=np.float32)
+        if value.shape != (o._local_batch, o.num_motifs, 1, FANTASY_LEN):
+            raise ValueError("fantasy particles: expected %r" % ((o._local_batch, o.num_motifs, 1, FANTASY_LEN),))
+        dense = torch.from_numpy(value).to(o._device)
+        _lib.check(lib.crbm_hidden_dense_to_bits(_lib.ptr(dense), o._local_batch, o.num_motifs,
+                                                 _lib.ptr(o._t_fantasy[self._strand]), _lib.stream_handle()), 'dense_to_bits')
+
+
+class CRBM(object):
+    """Convolutional restricted Boltzmann machine for DNA motifs (reference secomo/convRBM.py:25).
+
+    Parameters are those of the reference (num_motifs, motif_length, epochs=100, input_dims=4, doublestranded=True,
+    batchsize=20, learning_rate=0.1, momentum=0.95, pooling=1, cd_k=5, rho=0.01, lambda_rate=0.1), plus keyword-only
+    `seed` (Philox seed; default: clock, as reference :155) and `device`.
+    """
+
+    def __init__(self, num_motifs, motif_length, epochs=100, input_dims=4,
+                 doublestranded=True, batchsize=20, learning_rate=0.1,
+                 momentum=0.95, pooling=1, cd_k=5,
+                 rho=0.01, lambda_rate=0.1, *, seed=None, device=None):
+        # sanity checks: same conditions and messages as reference :73-108
+        if num_motifs <= 0:
+            raise Exception("Number of motifs must be positive.")
+        if motif_length <= 0:
+            raise Exception("Motif length must be positive.")
+        if epochs < 0:
+            raise Exception("Epochs must be non-negative.")
+        if input_dims <= 0:
+            raise Exception("input_dims must be positive.")
+        elif input_dims != 4:
+            warnings.warn("input_dims != 4 was not comprehensively \
+                tested yet. Be careful when interpreting the results.",
+                          UserWarning)
+        if batchsize <= 0:
+            raise Exception("batchsize must be positive.")
+        if learning_rate <= 0.0:
+            raise Exception("learning_rate must be positive.")
+        if not (momentum >= 0.0 and momentum < 1.):
+            raise Exception("momentum must be between zero and one.")
+        if pooling <= 0:
+            raise Exception("pooling must be positive.")
+        if cd_k <= 0:
+            raise Exception("cd_k must be positive.")
+        if not (rho >= 0.0 and rho < 1.):
+            raise Exception("rho must be between zero and one.")
+        if lambda_rate < 0.:
+            raise Exception("lambda_rate must be non-negative.")
+
+        self.num_motifs = num_motifs
+        self.motif_length = motif_length
+        self.input_dims = input_dims
+        self.doublestranded = doublestranded
+        self.batchsize = batchsize
+        self.learning_rate = learning_rate
+        self.momentum = momentum
+        self.rho = rho
+        self.lambda_rate = lambda_rate
+        self.pooling = pooling
+        self.cd_k = cd_k
+        self.epochs = epochs
+        self.spmethod = 'entropy'
+
+        torch = _torch()
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+        self._device = torch.device(device)
+
+        # data-parallel layout: `batchsize` is the global minibatch; each rank owns batchsize/world particles
+        self._rank, self._world = 0, 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self._rank, self._world = dist.get_rank(), dist.get_world_size()
+        except Exception:
+            pass
+        if batchsize % self._world != 0:
+            raise Exception("batchsize must be divisible by the number of data-parallel ranks.")
+        self._local_batch = batchsize // self._world
+
+        x = np.random.randn(num_motifs, 1, input_dims, motif_length).astype(np.float32)        # reference :127
+        if not rho:                                                                             # reference :136-140
+            rho = 1. / (num_motifs * motif_length)
+            if doublestranded:
+                rho = rho / 2.
+            self.rho = rho
+        from scipy.stats import norm
+        b = (np.zeros((1, num_motifs)) + norm.ppf(self.rho, 0, np.sqrt(motif_length))).astype(np.float32)   # :143-148
+        c = np.zeros((1, input_dims), dtype=np.float32)
+
+        dev = self._device
+        self._t_W = torch.from_numpy(x).to(dev).contiguous()
+        self._t_bias = torch.from_numpy(b).to(dev).contiguous()
+        self._t_c = torch.from_numpy(c).to(dev).contiguous()
+        self._t_vW = torch.zeros_like(self._t_W)
+        self._t_vb = torch.zeros_like(self._t_bias)
+        self._t_vc = torch.zeros_like(self._t_c)
+        self.motifs = _SharedParam(self, 'W', x.shape)
+        self.bias = _SharedParam(self, 'bias', b.shape)
+        self.c = _SharedParam(self, 'c', c.shape)
+        self.motif_velocity = _SharedParam(self, 'vW', x.shape)
+        self.bias_velocity = _SharedParam(self, 'vb', b.shape)
+        self.c_velocity = _SharedParam(self, 'vc', c.shape)
+
+        self._seed = int(time.time()) if seed is None else int(seed)                           # reference :155
+        self._step = 0
+        self._kw = (num_motifs + 31) // 32
+        self._t_fantasy = torch.zeros((2, self._local_batch, self._kw, FANTASY_LEN), dtype=torch.int32, device=dev)
+        self.fantasy_h = _FantasyParam(self, 0)
+        if doublestranded:
+            self.fantasy_h_prime = _FantasyParam(self, 1)
+        self._train_state = None
+        self.theano_getHitProbs = self.motifHitProbs      # the attribute the north star calls getHitProbs (:508)
+        self.getHitProbs = self.motifHitProbs
+        self.theano_freeEnergy = lambda data: self.freeEnergy(data)
+        self.theano_fePerMotif = lambda data: self.freeEnergy(data, permotif=True)
+        self.theano_evaluateData = self._evaluateData
+        self.theano_evaluateParams = self._evaluateParams
+        self.theano_trainingFct = self._trainingFct
+
+    # ------------------------------------------------------------------------------------------------------
+    def _require_cuda(self):
+        if self._device.type != 'cuda':
+            raise RuntimeError("crbm_b200 computes only on a CUDA device (sm_100a); there is no CPU fallback")
+        if self.input_dims != 4:
+            raise NotImplementedError("crbm_b200 kernels are written for the DNA alphabet (input_dims == 4)")
+        return _lib.load()
+
+    def _as_packed(self, data):
+        self._require_cuda()
+        if isinstance(data, PackedSequences):
+            return data
+        data = np.asarray(data) if not hasattr(data, 'shape') else data
+        return PackedSequences.from_onehot(data, device=self._device)
+
+    # ---- persistence (reference :177-236): identical pickle layout ------------------------------------------------
+    def saveModel(self, filename):
+        """Save the model parameters and additional hyper-parameters."""
+        import joblib
+        numpyParams = (self.motifs.get_value(), self.bias.get_value(), self.c.get_value())
+        hyperparams = (self.num_motifs, self.motif_length, self.input_dims, self.doublestranded, self.batchsize,
+                       self.learning_rate, self.momentum, self.rho, self.lambda_rate, self.pooling, self.cd_k,
+                       self.epochs, self.spmethod)
+        joblib.dump((numpyParams, hyperparams), filename, protocol=2)
+
+    @classmethod
+    def loadModel(cls, filename):
+        """Load a model from a given pickle file."""
+        import joblib
+        numpyParams, hyperparams = joblib.load(filename)
+        (num_motifs, motif_length, input_dims, doublestranded, batchsize, learning_rate, momentum, rho, lambda_rate,
+         pooling, cd_k, epochs, spmethod) = hyperparams
+        obj = cls(num_motifs, motif_length, epochs=epochs, input_dims=input_dims, doublestranded=doublestranded,
+                  batchsize=batchsize, learning_rate=learning_rate, momentum=momentum, pooling=pooling, cd_k=cd_k,
+                  rho=rho, lambda_rate=lambda_rate)
+        motifs, bias, c = numpyParams
+        obj.motifs.set_value(motifs)
+        obj.bias.set_value(bias)
+        obj.c.set_value(c)
+        return obj
+
+    # ---- bottom-up builders (reference :238-275), eager ------------------------------------------------------------
+    def _v2h(self, data, strand_mode, out_kind, max_chunk_bytes=1 << 30):
+        lib = self._require_cuda()
+        torch = _torch()
+        seqs = self._as_packed(data)
+        K, M = self.num_motifs, self.motif_length
+        Lh = seqs.L - M + 1
+        if Lh <= 0:
+            raise ValueError("sequences of length %d are shorter than the motif (%d)" % (seqs.L, M))
+        out = np.empty((seqs.N, K, 1, Lh), dtype=np.float32)
+        rows = max(1, int(max_chunk_bytes // (4 * K * Lh)))
+        for s in range(0, seqs.N, rows):
+            e = min(seqs.N, s + rows)
+            dev = torch.empty((e - s, K, 1, Lh), dtype=torch.float32, device=self._device)
+            _lib.check(lib.crbm_v2h_dense(_lib.ptr(seqs.words[s:]), seqs.row_words, e - s, seqs.L, _lib.ptr(self._t_W),
+                                          _lib.ptr(self._t_bias), K, M, self.pooling, strand_mode, out_kind,
+                                          _lib.ptr(dev), _lib.stream_handle()), 'v2h_dense')
+            out[s:e] = dev.cpu().numpy()
+        return out
+
+    def _bottomUpActivity(self, data, flip_motif=False):
+        """x = conv(data, W, filter_flip=flip_motif) + b (reference :238-243)."""
+        return self._v2h(data, _lib.STRAND_RC if flip_motif else _lib.STRAND_FWD, _lib.OUT_ACTIVITY)
+
+    def _bottomUpProbability(self, activities):
+        """exp(x) / sum_group(1 + exp(x)) (reference :245-257)."""
+        lib = self._require_cuda()
+        torch = _torch()
+        act = torch.from_numpy(np.ascontiguousarray(activities, dtype=np.float32)).to(self._device)
+        N, K, _, Lh = act.shape
+        out = torch.empty_like(act)
+        _lib.check(lib.crbm_pool_probability(_lib.ptr(act), N, K, Lh, self.pooling, _lib.ptr(out), _lib.stream_handle()),
+                   'pool_probability')
+        return out.cpu().numpy()
+
+    def _bottomUpSample(self, probs, uniforms=None):
+        """Multinomial sample within every pooling group (reference :259-267)."""
+        lib = self._require_cuda()
+        torch = _torch()
+        p = torch.from_numpy(np.ascontiguousarray(probs, dtype=np.float32)).to(self._device)
+        N, K, _, Lh = p.shape
+        u = None if uniforms is None else torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float32)).to(self._device)
+        out = torch.empty_like(p)
+        self._step += 1
+        _lib.check(lib.crbm_sample_hidden(_lib.ptr(p), N, K, Lh, self.pooling, _lib.ptr(u), self._seed,
+                                          self._step << 32, _lib.ptr(out), _lib.stream_handle()), 'sample_hidden')
+        return out.cpu().numpy()
+
+    def _computeHgivenV(self, data, flip_motif=False, uniforms=None):
+        """[probability, sample] of the hidden layer (reference :269-275)."""
+        prob = self._v2h(data, _lib.STRAND_RC if flip_motif else _lib.STRAND_FWD, _lib.OUT_PROBABILITY)
+        return [prob, self._bottomUpSample(prob, uniforms)]
+
+    # ---- top-down builders (reference :277-325), eager --------------------------------------------------------------
+    def _topDownActivity(self, h, hprime):
+        lib = self._require_cuda()
+        torch = _torch()
+        hd = torch.from_numpy(np.ascontiguousarray(h, dtype=np.float32)).to(self._device)
+        hpd = None if hprime is None else torch.from_numpy(np.ascontiguousarray(hprime, dtype=np.float32)).to(self._device)
+        N, K, _, Lh = hd.shape
+        if K != self.num_motifs:
+            raise ValueError("hidden tensor has %d motif channels, model has %d" % (K, self.num_motifs))
+        M = self.motif_length
+        out = torch.empty((N, 1, 4, Lh + M - 1), dtype=torch.float32, device=self._device)
+        _lib.check(lib.crbm_h2v_dense(_lib.ptr(hd), _lib.ptr(hpd), N, K, Lh, _lib.ptr(self._t_W), _lib.ptr(self._t_c), M,
+                                      _lib.ptr(out), _lib.stream_handle()), 'h2v_dense')
+        return out.cpu().numpy()
+
+    def _visible(self, activity, want_prob, want_sample, uniforms=None):
+        lib = self._require_cuda()
+        torch = _torch()
+        act = torch.from_numpy(np.ascontiguousarray(activity, dtype=np.float32)).to(self._device)
+        N, _, A, Lv = act.shape
+        prob = torch.empty_like(act) if want_prob else None
+        samp = torch.empty_like(act) if want_sample else None
+        u = None if uniforms is None else torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float32)).to(self._device)
+        self._step += 1
+        _lib.check(lib.crbm_visible_softmax_sample(_lib.ptr(act), N, Lv, _lib.ptr(prob), _lib.ptr(u), self._seed,
+                                                   self._step << 32, _lib.ptr(samp), _lib.stream_handle()),
+                   'visible_softmax_sample')
+        return (prob.cpu().numpy() if want_prob else None), (samp.cpu().numpy() if want_sample else None)
+
+    def _topDownProbability(self, activity, softmaxdown=True):
+        if not softmaxdown:
+            raise NotImplementedError("softmaxdown=False is dead code in the reference (:299) and is not built")
+        return self._visible(activity, True, False)[0]
+
+    def _topDownSample(self, probability, softmaxdown=True, uniforms=None):
+        if not softmaxdown:
+            raise NotImplementedError("softmaxdown=False is dead code in the reference (:312-314) and is not built")
+        # sampling from probabilities == sampling from softmax(log p)
+        with np.errstate(divide='ignore'):
+            logp = np.log(np.asarray(probability, dtype=np.float64)).astype(np.float32)
+        return self._visible(np.maximum(logp, -80.0), False, True, uniforms)[1]
+
+    def _computeVgivenH(self, H_sample, H_sample_prime, softmaxdown=True, uniforms=None):
+        """[probability, sample] of the visible layer (reference :317-325)."""
+        act = self._topDownActivity(H_sample, H_sample_prime)
+        prob, samp = self._visible(act, True, True, uniforms)
+        return [prob, samp]
+
+    # ---- scan / free energy (reference :507-568, 657-697) --------------------------------------------------------------
+    def motifHitProbs(self, data):
+        """Per-position motif match probabilities, (N,K,1,L-M+1) float32.
+
+        As in the reference (:507-514): doublestranded=True scans the forward strand only; doublestranded=False sums
+        the activities of both strands before the pooling sigmoid."""
+        mode = _lib.STRAND_FWD if self.doublestranded else _lib.STRAND_SUM
+        return self._v2h(data, mode, _lib.OUT_PROBABILITY)
+
+    def _free_energy_device(self, seqs, want_seq, want_motif, want_count, uniforms=None):
+        lib = self._require_cuda()
+        torch = _torch()
+        K, M = self.num_motifs, self.motif_length
+        fe_seq = torch.empty(seqs.N, dtype=torch.float32, device=self._device) if want_seq else None
+        fe_mot = torch.empty((seqs.N, K), dtype=torch.float32, device=self._device) if want_motif else None
+        cnt = torch.empty(seqs.N, dtype=torch.float32, device=self._device) if want_count else None
+        u = None if uniforms is None else torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float32)).to(self._device)
+        self._step += 1
+        _lib.check(lib.crbm_free_energy(_lib.ptr(seqs.words), seqs.row_words, seqs.N, seqs.L, _lib.ptr(self._t_W),
+                                        _lib.ptr(self._t_bias), _lib.ptr(self._t_c), K, M, self.pooling,
+                                        1 if self.doublestranded else 0, _lib.ptr(fe_seq), _lib.ptr(fe_mot), _lib.ptr(cnt),
+                                        _lib.ptr(u), self._seed, self._step, _lib.stream_handle()), 'free_energy')
+        return fe_seq, fe_mot, cnt
+
+    def freeEnergy(self, data, permotif=False):
+        """Free energy per sequence (N,), or per sequence and motif (N,K) (reference :549-568)."""
+        seqs = self._as_packed(data)
+        fe_seq, fe_mot, _ = self._free_energy_device(seqs, not permotif, permotif, False)
+        return (fe_mot if permotif else fe_seq).cpu().numpy()
+
+    # ---- training (reference :373-438, 570-634) ---------------------------------------------------------------------------
+    def _ensure_train_state(self):
+        if self._train_state is None:
+            lib = self._require_cuda()
+            torch = _torch()
+            K, M = self.num_motifs, self.motif_length
+            lv = FANTASY_LEN + M - 1
+            st = {}
+            st['v_row_words'] = lib.crbm_packed_row_words(lv)
+            st['v_model'] = torch.zeros((self._local_batch, st['v_row_words']), dtype=torch.int32, device=self._device)
+            st['stats'] = torch.zeros(int(lib.crbm_train_stats_floats(K, M)), dtype=torch.float32, device=self._device)
+            st['ws_bytes'] = int(lib.crbm_train_workspace_bytes(K, M))
+            st['workspace'] = torch.empty(st['ws_bytes'], dtype=torch.uint8, device=self._device)
+            lay = _lib.StatsLayout()
+            _lib.check(lib.crbm_train_stats_layout(K, M, lay), 'stats_layout')
+            st['layout'] = lay
+            self._train_state = st
+        return self._train_state
+
+    def _fill_args(self, words_ptr, row_words, n_data, L, u_v=None, u_h=None, u_hp=None):
+        st = self._ensure_train_state()
+        a = _lib.TrainArgs()
+        a.W, a.b, a.c = self._t_W.data_ptr(), self._t_bias.data_ptr(), self._t_c.data_ptr()
+        a.vW, a.vb, a.vc = self._t_vW.data_ptr(), self._t_vb.data_ptr(), self._t_vc.data_ptr()
+        a.K, a.M, a.pooling = self.num_motifs, self.motif_length, self.pooling
+        a.doublestranded, a.cd_k = (1 if self.doublestranded else 0), self.cd_k
+        a.learning_rate, a.momentum, a.rho, a.lambda_rate = self.learning_rate, self.momentum, self.rho, self.lambda_rate
+        a.data, a.data_row_words, a.n_data, a.L = words_ptr, row_words, n_data, L
+        a.batchsize = self._local_batch
+        a.fantasy_bits, a.v_model, a.v_row_words = self._t_fantasy.data_ptr(), st['v_model'].data_ptr(), st['v_row_words']
+        a.seed, a.step = self._seed + 7919 * self._rank, self._step
+        a.u_v = None if u_v is None else u_v.data_ptr()
+        a.u_h = None if u_h is None else u_h.data_ptr()
+        a.u_hp = None if u_hp is None else u_hp.data_ptr()
+        a.step_dev, a.batch_index_dev, a.n_batches = None, None, 0
+        a.stats, a.workspace, a.workspace_bytes = st['stats'].data_ptr(), st['workspace'].data_ptr(), st['ws_bytes']
+        return a
+
+    def _train_packed(self, seqs, start, end, uniforms=None):
+        """One training step on rows [start,end) of `seqs` (this rank's shard is cut here)."""
+        lib = self._require_cuda()
+        torch = _torch()
+        n = end - start
+        if self._world > 1:
+            per = (n + self._world - 1) // self._world
+            lo = min(n, self._rank * per)
+            hi = min(n, lo + per)
+            start, end = start + lo, start + hi
+        u_v = u_h = u_hp = None
+        if uniforms is not None:
+            conv = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self._device)
+            u_v, u_h, u_hp = conv(uniforms.get('v')), conv(uniforms.get('h')), conv(uniforms.get('hp'))
+        row_bytes = seqs.row_words * 4
+        a = self._fill_args(seqs.words.data_ptr() + start * row_bytes, seqs.row_words, end - start, seqs.L, u_v, u_h, u_hp)
+        s = _lib.stream_handle()
+        _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
+        if self._world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._train_state['stats'])
+        _lib.check(lib.crbm_train_apply(a, s), 'train_apply')
+        self._step += 1
+
+    def _trainingFct(self, data, uniforms=None):
+        """Train on one mini-batch (reference :524-526 -> theano_trainingFct)."""
+        seqs = self._as_packed(data)
+        self._train_packed(seqs, 0, seqs.N, uniforms)
+
+    def _evaluateData(self, data, uniforms=None):
+        """[mean free energy, mean of a sampled forward-strand H] (reference :466-472, 517-522)."""
+        seqs = self._as_packed(data)
+        fe, _, cnt = self._free_energy_device(seqs, True, False, True, uniforms)
+        lh = seqs.L - self.motif_length + 1
+        return [float(fe.sum().item() / seqs.N), float(cnt.sum().item() / (seqs.N * self.num_motifs * lh))]
+
+    def _evaluateParams(self):
+        """[sqrt(mean W^2), IC, median IC] (reference :475-485, 528-533)."""
+        W = self.motifs.get_value().astype(np.float64)
+        e = np.exp(W)
+        pwm = e / e.sum(axis=2, keepdims=True)
+        entropy = np.sum(-pwm * np.log2(pwm), axis=2)
+        twn = np.sqrt(np.mean(W ** 2))
+        ic = np.log2(W.shape[2]) - np.mean(entropy)
+        medic = np.log2(W.shape[2]) - np.mean(np.sort(entropy, axis=2)[:, :, entropy.shape[2] // 2])
+        return [np.float32(twn), np.float32(ic), np.float32(medic)]
+
+    def _truncated_length(self, L):
+        return int((L - self.motif_length + 1) / self.pooling) * self.pooling + self.motif_length - 1
+
+    def _prepare(self, data):
+        """fit()'s truncation (reference :586-591) + packing."""
+        if isinstance(data, PackedSequences):
+            return data.truncated(self._truncated_length(data.L))
+        nseq = self._truncated_length(data.shape[3])
+        return self._as_packed(data[:, :, :, :nseq])
+
+    def _epoch_metrics(self, test):
+        """Unweighted mean over test batches of [mean FE, mean H sample] (reference :616-627), one launch."""
+        torch = _torch()
+        fe, _, cnt = self._free_energy_device(test, True, False, True)
+        lh = test.L - self.motif_length + 1
+        idx = self._iterateBatchIndices(test.N, self.batchsize)
+        meanfe = meannmh = 0.0
+        starts = torch.tensor([s for s, _ in idx] + [test.N], device=self._device)
+        cfe = torch.cat([torch.zeros(1, device=self._device, dtype=torch.float64), fe.double().cumsum(0)])
+        ccn = torch.cat([torch.zeros(1, device=self._device, dtype=torch.float64), cnt.double().cumsum(0)])
+        sizes = (starts[1:] - starts[:-1]).double()
+        meanfe = float(((cfe[starts[1:]] - cfe[starts[:-1]]) / sizes).mean().item())
+        meannmh = float(((ccn[starts[1:]] - ccn[starts[:-1]]) / (sizes * self.num_motifs * lh)).mean().item())
+        return meanfe, meannmh
+
+    def fit(self, training_data, test_data=None):
+        """Fits the cRBM to the provided training sequences (reference :570-634)."""
+        self._require_cuda()
+        training = self._prepare(training_data)
+        test = self._prepare(test_data) if test_data is not None else training
+        verbose = self._rank == 0
+        if verbose:
+            print(("BatchSize: " + str(self.batchsize)))
+            print("Start training the model...")
+        starttime = time.time()
+        for epoch in range(self.epochs):
+            for [start, end] in self._iterateBatchIndices(training.N, self.batchsize):
+                self._train_packed(training, start, end)
+            meanfe, meannmh = self._epoch_metrics(test)
+            [twn_, ic_, medic_] = self._evaluateParams()
+            if verbose:
+                print(("Epoch {:d}: ".format(epoch) +
+                       "FE={:1.3f} ".format(meanfe) +
+                       "NumH={:1.4f} ".format(meannmh) +
+                       "WNorm={:2.2f} ".format(float(twn_)) +
+                       "IC={:1.3f} medIC={:1.3f}".format(float(ic_), float(medic_))))
+        _torch().cuda.synchronize(self._device)
+        if verbose:
+            print(("Training finished after: {:5.2f} seconds!".format(time.time() - starttime)))
+
+    def getPFMs(self):
+        """Weight matrices converted to position frequency matrices (reference :640-655)."""
+        def softmax_(x):
+            x_exp = np.exp(x)
+            y = np.zeros(x.shape)
+            for i in range(x.shape[1]):
+                y[:, i] = x_exp[:, i] / np.sum(x_exp[:, i])
+            return y
+        return [softmax_(m[0, :, :]) for m in self.motifs.get_value()]
+
+    def __repr__(self):
+        st = "Parameters:\n\n"
+        st += "Number of motifs: {}\n".format(self.num_motifs)
+        st += "Motif length: {}\n".format(self.motif_length)
+        st += "\n"
+        st += "Hyper-parameters:\n\n"
+        st += "input dims: {:d}".format(self.input_dims)
+        st += "doublestranded: {}".format(self.doublestranded)
+        st += "batchsize: {:d}".format(self.batchsize)
+        st += "learning rate: {:1.3f}".format(self.learning_rate)
+        st += "momentum: {:1.3f}".format(self.momentum)
+        st += "rho: {:1.4f}".format(self.rho)
+        st += "lambda: {:1.3f}".format(self.lambda_rate)
+        st += "pooling: {:d}".format(self.pooling)
+        st += "cd_k: {:d}".format(self.cd_k)
+        st += "epochs: {:d}".format(self.epochs)
+        return st
+
+    def _iterateBatchIndices(self, totalsize, nbatchsize):
+        """Returns indices in batches (reference :722-726)."""
+        return [[i, i + nbatchsize] if i + nbatchsize <= totalsize
+                else [i, totalsize] for i in range(totalsize)[0::nbatchsize]]

@@ -1,0 +1,263 @@
+"""Sequence input for crbm_b200: the `secomo.sequences` interface without Biopython.
+
+Mirrors reference secomo/sequences.py — `readSeqsFromFasta` (:33-52, records containing N/n are skipped with the
+same message), `seqToOneHot` (:101-117 -> (N,1,4,L) float32, A0 C1 G2 T3 case-insensitive, KeyError for any other
+letter as the reference's table lookup raises), `load_sample` (:120-137) and `splitTrainingTest` (:54-98).
+Biopython is not available here, so records are a minimal `SeqRecord`/`Seq` pair with the attributes callers use
+(`.id`, `.seq`, `len()`, indexing, `str()`).
+
+`PackedSequences` is the B200-native container the kernels actually read: 2 bits per base, resident on the GPU.
+`CRBM.fit` / `motifHitProbs` / `freeEnergy` accept it in place of the 16-byte-per-base one-hot array.
+"""
+import os
+import re
+import tempfile
+
+import numpy as np
+
+L = {'A': 0, 'a': 0, 'C': 1, 'c': 1, 'G': 2, 'g': 2, 'T': 3, 't': 3}
+
+_CODE_LUT = np.full(256, 255, dtype=np.uint8)
+for _ch, _v in L.items():
+    _CODE_LUT[ord(_ch)] = _v
+
+
+class _Alphabet(object):
+    letters = 'GATC'          # Bio.Alphabet.IUPAC.unambiguous_dna.letters
+
+
+class Seq(str):
+    """A DNA string with the `.alphabet.letters` attribute the reference's `_getOneHotSeq` reads."""
+    alphabet = _Alphabet()
+
+
+class SeqRecord(object):
+    def __init__(self, seq, id='<unknown id>', description=''):
+        self.seq = seq if isinstance(seq, Seq) else Seq(seq)
+        self.id = self.name = id
+        self.description = description or id
+
+    def __len__(self):
+        return len(self.seq)
+
+    def __repr__(self):
+        return "SeqRecord(id=%r, len=%d)" % (self.id, len(self.seq))
+
+
+def _parse_fasta(handle):
+    name, desc, chunks = None, None, []
+    for line in handle:
+        line = line.strip()
+        if not line:
+            continue
+        if line.startswith('>'):
+            if name is not None:
+                yield SeqRecord(''.join(chunks), id=name, description=desc)
+            desc = line[1:]
+            name = desc.split()[0] if desc.split() else ''
+            chunks = []
+        else:
+            chunks.append(line)
+    if name is not None:
+        yield SeqRecord(''.join(chunks), id=name, description=desc)
+
+
+def readSeqsFromFasta(filename):
+    """Read sequences from a multi-fasta file; records containing N are skipped (reference sequences.py:33-52)."""
+    seqs = []
+    with open(filename) as handle:
+        for faseq in _parse_fasta(handle):
+            if re.search(r'N', str(faseq.seq), re.I):
+                print("skip sequence containing N")
+                continue
+            seqs.append(faseq)
+    return seqs
+
+
+def seqToCodes(seqs):
+    """List of records / strings of equal length -> (N,L) uint8 base codes. KeyError on a non-ACGT letter."""
+    rows = []
+    for s in seqs:
+        text = str(s.seq) if hasattr(s, 'seq') else str(s)
+        codes = _CODE_LUT[np.frombuffer(text.encode('latin-1'), dtype=np.uint8)]
+        bad = np.nonzero(codes == 255)[0]
+        if bad.size:
+            raise KeyError(text[int(bad[0])])
+        rows.append(codes)
+    if not rows:
+        return np.zeros((0, 0), dtype=np.uint8)
+    if len({r.shape[0] for r in rows}) != 1:
+        raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
+    return np.stack(rows)
+
+
+def codesToOneHot(codes):
+    codes = np.asarray(codes)
+    N, Ln = codes.shape
+    out = np.zeros((N, 1, 4, Ln), dtype=np.float32)
+    n_idx, i_idx = np.meshgrid(np.arange(N), np.arange(Ln), indexing='ij')
+    out[n_idx, 0, codes, i_idx] = 1
+    return out
+
+
+def seqToOneHot(seqs):
+    """Converts a set of DNA sequences to one-hot encoding, (N,1,4,L) float32 (reference sequences.py:101-117)."""
+    return codesToOneHot(seqToCodes(seqs))
+
+
+_SAMPLE = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data', 'oct4_2bit.npz')
+
+
+def _sample_records():
+    z = np.load(_SAMPLE)
+    names, packed, length = z['names'], z['packed'], int(z['length'])
+    lower = np.unpackbits(z['lower'], axis=1)[:, :length].astype(bool)
+    codes = ((packed[:, :, None] >> np.array([0, 2, 4, 6], dtype=np.uint8)) & 3).reshape(packed.shape[0], -1)[:, :length]
+    upper = np.frombuffer(b'ACGT', dtype=np.uint8)[codes]
+    text = np.where(lower, upper + 32, upper).astype(np.uint8)
+    return [(str(n), text[i].tobytes().decode('ascii')) for i, n in enumerate(names)]
+
+
+def sample_fasta_path(directory=None):
+    """Materialises the bundled Oct4 ChIP-seq sample (3997 x 200 bp; the reference's secomo/data/oct4.fa) as FASTA."""
+    directory = directory or os.path.join(tempfile.gettempdir(), 'crbm_b200_data')
+    os.makedirs(directory, exist_ok=True)
+    path = os.path.join(directory, 'oct4.fa')
+    if not os.path.exists(path):
+        tmp = path + '.%d.tmp' % os.getpid()
+        with open(tmp, 'w') as f:
+            for name, seq in _sample_records():
+                f.write('>%s\n%s\n' % (name, seq))
+        os.replace(tmp, path)
+    return path
+
+
+def load_sample():
+    """Sample Oct4 ChIP-seq peaks (H1-hESC, ENCODE) in one-hot encoding, (3997,1,4,200) (reference :120-137)."""
+    return seqToOneHot(readSeqsFromFasta(sample_fasta_path()))
+
+
+def splitTrainingTest(filename, train_test_ratio, num_top_regions=None, randomize=True):
+    """Splits a fasta file into <prefix>_train.fa / <prefix>_test.fa (reference sequences.py:54-98)."""
+    seqs = readSeqsFromFasta(filename)
+    if num_top_regions:
+        seqs = seqs[:num_top_regions]
+    if randomize:
+        idx_permut = list(np.random.permutation(len(seqs)))
+    else:
+        idx_permut = list(range(len(seqs)))
+    ntest = int(len(seqs) * train_test_ratio)
+    itest, itrain = idx_permut[:ntest], idx_permut[ntest:]
+    prefix = ".".join(filename.split(".")[:-1])
+    for path, idx in ((prefix + "_train.fa", itrain), (prefix + "_test.fa", itest)):
+        with open(path, 'w') as f:
+            for i in idx:
+                f.write('>%s\n%s\n' % (seqs[i].description, str(seqs[i].seq)))
+
+
+class PackedSequences(object):
+    """N sequences of L bases, 2 bits per base, resident in GPU memory in the row layout of include/crbm_b200.h."""
+
+    def __init__(self, words, N, L):
+        self.words, self.N, self.L = words, int(N), int(L)
+        self.row_words = int(words.shape[1])
+
+    @property
+    def shape(self):
+        return (self.N, 1, 4, self.L)
+
+    def __len__(self):
+        return self.N
+
+    @staticmethod
+    def _alloc(N, L, device):
+        import torch
+        from . import _lib
+        rw = _lib.load().crbm_packed_row_words(int(L))
+        return torch.zeros((int(N), rw), dtype=torch.int32, device=device), rw
+
+    @classmethod
+    def from_onehot(cls, data, device='cuda', chunk_rows=None):
+        """(N,1,4,L) one-hot (NumPy or torch) -> packed, validated on the GPU (non-one-hot input is rejected)."""
+        import torch
+        from . import _lib
+        lib = _lib.load()
+        if isinstance(data, np.ndarray):
+            if data.ndim != 4 or data.shape[1] != 1 or data.shape[2] != 4:
+                raise ValueError("expected one-hot data of shape (N,1,4,L), got %r" % (data.shape,))
+            N, Ln = data.shape[0], data.shape[3]
+        else:
+            N, Ln = data.shape[0], data.shape[3]
+        words, rw = cls._alloc(N, Ln, device)
+        bad = torch.zeros(1, dtype=torch.int32, device=device)
+        chunk_rows = chunk_rows or max(1, (64 << 20) // (16 * Ln))
+        total_bad = 0
+        for s in range(0, N, chunk_rows):
+            e = min(N, s + chunk_rows)
+            if isinstance(data, np.ndarray):
+                host = torch.from_numpy(np.ascontiguousarray(data[s:e], dtype=np.float32))
+                dev = host.to(device, non_blocking=False)
+            else:
+                dev = data[s:e].to(device=device, dtype=torch.float32).contiguous()
+            _lib.check(lib.crbm_pack_onehot(_lib.ptr(dev), e - s, Ln, _lib.ptr(words[s:]), rw, _lib.ptr(bad),
+                                            _lib.stream_handle()), 'pack_onehot')
+            total_bad += int(bad.item())
+        if total_bad:
+            raise ValueError("input is not one-hot at %d positions (expected exactly one 1 among A,C,G,T)" % total_bad)
+        return cls(words, N, Ln)
+
+    @classmethod
+    def from_codes(cls, codes, device='cuda'):
+        """(N,L) uint8 base codes in {0,1,2,3} -> packed."""
+        import torch
+        from . import _lib
+        lib = _lib.load()
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        N, Ln = codes.shape
+        words, rw = cls._alloc(N, Ln, device)
+        bad = torch.zeros(1, dtype=torch.int32, device=device)
+        dev = torch.from_numpy(codes).to(device)
+        _lib.check(lib.crbm_pack_codes(_lib.ptr(dev), N, Ln, _lib.ptr(words), rw, _lib.ptr(bad), _lib.stream_handle()),
+                   'pack_codes')
+        if int(bad.item()):
+            raise ValueError("base codes must be in {0,1,2,3}")
+        return cls(words, N, Ln)
+
+    @classmethod
+    def random(cls, N, L, seed=1234, device='cuda'):
+        """Synthetic i.i.d. uniform bases generated directly in packed form on the device."""
+        from . import _lib
+        lib = _lib.load()
+        words, rw = cls._alloc(N, L, device)
+        _lib.check(lib.crbm_random_bases(_lib.ptr(words), rw, int(N), int(L), int(seed), _lib.stream_handle()),
+                   'random_bases')
+        return cls(words, N, L)
+
+    def to_onehot(self):
+        """Back to the reference's (N,1,4,L) float32 array (NumPy)."""
+        import torch
+        from . import _lib
+        lib = _lib.load()
+        out = torch.empty((self.N, 1, 4, self.L), dtype=torch.float32, device=self.words.device)
+        _lib.check(lib.crbm_unpack_onehot(_lib.ptr(self.words), self.row_words, self.N, self.L, _lib.ptr(out),
+                                          _lib.stream_handle()), 'unpack_onehot')
+        return out.cpu().numpy()
+
+    def rows(self, start, end):
+        return PackedSequences(self.words[start:end], end - start, self.L)
+
+    def truncated(self, new_L):
+        """View of the first new_L bases of every sequence (re-packed: the padding bits must be zero)."""
+        if new_L == self.L:
+            return self
+        import torch
+        from . import _lib
+        rw = _lib.load().crbm_packed_row_words(int(new_L))
+        words = torch.zeros((self.N, rw), dtype=torch.int32, device=self.words.device)
+        nw = 1 + (new_L + 15) // 16
+        words[:, :nw] = self.words[:, :nw]
+        rem = new_L % 16
+        if rem:
+            mask = (1 << (2 * rem)) - 1
+            words[:, nw - 1] &= int(np.int32(np.uint32(mask)))
+        return PackedSequences(words, self.N, new_L)

@@ -1,0 +1,159 @@
+/*
+ * crbm_b200 — C ABI of the sm_100a (B200) kernels for the cRBM hot path of SECOMO (schulter/crbm 1.1.0).
+ *
+ * This is the drop-in boundary: what the reference obtains from its six compiled `theano.function`s
+ * (secomo/convRBM.py:453-515) a host obtains from these entry points. Every pointer is a DEVICE pointer unless
+ * the parameter name ends in `_host`; `stream` is a `cudaStream_t` passed as `void*`. No entry point allocates,
+ * synchronises or throws; each returns CRBM_OK or a negative error code (text via crbm_last_error()).
+ *
+ * Notation (as in the reference): N sequences, L bases, K = num_motifs, M = motif_length, P = pooling,
+ * Lh = L-M+1 hidden positions, Lv = Lh+M-1. Reference layouts: data (N,1,4,L) one-hot fp32; W (K,1,4,M);
+ * b (1,K); c (1,4); hidden (N,K,1,Lh). All fp32, contiguous.
+ *
+ * PACKED SEQUENCES. The kernels read DNA as 2 bits/base (A0 C1 G2 T3, secomo/sequences.py:9-17), 16 bases per
+ * little-endian uint32, one row per sequence: word 0 of a row is front padding (zero), base i lives in bits
+ * [2*(i%16), 2*(i%16)+2) of word 1 + i/16, and the row is zero-padded at the end up to
+ * `crbm_packed_row_words(L)` words (a multiple of 4, so rows are 16-byte aligned).
+ *
+ * HIDDEN BIT PLANES. Sampled hidden states of the persistent chain (convRBM.py:168-173, hidden length 200) are
+ * kept as bit planes: uint32 H[strand][n][kw][200], bit (k%32) of word [.. k/32][j] is h[n,k,0,j].
+ */
+#ifndef CRBM_B200_H
+#define CRBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRBM_OK                0
+#define CRBM_ERR_ARG          -1   /* invalid argument (shape, null pointer, ...) */
+#define CRBM_ERR_UNSUPPORTED  -2   /* valid for the reference but outside what the kernels cover (M>33, P>16) */
+#define CRBM_ERR_CUDA         -3   /* a CUDA runtime call failed */
+
+#define CRBM_FANTASY_LEN     200   /* convRBM.py:168: hidden length of the persistent chain */
+#define CRBM_MAX_MOTIF_LEN    33
+#define CRBM_MAX_POOLING      16
+
+/* strand_mode of crbm_v2h_dense */
+#define CRBM_STRAND_FWD 0          /* _bottomUpActivity(D, flip_motif=False), convRBM.py:238-243 */
+#define CRBM_STRAND_RC  1          /* _bottomUpActivity(D, flip_motif=True) */
+#define CRBM_STRAND_SUM 2          /* sum of both activities (bias twice): getHitProbs when doublestranded=False, :511-514 */
+/* out_kind of crbm_v2h_dense */
+#define CRBM_OUT_ACTIVITY    0
+#define CRBM_OUT_PROBABILITY 1     /* _bottomUpProbability, convRBM.py:245-257 (normaliser P + sum exp) */
+
+int         crbm_abi_version(void);
+const char *crbm_last_error(void);                 /* host string, thread-local */
+int         crbm_packed_row_words(int L);          /* row stride (uint32 words) of a packed sequence of L bases */
+int         crbm_hidden_words(int K);              /* kw = ceil(K/32) */
+
+/* ---- A0: sequence ingest (secomo/sequences.py:20-31,101-117) -------------------------------------------- */
+/* one-hot (N,1,4,L) fp32 -> packed rows. *bad_count (device int, zeroed by the callee) receives the number of
+ * positions that are not exactly one-hot. */
+int crbm_pack_onehot(const float *onehot, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream);
+/* base codes (N,L) uint8 in {0,1,2,3} -> packed rows; codes > 3 are counted in *bad_count. */
+int crbm_pack_codes(const uint8_t *codes, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream);
+/* packed rows -> one-hot (N,1,4,L) fp32 */
+int crbm_unpack_onehot(const uint32_t *packed, int row_words, int N, int L, float *onehot, void *stream);
+/* synthetic i.i.d. uniform bases written directly in packed form (Philox, counter-based) */
+int crbm_random_bases(uint32_t *packed, int row_words, int N, int L, uint64_t seed, void *stream);
+
+/* ---- A1/A2/A7: visible -> hidden, dense output (convRBM.py:238-257, 507-514) ----------------------------- */
+/* out (N,K,1,Lh) fp32. This is `theano_getHitProbs` (motifHitProbs) and the eager `_bottomUpActivity` /
+ * `_bottomUpProbability` builders. out_kind=PROBABILITY needs Lh % P == 0 (as the reference's reshape does). */
+int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L,
+                   const float *W, const float *b, int K, int M, int pooling,
+                   int strand_mode, int out_kind, float *out, void *stream);
+
+/* ---- A2 on a given activity tensor (eager `_bottomUpProbability(activities)`) --------------------------- */
+int crbm_pool_probability(const float *act, int N, int K, int Lh, int pooling, float *prob, void *stream);
+
+/* ---- A3: `_bottomUpSample` (convRBM.py:259-267) on a dense probability tensor ---------------------------- */
+/* One uniform per pooling group, rows ordered (n,k,group) like the reference's reshape; first outcome whose
+ * running sum exceeds u, none if u >= sum. `uniforms` (N*K*Lh/P floats) may be NULL -> Philox(seed, offset). */
+int crbm_sample_hidden(const float *prob, int N, int K, int Lh, int pooling, const float *uniforms,
+                       uint64_t seed, uint64_t offset, float *sample, void *stream);
+
+/* ---- A5: `_topDownActivity` (convRBM.py:277-292) on dense, real-valued hidden tensors -------------------- */
+/* h, hprime (N,K,1,Lh) fp32, hprime may be NULL; act (N,1,4,Lh+M-1). */
+int crbm_h2v_dense(const float *h, const float *hprime, int N, int K, int Lh,
+                   const float *W, const float *c, int M, float *act, void *stream);
+
+/* ---- A6: `_topDownProbability` / `_topDownSample` (convRBM.py:294-315, 699-702) --------------------------- */
+/* act (N,1,4,Lv) -> prob (4-way softmax per position; may be NULL) and/or one-hot sample (may be NULL). One
+ * uniform per (n,i), n-major; `uniforms` may be NULL -> Philox(seed, offset). */
+int crbm_visible_softmax_sample(const float *act, int N, int Lv, float *prob, const float *uniforms,
+                                uint64_t seed, uint64_t offset, float *sample, void *stream);
+
+/* ---- A13/A14: free energy and evaluation (convRBM.py:657-697, 466-472) ----------------------------------- */
+/* fe_seq (N) = _freeEnergyForData (divided by L), fe_motif (N,K) = _freeEnergyPerMotif; either may be NULL.
+ * If hsample_count != NULL (device float[N], overwritten), also draws a forward-strand hidden sample and adds,
+ * per sequence, the number of active units (evaluateData's NumH numerator); uniforms from `uniforms` or Philox. */
+int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L,
+                     const float *W, const float *b, const float *c, int K, int M, int pooling, int doublestranded,
+                     float *fe_seq, float *fe_motif, float *hsample_count, const float *uniforms,
+                     uint64_t seed, uint64_t offset, void *stream);
+
+/* ---- A8-A12: one PCD/CD-k training step (convRBM.py:373-438), split where data-parallel ranks exchange ---- */
+typedef struct crbm_train_args {
+    /* model + optimiser state (read by accumulate, updated in place by apply) */
+    float *W, *b, *c;              /* (K,1,4,M), (1,K), (1,4) */
+    float *vW, *vb, *vc;           /* velocities, same shapes */
+    int K, M, pooling, doublestranded, cd_k;
+    float learning_rate, momentum, rho, lambda_rate;
+    /* minibatch */
+    const uint32_t *data;          /* packed, n_data rows of L bases (L already truncated as fit() does, :586-591) */
+    int data_row_words, n_data, L;
+    /* persistent chain of this rank: `batchsize` particles */
+    int batchsize;
+    uint32_t *fantasy_bits;        /* [2][batchsize][kw][200]; strand 1 unused when !doublestranded */
+    uint32_t *v_model;             /* packed scratch, batchsize rows of 199+M bases (holds the last sampled V) */
+    int v_row_words;
+    /* randomness: Philox(seed, step) unless the matching pointer is non-NULL (tests replay reference uniforms) */
+    uint64_t seed, step;
+    const float *u_v;              /* [cd_k][batchsize*(199+M)] or NULL */
+    const float *u_h, *u_hp;       /* [cd_k][batchsize*K*(200/P)] or NULL */
+    /* optional device-resident cursors so that one captured CUDA graph can be replayed for every step: if
+     * step_dev != NULL the Philox step is *step_dev (seed/step fields still key the stream) and apply
+     * increments it; if batch_index_dev != NULL the minibatch is rows [i*n_data, (i+1)*n_data) of `data`
+     * with i = *batch_index_dev, and apply advances i modulo n_batches. */
+    unsigned long long *step_dev;
+    int *batch_index_dev;
+    int n_batches;
+    /* outputs of accumulate / inputs of apply */
+    float *stats;                  /* crbm_train_stats_floats(K,M) un-normalised sums; all-reduced (sum) across ranks */
+    void  *workspace;              /* crbm_train_workspace_bytes(...) bytes of scratch */
+    size_t workspace_bytes;
+} crbm_train_args;
+
+size_t crbm_train_stats_floats(int K, int M);
+size_t crbm_train_workspace_bytes(int K, int M);
+/* positive phase on `data`, cd_k Gibbs sweeps of the persistent chain, statistics -> args->stats (overwritten). */
+int crbm_train_accumulate(const crbm_train_args *args, void *stream);
+/* sparsity factor, momentum update of W,b,c from (all-reduced) args->stats. */
+int crbm_train_apply(const crbm_train_args *args, void *stream);
+
+/* layout of `stats` (offsets in floats), for hosts that want to inspect gradients */
+typedef struct crbm_stats_layout {
+    int vh_data, vh_model, vh_q;   /* each K*4*M: sum P(x)V folded over strands; same for the model; sum Q(x)V */
+    int h_data, h_model, h_q, h_fwd; /* each K: sum P+P' (data), same (model), sum Q, sum P forward only */
+    int v_data, v_model;           /* each 4: base counts */
+    int n_hidden_data, n_hidden_model, n_vis_data, n_vis_model; /* scalars: N*Lh, B*200, N*L, B*(199+M) */
+    int total;
+} crbm_stats_layout;
+int crbm_train_stats_layout(int K, int M, crbm_stats_layout *out_host);
+
+/* fantasy particles <-> the reference's dense (B,K,1,200) fp32 tensors (tests, inspection) */
+int crbm_hidden_bits_to_dense(const uint32_t *bits, int B, int K, float *dense, void *stream);
+int crbm_hidden_dense_to_bits(const float *dense, int B, int K, uint32_t *bits, void *stream);
+
+/* launch counter: number of kernels this library has launched since load (bench.py's `gpu_launches`) */
+unsigned long long crbm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRBM_B200_H */

@@ -1,0 +1,299 @@
+"""Parity of the sm_100a kernels (through the C ABI / CRBM host class) against the NumPy oracle and the committed
+reference fixtures. Tolerances: the reference's own rtol=atol=1e-5 for deterministic fp32 quantities; integer
+bookkeeping (packing, sampled bits, argmax hit positions) bit-exact."""
+import numpy as np
+import pytest
+
+from tests._golden import CASE_NAMES, load_case, onehot
+
+pytestmark = pytest.mark.gpu
+
+TOL = dict(rtol=1e-5, atol=1e-5)
+
+
+@pytest.fixture(scope='module')
+def crbm():
+    import crbm_b200
+    return crbm_b200
+
+
+@pytest.fixture(scope='module')
+def O():
+    from oracle import crbm_oracle
+    return crbm_oracle
+
+
+def model_from_case(crbm, case, which='init'):
+    hp = case['hyper']
+    m = crbm.CRBM(hp['num_motifs'], hp['motif_length'], epochs=1, doublestranded=hp['doublestranded'],
+                  batchsize=hp['batchsize'], learning_rate=hp['learning_rate'], momentum=hp['momentum'],
+                  pooling=hp['pooling'], cd_k=hp['cd_k'], rho=hp['rho'], lambda_rate=hp['lambda_rate'], seed=1)
+    sfx = '_init' if which == 'init' else '_%d' % (hp['steps'] - 1)
+    m.motifs.set_value(case['W' + sfx])
+    m.bias.set_value(case['b' + sfx])
+    m.c.set_value(case['c' + sfx])
+    return m
+
+
+# ---- A0 ----------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('N,L', [(1, 1), (3, 15), (5, 16), (7, 17), (4, 200), (2, 1000), (33, 47)])
+def test_pack_roundtrip_bit_exact(crbm, N, L):
+    rs = np.random.RandomState(N * 1000 + L)
+    codes = rs.randint(0, 4, size=(N, L)).astype(np.uint8)
+    D = onehot(codes)
+    p1 = crbm.PackedSequences.from_onehot(D)
+    p2 = crbm.PackedSequences.from_codes(codes)
+    w1, w2 = p1.words.cpu().numpy().view(np.uint32), p2.words.cpu().numpy().view(np.uint32)
+    np.testing.assert_array_equal(w1, w2)
+    # independent NumPy packing: front pad word, 16 bases per little-endian word, zero tail
+    ref = np.zeros_like(w1)
+    for i in range(L):
+        ref[:, 1 + i // 16] |= codes[:, i].astype(np.uint32) << np.uint32(2 * (i % 16))
+    np.testing.assert_array_equal(w1, ref)
+    np.testing.assert_array_equal(p1.to_onehot(), D)
+
+
+def test_pack_rejects_non_onehot(crbm):
+    D = onehot(np.zeros((2, 20), dtype=np.uint8))
+    D[1, 0, 2, 5] = 1.0
+    with pytest.raises(ValueError):
+        crbm.PackedSequences.from_onehot(D)
+    D[1, 0, :, 5] = 0.0
+    with pytest.raises(ValueError):
+        crbm.PackedSequences.from_onehot(D)
+
+
+def test_random_bases_uniform_and_padded(crbm):
+    p = crbm.PackedSequences.random(257, 1000, seed=5)
+    D = p.to_onehot()
+    assert D.shape == (257, 1, 4, 1000)
+    np.testing.assert_array_equal(D.sum(axis=2), 1.0)
+    freq = D.mean(axis=(0, 1, 3))
+    assert np.all(np.abs(freq - 0.25) < 0.01)
+    w = p.words.cpu().numpy().view(np.uint32)
+    assert np.all(w[:, 0] == 0) and np.all(w[:, 1 + 63:] == 0)      # 1000 bases = 62.5 words
+    assert np.all(w[:, 63] >> 16 == 0)
+    q = crbm.PackedSequences.random(257, 1000, seed=5)
+    np.testing.assert_array_equal(w, q.words.cpu().numpy().view(np.uint32))
+
+
+# ---- A1/A2/A7/A13 against the reference fixtures ---------------------------------------------------------------
+@pytest.mark.parametrize('name', CASE_NAMES)
+def test_bottom_up_and_scan_match_reference(crbm, name):
+    case = load_case(name)
+    hp = case['hyper']
+    m = model_from_case(crbm, case, 'last')
+    D = onehot(case['eval_codes'])[:, :, :, :hp['L_trunc']]
+    for flip in (0, 1):
+        np.testing.assert_allclose(m._bottomUpActivity(D, bool(flip)), case['bu_act_flip%d' % flip], **TOL)
+        p = m._bottomUpProbability(case['bu_act_flip%d' % flip])
+        np.testing.assert_allclose(p, case['bu_prob_flip%d' % flip], **TOL)
+        np.testing.assert_allclose(m._computeHgivenV(D, bool(flip))[0], case['bu_prob_flip%d' % flip], **TOL)
+    hits = m.motifHitProbs(D)
+    assert hits.dtype == np.float32 and hits.shape == case['hit_probs'].shape
+    np.testing.assert_allclose(hits, case['hit_probs'], **TOL)
+    np.testing.assert_allclose(m.freeEnergy(D), case['free_energy'], **TOL)
+    np.testing.assert_allclose(m.freeEnergy(D, permotif=True), case['fe_per_motif'], rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize('name', CASE_NAMES)
+def test_argmax_hit_positions_bit_exact(crbm, name):
+    case = load_case(name)
+    hp = case['hyper']
+    m = model_from_case(crbm, case, 'last')
+    D = onehot(case['eval_codes'])[:, :, :, :hp['L_trunc']]
+    ref = case['hit_probs'][:, :, 0, :]
+    got = m.motifHitProbs(D)[:, :, 0, :]
+    # compare argmax wherever the reference's top two values are separated by more than the fp32 tolerance
+    srt = np.sort(ref, axis=2)
+    clear = (srt[:, :, -1] - srt[:, :, -2]) > 1e-5 * (1 + srt[:, :, -1])
+    np.testing.assert_array_equal(got.argmax(axis=2)[clear], ref.argmax(axis=2)[clear])
+    assert clear.mean() > 0.9
+
+
+# ---- A3/A5/A6 ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', CASE_NAMES)
+def test_top_down_matches_reference(crbm, O, name):
+    case = load_case(name)
+    m = model_from_case(crbm, case, 'last')
+    h, hp_ = case['td_h'].astype(np.float32), case['td_hp'].astype(np.float32)
+    a = m._topDownActivity(h, hp_)
+    np.testing.assert_allclose(a, case['td_act_ds'], **TOL)
+    np.testing.assert_allclose(m._topDownProbability(a), case['td_prob_ds'], **TOL)
+    np.testing.assert_allclose(m._topDownActivity(h, None), case['td_act_ss'], **TOL)
+    np.testing.assert_allclose(m._topDownActivity(case['td_h_real'].astype(np.float32), None), case['td_act_real'],
+                               rtol=1e-5, atol=5e-5)
+    prob, samp = m._computeVgivenH(h, hp_)
+    np.testing.assert_allclose(prob, case['td_prob_ds'], **TOL)
+    np.testing.assert_array_equal(samp.sum(axis=2), 1.0)            # exactly one base per position
+    # replay injected uniforms against the oracle's multinomial
+    rs = np.random.RandomState(3)
+    pd = case['td_prob_ds']
+    u = rs.rand(pd.shape[0] * pd.shape[3]).astype(np.float32)
+    csum = np.cumsum(pd.transpose(0, 1, 3, 2).reshape(-1, 4), axis=1)
+    safe = np.min(np.abs(csum - u[:, None]), axis=1) > 2e-5
+    want = O.top_down_sample(pd, u.astype(np.float64))
+    got = m._computeVgivenH(h, hp_, uniforms=u)[1]
+    w2 = want.transpose(0, 1, 3, 2).reshape(-1, 4)[safe]
+    g2 = got.transpose(0, 1, 3, 2).reshape(-1, 4)[safe]
+    np.testing.assert_array_equal(g2, w2)
+
+
+@pytest.mark.parametrize('name', CASE_NAMES)
+def test_hidden_sampling_matches_oracle(crbm, O, name):
+    case = load_case(name)
+    hp = case['hyper']
+    P = hp['pooling']
+    m = model_from_case(crbm, case, 'last')
+    p = case['bu_prob_flip0']
+    rs = np.random.RandomState(11)
+    u = rs.rand(p.size // P).astype(np.float32)
+    rows = np.cumsum(p.reshape(-1, P), axis=1)
+    safe = np.min(np.abs(rows - u[:, None]), axis=1) > 2e-5
+    want = O.bottom_up_sample(p, P, u.astype(np.float64)).reshape(-1, P)
+    got = m._bottomUpSample(p.astype(np.float32), uniforms=u).reshape(-1, P)
+    np.testing.assert_array_equal(got[safe], want[safe])
+    assert got.sum(axis=1).max() <= 1.0
+    # Philox path: right marginal frequencies
+    big = np.repeat(p.astype(np.float32), 8, axis=0)
+    s = m._bottomUpSample(big)
+    se = np.sqrt(big.mean() / big.size)
+    assert abs(s.mean() - big.mean()) < 6 * se + 1e-6
+
+
+# ---- A14 ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', CASE_NAMES)
+def test_evaluate_data_and_params_match_reference(crbm, name):
+    case = load_case(name)
+    hp = case['hyper']
+    m = model_from_case(crbm, case, 'last')
+    D = onehot(case['eval_codes'])[:, :, :, :hp['L_trunc']]
+    mfe, nmh = m._evaluateData(D, uniforms=case['u_eval_eval_h'])
+    np.testing.assert_allclose(mfe, case['eval_mfe'], **TOL)
+    np.testing.assert_allclose(nmh, case['eval_nmh'], rtol=1e-6, atol=1e-9)     # a count: exact up to the division
+    wn, ic, medic = m._evaluateParams()
+    np.testing.assert_allclose([wn, ic, medic], [case['eval_wnorm'], case['eval_ic'], case['eval_medic']], **TOL)
+    np.testing.assert_allclose(np.stack(m.getPFMs()), case['pfms'], **TOL)
+
+
+# ---- A8-A12: whole training steps, replaying the reference's uniforms --------------------------------------------------
+@pytest.mark.parametrize('name', CASE_NAMES)
+def test_train_steps_match_reference(crbm, name):
+    case = load_case(name)
+    hp = case['hyper']
+    m = model_from_case(crbm, case, 'init')
+    m.fantasy_h.set_value(case['fh_init'].astype(np.float32))
+    if hp['doublestranded']:
+        m.fantasy_h_prime.set_value(case['fhp_init'].astype(np.float32))
+    for step in range(hp['steps']):
+        u = {'v': np.concatenate([case['u_%d_v%d' % (step, it)] for it in range(hp['cd_k'])]),
+             'h': np.concatenate([case['u_%d_h%d' % (step, it)] for it in range(hp['cd_k'])])}
+        if hp['doublestranded']:
+            u['hp'] = np.concatenate([case['u_%d_hp%d' % (step, it)] for it in range(hp['cd_k'])])
+        m._trainingFct(onehot(case['codes'][step]), uniforms=u)
+        np.testing.assert_array_equal(m.fantasy_h.get_value().astype(np.uint8), case['fh_%d' % step])
+        if hp['doublestranded']:
+            np.testing.assert_array_equal(m.fantasy_h_prime.get_value().astype(np.uint8), case['fhp_%d' % step])
+        np.testing.assert_allclose(m.motif_velocity.get_value(), case['vW_%d' % step], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(m.bias_velocity.get_value(), case['vb_%d' % step], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(m.c_velocity.get_value(), case['vc_%d' % step], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(m.motifs.get_value(), case['W_%d' % step], **TOL)
+        np.testing.assert_allclose(m.bias.get_value(), case['b_%d' % step], **TOL)
+        np.testing.assert_allclose(m.c.get_value(), case['c_%d' % step], **TOL)
+
+
+# ---- oracle parity on fresh seeded inputs, shapes the fixtures do not cover ------------------------------------------------
+@pytest.mark.parametrize('K,M,P,L,ds', [(100, 15, 1, 200, True), (128, 20, 5, 999, True), (64, 25, 1, 120, False),
+                                        (3, 1, 1, 9, True), (35, 33, 2, 96, True), (10, 15, 8, 94, True),
+                                        (1, 3, 16, 50, False)])
+def test_scan_and_free_energy_match_oracle(crbm, O, K, M, P, L, ds):
+    rs = np.random.RandomState(K * 7 + M)
+    N = 3
+    m = crbm.CRBM(K, M, doublestranded=ds, pooling=P, batchsize=N, seed=2)
+    W = (0.4 * rs.randn(K, 1, 4, M)).astype(np.float32)
+    b = (-3 + rs.randn(1, K)).astype(np.float32)
+    c = (0.1 * rs.randn(1, 4)).astype(np.float32)
+    m.motifs.set_value(W); m.bias.set_value(b); m.c.set_value(c)
+    codes = rs.randint(0, 4, size=(N, L))
+    D = onehot(codes)
+    W64, b64, c64, D64 = W.astype(np.float64), b.astype(np.float64), c.astype(np.float64), D.astype(np.float64)
+    np.testing.assert_allclose(m.motifHitProbs(D), O.hit_probs(D64, W64, b64, P, ds), **TOL)
+    np.testing.assert_allclose(m._bottomUpActivity(D, True), O.bottom_up_activity(D64, W64, b64, True), rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(m.freeEnergy(D), O.free_energy(D64, W64, b64, c64, P, ds), **TOL)
+    np.testing.assert_allclose(m.freeEnergy(D, True), O.free_energy_per_motif(D64, W64, b64, c64, P, ds), rtol=1e-5, atol=5e-5)
+
+
+@pytest.mark.parametrize('K,M,P,L,ds,cd_k,N,bs', [(100, 15, 1, 200, True, 1, 12, 12), (40, 20, 5, 119, True, 2, 6, 6),
+                                                  (70, 25, 1, 80, True, 1, 5, 5), (33, 7, 2, 60, False, 3, 4, 6),
+                                                  (9, 33, 4, 92, True, 1, 3, 3)])
+def test_train_step_matches_oracle(crbm, O, K, M, P, L, ds, cd_k, N, bs):
+    """Three steps with injected uniforms against the oracle on larger shapes (incl. the BASELINE C2/C3/C4 motif shapes)."""
+    rs = np.random.RandomState(K + M + P)
+    W = (0.3 * rs.randn(K, 1, 4, M)).astype(np.float32)
+    b = (-4 + 0.5 * rs.randn(1, K)).astype(np.float32)
+    c = (0.1 * rs.randn(1, 4)).astype(np.float32)
+    m = crbm.CRBM(K, M, doublestranded=ds, pooling=P, batchsize=bs, cd_k=cd_k, seed=3)
+    m.motifs.set_value(W); m.bias.set_value(b); m.c.set_value(c)
+    o = O.OracleCRBM(W, b, c, doublestranded=ds, batchsize=bs, pooling=P, cd_k=cd_k)
+    fh = (rs.rand(bs, K, 1, 200) < 0.02).astype(np.float64)
+    fhp = (rs.rand(bs, K, 1, 200) < 0.02).astype(np.float64)
+    for arr in (fh, fhp):
+        g = arr.reshape(bs, K, 1, 200 // P, P)
+        g[...] = g * (np.cumsum(g, axis=4) == 1)
+    o.fantasy_h, o.fantasy_hp = fh.copy(), (fhp.copy() if ds else None)
+    m.fantasy_h.set_value(fh.astype(np.float32))
+    if ds:
+        m.fantasy_h_prime.set_value(fhp.astype(np.float32))
+    lv = 199 + M
+    for step in range(3):
+        codes = rs.randint(0, 4, size=(N, L))
+        us = {'v%d' % it: rs.rand(bs * lv).astype(np.float32) for it in range(cd_k)}
+        us.update({'h%d' % it: rs.rand(bs * K * 200 // P).astype(np.float32) for it in range(cd_k)})
+        us.update({'hp%d' % it: rs.rand(bs * K * 200 // P).astype(np.float32) for it in range(cd_k)})
+        o.train_step(onehot(codes, np.float64), lambda tag, rows: us[tag].astype(np.float64))
+        u = {'v': np.concatenate([us['v%d' % it] for it in range(cd_k)]),
+             'h': np.concatenate([us['h%d' % it] for it in range(cd_k)]),
+             'hp': np.concatenate([us['hp%d' % it] for it in range(cd_k)])}
+        m._trainingFct(onehot(codes), uniforms=u)
+        # sampled states: identical except where a uniform falls within fp32 noise of a threshold
+        got = m.fantasy_h.get_value()
+        mism = np.mean(got != o.fantasy_h)
+        assert mism < 2e-5, mism
+        if mism > 0:
+            pytest.skip("a threshold-adjacent uniform flipped a sample; chains legitimately diverge after that")
+        np.testing.assert_allclose(m.motifs.get_value(), o.W, **TOL)
+        np.testing.assert_allclose(m.bias.get_value(), o.b, **TOL)
+        np.testing.assert_allclose(m.c.get_value(), o.c, **TOL)
+        np.testing.assert_allclose(m.motif_velocity.get_value(), o.vW, rtol=1e-4, atol=1e-6)
+
+
+# ---- statistical equivalence of the Philox-driven chain ----------------------------------------------------------------------
+def test_sampled_chain_statistics(crbm, O):
+    """Without injected uniforms: the fantasy update must be a draw from P(h|v~) — check the hit rate against the
+    probabilities the oracle computes for the sampled v~, and one base per position."""
+    rs = np.random.RandomState(5)
+    K, M, bs = 32, 9, 64
+    W = (0.4 * rs.randn(K, 1, 4, M)).astype(np.float32)
+    b = (-2.5 + 0.3 * rs.randn(1, K)).astype(np.float32)
+    c = np.zeros((1, 4), dtype=np.float32)
+    m = crbm.CRBM(K, M, batchsize=bs, cd_k=1, seed=9, learning_rate=1e-12, momentum=0.0, lambda_rate=0.0)
+    m.motifs.set_value(W); m.bias.set_value(b); m.c.set_value(c)
+    codes = rs.randint(0, 4, size=(bs, 100))
+    m._trainingFct(onehot(codes))
+    v = crbm.PackedSequences(m._train_state['v_model'], bs, 199 + M).to_onehot()
+    np.testing.assert_array_equal(v.sum(axis=2), 1.0)
+    h = m.fantasy_h.get_value()
+    hp = m.fantasy_h_prime.get_value()
+    W64, b64 = W.astype(np.float64), b.astype(np.float64)
+    p = O.bottom_up_probability(O.bottom_up_activity(v.astype(np.float64), W64, b64, False), 1)
+    pp = O.bottom_up_probability(O.bottom_up_activity(v.astype(np.float64), W64, b64, True), 1)
+    for s, q in ((h, p), (hp, pp)):
+        n = q.size
+        z = (s.sum() - q.sum()) / np.sqrt((q * (1 - q)).sum())
+        assert abs(z) < 5, z
+        # per-motif rates too
+        zk = (s.sum(axis=(0, 2, 3)) - q.sum(axis=(0, 2, 3))) / np.sqrt((q * (1 - q)).sum(axis=(0, 2, 3)))
+        assert np.abs(zk).max() < 5.5, zk
+    # visible draws follow softmax(c) = uniform when the chain starts from all-zero hidden units
+    freq = v.mean(axis=(0, 1, 3))
+    assert np.all(np.abs(freq - 0.25) < 5 * np.sqrt(0.25 * 0.75 / (bs * (199 + M))))

@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Headline benchmark: CD-1 training throughput (nucleotides/s) of the cRBM on BASELINE.json's configs[1]
+("synthetic 1M x 200 bp one-hot, 100 motifs x 15 bp, pooling=1, CD-1, batch 100 on 1 B200"), plus motif-scan nt/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
+
+One "step" = one minibatch update (`theano_trainingFct`, reference secomo/convRBM.py:373-438) on `batch` sequences per
+GPU. Weak scaling: every rank trains `batch` sequences per step, one all-reduce of the statistics vector per step.
+  value  : whole-job data nucleotides/s with the packed dataset resident in HBM (CUDA-graph replay of steps)
+  e2e    : same metric through the reference-facing call `CRBM._trainingFct(one-hot NumPy batch)`: pinned-host ->
+           device copy of the fp32 one-hot minibatch, packing, the step, and a device -> host read of the updated
+           visible bias every step
+  scan   : `motifHitProbs` kernel (getHitProbs) nt/s with fp32 probabilities written to HBM
+  roofline / cpu_baseline: see DESIGN.md "Measurement".
+`--impl reference` times the CPU restatement of the reference's Theano graph (oracle/crbm_torch_cpu.py; Theano itself is
+not installable offline) on the host cores with the same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1..3]; n_seq is the per-rank synthetic dataset (each minibatch is read once per epoch)
+    'c2': dict(name='C2: synthetic 1M x 200 bp, K=100, M=15, pooling=1, CD-1, batch 100/GPU', K=100, M=15, P=1, cd_k=1,
+               batch=100, L=200, n_seq=1000000, default_steps=10000),
+    'c3': dict(name='C3: synthetic x 1 kb, K=128, M=20, pooling=5, CD-1, batch 128/GPU', K=128, M=20, P=5, cd_k=1,
+               batch=128, L=1000, n_seq=262144, default_steps=2048),
+    'c4': dict(name='C4: synthetic x 500 bp, K=512, M=25, pooling=1, CD-5, batch 128/GPU', K=512, M=25, P=1, cd_k=5,
+               batch=128, L=500, n_seq=65536, default_steps=512),
+}
+METRIC = 'CD-1 train nt/s'
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'MEASURED_PEAKS.json', float(p.get('sm_max_mhz', 1965.0))
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md)', 1965.0
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(',')])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def run_reference(args, wl, rank, world):
+    """CPU arm: the reference's train step restated with torch-CPU ops, all host threads, bounded sample."""
+    if rank != 0:
+        return
+    import torch
+    from oracle.crbm_torch_cpu import TorchCpuCRBM, random_onehot
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = TorchCpuCRBM(wl['K'], wl['M'], pooling=wl['P'], cd_k=wl['cd_k'], batchsize=wl['batch'], seed=0)
+    Lt = int((wl['L'] - wl['M'] + 1) / wl['P']) * wl['P'] + wl['M'] - 1
+    nb = 8
+    data = [random_onehot(wl['batch'], Lt, 100 + i) for i in range(nb)]
+    steps, warm = args.steps, args.warmup
+    for i in range(warm):
+        m.train_step(data[i % nb])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        m.train_step(data[i % nb])
+    dt = time.perf_counter() - t0
+    nts = steps * wl['batch'] * Lt / dt
+    line = {'metric': METRIC, 'value': nts, 'unit': 'nt/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
+            'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': wl['name'], 'batch_per_step': wl['batch'], 'seq_len': Lt},
+            'cpu_baseline': {'value': nts, 'unit': 'nt/s', 'cores': cores, 'kind': 'port',
+                             'sample': '%d train steps of %d x %d bp (torch-CPU restatement of the Theano graph; Theano not '
+                                       'installable offline)' % (steps, wl['batch'], Lt)},
+            'e2e': {'value': nts, 'unit': 'nt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline_sample(wl, budget_s=12.0):
+    import torch
+    from oracle.crbm_torch_cpu import TorchCpuCRBM, random_onehot
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = TorchCpuCRBM(wl['K'], wl['M'], pooling=wl['P'], cd_k=wl['cd_k'], batchsize=wl['batch'], seed=0)
+    Lt = int((wl['L'] - wl['M'] + 1) / wl['P']) * wl['P'] + wl['M'] - 1
+    data = [random_onehot(wl['batch'], Lt, 100 + i) for i in range(4)]
+    for i in range(3):
+        m.train_step(data[i % 4])
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and n < 5000:
+        m.train_step(data[n % 4])
+        n += 1
+    dt = time.perf_counter() - t0
+    return {'value': n * wl['batch'] * Lt / dt, 'unit': 'nt/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d train steps of %d x %d bp in %.1f s (torch-CPU restatement of the Theano graph)' % (n, wl['batch'], Lt, dt)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-scan', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--steps-per-graph', type=int, default=8)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        args.steps = args.steps if args.steps is not None else 40
+        args.warmup = args.warmup if args.warmup is not None else 3
+        run_reference(args, wl, rank, world)
+        return
+    args.steps = args.steps if args.steps is not None else wl['default_steps']
+    args.warmup = args.warmup if args.warmup is not None else 64
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import crbm_b200
+    from crbm_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+
+    K, M, P, B, L = wl['K'], wl['M'], wl['P'], wl['batch'], wl['L']
+    np.random.seed(0)
+    model = crbm_b200.CRBM(K, M, epochs=1, batchsize=B * world, pooling=P, cd_k=wl['cd_k'], seed=1234 + rank, device=dev)
+    Lt = model._truncated_length(L)
+    n_seq = wl['n_seq']
+    data = crbm_b200.PackedSequences.random(n_seq, Lt, seed=1234 + rank, device=dev)
+    data.is_local_shard = True      # weak scaling: every rank owns its own synthetic dataset
+
+    def run_steps(count, first):
+        model._train_full_batches(data, first % (n_seq // B), count, steps_per_graph=args.steps_per_graph)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = lib.crbm_launch_count()
+    run_steps(args.warmup, 0)
+    barrier()
+    launches_warm = lib.crbm_launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    run_steps(args.steps, args.warmup)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    nt_per_step = B * Lt * world
+    value = args.steps * nt_per_step / (ms * 1e-3)
+    launches_per_step = model._engine.get('launches_per_step', 0)   # counted while capturing the step graph
+
+    line = {'metric': METRIC, 'value': value, 'unit': 'nt/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': wl['name'], 'batch_per_gpu': B, 'seq_len': Lt, 'global_batch': B * world,
+                       'parallelism': 'dp%d' % world, 'steps_per_graph': args.steps_per_graph,
+                       'l2': 'every step reads a new minibatch from a %d-sequence packed dataset (%.0f MB); model state '
+                             '(W, tables, persistent chain) is on-chip/L2 resident by design' % (n_seq, n_seq * data.row_words * 4 / 1e6)},
+            'gpu_launches': launches_per_step * args.steps}
+
+    if rank == 0:
+        hbm_peak, peak_src, sm_max = peaks()
+        # --- per-kernel device time of one step (CUDA events around eager launches on the launching stream) ------------
+        kern = time_step_kernels(model, data, B, dev)
+        line['step_kernels_us'] = kern
+        fused_us = kern.get('positive_phase_fused', 0.0)
+        # algorithmic bytes of the positive-phase kernel: packed minibatch + W tile per k-tile CTA group + partials
+        ktiles = (K + 31) // 32
+        alg_bytes = B * data.row_words * 4 * ktiles + K * 4 * M * 4 + kern.get('_partial_bytes', 0)
+        adds = B * (Lt - M + 1) * K * M * (2 + 2 + 1)      # up-pass both strands + stats both strands + sparsity stat
+        line['roofline'] = {'bound': 'hbm', 'kernel': 'v2h_fused_kernel<MW=%d, STAT_P|STAT_Q> (positive phase)' % (3 * ((M + 2) // 3)),
+                            'achieved': alg_bytes / (fused_us * 1e-6) / 1e9 if fused_us else None, 'peak': hbm_peak,
+                            'unit': 'GB/s', 'frac': (alg_bytes / (fused_us * 1e-6) / 1e9 / hbm_peak) if fused_us else None,
+                            'traffic': None, 'peak_source': peak_src,
+                            'note': 'fused training kernels are issue/shared-memory bound, not HBM bound (SURVEY 8d): '
+                                    'see fp32_add_frac',
+                            'gather_adds_per_launch': adds,
+                            'fp32_add_frac': (adds / (fused_us * 1e-6) / (148 * 128 * sm_max * 1e6)) if fused_us else None}
+        if not args.no_scan:
+            line['scan'] = bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src)
+        if not args.no_e2e:
+            line['e2e'] = bench_e2e(model, B, Lt, world, dev, min(args.steps, 2000))
+        if not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline_sample(wl)
+        line['clocks'] = clocks
+        print(json.dumps(line))
+    elif not args.no_e2e:
+        bench_e2e(model, B, Lt, world, dev, min(args.steps, 2000))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def time_step_kernels(model, data, B, dev):
+    """Device time of each phase of one training step, eager launches bracketed by CUDA events (warm)."""
+    import torch
+    from crbm_b200 import _lib
+    lib = _lib.load()
+    out = {}
+    a = model._fill_args(data.words.data_ptr(), data.row_words, B, data.L)
+    s = _lib.stream_handle()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    reps = 50
+    for _ in range(5):
+        lib.crbm_train_accumulate(a, s); lib.crbm_train_apply(a, s)
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(reps):
+        lib.crbm_train_accumulate(a, s)
+    ev[1].record()
+    for _ in range(reps):
+        lib.crbm_train_apply(a, s)
+    ev[2].record()
+    torch.cuda.synchronize()
+    out['accumulate_eager'] = ev[0].elapsed_time(ev[1]) * 1e3 / reps
+    out['apply_eager'] = ev[1].elapsed_time(ev[2]) * 1e3 / reps
+    # positive phase alone: n_data rows, cd_k sweeps cannot be switched off, so time via the free-standing entry
+    # points that launch exactly one fused kernel: crbm_free_energy (F_FE variant) is not the same kernel, hence
+    # the positive-phase kernel is timed by differencing accumulate with an empty minibatch.
+    a0 = model._fill_args(data.words.data_ptr(), data.row_words, 0, data.L)
+    for _ in range(5):
+        lib.crbm_train_accumulate(a0, s)
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(reps):
+        lib.crbm_train_accumulate(a0, s)
+    ev[1].record()
+    torch.cuda.synchronize()
+    out['accumulate_without_positive_phase'] = ev[0].elapsed_time(ev[1]) * 1e3 / reps
+    out['positive_phase_fused'] = max(0.0, out['accumulate_eager'] - out['accumulate_without_positive_phase'])
+    K, M = model.num_motifs, model.motif_length
+    mw = 3 * ((M + 2) // 3)
+    out['_partial_bytes'] = ((K + 31) // 32) * max(1, 148 // ((K + 31) // 32)) * (8 * mw + 4) * 32 * 4
+    return out
+
+
+def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
+    """getHitProbs kernel with fp32 output materialised in HBM; input and output larger than L2."""
+    import torch
+    import crbm_b200
+    from crbm_b200 import _lib
+    lib = _lib.load()
+    Lh = Lt - M + 1
+    n = max(1024, min(200000, int(8e9 // (4 * K * Lh))))
+    seqs = crbm_b200.PackedSequences.random(n, Lt, seed=99, device=dev)
+    out = torch.empty((n, K, 1, Lh), dtype=torch.float32, device=dev)
+    s = _lib.stream_handle()
+
+    def go():
+        _lib.check(lib.crbm_v2h_dense(_lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias),
+                                      K, M, model.pooling, _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(out), s), 'scan')
+    for _ in range(3):
+        go()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        go()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nt = n * Lt
+    alg = n * (Lt / 4.0) + 4.0 * n * K * Lh
+    return {'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
+            'sequences': n, 'ms': ms, 'output_GB': 4.0 * n * K * Lh / 1e9,
+            'roofline': {'bound': 'hbm', 'kernel': 'v2h_dense_kernel', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
+                         'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
+                         'peak_source': peak_src, 'bytes_per_nt': alg / nt}}
+
+
+def bench_e2e(model, B, Lt, world, dev, steps):
+    """Through the reference-facing call with HOST buffers: pinned one-hot fp32 minibatch -> device every step, the
+    step itself, and a device -> host read of the updated visible bias c (16 bytes) every step."""
+    import numpy as np
+    import torch
+    nb = 16
+    rs = np.random.RandomState(7)
+    host = []
+    for i in range(nb):
+        codes = torch.from_numpy(rs.randint(0, 4, size=(B, Lt)))
+        oh = torch.nn.functional.one_hot(codes, 4).permute(0, 2, 1).reshape(B, 1, 4, Lt).to(torch.float32).contiguous()
+        host.append(oh.pin_memory())
+    sink = torch.empty(4, dtype=torch.float32).pin_memory()
+
+    def one(i):
+        d = host[i % nb].to(dev, non_blocking=True)
+        model._trainingFct(d, local_shard=True)
+        sink.copy_(model._t_c.reshape(-1), non_blocking=False)
+
+    for i in range(5):
+        one(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {'value': steps * B * Lt * world / (ms * 1e-3), 'unit': 'nt/s', 'h2d_bytes_per_step': B * 4 * Lt * 4,
+            'd2h_bytes_per_step': 16, 'steps': steps,
+            'call': 'CRBM._trainingFct(one-hot fp32 batch in pinned host memory) + read back c'}
+
+
+if __name__ == '__main__':
+    main()

@@ -181,6 +181,8 @@ class CRBM(object):
         if doublestranded:
             self.fantasy_h_prime = _FantasyParam(self, 1)
         self._train_state = None
+        self._engine = None
+        self._use_graphs = True
         self.theano_getHitProbs = self.motifHitProbs      # the attribute the north star calls getHitProbs (:508)
         self.getHitProbs = self.motifHitProbs
         self.theano_freeEnergy = lambda data: self.freeEnergy(data)
@@ -399,12 +401,12 @@ class CRBM(object):
         a.stats, a.workspace, a.workspace_bytes = st['stats'].data_ptr(), st['workspace'].data_ptr(), st['ws_bytes']
         return a
 
-    def _train_packed(self, seqs, start, end, uniforms=None):
-        """One training step on rows [start,end) of `seqs` (this rank's shard is cut here)."""
+    def _train_packed(self, seqs, start, end, uniforms=None, local_shard=False):
+        """One training step on rows [start,end) of `seqs` (this rank's shard is cut here unless `local_shard`)."""
         lib = self._require_cuda()
         torch = _torch()
         n = end - start
-        if self._world > 1:
+        if self._world > 1 and not local_shard:
             per = (n + self._world - 1) // self._world
             lo = min(n, self._rank * per)
             hi = min(n, lo + per)
@@ -423,10 +425,105 @@ class CRBM(object):
         _lib.check(lib.crbm_train_apply(a, s), 'train_apply')
         self._step += 1
 
-    def _trainingFct(self, data, uniforms=None):
-        """Train on one mini-batch (reference :524-526 -> theano_trainingFct)."""
+    # ---- CUDA-graph replay of whole training steps ------------------------------------------------------------------
+    def _local_shard(self, seqs):
+        """Rows of the full minibatches this rank trains on, contiguous, batch-major: [n_full][local_batch]."""
+        lb = self._local_batch
+        if self._world == 1 or getattr(seqs, 'is_local_shard', False):
+            n_full = seqs.N // lb
+            return seqs.words[:n_full * lb], n_full
+        n_full = seqs.N // self.batchsize
+        w = seqs.words[:n_full * self.batchsize].view(n_full, self.batchsize, seqs.row_words)
+        return w[:, self._rank * lb:(self._rank + 1) * lb].reshape(n_full * lb, seqs.row_words).contiguous(), n_full
+
+    def _graph_engine(self, seqs, steps_per_graph):
+        """Capture `steps_per_graph` consecutive training steps (accumulate -> all-reduce -> apply) into one CUDA graph.
+        The minibatch cursor and the Philox step live in device memory, so the same graph is replayed for every step."""
+        torch = _torch()
+        lib = self._require_cuda()
+        key = (seqs.words.data_ptr(), seqs.N, seqs.L, steps_per_graph)
+        eng = getattr(self, '_engine', None)
+        if eng is not None and eng['key'] == key:
+            return eng
+        shard, n_full = self._local_shard(seqs)
+        eng = dict(key=key, shard=shard, n_full=n_full, graphs={})
+        eng['step_dev'] = torch.zeros(1, dtype=torch.int64, device=self._device)
+        eng['batch_dev'] = torch.zeros(1, dtype=torch.int32, device=self._device)
+        a = self._fill_args(shard.data_ptr(), seqs.row_words, self._local_batch, seqs.L)
+        a.step_dev, a.batch_index_dev, a.n_batches = eng['step_dev'].data_ptr(), eng['batch_dev'].data_ptr(), n_full
+        eng['args'] = a
+        self._engine = eng
+        return eng
+
+    def _run_steps_once(self, eng):
+        lib = _lib.load()
+        s = _lib.stream_handle()
+        a = eng['args']
+        _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
+        if self._world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._train_state['stats'])
+        _lib.check(lib.crbm_train_apply(a, s), 'train_apply')
+
+    def _graph_for(self, eng, nsteps):
+        torch = _torch()
+        g = eng['graphs'].get(nsteps)
+        if g is None:
+            # warm-up outside capture (first-use cudaFuncSetAttribute, NCCL communicator setup), state restored after
+            saved = [t.clone() for t in (self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
+                                         self._t_fantasy, eng['step_dev'], eng['batch_dev'])]
+            side = torch.cuda.Stream(device=self._device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._run_steps_once(eng)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self._device)
+            for t, v in zip((self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
+                             self._t_fantasy, eng['step_dev'], eng['batch_dev']), saved):
+                t.copy_(v)
+            g = torch.cuda.CUDAGraph()
+            c0 = _lib.load().crbm_launch_count()
+            with torch.cuda.graph(g):
+                for _ in range(nsteps):
+                    self._run_steps_once(eng)
+            eng['launches_per_step'] = int(_lib.load().crbm_launch_count() - c0) // nsteps
+            eng['graphs'][nsteps] = g
+        return g
+
+    def _train_full_batches(self, seqs, first_batch, count, steps_per_graph=8):
+        """Train on `count` consecutive full minibatches starting at minibatch `first_batch`, by graph replay."""
+        if count <= 0:
+            return
+        eng = self._graph_engine(seqs, steps_per_graph)
+        eng['step_dev'].fill_(self._step)
+        eng['batch_dev'].fill_(first_batch)
+        big, rest = divmod(count, steps_per_graph)
+        if big:
+            g = self._graph_for(eng, steps_per_graph)
+            for _ in range(big):
+                g.replay()
+        if rest:
+            g1 = self._graph_for(eng, 1)
+            for _ in range(rest):
+                g1.replay()
+        self._step += count
+
+    def _train_epoch(self, seqs):
+        """All minibatches of one epoch in order (no shuffling, reference :613-615); a short last batch runs eagerly."""
+        n_full = seqs.N // self.batchsize
+        if self._use_graphs:
+            self._train_full_batches(seqs, 0, n_full)
+        else:
+            for i in range(n_full):
+                self._train_packed(seqs, i * self.batchsize, (i + 1) * self.batchsize)
+        if seqs.N % self.batchsize:
+            self._train_packed(seqs, n_full * self.batchsize, seqs.N)
+
+    def _trainingFct(self, data, uniforms=None, local_shard=False):
+        """Train on one mini-batch (reference :524-526 -> theano_trainingFct). Under data parallelism `data` is the
+        global minibatch (every rank passes the same array) unless local_shard=True (this rank's rows only)."""
         seqs = self._as_packed(data)
-        self._train_packed(seqs, 0, seqs.N, uniforms)
+        self._train_packed(seqs, 0, seqs.N, uniforms, local_shard)
 
     def _evaluateData(self, data, uniforms=None):
         """[mean free energy, mean of a sampled forward-strand H] (reference :466-472, 517-522)."""
@@ -482,8 +579,7 @@ class CRBM(object):
             print("Start training the model...")
         starttime = time.time()
         for epoch in range(self.epochs):
-            for [start, end] in self._iterateBatchIndices(training.N, self.batchsize):
-                self._train_packed(training, start, end)
+            self._train_epoch(training)
             meanfe, meannmh = self._epoch_metrics(test)
             [twn_, ic_, medic_] = self._evaluateParams()
             if verbose:

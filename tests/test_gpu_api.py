@@ -1,0 +1,102 @@
+"""The secomo.CRBM call sequences the reference's own tests and tutorial exercise (reference tests/testcrbm.py:100-146,
+257-363, 507-519; secomo/tutorial.py:13-44), run on the GPU path, plus graph-replay == eager training."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def data():
+    import crbm_b200
+    return crbm_b200.load_sample()
+
+
+def test_training_runs_both_strand_modes(data, capsys):
+    """reference test_training: fit(data[:100]) and fit(data, data[:10]) for ds in (True, False)."""
+    from crbm_b200 import CRBM
+    for ds in (True, False):
+        model = CRBM(num_motifs=10, motif_length=15, doublestranded=ds, epochs=1, seed=4)
+        w0 = model.motifs.get_value()
+        model.fit(data[:100])
+        model.fit(data[:95], data[:10])        # 95: exercises the short last batch
+        assert np.all(np.isfinite(model.motifs.get_value())) and not np.allclose(w0, model.motifs.get_value())
+    out = capsys.readouterr().out
+    assert "BatchSize: 20" in out and "Epoch 0: FE=" in out and "Training finished after:" in out
+    assert "NumH=" in out and "WNorm=" in out and "medIC=" in out
+
+
+def test_motifhitprobs_dims_and_free_energy_dims(data):
+    from crbm_b200 import CRBM
+    d = data[:100]
+    for ds in (True, False):
+        model = CRBM(num_motifs=10, motif_length=15, doublestranded=ds, epochs=1)
+        pred = model.motifHitProbs(d)
+        assert pred.shape == (100, 10, 1, 200 - 15 + 1) and pred.dtype == np.float32
+        assert np.all((pred >= 0) & (pred <= 1))
+        assert model.freeEnergy(d[:11]).shape == (11,)
+        assert model.freeEnergy(d[:11], permotif=True).shape == (11, 10)
+        assert model.getHitProbs(d[:3]).shape == (3, 10, 1, 186)
+
+
+def test_topdown_full_pipeline_properties(data):
+    """reference test_topdown_*_full: V | H(D) has the data's shape, probabilities and samples sum to N*L."""
+    from crbm_b200 import CRBM
+    d = data[:11]
+    model = CRBM(num_motifs=10, motif_length=5, seed=5)
+    _, h1 = model._computeHgivenV(d, False)
+    _, h2 = model._computeHgivenV(d, True)
+    for hp in (None, h2):
+        p, s = model._computeVgivenH(h1, hp)
+        assert p.shape == d.shape and s.shape == d.shape
+        np.testing.assert_allclose(p.sum(), d.shape[0] * d.shape[3], rtol=1e-4, atol=1e-4)
+        np.testing.assert_allclose(s.sum(), d.shape[0] * d.shape[3], rtol=1e-4, atol=1e-4)
+    zeros = np.zeros((11, 10, 1, 196), dtype=np.float32)
+    p, _ = model._computeVgivenH(zeros, zeros)
+    np.testing.assert_allclose(p, 0.25, rtol=1e-5, atol=1e-5)     # c == 0 at construction
+
+
+def test_tutorial_flow(tmpdir, data):
+    """secomo/tutorial.py:13-44 without the plotting calls."""
+    from crbm_b200 import CRBM
+    model = CRBM(num_motifs=10, motif_length=15, epochs=1, seed=6)
+    model.fit(data)
+    path = os.path.join(tmpdir.strpath, 'oct4_model_params.pkl')
+    model.saveModel(path)
+    model2 = CRBM.loadModel(path)
+    np.testing.assert_array_equal(model.motifs.get_value(), model2.motifs.get_value())
+    assert len(model2.getPFMs()) == 10
+    matches = model2.motifHitProbs(data[:100])
+    assert matches.shape == (100, 10, 1, 186)
+    np.testing.assert_array_equal(matches, model.motifHitProbs(data[:100]))
+
+
+def test_graph_replay_equals_eager_steps(data):
+    """Replaying the captured step graph must give bit-identical parameters to launching every step eagerly."""
+    import crbm_b200
+    from crbm_b200 import CRBM
+    seqs = crbm_b200.PackedSequences.from_onehot(data[:20 * 13 + 7])
+    out = []
+    for graphs in (True, False):
+        np.random.seed(1)
+        m = CRBM(num_motifs=12, motif_length=9, epochs=2, cd_k=2, seed=77)
+        m._use_graphs = graphs
+        m.fit(seqs)
+        out.append((m.motifs.get_value(), m.bias.get_value(), m.c.get_value(), m.fantasy_h.get_value()))
+    for a, b in zip(*out):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_unsupported_shapes_fail_loudly(data):
+    from crbm_b200 import CRBM
+    m = CRBM(num_motifs=2, motif_length=34)
+    with pytest.raises(NotImplementedError):
+        m.motifHitProbs(data[:2])
+    m = CRBM(num_motifs=2, motif_length=5, pooling=3)       # 196 % 3 != 0: the reference's reshape fails too
+    with pytest.raises(ValueError):
+        m.motifHitProbs(data[:2])
+    m = CRBM(num_motifs=2, motif_length=5, pooling=7)       # 7 does not divide the 200-long persistent chain
+    with pytest.raises(ValueError):
+        m.fit(data[:20])

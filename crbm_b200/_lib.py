@@ -15,6 +15,7 @@ c_u64, c_size_t = ctypes.c_uint64, ctypes.c_size_t
 
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA = 0, -1, -2, -3
 FANTASY_LEN = 200
+FANTASY_WORDS = 208
 MAX_MOTIF_LEN = 33
 MAX_POOLING = 16
 STRAND_FWD, STRAND_RC, STRAND_SUM = 0, 1, 2
@@ -51,6 +52,7 @@ SIGNATURES = {
     'crbm_last_error': (ctypes.c_char_p, []),
     'crbm_packed_row_words': (c_int, [c_int]),
     'crbm_hidden_words': (c_int, [c_int]),
+    'crbm_fantasy_words': (c_int, []),
     'crbm_pack_onehot': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'crbm_pack_codes': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'crbm_unpack_onehot': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -16,6 +16,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(CSRC, '_build')
 LIB = os.path.join(HERE, 'libcrbm_b200.so')
 MWS = (3, 6, 9, 12, 15, 18, 21, 24, 27, 30, 33)
+KSS = (1, 2, 3, 4, 5, 6, 7, 8, 9)
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -39,6 +40,8 @@ def _jobs():
         jobs.append((os.path.join(CSRC, src), os.path.join(OBJ, src[:-3] + '.o'), []))
     for mw in MWS:
         jobs.append((os.path.join(CSRC, 'v2h_inst.cu'), os.path.join(OBJ, 'v2h_inst_%d.o' % mw), ['-DCRBM_MW=%d' % mw]))
+    for ks in KSS:
+        jobs.append((os.path.join(CSRC, 'v2h_mma_inst.cu'), os.path.join(OBJ, 'v2h_mma_inst_%d.o' % ks), ['-DCRBM_KS=%d' % ks]))
     return jobs
 
 

@@ -176,7 +176,7 @@ class CRBM(object):
         self._seed = int(time.time()) if seed is None else int(seed)                           # reference :155
         self._step = 0
         self._kw = (num_motifs + 31) // 32
-        self._t_fantasy = torch.zeros((2, self._local_batch, self._kw, FANTASY_LEN), dtype=torch.int32, device=dev)
+        self._t_fantasy = torch.zeros((2, self._local_batch, self._kw, _lib.FANTASY_WORDS), dtype=torch.int32, device=dev)
         self.fantasy_h = _FantasyParam(self, 0)
         if doublestranded:
             self.fantasy_h_prime = _FantasyParam(self, 1)

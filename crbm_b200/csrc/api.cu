@@ -34,6 +34,7 @@ int crbm_abi_version(void) { return 1; }
 const char *crbm_last_error(void) { return crbm::g_error; }
 int crbm_packed_row_words(int L) { return L > 0 ? crbm::packed_row_words(L) : CRBM_ERR_ARG; }
 int crbm_hidden_words(int K) { return K > 0 ? crbm::ceil_div(K, 32) : CRBM_ERR_ARG; }
+int crbm_fantasy_words(void) { return crbm::FANTASY_WORDS; }
 unsigned long long crbm_launch_count(void) { return crbm::g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

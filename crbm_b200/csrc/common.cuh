@@ -26,6 +26,17 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 inline int packed_row_words(int L) { return 4 * ceil_div(FRONT_PAD_WORDS + ceil_div(L, 16) + BACK_PAD_WORDS, 4); }
 int num_sms();
 
+// ---- hidden bit planes (fantasy particles) --------------------------------------------------------------------------
+// uint32 H[strand][n][kt][jb][16], jb = j/16. The 16 words of a (k-tile, position block) are the 16 warp ballots of the
+// MMA accumulator fragments: word ((mt*2+h)*2+nt)*2+e, bit 4g+q  <->  motif 32kt+16mt+8h+g, position 16jb+8nt+2q+e.
+constexpr int FANTASY_BLOCKS = (FANTASY_LEN + 15) / 16;
+constexpr int FANTASY_WORDS = FANTASY_BLOCKS * 16;          // words per (strand, particle, k-tile)
+__host__ __device__ inline int hbit_word(int j, int kl) {   // kl = motif index inside its k-tile (0..31)
+    const int jb = j >> 4, nt = (j >> 3) & 1, e = j & 1, mt = kl >> 4, h = (kl >> 3) & 1;
+    return jb * 16 + ((mt * 2 + h) * 2 + nt) * 2 + e;
+}
+__host__ __device__ inline int hbit_bit(int j, int kl) { return 4 * (kl & 7) + ((j >> 1) & 3); }
+
 // ---- Philox4x32-10 (counter-based; Salmon et al. 2011) ----------------------------------------------------
 __host__ __device__ inline uint4 philox4x32(uint4 ctr, uint2 key) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

@@ -187,27 +187,29 @@ __global__ void visible_softmax_sample_kernel(const float *__restrict__ act, int
     }
 }
 
-// ---- fantasy particles: bit planes [s][n][kw][200] <-> dense (B,K,1,200) -------------------------------------------
+// ---- fantasy particles: bit planes [n][kt][FANTASY_WORDS] (layout: common.cuh) <-> dense (B,K,1,200) -----------------
 __global__ void bits_to_dense_kernel(const uint32_t *__restrict__ bits, int Bn, int K, int kw, float *__restrict__ dense) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)Bn * K * FANTASY_LEN) return;
     const int j = (int)(gid % FANTASY_LEN);
     const int k = (int)((gid / FANTASY_LEN) % K);
     const int n = (int)(gid / ((long long)FANTASY_LEN * K));
-    const uint32_t w = bits[((size_t)n * kw + (k >> 5)) * FANTASY_LEN + j];
-    dense[gid] = (float)((w >> (k & 31)) & 1u);
+    const uint32_t w = bits[((size_t)n * kw + (k >> 5)) * FANTASY_WORDS + hbit_word(j, k & 31)];
+    dense[gid] = (float)((w >> hbit_bit(j, k & 31)) & 1u);
 }
 
 __global__ void dense_to_bits_kernel(const float *__restrict__ dense, int Bn, int K, int kw, uint32_t *__restrict__ bits) {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)Bn * kw * FANTASY_LEN) return;
-    const int j = (int)(gid % FANTASY_LEN);
-    const int t = (int)((gid / FANTASY_LEN) % kw);
-    const int n = (int)(gid / ((long long)FANTASY_LEN * kw));
+    if (gid >= (long long)Bn * kw * FANTASY_WORDS) return;
+    const int wi = (int)(gid % FANTASY_WORDS);
+    const int t = (int)((gid / FANTASY_WORDS) % kw);
+    const int n = (int)(gid / ((long long)FANTASY_WORDS * kw));
+    const int jb = wi >> 4, f = wi & 15, mt = f >> 3, h = (f >> 2) & 1, nt = (f >> 1) & 1, e = f & 1;
     uint32_t w = 0u;
-    for (int q = 0; q < 32; ++q) {
-        const int k = t * 32 + q;
-        if (k < K && dense[((size_t)n * K + k) * FANTASY_LEN + j] != 0.f) w |= 1u << q;
+    for (int b = 0; b < 32; ++b) {
+        const int g = b >> 2, q = b & 3;
+        const int k = t * 32 + 16 * mt + 8 * h + g, j = 16 * jb + 8 * nt + 2 * q + e;
+        if (k < K && j < FANTASY_LEN && dense[((size_t)n * K + k) * FANTASY_LEN + j] != 0.f) w |= 1u << b;
     }
     bits[gid] = w;
 }
@@ -303,7 +305,7 @@ int crbm_hidden_bits_to_dense(const uint32_t *bits, int B, int K, float *dense, 
 int crbm_hidden_dense_to_bits(const float *dense, int B, int K, uint32_t *bits, void *stream) {
     CRBM_CHECK_ARG(bits && dense && B > 0 && K > 0, "crbm_hidden_dense_to_bits: bad arguments");
     const int kw = ceil_div(K, 32);
-    dense_to_bits_kernel<<<blocks_for((long long)B * kw * FANTASY_LEN, 256), 256, 0, (cudaStream_t)stream>>>(
+    dense_to_bits_kernel<<<blocks_for((long long)B * kw * FANTASY_WORDS, 256), 256, 0, (cudaStream_t)stream>>>(
         dense, B, K, kw, bits);
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;

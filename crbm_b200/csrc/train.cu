@@ -4,7 +4,7 @@
 //   h2v_bits_kernel     A5+A6: sparse hidden bit planes -> visible activity -> 4-way softmax -> sampled packed V
 //   reduce_partials     per-CTA register accumulators -> the rank's `stats` vector
 //   apply_update        A11 sparsity factor + A12 momentum update of W, b, c
-#include "v2h.cuh"
+#include "v2h_mma.cuh"
 
 namespace crbm {
 
@@ -22,6 +22,19 @@ static int dispatch_fused(int MW, int flags, const V2HParams &p, dim3 grid, cuda
 #undef CRBM_CASE
     }
     set_error("motif length bucket %d not built", MW);
+    return CRBM_ERR_UNSUPPORTED;
+}
+#define CRBM_FOR_EACH_KS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
+#define CRBM_DECLARE_KS(KSV) template <> int launch_v2h_mma<KSV>(int, const V2HParams &, dim3, cudaStream_t);
+CRBM_FOR_EACH_KS(CRBM_DECLARE_KS)
+#undef CRBM_DECLARE_KS
+static int dispatch_mma(int KS, int flags, const V2HParams &p, dim3 grid, cudaStream_t s) {
+    switch (KS) {
+#define CRBM_CASE(KSV) case KSV: return launch_v2h_mma<KSV>(flags, p, grid, s);
+        CRBM_FOR_EACH_KS(CRBM_CASE)
+#undef CRBM_CASE
+    }
+    set_error("MMA k-step bucket %d not built", KS);
     return CRBM_ERR_UNSUPPORTED;
 }
 static int dispatch_dense(int MW, const DenseParams &p, dim3 grid, cudaStream_t s) {
@@ -59,10 +72,15 @@ static Tiling make_tiling(int K, int M, int pooling, int Lh, int n_rows) {
 static int max_gy(int K) { const int kt = ceil_div(K, KTILE); return num_sms() / kt > 0 ? num_sms() / kt : 1; }
 
 // ---- A5 + A6 on bit planes ------------------------------------------------------------------------------------
-// One CTA per particle, one thread per visible position (Lv = 199+M <= 256).
+// grid (particles, 2 halves of the visible sequence), 128 threads = one visible position each (Lv = 199+M <= 232).
+//  1. the particle's bit planes (MMA-fragment order, common.cuh) are re-ordered in shared memory into one word of 32
+//     motif bits per hidden position;
+//  2. W is staged as float4 {A,C,G,T} per (k, m) when it fits, so a hit costs one LDS.128 and four adds;
+//  3. every thread gathers the hits that reach its position, takes the 4-way softmax, samples one base and the
+//     half-warps assemble the packed 2-bit words.
 struct H2VParams {
-    const uint32_t *bits;     // [2][B][kw][200]
-    int Bn, K, kw, M, ds;
+    const uint32_t *bits;     // [2][B][kw][FANTASY_WORDS]
+    int Bn, K, kw, M, ds, w4_in_smem;
     const float *W, *c;
     uint32_t *v_packed;       // rows of Lv bases
     int v_row_words;
@@ -72,41 +90,69 @@ struct H2VParams {
     const unsigned long long *step_dev;
     float *base_counts;       // stats slot (4 floats) or null
 };
+constexpr int H2V_THREADS = 128, H2V_SPLIT = 112;      // positions [0,112) and [112, Lv): both multiples of 16 bases/word
 
-__global__ void __launch_bounds__(256) h2v_bits_kernel(const H2VParams p) {
-    extern __shared__ uint32_t sbits[];            // [2][kw][200]
-    const int n = blockIdx.x, i = threadIdx.x;
-    const int Lv = FANTASY_LEN + p.M - 1;
-    const int per_strand = p.kw * FANTASY_LEN;
+__device__ __forceinline__ uint32_t gather_stride4(uint32_t x) {   // bits 0,4,..,28 -> bits 0..7
+    x = (x | (x >> 3)) & 0x03030303u;
+    x = (x | (x >> 6)) & 0x000F000Fu;
+    return (x | (x >> 12)) & 0xFFu;
+}
+
+__global__ void __launch_bounds__(H2V_THREADS) h2v_bits_kernel(const H2VParams p) {
+    extern __shared__ __align__(16) unsigned char h2v_smem[];
+    const int M = p.M, Lv = FANTASY_LEN + M - 1;
     const int strands = p.ds ? 2 : 1;
-    for (int e = threadIdx.x; e < strands * per_strand; e += blockDim.x) {
-        const int s = e / per_strand, r = e - s * per_strand;
-        sbits[e] = p.bits[((size_t)s * p.Bn + n) * per_strand + r];
+    uint32_t *posw = reinterpret_cast<uint32_t *>(h2v_smem);                                    // [strand][kw][FANTASY_WORDS]
+    float4 *w4 = reinterpret_cast<float4 *>(h2v_smem + (size_t)strands * p.kw * FANTASY_WORDS * 4);  // [K][M]
+    const int n = blockIdx.x, half = blockIdx.y;
+    const int i = half * H2V_SPLIT + threadIdx.x;
+    const int ilo = half * H2V_SPLIT, ihi = half == 0 ? min(H2V_SPLIT, Lv) : Lv;               // visible range of this CTA
+    const int jlo = max(0, ilo - (M - 1)), jhi = min(FANTASY_LEN, ihi);                         // hidden range it needs
+    for (int e = threadIdx.x; e < strands * p.kw * (jhi - jlo); e += blockDim.x) {
+        const int j = jlo + e % (jhi - jlo), rest = e / (jhi - jlo);
+        const int t = rest % p.kw, s = rest / p.kw;
+        const uint32_t *src = p.bits + (((size_t)s * p.Bn + n) * p.kw + t) * FANTASY_WORDS + (j >> 4) * 16;
+        const int nt = (j >> 3) & 1, q = (j >> 1) & 3, ee = j & 1;
+        uint32_t word = 0u;
+#pragma unroll
+        for (int mh = 0; mh < 4; ++mh)      // mh = 2*mt + h -> motifs 8*mh .. 8*mh+7 of the k-tile
+            word |= gather_stride4((__ldg(src + (mh * 2 + nt) * 2 + ee) >> q) & 0x11111111u) << (8 * mh);
+        posw[(s * p.kw + t) * FANTASY_WORDS + j] = word;
+    }
+    if (p.w4_in_smem) {
+        for (int e = threadIdx.x; e < p.K * M; e += blockDim.x) {
+            const int k = e / M, m = e - k * M;
+            const float *wk = p.W + (size_t)k * 4 * M + m;
+            w4[e] = make_float4(__ldg(wk), __ldg(wk + M), __ldg(wk + 2 * M), __ldg(wk + 3 * M));
+        }
     }
     __syncthreads();
     int pick = 0;
-    const bool active = i < Lv;
+    const bool active = i < ihi;
     if (active) {
         float v0 = __ldg(p.c), v1 = __ldg(p.c + 1), v2 = __ldg(p.c + 2), v3 = __ldg(p.c + 3);
-        const int M = p.M;
         const int mlo = max(0, i - (FANTASY_LEN - 1)), mhi = min(M - 1, i);
         for (int m = mlo; m <= mhi; ++m) {
             const int j = i - m;
             for (int t = 0; t < p.kw; ++t) {
-                uint32_t w = sbits[t * FANTASY_LEN + j];
+                uint32_t w = posw[t * FANTASY_WORDS + j];
                 while (w) {
                     const int k = t * 32 + __ffs(w) - 1;
                     w &= w - 1;
-                    const float *wk = p.W + (size_t)k * 4 * M + m;
-                    v0 += __ldg(wk); v1 += __ldg(wk + M); v2 += __ldg(wk + 2 * M); v3 += __ldg(wk + 3 * M);
+                    float4 f;
+                    if (p.w4_in_smem) f = w4[k * M + m];
+                    else { const float *wk = p.W + (size_t)k * 4 * M + m; f = make_float4(__ldg(wk), __ldg(wk + M), __ldg(wk + 2 * M), __ldg(wk + 3 * M)); }
+                    v0 += f.x; v1 += f.y; v2 += f.z; v3 += f.w;
                 }
                 if (p.ds) {
-                    uint32_t w2 = sbits[per_strand + t * FANTASY_LEN + j];
+                    uint32_t w2 = posw[(p.kw + t) * FANTASY_WORDS + j];
                     while (w2) {
                         const int k = t * 32 + __ffs(w2) - 1;
                         w2 &= w2 - 1;
-                        const float *wk = p.W + (size_t)k * 4 * M + (M - 1 - m);      // W[k, 3-a, M-1-m]
-                        v0 += __ldg(wk + 3 * M); v1 += __ldg(wk + 2 * M); v2 += __ldg(wk + M); v3 += __ldg(wk);
+                        float4 f;                                                    // W[k, 3-a, M-1-m]
+                        if (p.w4_in_smem) f = w4[k * M + (M - 1 - m)];
+                        else { const float *wk = p.W + (size_t)k * 4 * M + (M - 1 - m); f = make_float4(__ldg(wk), __ldg(wk + M), __ldg(wk + 2 * M), __ldg(wk + 3 * M)); }
+                        v0 += f.w; v1 += f.z; v2 += f.y; v3 += f.x;
                     }
                 }
             }
@@ -117,8 +163,8 @@ __global__ void __launch_bounds__(256) h2v_bits_kernel(const H2VParams p) {
         float u;
         if (p.u_v) u = p.u_v[(size_t)n * Lv + i];
         else {
-            const uint32_t step = p.step_dev ? (uint32_t)*p.step_dev : 0u;
-            u = u01(philox4x32(make_uint4((uint32_t)(n * Lv + i), step, p.ctr_hi, RNG_VISIBLE),
+            const uint32_t hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) * 64u : 0u);
+            u = u01(philox4x32(make_uint4((uint32_t)(n * Lv + i), 0u, hi, RNG_VISIBLE),
                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32))).x);
         }
         const float ut = u * tot;
@@ -129,7 +175,7 @@ __global__ void __launch_bounds__(256) h2v_bits_kernel(const H2VParams p) {
     uint32_t v = active ? ((uint32_t)pick << (2 * (lane & 15))) : 0u;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-    if ((lane & 15) == 0 && (i >> 4) < p.v_row_words - FRONT_PAD_WORDS)
+    if ((lane & 15) == 0 && i < ihi)
         p.v_packed[(size_t)n * p.v_row_words + FRONT_PAD_WORDS + (i >> 4)] = v;
     if (p.base_counts) {
 #pragma unroll
@@ -190,6 +236,35 @@ __global__ void reduce_partials_kernel(const ReduceParams p) {
         if (w == 0) { if (p.h_fwd) p.h_fwd[k] = v; if (p.h_sum) atomicAdd(p.h_sum + k, v); }
         else if (w == 1) { if (p.h_sum) atomicAdd(p.h_sum + k, v); }
         else if (w == 2) { if (p.h_q) p.h_q[k] = v; }
+    }
+}
+
+// Same for the MMA kernels, whose accumulators are in fragment order (v2h_mma.cuh): register o of lane (g,q) holds
+// motif 16mt + 8(r>>1) + g, column c = 8t + 2q + (r&1) = 4m + a.
+__global__ void reduce_partials_mma_kernel(const ReduceParams p, int KS) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = p.ktiles * p.nacc * 32;
+    if (gid >= total) return;
+    const int lane = gid & 31, o = (gid >> 5) % p.nacc, kt = gid / (32 * p.nacc);
+    const int g = lane >> 2, q = lane & 3;
+    const float *src = p.partial + ((size_t)kt * p.gy * p.nacc + o) * 32 + lane;
+    float v = 0.f;
+    for (int c = 0; c < p.gy; ++c) v += src[(size_t)c * p.nacc * 32];
+    if (o < p.np + p.nq) {
+        const bool isq = o >= p.np;
+        const int oo = isq ? o - p.np : o;
+        const int r = oo & 3, t = (oo >> 2) % (2 * KS), mt = oo / (8 * KS);
+        const int k = kt * KTILE + 16 * mt + 8 * (r >> 1) + g;
+        const int col = 8 * t + 2 * q + (r & 1), m = col >> 2, a = col & 3;
+        if (k < p.K && m < p.M) (isq ? p.vh_q : p.vh_p)[((size_t)k * 4 + a) * p.M + m] = v;
+    } else if (q == 0) {
+        const int w = o - p.np - p.nq, which = w >> 2, r4 = w & 3;
+        const int k = kt * KTILE + 16 * (r4 >> 1) + 8 * (r4 & 1) + g;
+        if (k < p.K) {
+            if (which == 0) { if (p.h_fwd) p.h_fwd[k] = v; if (p.h_sum) atomicAdd(p.h_sum + k, v); }
+            else if (which == 1) { if (p.h_sum) atomicAdd(p.h_sum + k, v); }
+            else if (p.h_q) p.h_q[k] = v;
+        }
     }
 }
 
@@ -274,7 +349,8 @@ __global__ void fe_finish_kernel(const uint32_t *__restrict__ packed, int row_wo
 
 static size_t partial_floats(int K, int M) {
     const int MW = 3 * ceil_div(M, 3);
-    const size_t nacc = 8 * (size_t)MW + 4;
+    const size_t nacc_cc = 8 * (size_t)MW + 4, nacc_mma = 32 * (size_t)ceil_div(M, 4) + 12;
+    const size_t nacc = nacc_cc > nacc_mma ? nacc_cc : nacc_mma;
     return (size_t)ceil_div(K, KTILE) * max_gy(K) * nacc * 32;
 }
 
@@ -384,6 +460,24 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     float *part0 = reinterpret_cast<float *>(a->workspace);
     float *part1 = part0 + partial_floats(K, M);
     float *part2 = part1 + partial_floats(K, M);
+    // pooling == 1: both contractions on the tensor pipe (v2h_mma.cuh); otherwise the CUDA-core kernel (v2h.cuh)
+    const bool mma = P == 1;
+    const int KS = ceil_div(M, 4);
+    const int nthreads = 256;
+
+    auto run_fused = [&](int flags, const V2HParams &p, const Tiling &t) -> int {
+        return mma ? dispatch_mma(KS, flags, p, dim3(t.ktiles, t.gy), s) : dispatch_fused(t.MW, flags, p, dim3(t.ktiles, t.gy), s);
+    };
+    auto run_reduce = [&](ReduceParams r, const Tiling &t, bool has_p, bool has_q) -> int {
+        r.ktiles = t.ktiles; r.gy = t.gy; r.MW = t.MW; r.M = M; r.K = K;
+        const int per = mma ? 16 * KS : 4 * t.MW;
+        r.np = has_p ? per : 0; r.nq = has_q ? per : 0; r.nacc = r.np + r.nq + (mma ? 12 : 4);
+        const int blocks = ceil_div(r.ktiles * r.nacc * 32, nthreads);
+        if (mma) reduce_partials_mma_kernel<<<blocks, nthreads, 0, s>>>(r, KS);
+        else reduce_partials_kernel<<<blocks, nthreads, 0, s>>>(r);
+        CRBM_CHECK_LAUNCH();
+        return CRBM_OK;
+    };
 
     // ---- positive phase on the minibatch (convRBM.py:377-388) and the sparsity statistic (:440-451) ----------
     Tiling t = make_tiling(K, M, P, Lh, a->n_data);
@@ -392,37 +486,27 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     p.W = a->W; p.b = a->b; p.K = K; p.M = M; p.pooling = P; p.ds = ds;
     p.bv = t.bv; p.nblk = t.nblk; p.n_items = t.n_items;
     p.batch_index = a->batch_index_dev;
-    ReduceParams r{};
-    r.ktiles = t.ktiles; r.gy = t.gy; r.MW = t.MW; r.M = M; r.K = K;
-    const int nthreads = 256;
+    const bool combined = mma ? KS <= 4 : t.MW <= 15;
     if (a->n_data == 0) {
         // a data-parallel rank whose shard of a short batch is empty contributes zeros
-    } else if (t.MW <= 15) {
+    } else if (combined) {
         p.partial = part0;
-        rc = dispatch_fused(t.MW, F_STAT_P | F_STAT_Q, p, dim3(t.ktiles, t.gy), s);
-        if (rc) return rc;
-        r.partial = part0; r.np = 4 * t.MW; r.nq = 4 * t.MW; r.nacc = r.np + r.nq + 4;
-        r.vh_p = st + lay.vh_data; r.vh_q = st + lay.vh_q;
+        if ((rc = run_fused(F_STAT_P | F_STAT_Q, p, t))) return rc;
+        ReduceParams r{};
+        r.partial = part0; r.vh_p = st + lay.vh_data; r.vh_q = st + lay.vh_q;
         r.h_sum = st + lay.h_data; r.h_fwd = st + lay.h_fwd; r.h_q = st + lay.h_q;
-        reduce_partials_kernel<<<ceil_div(r.ktiles * r.nacc * 32, nthreads), nthreads, 0, s>>>(r);
-        CRBM_CHECK_LAUNCH();
+        if ((rc = run_reduce(r, t, true, true))) return rc;
     } else {
         p.partial = part0;
-        rc = dispatch_fused(t.MW, F_STAT_P, p, dim3(t.ktiles, t.gy), s);
-        if (rc) return rc;
-        r.partial = part0; r.np = 4 * t.MW; r.nq = 0; r.nacc = r.np + 4;
-        r.vh_p = st + lay.vh_data; r.vh_q = nullptr;
-        r.h_sum = st + lay.h_data; r.h_fwd = st + lay.h_fwd; r.h_q = nullptr;
-        reduce_partials_kernel<<<ceil_div(r.ktiles * r.nacc * 32, nthreads), nthreads, 0, s>>>(r);
-        CRBM_CHECK_LAUNCH();
+        if ((rc = run_fused(F_STAT_P, p, t))) return rc;
+        ReduceParams r{};
+        r.partial = part0; r.vh_p = st + lay.vh_data; r.h_sum = st + lay.h_data; r.h_fwd = st + lay.h_fwd;
+        if ((rc = run_reduce(r, t, true, false))) return rc;
         p.partial = part2;
-        rc = dispatch_fused(t.MW, F_STAT_Q, p, dim3(t.ktiles, t.gy), s);
-        if (rc) return rc;
-        r.partial = part2; r.np = 0; r.nq = 4 * t.MW; r.nacc = r.nq + 4;
-        r.vh_p = nullptr; r.vh_q = st + lay.vh_q;
-        r.h_sum = nullptr; r.h_fwd = nullptr; r.h_q = st + lay.h_q;
-        reduce_partials_kernel<<<ceil_div(r.ktiles * r.nacc * 32, nthreads), nthreads, 0, s>>>(r);
-        CRBM_CHECK_LAUNCH();
+        if ((rc = run_fused(F_STAT_Q, p, t))) return rc;
+        ReduceParams rq{};
+        rq.partial = part2; rq.vh_q = st + lay.vh_q; rq.h_q = st + lay.h_q;
+        if ((rc = run_reduce(rq, t, false, true))) return rc;
     }
     if (a->n_data > 0) {
         const int cb = ceil_div(a->n_data * ceil_div(a->L, 16), 256);
@@ -437,17 +521,26 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     // ---- negative phase: cd_k Gibbs sweeps of the persistent chain (convRBM.py:391-413) -----------------------------
     Tiling tn = make_tiling(K, M, P, FANTASY_LEN, a->batchsize);
     const size_t n_u_v = (size_t)a->batchsize * Lv, n_u_h = (size_t)a->batchsize * K * (FANTASY_LEN / P);
+    const size_t bits_bytes = (size_t)2 * a->batchsize * kw * FANTASY_WORDS * sizeof(uint32_t);
+    const size_t w4_bytes = (size_t)K * M * sizeof(float4);
+    const size_t posw_bytes = (size_t)(ds ? 2 : 1) * kw * FANTASY_WORDS * sizeof(uint32_t);
+    const int w4_in_smem = posw_bytes + w4_bytes <= 160 * 1024;
+    const size_t h2v_smem = posw_bytes + (w4_in_smem ? w4_bytes : 0);
+    static size_t h2v_smem_configured = 0;
+    if (h2v_smem > h2v_smem_configured) {
+        CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h2v_smem));
+        h2v_smem_configured = h2v_smem;
+    }
     for (int it = 0; it < a->cd_k; ++it) {
         const bool last = it == a->cd_k - 1;
         H2VParams h{};
-        h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.kw = kw; h.M = M; h.ds = ds;
+        h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.kw = kw; h.M = M; h.ds = ds; h.w4_in_smem = w4_in_smem;
         h.W = a->W; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words;
         h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
-        h.seed = a->seed; h.ctr_hi = (uint32_t)it; h.step_dev = a->step_dev;
+        h.seed = a->seed; h.step_dev = a->step_dev;
+        h.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
         h.base_counts = last ? st + lay.v_model : nullptr;
-        if (!a->step_dev) h.ctr_hi = (uint32_t)(a->step * 64u + it);
-        const size_t smem = (size_t)(ds ? 2 : 1) * kw * FANTASY_LEN * sizeof(uint32_t);
-        h2v_bits_kernel<<<a->batchsize, 256, smem, s>>>(h);
+        h2v_bits_kernel<<<dim3(a->batchsize, 2), H2V_THREADS, h2v_smem, s>>>(h);
         CRBM_CHECK_LAUNCH();
 
         V2HParams q{};
@@ -459,15 +552,12 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
         q.u_rc = a->u_hp ? a->u_hp + it * n_u_h : nullptr;
         q.seed = a->seed; q.step_dev = a->step_dev;
         q.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
-        rc = dispatch_fused(tn.MW, last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, dim3(tn.ktiles, tn.gy), s);
-        if (rc) return rc;
+        if (!mma) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));   // CUDA-core sampler ORs its hits in
+        if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
     }
     ReduceParams rn{};
-    rn.partial = part1; rn.ktiles = tn.ktiles; rn.gy = tn.gy; rn.MW = tn.MW; rn.M = M; rn.K = K;
-    rn.np = 4 * tn.MW; rn.nq = 0; rn.nacc = rn.np + 4;
-    rn.vh_p = st + lay.vh_model; rn.h_sum = st + lay.h_model;
-    reduce_partials_kernel<<<ceil_div(rn.ktiles * rn.nacc * 32, nthreads), nthreads, 0, s>>>(rn);
-    CRBM_CHECK_LAUNCH();
+    rn.partial = part1; rn.vh_p = st + lay.vh_model; rn.h_sum = st + lay.h_model;
+    if ((rc = run_reduce(rn, tn, true, false))) return rc;
     return CRBM_OK;
 }
 

@@ -35,7 +35,7 @@ struct V2HParams {
     int bv, nblk, n_items;    // valid block length (multiple of pooling), blocks per sequence, n_rows*nblk
     // outputs
     float *partial;           // [ktiles][gridDim.y][nacc][32]
-    uint32_t *bits;           // [2][n_rows][ktiles][Lh] sampled hidden bit planes (F_SAMPLE)
+    uint32_t *bits;           // [2][n_rows][ktiles][FANTASY_WORDS] sampled hidden bit planes (F_SAMPLE; layout: common.cuh)
     float *fe_motif;          // [n_rows][K] accumulated (F_FE), may be null
     float *fe_seq;            // [n_rows] accumulated (F_FE), may be null
     float *count;             // [n_rows] accumulated number of sampled forward units per sequence (F_COUNT)
@@ -232,6 +232,16 @@ __device__ __forceinline__ uint32_t sample_block(const float (&cumn)[BLOCK_POS],
     return bits;
 }
 
+// Sampled units of one lane (= motif) for the block's positions -> bit planes (layout: common.cuh). The planes were
+// zeroed before the launch; hits are rare (target sparsity rho), so one atomicOr per hit is cheap.
+__device__ __forceinline__ void scatter_sample_bits(uint32_t *tile_bits, uint32_t sb, int j0, int lane) {
+    while (sb) {
+        const int r = __ffs(sb) - 1;
+        sb &= sb - 1;
+        atomicOr(tile_bits + hbit_word(j0 + r, lane), 1u << hbit_bit(j0 + r, lane));
+    }
+}
+
 // acc[a][m] += v[s-m] over the block, a = base at position s of window array `w`, warp-uniform switch.
 // REVERSE: target column MW-1-m and base 3-a (the strand fold of convRBM.py:367).
 template <int MW, bool REVERSE, bool WITH_Q>
@@ -328,16 +338,7 @@ __global__ void __launch_bounds__(256, 1) v2h_fused_kernel(const V2HParams p) {
                 const float tot = warp_sum((float)__popc(sb));
                 if (lane == 0 && tot != 0.f) atomicAdd(p.count + n, tot);
             }
-            if (SAMPLE) {
-                uint32_t mine = 0u;
-#pragma unroll
-                for (int r = 0; r < B; ++r) {
-                    const uint32_t word = __ballot_sync(0xffffffffu, (sb >> r) & 1u);
-                    if (lane == r) mine = word;
-                }
-                if (lane < B && ((mk.valid >> lane) & 1u))
-                    p.bits[((size_t)(0 * p.n_rows + n) * ktiles + kt) * p.Lh + j0 + lane] = mine;
-            }
+            if (SAMPLE) scatter_sample_bits(p.bits + ((size_t)(0 * p.n_rows + n) * ktiles + kt) * FANTASY_WORDS, sb, j0, lane);
         }
         if (STAT_P || STAT_Q) {
             float q[B];
@@ -360,14 +361,7 @@ __global__ void __launch_bounds__(256, 1) v2h_fused_kernel(const V2HParams p) {
                 gu_r.cached_q = -1;
                 uint32_t sb = sample_block(cumn, mk, gu_r, j0 / p.pooling);
                 if (!kvalid) sb = 0u;
-                uint32_t mine = 0u;
-#pragma unroll
-                for (int r = 0; r < B; ++r) {
-                    const uint32_t word = __ballot_sync(0xffffffffu, (sb >> r) & 1u);
-                    if (lane == r) mine = word;
-                }
-                if (lane < B && ((mk.valid >> lane) & 1u))
-                    p.bits[((size_t)(1 * p.n_rows + n) * ktiles + kt) * p.Lh + j0 + lane] = mine;
+                scatter_sample_bits(p.bits + ((size_t)(1 * p.n_rows + n) * ktiles + kt) * FANTASY_WORDS, sb, j0, lane);
             }
             if (STAT_P) {
 #pragma unroll

@@ -1,0 +1,39 @@
+// One translation unit per number of MMA k-steps: compiled with -DCRBM_KS=<1..9> (motif_length <= 4*KS).
+#include "v2h_mma.cuh"
+
+#ifndef CRBM_KS
+#error "compile with -DCRBM_KS=<1..9>"
+#endif
+
+namespace crbm {
+
+template <int KS, int FLAGS>
+static int launch_mma_variant(const V2HParams &p, dim3 grid, cudaStream_t stream) {
+    static bool configured = false;
+    constexpr size_t smem = mma_smem_bytes<KS, FLAGS>();
+    if (!configured) {
+        CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_mma_kernel<KS, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    v2h_mma_kernel<KS, FLAGS><<<grid, 256, smem, stream>>>(p);
+    CRBM_CHECK_LAUNCH();
+    return CRBM_OK;
+}
+
+template <>
+int launch_v2h_mma<CRBM_KS>(int flags, const V2HParams &p, dim3 grid, cudaStream_t stream) {
+    switch (flags) {
+#if CRBM_KS <= 4
+        case F_STAT_P | F_STAT_Q: return launch_mma_variant<CRBM_KS, F_STAT_P | F_STAT_Q>(p, grid, stream);
+#endif
+        case F_STAT_P: return launch_mma_variant<CRBM_KS, F_STAT_P>(p, grid, stream);
+        case F_STAT_Q: return launch_mma_variant<CRBM_KS, F_STAT_Q>(p, grid, stream);
+        case F_STAT_P | F_SAMPLE: return launch_mma_variant<CRBM_KS, F_STAT_P | F_SAMPLE>(p, grid, stream);
+        case F_SAMPLE: return launch_mma_variant<CRBM_KS, F_SAMPLE>(p, grid, stream);
+        default:
+            set_error("v2h_mma<KS=%d>: variant 0x%x not built", CRBM_KS, flags);
+            return CRBM_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace crbm

@@ -16,7 +16,11 @@
  * `crbm_packed_row_words(L)` words (a multiple of 4, so rows are 16-byte aligned).
  *
  * HIDDEN BIT PLANES. Sampled hidden states of the persistent chain (convRBM.py:168-173, hidden length 200) are
- * kept as bit planes: uint32 H[strand][n][kw][200], bit (k%32) of word [.. k/32][j] is h[n,k,0,j].
+ * kept as bit planes: uint32 H[strand][n][kt][jb][16] with kt = k/32, jb = j/16 (13 position blocks, so
+ * crbm_fantasy_words() = 208 words per (strand, particle, k-tile)). The 16 words of a block are the warp ballots of
+ * the tensor-core accumulator fragments that produce them: with k%32 = 16*mt + 8*h + g and j%16 = 8*nt + 2*q + e,
+ * h[n,k,0,j] is bit 4*g+q of word ((mt*2+h)*2+nt)*2+e. crbm_hidden_bits_to_dense / _dense_to_bits convert to and from
+ * the reference's dense (B,K,1,200) tensors.
  */
 #ifndef CRBM_B200_H
 #define CRBM_B200_H
@@ -49,6 +53,7 @@ int         crbm_abi_version(void);
 const char *crbm_last_error(void);                 /* host string, thread-local */
 int         crbm_packed_row_words(int L);          /* row stride (uint32 words) of a packed sequence of L bases */
 int         crbm_hidden_words(int K);              /* kw = ceil(K/32) */
+int         crbm_fantasy_words(void);              /* uint32 words per (strand, particle, k-tile) of the bit planes */
 
 /* ---- A0: sequence ingest (secomo/sequences.py:20-31,101-117) -------------------------------------------- */
 /* one-hot (N,1,4,L) fp32 -> packed rows. *bad_count (device int, zeroed by the callee) receives the number of
@@ -109,7 +114,7 @@ typedef struct crbm_train_args {
     int data_row_words, n_data, L;
     /* persistent chain of this rank: `batchsize` particles */
     int batchsize;
-    uint32_t *fantasy_bits;        /* [2][batchsize][kw][200]; strand 1 unused when !doublestranded */
+    uint32_t *fantasy_bits;        /* [2][batchsize][kw][crbm_fantasy_words()]; strand 1 unused when !doublestranded */
     uint32_t *v_model;             /* packed scratch, batchsize rows of 199+M bases (holds the last sampled V) */
     int v_row_words;
     /* randomness: Philox(seed, step) unless the matching pointer is non-NULL (tests replay reference uniforms) */

@@ -25,12 +25,22 @@ static int dispatch_fused(int MW, int flags, const V2HParams &p, dim3 grid, cuda
     return CRBM_ERR_UNSUPPORTED;
 }
 #define CRBM_FOR_EACH_KS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
-#define CRBM_DECLARE_KS(KSV) template <> int launch_v2h_mma<KSV>(int, const V2HParams &, dim3, cudaStream_t);
+#define CRBM_DECLARE_KS(KSV) template <> int launch_v2h_mma<KSV>(int, const V2HParams &, dim3, cudaStream_t); \
+    template <> int launch_v2h_dense_mma<KSV>(const DenseParams &, dim3, cudaStream_t);
 CRBM_FOR_EACH_KS(CRBM_DECLARE_KS)
 #undef CRBM_DECLARE_KS
 static int dispatch_mma(int KS, int flags, const V2HParams &p, dim3 grid, cudaStream_t s) {
     switch (KS) {
 #define CRBM_CASE(KSV) case KSV: return launch_v2h_mma<KSV>(flags, p, grid, s);
+        CRBM_FOR_EACH_KS(CRBM_CASE)
+#undef CRBM_CASE
+    }
+    set_error("MMA k-step bucket %d not built", KS);
+    return CRBM_ERR_UNSUPPORTED;
+}
+static int dispatch_dense_mma(int KS, const DenseParams &p, dim3 grid, cudaStream_t s) {
+    switch (KS) {
+#define CRBM_CASE(KSV) case KSV: return launch_v2h_dense_mma<KSV>(p, grid, s);
         CRBM_FOR_EACH_KS(CRBM_CASE)
 #undef CRBM_CASE
     }
@@ -72,15 +82,16 @@ static Tiling make_tiling(int K, int M, int pooling, int Lh, int n_rows) {
 static int max_gy(int K) { const int kt = ceil_div(K, KTILE); return num_sms() / kt > 0 ? num_sms() / kt : 1; }
 
 // ---- A5 + A6 on bit planes ------------------------------------------------------------------------------------
-// grid (particles, 2 halves of the visible sequence), 128 threads = one visible position each (Lv = 199+M <= 232).
-//  1. the particle's bit planes (MMA-fragment order, common.cuh) are re-ordered in shared memory into one word of 32
-//     motif bits per hidden position;
-//  2. W is staged as float4 {A,C,G,T} per (k, m) when it fits, so a hit costs one LDS.128 and four adds;
-//  3. every thread gathers the hits that reach its position, takes the 4-way softmax, samples one base and the
-//     half-warps assemble the packed 2-bit words.
+// Hit-parallel: one CTA per particle, one warp per 16 visible positions (= one packed output word). The warp scans the
+// bit-plane words of the 2-3 hidden position blocks that can reach its positions (MMA-fragment order, common.cuh: a word
+// holds 8 motifs x 4 positions), and for every set bit (k, j, strand) — warp-uniform — lane (p, ah) adds
+// W[k, a, i-j] for its position i = 16w+p and its two bases a = 2ah, 2ah+1 into two registers (reverse strand:
+// W[k, 3-a, M-1-(i-j)], convRBM.py:285). No shared memory, no atomics, no divergence beyond the range predicate.
+// Then the two lanes of a position exchange their halves, take the 4-way softmax, draw the base and the warp ORs the
+// 2-bit codes into the packed word.
 struct H2VParams {
     const uint32_t *bits;     // [2][B][kw][FANTASY_WORDS]
-    int Bn, K, kw, M, ds, w4_in_smem;
+    int Bn, K, kw, M, ds, w_in_smem, words_per_row;
     const float *W, *c;
     uint32_t *v_packed;       // rows of Lv bases
     int v_row_words;
@@ -88,75 +99,73 @@ struct H2VParams {
     uint64_t seed;
     uint32_t ctr_hi;
     const unsigned long long *step_dev;
-    float *base_counts;       // stats slot (4 floats) or null
 };
-constexpr int H2V_THREADS = 128, H2V_SPLIT = 112;      // positions [0,112) and [112, Lv): both multiples of 16 bases/word
 
-__device__ __forceinline__ uint32_t gather_stride4(uint32_t x) {   // bits 0,4,..,28 -> bits 0..7
-    x = (x | (x >> 3)) & 0x03030303u;
-    x = (x | (x >> 6)) & 0x000F000Fu;
-    return (x | (x >> 12)) & 0xFFu;
-}
-
-__global__ void __launch_bounds__(H2V_THREADS) h2v_bits_kernel(const H2VParams p) {
-    extern __shared__ __align__(16) unsigned char h2v_smem[];
+__global__ void __launch_bounds__(512) h2v_bits_kernel(const H2VParams p) {
+    extern __shared__ __align__(128) unsigned char h2v_smem[];
     const int M = p.M, Lv = FANTASY_LEN + M - 1;
-    const int strands = p.ds ? 2 : 1;
-    uint32_t *posw = reinterpret_cast<uint32_t *>(h2v_smem);                                    // [strand][kw][FANTASY_WORDS]
-    float4 *w4 = reinterpret_cast<float4 *>(h2v_smem + (size_t)strands * p.kw * FANTASY_WORDS * 4);  // [K][M]
-    const int n = blockIdx.x, half = blockIdx.y;
-    const int i = half * H2V_SPLIT + threadIdx.x;
-    const int ilo = half * H2V_SPLIT, ihi = half == 0 ? min(H2V_SPLIT, Lv) : Lv;               // visible range of this CTA
-    const int jlo = max(0, ilo - (M - 1)), jhi = min(FANTASY_LEN, ihi);                         // hidden range it needs
-    for (int e = threadIdx.x; e < strands * p.kw * (jhi - jlo); e += blockDim.x) {
-        const int j = jlo + e % (jhi - jlo), rest = e / (jhi - jlo);
-        const int t = rest % p.kw, s = rest / p.kw;
-        const uint32_t *src = p.bits + (((size_t)s * p.Bn + n) * p.kw + t) * FANTASY_WORDS + (j >> 4) * 16;
-        const int nt = (j >> 3) & 1, q = (j >> 1) & 3, ee = j & 1;
-        uint32_t word = 0u;
-#pragma unroll
-        for (int mh = 0; mh < 4; ++mh)      // mh = 2*mt + h -> motifs 8*mh .. 8*mh+7 of the k-tile
-            word |= gather_stride4((__ldg(src + (mh * 2 + nt) * 2 + ee) >> q) & 0x11111111u) << (8 * mh);
-        posw[(s * p.kw + t) * FANTASY_WORDS + j] = word;
-    }
-    if (p.w4_in_smem) {
-        for (int e = threadIdx.x; e < p.K * M; e += blockDim.x) {
-            const int k = e / M, m = e - k * M;
-            const float *wk = p.W + (size_t)k * 4 * M + m;
-            w4[e] = make_float4(__ldg(wk), __ldg(wk + M), __ldg(wk + 2 * M), __ldg(wk + 3 * M));
+    // the motif bank is staged once per CTA by the TMA engine: L1 is cold at kernel start, and every hit reads two
+    // short rows of W, so fetching them one miss at a time would serialise L2 round trips
+    const float *Wsm = p.W;
+    if (p.w_in_smem) {
+        float *wbuf = reinterpret_cast<float *>(h2v_smem + 16);
+        uint64_t *bar = reinterpret_cast<uint64_t *>(h2v_smem);
+        const uint32_t bytes = (uint32_t)p.K * 16u * (uint32_t)M;
+        if (threadIdx.x == 0) mbar_init(bar, 1);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(wbuf, p.W, bytes, bar);
         }
+        mbar_wait(bar, 0);
+        Wsm = wbuf;
     }
-    __syncthreads();
-    int pick = 0;
-    const bool active = i < ihi;
-    if (active) {
-        float v0 = __ldg(p.c), v1 = __ldg(p.c + 1), v2 = __ldg(p.c + 2), v3 = __ldg(p.c + 3);
-        const int mlo = max(0, i - (FANTASY_LEN - 1)), mhi = min(M - 1, i);
-        for (int m = mlo; m <= mhi; ++m) {
-            const int j = i - m;
-            for (int t = 0; t < p.kw; ++t) {
-                uint32_t w = posw[t * FANTASY_WORDS + j];
-                while (w) {
-                    const int k = t * 32 + __ffs(w) - 1;
-                    w &= w - 1;
-                    float4 f;
-                    if (p.w4_in_smem) f = w4[k * M + m];
-                    else { const float *wk = p.W + (size_t)k * 4 * M + m; f = make_float4(__ldg(wk), __ldg(wk + M), __ldg(wk + 2 * M), __ldg(wk + 3 * M)); }
-                    v0 += f.x; v1 += f.y; v2 += f.z; v3 += f.w;
-                }
-                if (p.ds) {
-                    uint32_t w2 = posw[(p.kw + t) * FANTASY_WORDS + j];
-                    while (w2) {
-                        const int k = t * 32 + __ffs(w2) - 1;
-                        w2 &= w2 - 1;
-                        float4 f;                                                    // W[k, 3-a, M-1-m]
-                        if (p.w4_in_smem) f = w4[k * M + (M - 1 - m)];
-                        else { const float *wk = p.W + (size_t)k * 4 * M + (M - 1 - m); f = make_float4(__ldg(wk), __ldg(wk + M), __ldg(wk + 2 * M), __ldg(wk + 3 * M)); }
-                        v0 += f.w; v1 += f.z; v2 += f.y; v3 += f.x;
+    // work item = (particle n, 16-position word w); one item per warp, CTAs sized so that one wave covers the SMs
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= p.Bn * p.words_per_row) return;
+    const int n = item / p.words_per_row, w = item - n * p.words_per_row, lane = threadIdx.x & 31;
+    const int pidx = lane & 15, ah = lane >> 4;
+    const int i = 16 * w + pidx;
+    const int strands = p.ds ? 2 : 1;
+    const int jb_lo = max(0, 16 * w - (M - 1)) >> 4, jb_hi = min(FANTASY_BLOCKS - 1, w);
+    float acc0 = 0.f, acc1 = 0.f;
+    // one round = the 2 x 16 words of two position blocks of one (strand, k-tile): no index arithmetic beyond shifts
+    for (int s = 0; s < strands; ++s) {
+        const float *Wbase = s == 0 ? Wsm + (size_t)(2 * ah) * M : Wsm + (size_t)(3 - 2 * ah) * M;
+        const int dir = s == 0 ? M : -M;                     // second base row: +M (forward) / -M (reverse)
+        for (int t = 0; t < p.kw; ++t) {
+            const uint32_t *tile = p.bits + (((size_t)s * p.Bn + n) * p.kw + t) * FANTASY_WORDS;
+            for (int jb0 = jb_lo; jb0 <= jb_hi; jb0 += 2) {
+                const int jbl = jb0 + (lane >> 4);
+                const uint32_t word = jbl <= jb_hi ? __ldg(tile + jbl * 16 + (lane & 15)) : 0u;
+                uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
+                while (nz) {
+                    const int src = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    uint32_t ww = __shfl_sync(0xffffffffu, word, src);
+                    const int f = src & 15;
+                    const int jbase = 16 * (jb0 + (src >> 4)) + 8 * ((f >> 1) & 1) + (f & 1);
+                    const float *Ws = Wbase + (size_t)(32 * t + 8 * (f >> 2)) * 4 * M;
+                    while (ww) {
+                        const int b = __ffs(ww) - 1;
+                        ww &= ww - 1;
+                        const int m = i - (jbase + 2 * (b & 3));
+                        if (m >= 0 && m < M) {
+                            const float *wk = Ws + (b >> 2) * 4 * M + (s == 0 ? m : M - 1 - m);
+                            acc0 += wk[0];
+                            acc1 += wk[dir];
+                        }
                     }
                 }
             }
         }
+    }
+    // lanes (p, 0) and (p, 1) hold bases {A,C} and {G,T} of position i
+    const float o0 = __shfl_xor_sync(0xffffffffu, acc0, 16), o1 = __shfl_xor_sync(0xffffffffu, acc1, 16);
+    const bool active = ah == 0 && i < Lv;
+    int pick = 0;
+    if (active) {
+        const float v0 = acc0 + __ldg(p.c), v1 = acc1 + __ldg(p.c + 1), v2 = o0 + __ldg(p.c + 2), v3 = o1 + __ldg(p.c + 3);
         const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
         const float e0 = __expf(v0 - mx), e1 = __expf(v1 - mx), e2 = __expf(v2 - mx), e3 = __expf(v3 - mx);
         const float tot = e0 + e1 + e2 + e3;
@@ -170,108 +179,120 @@ __global__ void __launch_bounds__(H2V_THREADS) h2v_bits_kernel(const H2VParams p
         const float ut = u * tot;
         pick = (e0 > ut) ? 0 : (e0 + e1 > ut) ? 1 : (e0 + e1 + e2 > ut) ? 2 : 3;
     }
-    // assemble 16 bases per word inside each half warp
-    const int lane = threadIdx.x & 31;
-    uint32_t v = active ? ((uint32_t)pick << (2 * (lane & 15))) : 0u;
+    uint32_t v = active ? ((uint32_t)pick << (2 * pidx)) : 0u;
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-    if ((lane & 15) == 0 && i < ihi)
-        p.v_packed[(size_t)n * p.v_row_words + FRONT_PAD_WORDS + (i >> 4)] = v;
-    if (p.base_counts) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            const int cnt = __popc(__ballot_sync(0xffffffffu, active && pick == a));
-            if (lane == 0 && cnt) atomicAdd(p.base_counts + a, (float)cnt);
-        }
-    }
+    if (lane == 0) p.v_packed[(size_t)n * p.v_row_words + FRONT_PAD_WORDS + w] = v;
 }
 
-// ---- base counts of a packed batch (A9 `_collectVStatistics` numerator) -----------------------------------------------
-__global__ void count_bases_kernel(const uint32_t *__restrict__ packed, int row_words, int n_rows, int L,
-                                   const int *__restrict__ batch_index, float *__restrict__ counts) {
+// ---- per-CTA partial accumulators -> stats ------------------------------------------------------------------------------
+// One launch reduces every partial buffer of the step (positive phase P|Q, optional separate Q, negative phase).
+// One CTA of 128 threads per (set, k-tile, accumulator slot): its four warps each add a quarter of the CTA partials
+// (coalesced over the 32 lanes), combine through shared memory, and warp 0 scatters the 32 totals to `stats`.
+struct ReduceSet {
+    const float *partial;   // [ktiles][gy][nacc][32]
+    int gy, nacc, np, nq;
+    float *vh_p, *vh_q;     // K*4*M destinations (np/nq accumulators), may be null when np/nq == 0
+    float *h_sum, *h_fwd, *h_q;   // K each; h_sum += sum_p + sum_pr; may be null
+};
+struct ReduceParams {
+    ReduceSet set[3];
+    int nsets, ktiles, MW, KS, mma, M, K;
+    int block_start[4];     // first blockIdx.x of each set
+    float *counts;          // stats + n_hidden_data (4 consecutive scalars) or null
+    float c0, c1, c2, c3;
+    // base counts (A9 `_collectVStatistics` numerators) are taken by two extra CTAs: [0] minibatch, [1] sampled V of the model
+    const uint32_t *cnt_rows[2];
+    int cnt_row_words[2], cnt_n[2], cnt_L[2];
+    const int *batch_index;
+    float *cnt_out[2];      // 4 floats each
+};
+
+// Counts of the four base codes over n rows of L packed bases; one CTA, result written (not accumulated).
+__device__ void count_bases_block(const uint32_t *__restrict__ rows, int row_words, int n_rows, int L, float *out) {
+    __shared__ int tot[4];
+    if (threadIdx.x < 4) tot[threadIdx.x] = 0;
+    __syncthreads();
     const int data_words = ceil_div(L, 16);
-    const long long total = (long long)n_rows * data_words;
-    const uint32_t *base = packed + (batch_index ? (size_t)(*batch_index) * n_rows * row_words : 0);
     int c[4] = {0, 0, 0, 0};
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-        const int n = (int)(g / data_words), w = (int)(g - (long long)n * data_words);
-        const uint32_t word = base[(size_t)n * row_words + FRONT_PAD_WORDS + w];
+    for (int e = threadIdx.x; e < n_rows * data_words; e += blockDim.x) {
+        const int n = e / data_words, w = e - n * data_words;
+        const uint32_t word = __ldg(rows + (size_t)n * row_words + FRONT_PAD_WORDS + w);
         const int nb = min(16, L - 16 * w);
-        // count codes 1,2,3 with bit tricks; code 0 = nb - others
         const uint32_t lo = word & 0x55555555u, hi = (word >> 1) & 0x55555555u;
         const int c3 = __popc(lo & hi), c1 = __popc(lo & ~hi), c2 = __popc(hi & ~lo);
         c[1] += c1; c[2] += c2; c[3] += c3; c[0] += nb - c1 - c2 - c3;
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-        const float t = warp_sum((float)c[a]);
-        if ((threadIdx.x & 31) == 0 && t != 0.f) atomicAdd(counts + a, t);
+        int v = c[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&tot[a], v);
     }
+    __syncthreads();
+    if (threadIdx.x < 4) out[threadIdx.x] = (float)tot[threadIdx.x];
 }
-
-// ---- per-CTA partial accumulators -> stats ------------------------------------------------------------------------------
-struct ReduceParams {
-    const float *partial;   // [ktiles][gy][nacc][32]
-    int ktiles, gy, nacc, np, nq, MW, M, K;
-    float *vh_p, *vh_q;     // K*4*M destinations (np/nq accumulators), may be null when np/nq == 0
-    float *h_sum, *h_fwd, *h_q;   // K each; h_sum += sum_p + sum_pr; may be null
-};
-__global__ void reduce_partials_kernel(const ReduceParams p) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = p.ktiles * p.nacc * 32;
-    if (gid >= total) return;
-    const int lane = gid & 31, o = (gid >> 5) % p.nacc, kt = gid / (32 * p.nacc);
-    const int k = kt * KTILE + lane;
-    if (k >= p.K) return;
-    const float *src = p.partial + ((size_t)kt * p.gy * p.nacc + o) * 32 + lane;
-    float v = 0.f;
-    for (int c = 0; c < p.gy; ++c) v += src[(size_t)c * p.nacc * 32];
-    if (o < p.np + p.nq) {
-        const bool isq = o >= p.np;
-        const int oo = isq ? o - p.np : o;
-        const int a = oo / p.MW, m = oo - a * p.MW;
-        if (m < p.M) (isq ? p.vh_q : p.vh_p)[((size_t)k * 4 + a) * p.M + m] = v;
-    } else {
-        const int w = o - p.np - p.nq;
-        if (w == 0) { if (p.h_fwd) p.h_fwd[k] = v; if (p.h_sum) atomicAdd(p.h_sum + k, v); }
-        else if (w == 1) { if (p.h_sum) atomicAdd(p.h_sum + k, v); }
-        else if (w == 2) { if (p.h_q) p.h_q[k] = v; }
-    }
-}
-
-// Same for the MMA kernels, whose accumulators are in fragment order (v2h_mma.cuh): register o of lane (g,q) holds
-// motif 16mt + 8(r>>1) + g, column c = 8t + 2q + (r&1) = 4m + a.
-__global__ void reduce_partials_mma_kernel(const ReduceParams p, int KS) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = p.ktiles * p.nacc * 32;
-    if (gid >= total) return;
-    const int lane = gid & 31, o = (gid >> 5) % p.nacc, kt = gid / (32 * p.nacc);
-    const int g = lane >> 2, q = lane & 3;
-    const float *src = p.partial + ((size_t)kt * p.gy * p.nacc + o) * 32 + lane;
-    float v = 0.f;
-    for (int c = 0; c < p.gy; ++c) v += src[(size_t)c * p.nacc * 32];
-    if (o < p.np + p.nq) {
-        const bool isq = o >= p.np;
-        const int oo = isq ? o - p.np : o;
-        const int r = oo & 3, t = (oo >> 2) % (2 * KS), mt = oo / (8 * KS);
-        const int k = kt * KTILE + 16 * mt + 8 * (r >> 1) + g;
-        const int col = 8 * t + 2 * q + (r & 1), m = col >> 2, a = col & 3;
-        if (k < p.K && m < p.M) (isq ? p.vh_q : p.vh_p)[((size_t)k * 4 + a) * p.M + m] = v;
-    } else if (q == 0) {
-        const int w = o - p.np - p.nq, which = w >> 2, r4 = w & 3;
-        const int k = kt * KTILE + 16 * (r4 >> 1) + 8 * (r4 & 1) + g;
-        if (k < p.K) {
-            if (which == 0) { if (p.h_fwd) p.h_fwd[k] = v; if (p.h_sum) atomicAdd(p.h_sum + k, v); }
-            else if (which == 1) { if (p.h_sum) atomicAdd(p.h_sum + k, v); }
-            else if (p.h_q) p.h_q[k] = v;
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const ReduceParams p) {
+    __shared__ float sh[4][32];
+    if ((int)blockIdx.x >= p.block_start[p.nsets]) {
+        const int w = blockIdx.x - p.block_start[p.nsets];
+        if (p.cnt_n[w] > 0) {
+            const uint32_t *rows = p.cnt_rows[w];
+            if (w == 0 && p.batch_index) rows += (size_t)(*p.batch_index) * p.cnt_n[0] * p.cnt_row_words[0];
+            count_bases_block(rows, p.cnt_row_words[w], p.cnt_n[w], p.cnt_L[w], p.cnt_out[w]);
         }
+        return;
     }
-}
-
-__global__ void write_counts_kernel(float *stats, crbm_stats_layout lay, float nhd, float nhm, float nvd, float nvm) {
-    if (threadIdx.x == 0) {
-        stats[lay.n_hidden_data] = nhd; stats[lay.n_hidden_model] = nhm;
-        stats[lay.n_vis_data] = nvd; stats[lay.n_vis_model] = nvm;
+    int si = 0;
+    while (si + 1 < p.nsets && (int)blockIdx.x >= p.block_start[si + 1]) ++si;
+    const ReduceSet &S = p.set[si];
+    const int local = blockIdx.x - p.block_start[si];
+    const int kt = local / S.nacc, o = local - kt * S.nacc;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.counts) {
+        p.counts[0] = p.c0; p.counts[1] = p.c1; p.counts[2] = p.c2; p.counts[3] = p.c3;
+    }
+    const float *src = S.partial + ((size_t)kt * S.gy * S.nacc + o) * 32 + lane;
+    float v = 0.f;
+    for (int c = warp; c < S.gy; c += 4) v += src[(size_t)c * S.nacc * 32];
+    sh[warp][lane] = v;
+    __syncthreads();
+    if (warp != 0) return;
+    v = (sh[0][lane] + sh[1][lane]) + (sh[2][lane] + sh[3][lane]);
+    if (p.mma) {
+        // fragment order (v2h_mma.cuh): register o of lane (g,q) = motif 16mt + 8(r>>1) + g, column 8t + 2q + (r&1) = 4m + a
+        const int g = lane >> 2, q = lane & 3;
+        if (o < S.np + S.nq) {
+            const bool isq = o >= S.np;
+            const int oo = isq ? o - S.np : o;
+            const int r = oo & 3, t = (oo >> 2) % (2 * p.KS), mt = oo / (8 * p.KS);
+            const int k = kt * KTILE + 16 * mt + 8 * (r >> 1) + g;
+            const int col = 8 * t + 2 * q + (r & 1), m = col >> 2, a = col & 3;
+            if (k < p.K && m < p.M) (isq ? S.vh_q : S.vh_p)[((size_t)k * 4 + a) * p.M + m] = v;
+        } else if (q == 0) {
+            const int w = o - S.np - S.nq, which = w >> 2, r4 = w & 3;
+            const int k = kt * KTILE + 16 * (r4 >> 1) + 8 * (r4 & 1) + g;
+            if (k < p.K) {
+                if (which == 0) { if (S.h_fwd) S.h_fwd[k] = v; if (S.h_sum) atomicAdd(S.h_sum + k, v); }
+                else if (which == 1) { if (S.h_sum) atomicAdd(S.h_sum + k, v); }
+                else if (S.h_q) S.h_q[k] = v;
+            }
+        }
+    } else {
+        const int k = kt * KTILE + lane;
+        if (k >= p.K) return;
+        if (o < S.np + S.nq) {
+            const bool isq = o >= S.np;
+            const int oo = isq ? o - S.np : o;
+            const int a = oo / p.MW, m = oo - a * p.MW;
+            if (m < p.M) (isq ? S.vh_q : S.vh_p)[((size_t)k * 4 + a) * p.M + m] = v;
+        } else {
+            const int w = o - S.np - S.nq;
+            if (w == 0) { if (S.h_fwd) S.h_fwd[k] = v; if (S.h_sum) atomicAdd(S.h_sum + k, v); }
+            else if (w == 1) { if (S.h_sum) atomicAdd(S.h_sum + k, v); }
+            else if (w == 2) { if (S.h_q) S.h_q[k] = v; }
+        }
     }
 }
 
@@ -405,6 +426,13 @@ int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const fl
     else pool = 1;
     Tiling t = make_tiling(K, M, pool, Lh, N);
     DenseParams p{packed, row_words, N, L, Lh, W, b, K, M, pool, strand_mode, out_kind, t.bv, t.nblk, t.n_items, out};
+    if (pool == 1) {
+        // tensor-pipe kernel, three CTAs per SM: size the grid to one full wave
+        int gy = ceil_div(t.n_items, 8);
+        const int cap = (3 * num_sms()) / t.ktiles > 0 ? (3 * num_sms()) / t.ktiles : 1;
+        if (gy > cap) gy = cap;
+        return dispatch_dense_mma(ceil_div(M, 4), p, dim3(t.ktiles, gy), (cudaStream_t)stream);
+    }
     return dispatch_dense(t.MW, p, dim3(t.ktiles, t.gy), (cudaStream_t)stream);
 }
 
@@ -463,20 +491,19 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     // pooling == 1: both contractions on the tensor pipe (v2h_mma.cuh); otherwise the CUDA-core kernel (v2h.cuh)
     const bool mma = P == 1;
     const int KS = ceil_div(M, 4);
-    const int nthreads = 256;
-
     auto run_fused = [&](int flags, const V2HParams &p, const Tiling &t) -> int {
         return mma ? dispatch_mma(KS, flags, p, dim3(t.ktiles, t.gy), s) : dispatch_fused(t.MW, flags, p, dim3(t.ktiles, t.gy), s);
     };
-    auto run_reduce = [&](ReduceParams r, const Tiling &t, bool has_p, bool has_q) -> int {
-        r.ktiles = t.ktiles; r.gy = t.gy; r.MW = t.MW; r.M = M; r.K = K;
+    ReduceParams red{};
+    red.ktiles = ceil_div(K, KTILE); red.MW = 3 * ceil_div(M, 3); red.KS = KS; red.mma = mma ? 1 : 0; red.M = M; red.K = K;
+    auto add_set = [&](const float *partial, const Tiling &t, bool has_p, bool has_q) -> ReduceSet & {
+        ReduceSet &S = red.set[red.nsets];
         const int per = mma ? 16 * KS : 4 * t.MW;
-        r.np = has_p ? per : 0; r.nq = has_q ? per : 0; r.nacc = r.np + r.nq + (mma ? 12 : 4);
-        const int blocks = ceil_div(r.ktiles * r.nacc * 32, nthreads);
-        if (mma) reduce_partials_mma_kernel<<<blocks, nthreads, 0, s>>>(r, KS);
-        else reduce_partials_kernel<<<blocks, nthreads, 0, s>>>(r);
-        CRBM_CHECK_LAUNCH();
-        return CRBM_OK;
+        S.partial = partial; S.gy = t.gy;
+        S.np = has_p ? per : 0; S.nq = has_q ? per : 0; S.nacc = S.np + S.nq + (mma ? 12 : 4);
+        red.block_start[red.nsets + 1] = red.block_start[red.nsets] + red.ktiles * S.nacc;
+        ++red.nsets;
+        return S;
     };
 
     // ---- positive phase on the minibatch (convRBM.py:377-388) and the sparsity statistic (:440-451) ----------
@@ -492,41 +519,27 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     } else if (combined) {
         p.partial = part0;
         if ((rc = run_fused(F_STAT_P | F_STAT_Q, p, t))) return rc;
-        ReduceParams r{};
-        r.partial = part0; r.vh_p = st + lay.vh_data; r.vh_q = st + lay.vh_q;
-        r.h_sum = st + lay.h_data; r.h_fwd = st + lay.h_fwd; r.h_q = st + lay.h_q;
-        if ((rc = run_reduce(r, t, true, true))) return rc;
+        ReduceSet &S = add_set(part0, t, true, true);
+        S.vh_p = st + lay.vh_data; S.vh_q = st + lay.vh_q;
+        S.h_sum = st + lay.h_data; S.h_fwd = st + lay.h_fwd; S.h_q = st + lay.h_q;
     } else {
         p.partial = part0;
         if ((rc = run_fused(F_STAT_P, p, t))) return rc;
-        ReduceParams r{};
-        r.partial = part0; r.vh_p = st + lay.vh_data; r.h_sum = st + lay.h_data; r.h_fwd = st + lay.h_fwd;
-        if ((rc = run_reduce(r, t, true, false))) return rc;
+        ReduceSet &S = add_set(part0, t, true, false);
+        S.vh_p = st + lay.vh_data; S.h_sum = st + lay.h_data; S.h_fwd = st + lay.h_fwd;
         p.partial = part2;
         if ((rc = run_fused(F_STAT_Q, p, t))) return rc;
-        ReduceParams rq{};
-        rq.partial = part2; rq.vh_q = st + lay.vh_q; rq.h_q = st + lay.h_q;
-        if ((rc = run_reduce(rq, t, false, true))) return rc;
+        ReduceSet &Sq = add_set(part2, t, false, true);
+        Sq.vh_q = st + lay.vh_q; Sq.h_q = st + lay.h_q;
     }
-    if (a->n_data > 0) {
-        const int cb = ceil_div(a->n_data * ceil_div(a->L, 16), 256);
-        count_bases_kernel<<<cb > 64 ? 64 : cb, 256, 0, s>>>(a->data, a->data_row_words, a->n_data, a->L,
-                                                            a->batch_index_dev, st + lay.v_data);
-        CRBM_CHECK_LAUNCH();
-    }
-    write_counts_kernel<<<1, 32, 0, s>>>(st, lay, (float)a->n_data * Lh, (float)a->batchsize * FANTASY_LEN,
-                                         (float)a->n_data * a->L, (float)a->batchsize * Lv);
-    CRBM_CHECK_LAUNCH();
-
     // ---- negative phase: cd_k Gibbs sweeps of the persistent chain (convRBM.py:391-413) -----------------------------
     Tiling tn = make_tiling(K, M, P, FANTASY_LEN, a->batchsize);
     const size_t n_u_v = (size_t)a->batchsize * Lv, n_u_h = (size_t)a->batchsize * K * (FANTASY_LEN / P);
     const size_t bits_bytes = (size_t)2 * a->batchsize * kw * FANTASY_WORDS * sizeof(uint32_t);
-    const size_t w4_bytes = (size_t)K * M * sizeof(float4);
-    const size_t posw_bytes = (size_t)(ds ? 2 : 1) * kw * FANTASY_WORDS * sizeof(uint32_t);
-    const int w4_in_smem = posw_bytes + w4_bytes <= 160 * 1024;
-    const size_t h2v_smem = posw_bytes + (w4_in_smem ? w4_bytes : 0);
-    static size_t h2v_smem_configured = 0;
+    const size_t w_bytes = (size_t)K * 16 * M;
+    const int w_in_smem = w_bytes + 16 <= 200 * 1024;
+    const size_t h2v_smem = w_in_smem ? w_bytes + 16 : 0;
+    static size_t h2v_smem_configured = 48 * 1024;
     if (h2v_smem > h2v_smem_configured) {
         CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h2v_smem));
         h2v_smem_configured = h2v_smem;
@@ -534,13 +547,17 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     for (int it = 0; it < a->cd_k; ++it) {
         const bool last = it == a->cd_k - 1;
         H2VParams h{};
-        h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.kw = kw; h.M = M; h.ds = ds; h.w4_in_smem = w4_in_smem;
+        h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.kw = kw; h.M = M; h.ds = ds; h.w_in_smem = w_in_smem; h.words_per_row = ceil_div(Lv, 16);
         h.W = a->W; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words;
         h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
         h.seed = a->seed; h.step_dev = a->step_dev;
         h.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
-        h.base_counts = last ? st + lay.v_model : nullptr;
-        h2v_bits_kernel<<<dim3(a->batchsize, 2), H2V_THREADS, h2v_smem, s>>>(h);
+        {
+            const int items = a->batchsize * ceil_div(Lv, 16);
+            int nw = ceil_div(items, num_sms());
+            nw = nw < 2 ? 2 : nw > 16 ? 16 : nw;
+            h2v_bits_kernel<<<ceil_div(items, nw), 32 * nw, h2v_smem, s>>>(h);
+        }
         CRBM_CHECK_LAUNCH();
 
         V2HParams q{};
@@ -555,9 +572,17 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
         if (!mma) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));   // CUDA-core sampler ORs its hits in
         if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
     }
-    ReduceParams rn{};
-    rn.partial = part1; rn.vh_p = st + lay.vh_model; rn.h_sum = st + lay.h_model;
-    if ((rc = run_reduce(rn, tn, true, false))) return rc;
+    ReduceSet &Sn = add_set(part1, tn, true, false);
+    Sn.vh_p = st + lay.vh_model; Sn.h_sum = st + lay.h_model;
+    red.counts = st + lay.n_hidden_data;
+    red.c0 = (float)a->n_data * Lh; red.c1 = (float)a->batchsize * FANTASY_LEN;
+    red.c2 = (float)a->n_data * a->L; red.c3 = (float)a->batchsize * Lv;
+    red.cnt_rows[0] = a->data; red.cnt_row_words[0] = a->data_row_words; red.cnt_n[0] = a->n_data; red.cnt_L[0] = a->L;
+    red.cnt_rows[1] = a->v_model; red.cnt_row_words[1] = a->v_row_words; red.cnt_n[1] = a->batchsize; red.cnt_L[1] = Lv;
+    red.batch_index = a->batch_index_dev;
+    red.cnt_out[0] = st + lay.v_data; red.cnt_out[1] = st + lay.v_model;
+    reduce_partials_kernel<<<red.block_start[red.nsets] + 2, 128, 0, s>>>(red);
+    CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }
 

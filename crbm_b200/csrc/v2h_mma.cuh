@@ -405,6 +405,109 @@ __global__ void __launch_bounds__(256, 1) v2h_mma_kernel(const V2HParams p) {
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Dense output (motif scan `getHitProbs`, eager `_bottomUpActivity` / `_bottomUpProbability`) for pooling == 1:
+// the same tensor-pipe up-pass, accumulator fragments stored straight to out[n][k][j] (each quad writes 32 contiguous
+// bytes of one motif row; the two n-tiles of a block complete a 64-byte run). HBM-write bound by design: 4*K bytes
+// per nucleotide against 0.25 bytes read.
+// ----------------------------------------------------------------------------------------------------------
+template <int KS>
+__global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams p) {
+    using Sh = MmaShape<KS>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t *wimg = reinterpret_cast<uint32_t *>(smem);
+    float *wtile = reinterpret_cast<float *>(smem + Sh::wimg_bytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + Sh::wimg_bytes + Sh::wtile_bytes);
+    const int kt = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    build_w_fragments<KS>(wimg, wtile, bar, p.W, p.K, p.M, kt);
+    const uint4 *wfrag = reinterpret_cast<const uint4 *>(wimg) + lane;
+    const bool want_f = p.strand_mode != CRBM_STRAND_RC, want_r = p.strand_mode != CRBM_STRAND_FWD;
+    const float bscale = p.strand_mode == CRBM_STRAND_SUM ? 2.f : 1.f;        // both activities carry the bias (convRBM.py:513)
+    float bias[4];
+    bool kval[4];
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4) {
+        const int k = kt * KTILE + 16 * (r4 >> 1) + 8 * (r4 & 1) + g;
+        kval[r4] = k < p.K;
+        bias[r4] = kval[r4] ? bscale * __ldg(p.b + k) : 0.f;
+    }
+    const bool mt_on[2] = {kt * KTILE < p.K, kt * KTILE + 16 < p.K};
+    const int lo1 = g + (q >> 1);
+    const uint32_t qodd = q & 1;
+    const bool prob = p.out_kind == CRBM_OUT_PROBABILITY;
+    // Lh even and 8-byte aligned rows allow float2 stores
+    const bool vec2 = (p.Lh & 1) == 0;
+
+    for (int item = blockIdx.y * nwarps + warp; item < p.n_items; item += gridDim.y * nwarps) {
+        const int n = item / p.nblk, jb = item - n * p.nblk, j0 = jb * 16;
+        const uint32_t *row = p.packed + (size_t)n * p.row_words + (j0 >> 4);
+        uint32_t wd[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) wd[i] = __ldg(row + i);
+        float d1[2][2][4];                                  // [mt][nt][reg]
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) d1[mt][nt][r] = 0.f;
+        uint32_t v[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(wd[1 + i], wd[2 + i], 2 * lo1);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            uint32_t bx[2][2];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int hb = 0; hb < 2; ++hb) {
+                    const uint32_t bb = window_bits<1, 3>(v, 8 * nt + 4 * ks + 2 * hb);
+                    bx[nt][hb] = ((bb >> 1) == qodd) ? (0x3F80u << ((bb & 1u) << 4)) : 0u;
+                }
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s == 0 ? !want_f : !want_r) continue;
+#pragma unroll
+                for (int sp = 0; sp < 3; ++sp)
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        if (!mt_on[mt]) continue;
+                        const uint4 a = wfrag[(((s * 3 + sp) * 2 + mt) * KS + ks) * 32];
+                        hmma_bf16(d1[mt][0], a, bx[0][0], bx[0][1]);
+                        hmma_bf16(d1[mt][1], a, bx[1][0], bx[1][1]);
+                    }
+            }
+        }
+        const int jrem = p.Lh - j0 - 2 * q;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            if (!mt_on[mt]) continue;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r4 = 2 * mt + h;
+                if (!kval[r4]) continue;
+                float *orow = p.out + ((size_t)n * p.K + kt * KTILE + 16 * mt + 8 * h + g) * p.Lh + j0 + 2 * q;
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    float x0 = d1[mt][nt][2 * h] + bias[r4], x1 = d1[mt][nt][2 * h + 1] + bias[r4];
+                    if (prob) {
+                        x0 = __fdividef(1.0f, 1.0f + __expf(-x0));
+                        x1 = __fdividef(1.0f, 1.0f + __expf(-x1));
+                    }
+                    if (vec2 && 8 * nt + 1 < jrem) {
+                        __stcs(reinterpret_cast<float2 *>(orow + 8 * nt), make_float2(x0, x1));
+                    } else {
+                        if (8 * nt < jrem) __stcs(orow + 8 * nt, x0);
+                        if (8 * nt + 1 < jrem) __stcs(orow + 8 * nt + 1, x1);
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int KS> int launch_v2h_mma(int flags, const V2HParams &p, dim3 grid, cudaStream_t stream);
+template <int KS> int launch_v2h_dense_mma(const DenseParams &p, dim3 grid, cudaStream_t stream);
 
 }  // namespace crbm

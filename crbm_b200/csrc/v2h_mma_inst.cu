@@ -36,4 +36,17 @@ int launch_v2h_mma<CRBM_KS>(int flags, const V2HParams &p, dim3 grid, cudaStream
     }
 }
 
+template <>
+int launch_v2h_dense_mma<CRBM_KS>(const DenseParams &p, dim3 grid, cudaStream_t stream) {
+    static bool configured = false;
+    constexpr size_t smem = MmaShape<CRBM_KS>::smem_bytes;
+    if (!configured) {
+        CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_dense_mma_kernel<CRBM_KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    v2h_dense_mma_kernel<CRBM_KS><<<grid, 256, smem, stream>>>(p);
+    CRBM_CHECK_LAUNCH();
+    return CRBM_OK;
+}
+
 }  // namespace crbm

@@ -91,7 +91,7 @@ static int max_gy(int K) { const int kt = ceil_div(K, KTILE); return num_sms() /
 // 2-bit codes into the packed word.
 struct H2VParams {
     const uint32_t *bits;     // [2][B][kw][FANTASY_WORDS]
-    int Bn, K, kw, M, ds, w_in_smem, words_per_row;
+    int Bn, K, kw, M, ds, w_in_smem, words_per_row, list_offset;
     const float *W, *c;
     uint32_t *v_packed;       // rows of Lv bases
     int v_row_words;
@@ -100,6 +100,8 @@ struct H2VParams {
     uint32_t ctr_hi;
     const unsigned long long *step_dev;
 };
+
+constexpr int H2V_LIST = 1024 + 4;     // a round holds at most 32 words x 32 bits hits (+ padding quad)
 
 __global__ void __launch_bounds__(512) h2v_bits_kernel(const H2VParams p) {
     extern __shared__ __align__(128) unsigned char h2v_smem[];
@@ -129,34 +131,54 @@ __global__ void __launch_bounds__(512) h2v_bits_kernel(const H2VParams p) {
     const int strands = p.ds ? 2 : 1;
     const int jb_lo = max(0, 16 * w - (M - 1)) >> 4, jb_hi = min(FANTASY_BLOCKS - 1, w);
     float acc0 = 0.f, acc1 = 0.f;
-    // one round = the 2 x 16 words of two position blocks of one (strand, k-tile): no index arithmetic beyond shifts
+    // One round = the 2 x 16 bit-plane words of two position blocks of one (strand, k-tile), one word per lane.
+    // The lanes first compact their set bits into a warp-private list of (motif row offset, hidden position) in
+    // shared memory (warp prefix sum over popcounts), then the whole warp consumes the list four hits at a time:
+    // the descriptor reads are broadcast LDS.128 and the eight weight loads of a quad of hits are independent.
+    uint32_t *list = reinterpret_cast<uint32_t *>(h2v_smem + p.list_offset) + (threadIdx.x >> 5) * H2V_LIST;
     for (int s = 0; s < strands; ++s) {
         const float *Wbase = s == 0 ? Wsm + (size_t)(2 * ah) * M : Wsm + (size_t)(3 - 2 * ah) * M;
         const int dir = s == 0 ? M : -M;                     // second base row: +M (forward) / -M (reverse)
         for (int t = 0; t < p.kw; ++t) {
             const uint32_t *tile = p.bits + (((size_t)s * p.Bn + n) * p.kw + t) * FANTASY_WORDS;
             for (int jb0 = jb_lo; jb0 <= jb_hi; jb0 += 2) {
-                const int jbl = jb0 + (lane >> 4);
-                const uint32_t word = jbl <= jb_hi ? __ldg(tile + jbl * 16 + (lane & 15)) : 0u;
-                uint32_t nz = __ballot_sync(0xffffffffu, word != 0u);
-                while (nz) {
-                    const int src = __ffs(nz) - 1;
-                    nz &= nz - 1;
-                    uint32_t ww = __shfl_sync(0xffffffffu, word, src);
-                    const int f = src & 15;
-                    const int jbase = 16 * (jb0 + (src >> 4)) + 8 * ((f >> 1) & 1) + (f & 1);
-                    const float *Ws = Wbase + (size_t)(32 * t + 8 * (f >> 2)) * 4 * M;
-                    while (ww) {
-                        const int b = __ffs(ww) - 1;
-                        ww &= ww - 1;
-                        const int m = i - (jbase + 2 * (b & 3));
-                        if (m >= 0 && m < M) {
-                            const float *wk = Ws + (b >> 2) * 4 * M + (s == 0 ? m : M - 1 - m);
-                            acc0 += wk[0];
-                            acc1 += wk[dir];
-                        }
-                    }
+                const int jbl = jb0 + (lane >> 4), f = lane & 15;
+                uint32_t word = jbl <= jb_hi ? __ldg(tile + jbl * 16 + f) : 0u;
+                if (__ballot_sync(0xffffffffu, word != 0u) == 0u) continue;
+                const int cnt = __popc(word);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
                 }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                int pos = incl - cnt;
+                const int jbase = 16 * jbl + 8 * ((f >> 1) & 1) + (f & 1);
+                const int krow = (32 * t + 8 * (f >> 2)) * 4 * M;
+                while (word) {
+                    const int b = __ffs(word) - 1;
+                    word &= word - 1;
+                    list[pos++] = ((uint32_t)(krow + (b >> 2) * 4 * M) << 8) | (uint32_t)(jbase + 2 * (b & 3));
+                }
+                if (lane < 4) list[total + lane] = 0xFFu;            // padding entries: position 255 never matches
+                __syncwarp();
+                for (int h0 = 0; h0 < total; h0 += 4) {
+                    const uint4 d = *reinterpret_cast<const uint4 *>(list + h0);
+                    const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+                    float x0[4], x1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int m = i - (int)(dd[u] & 0xFFu);
+                        const bool ok = m >= 0 && m < M;
+                        const float *wk = Wbase + (dd[u] >> 8) + (s == 0 ? m : M - 1 - m);
+                        x0[u] = ok ? wk[0] : 0.f;
+                        x1[u] = ok ? wk[dir] : 0.f;
+                    }
+                    acc0 += (x0[0] + x0[1]) + (x0[2] + x0[3]);
+                    acc1 += (x1[0] + x1[1]) + (x1[2] + x1[3]);
+                }
+                __syncwarp();
             }
         }
     }
@@ -537,8 +559,13 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     const size_t n_u_v = (size_t)a->batchsize * Lv, n_u_h = (size_t)a->batchsize * K * (FANTASY_LEN / P);
     const size_t bits_bytes = (size_t)2 * a->batchsize * kw * FANTASY_WORDS * sizeof(uint32_t);
     const size_t w_bytes = (size_t)K * 16 * M;
-    const int w_in_smem = w_bytes + 16 <= 200 * 1024;
-    const size_t h2v_smem = w_in_smem ? w_bytes + 16 : 0;
+    const int h2v_items = a->batchsize * ceil_div(Lv, 16);
+    int h2v_nw = ceil_div(h2v_items, num_sms());
+    h2v_nw = h2v_nw < 2 ? 2 : h2v_nw > 16 ? 16 : h2v_nw;
+    const size_t list_bytes = (size_t)h2v_nw * H2V_LIST * sizeof(uint32_t);
+    const int w_in_smem = w_bytes + 16 + list_bytes <= 200 * 1024;
+    const size_t list_offset = w_in_smem ? w_bytes + 16 : 16;
+    const size_t h2v_smem = list_offset + list_bytes;
     static size_t h2v_smem_configured = 48 * 1024;
     if (h2v_smem > h2v_smem_configured) {
         CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h2v_smem));
@@ -547,17 +574,12 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     for (int it = 0; it < a->cd_k; ++it) {
         const bool last = it == a->cd_k - 1;
         H2VParams h{};
-        h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.kw = kw; h.M = M; h.ds = ds; h.w_in_smem = w_in_smem; h.words_per_row = ceil_div(Lv, 16);
+        h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.kw = kw; h.M = M; h.ds = ds; h.w_in_smem = w_in_smem; h.words_per_row = ceil_div(Lv, 16); h.list_offset = (int)list_offset;
         h.W = a->W; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words;
         h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
         h.seed = a->seed; h.step_dev = a->step_dev;
         h.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
-        {
-            const int items = a->batchsize * ceil_div(Lv, 16);
-            int nw = ceil_div(items, num_sms());
-            nw = nw < 2 ? 2 : nw > 16 ? 16 : nw;
-            h2v_bits_kernel<<<ceil_div(items, nw), 32 * nw, h2v_smem, s>>>(h);
-        }
+        h2v_bits_kernel<<<ceil_div(h2v_items, h2v_nw), 32 * h2v_nw, h2v_smem, s>>>(h);
         CRBM_CHECK_LAUNCH();
 
         V2HParams q{};

@@ -455,57 +455,72 @@ class CRBM(object):
         self._engine = eng
         return eng
 
-    def _run_steps_once(self, eng):
+    def _run_steps_once(self, eng, part='both'):
         lib = _lib.load()
         s = _lib.stream_handle()
         a = eng['args']
-        _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
-        if self._world > 1:
+        if part in ('both', 'accumulate'):
+            _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
+        if part == 'both' and self._world > 1:
             import torch.distributed as dist
             dist.all_reduce(self._train_state['stats'])
-        _lib.check(lib.crbm_train_apply(a, s), 'train_apply')
+        if part in ('both', 'apply'):
+            _lib.check(lib.crbm_train_apply(a, s), 'train_apply')
 
-    def _graph_for(self, eng, nsteps):
+    def _graph_for(self, eng, nsteps, part='both'):
         torch = _torch()
-        g = eng['graphs'].get(nsteps)
+        key = (nsteps, part)
+        g = eng['graphs'].get(key)
         if g is None:
-            # warm-up outside capture (first-use cudaFuncSetAttribute, NCCL communicator setup), state restored after
-            saved = [t.clone() for t in (self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
-                                         self._t_fantasy, eng['step_dev'], eng['batch_dev'])]
+            # warm-up outside capture (first-use cudaFuncSetAttribute), state restored after
+            tensors = (self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
+                       self._t_fantasy, eng['step_dev'], eng['batch_dev'])
+            saved = [t.clone() for t in tensors]
             side = torch.cuda.Stream(device=self._device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._run_steps_once(eng)
+                self._run_steps_once(eng, part)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(self._device)
-            for t, v in zip((self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
-                             self._t_fantasy, eng['step_dev'], eng['batch_dev']), saved):
+            for t, v in zip(tensors, saved):
                 t.copy_(v)
             g = torch.cuda.CUDAGraph()
             c0 = _lib.load().crbm_launch_count()
             with torch.cuda.graph(g):
                 for _ in range(nsteps):
-                    self._run_steps_once(eng)
-            eng['launches_per_step'] = int(_lib.load().crbm_launch_count() - c0) // nsteps
-            eng['graphs'][nsteps] = g
+                    self._run_steps_once(eng, part)
+            if part in ('both', 'accumulate'):
+                eng['launches_per_step'] = int(_lib.load().crbm_launch_count() - c0) // nsteps + (1 if part == 'accumulate' else 0)
+            eng['graphs'][key] = g
         return g
 
     def _train_full_batches(self, seqs, first_batch, count, steps_per_graph=8):
-        """Train on `count` consecutive full minibatches starting at minibatch `first_batch`, by graph replay."""
+        """Train on `count` consecutive full minibatches starting at minibatch `first_batch`, by graph replay.
+        Single GPU: `steps_per_graph` whole steps per graph. Data parallel: the NCCL all-reduce of the statistics
+        vector stays outside the graphs (accumulate graph -> all_reduce -> apply graph), one step at a time."""
         if count <= 0:
             return
         eng = self._graph_engine(seqs, steps_per_graph)
         eng['step_dev'].fill_(self._step)
         eng['batch_dev'].fill_(first_batch)
-        big, rest = divmod(count, steps_per_graph)
-        if big:
-            g = self._graph_for(eng, steps_per_graph)
-            for _ in range(big):
-                g.replay()
-        if rest:
-            g1 = self._graph_for(eng, 1)
-            for _ in range(rest):
-                g1.replay()
+        if self._world > 1:
+            import torch.distributed as dist
+            ga, gb = self._graph_for(eng, 1, 'accumulate'), self._graph_for(eng, 1, 'apply')
+            stats = self._train_state['stats']
+            for _ in range(count):
+                ga.replay()
+                dist.all_reduce(stats)
+                gb.replay()
+        else:
+            big, rest = divmod(count, steps_per_graph)
+            if big:
+                g = self._graph_for(eng, steps_per_graph)
+                for _ in range(big):
+                    g.replay()
+            if rest:
+                g1 = self._graph_for(eng, 1)
+                for _ in range(rest):
+                    g1.replay()
         self._step += count
 
     def _train_epoch(self, seqs):

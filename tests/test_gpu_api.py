@@ -100,3 +100,52 @@ def test_unsupported_shapes_fail_loudly(data):
     m = CRBM(num_motifs=2, motif_length=5, pooling=7)       # 7 does not divide the 200-long persistent chain
     with pytest.raises(ValueError):
         m.fit(data[:20])
+
+
+def test_statistics_vector_is_additive_across_shards(data):
+    """Data-parallel contract on the real kernels, emulating two ranks on one GPU: summing the statistics vectors that
+    crbm_train_accumulate produces for two shards (half the minibatch + half the fantasy particles each) and applying the
+    update gives the parameters of one step on the whole minibatch (same injected uniforms)."""
+    import torch
+    import crbm_b200
+    from crbm_b200 import CRBM, _lib
+    lib = _lib.load()
+    K, M, B, N = 40, 15, 8, 10
+    rs = np.random.RandomState(0)
+    W = (0.3 * rs.randn(K, 1, 4, M)).astype(np.float32)
+    b = (-3 + 0.3 * rs.randn(1, K)).astype(np.float32)
+    fh = (rs.rand(B, K, 1, 200) < 0.03).astype(np.float32)
+    fhp = (rs.rand(B, K, 1, 200) < 0.03).astype(np.float32)
+    lv = 199 + M
+    u_v, u_h, u_hp = rs.rand(B, lv).astype(np.float32), rs.rand(B, K * 200).astype(np.float32), rs.rand(B, K * 200).astype(np.float32)
+    d = data[:N]
+
+    def make(bs, fsl):
+        m = CRBM(K, M, batchsize=bs, cd_k=1, seed=1)
+        m.motifs.set_value(W); m.bias.set_value(b)
+        m.fantasy_h.set_value(fh[fsl]); m.fantasy_h_prime.set_value(fhp[fsl])
+        return m
+    full = make(B, slice(0, B))
+    full._trainingFct(d, uniforms={'v': u_v.ravel(), 'h': u_h.ravel(), 'hp': u_hp.ravel()})
+
+    shards, stats = [], []
+    for r in range(2):
+        fsl, dsl = slice(r * B // 2, (r + 1) * B // 2), slice(r * N // 2, (r + 1) * N // 2)
+        m = make(B // 2, fsl)
+        seqs = crbm_b200.PackedSequences.from_onehot(d[dsl])
+        dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        uv, uh, uhp = dev(u_v[fsl].ravel()), dev(u_h[fsl].ravel()), dev(u_hp[fsl].ravel())
+        a = m._fill_args(seqs.words.data_ptr(), seqs.row_words, seqs.N, seqs.L, uv, uh, uhp)
+        _lib.check(lib.crbm_train_accumulate(a, _lib.stream_handle()), 'accumulate')
+        torch.cuda.synchronize()
+        shards.append((m, a, seqs, (uv, uh, uhp)))
+        stats.append(m._train_state['stats'].clone())
+    total = stats[0] + stats[1]                     # what the NCCL all-reduce computes
+    for m, a, _, _ in shards:
+        m._train_state['stats'].copy_(total)
+        _lib.check(lib.crbm_train_apply(a, _lib.stream_handle()), 'apply')
+        np.testing.assert_allclose(m.motifs.get_value(), full.motifs.get_value(), rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(m.bias.get_value(), full.bias.get_value(), rtol=1e-5, atol=2e-6)
+        np.testing.assert_allclose(m.c.get_value(), full.c.get_value(), rtol=1e-5, atol=2e-6)
+    got = np.concatenate([shards[0][0].fantasy_h.get_value(), shards[1][0].fantasy_h.get_value()])
+    np.testing.assert_array_equal(got, full.fantasy_h.get_value())

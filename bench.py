@@ -48,6 +48,15 @@ def peaks():
         return 6650.0, 'fallback (B200_PROFILING.md)', 1965.0
 
 
+def tensor_peak():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['bf16_tflops']), 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)'
+    except Exception:
+        return 1590.0, 'fallback (B200_PROFILING.md)'
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -195,7 +204,7 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    if rank == 0:
+    if rank == 0 and world == 1:
         # short runs end before nvidia-smi's first 100 ms sample: keep the load on until a few samples exist
         t_end = time.time() + 1.5
         while len(sampler.rows) < 4 and time.time() < t_end:
@@ -224,19 +233,27 @@ def main():
         # --- per-kernel device time of one step (CUDA events around eager launches on the launching stream) ------------
         kern = time_step_kernels(model, data, B, dev)
         line['step_kernels_us'] = kern
-        fused_us = kern.get('positive_phase_fused', 0.0)
-        # algorithmic bytes of the positive-phase kernel: packed minibatch + W tile per k-tile CTA group + partials
-        ktiles = (K + 31) // 32
-        alg_bytes = B * data.row_words * 4 * ktiles + K * 4 * M * 4 + kern.get('_partial_bytes', 0)
-        adds = B * (Lt - M + 1) * K * M * (2 + 2 + 1)      # up-pass both strands + stats both strands + sparsity stat
-        line['roofline'] = {'bound': 'hbm', 'kernel': 'v2h_fused_kernel<MW=%d, STAT_P|STAT_Q> (positive phase)' % (3 * ((M + 2) // 3)),
-                            'achieved': alg_bytes / (fused_us * 1e-6) / 1e9 if fused_us else None, 'peak': hbm_peak,
-                            'unit': 'GB/s', 'frac': (alg_bytes / (fused_us * 1e-6) / 1e9 / hbm_peak) if fused_us else None,
-                            'traffic': None, 'peak_source': peak_src,
-                            'note': 'fused training kernels are issue/shared-memory bound, not HBM bound (SURVEY 8d): '
-                                    'see fp32_add_frac',
-                            'gather_adds_per_launch': adds,
-                            'fp32_add_frac': (adds / (fused_us * 1e-6) / (148 * 128 * sm_max * 1e6)) if fused_us else None}
+        pos_us = kern['positive_phase_kernel']
+        Lh = Lt - M + 1
+        # Algorithmic work of the positive-phase launch (DESIGN.md "Measurement"): per hidden position and motif the
+        # one-hot contraction over 4*M inputs, 2 flops each, for x and x' (up-pass) and for the P, P', Q statistics.
+        alg_flops = 2.0 * B * Lh * K * 4 * M * 5
+        alg_bytes = B * data.row_words * 4 + K * 4 * M * 4 + K * 4          # packed minibatch + W + b, read once
+        adds = B * Lh * K * M * 5                                           # SURVEY 8d gather-add count of the same work
+        tf = alg_flops / (pos_us * 1e-6) / 1e12 if pos_us else None
+        tpeak = tensor_peak()
+        pooled = P != 1
+        line['roofline'] = {
+            'bound': 'tensor', 'kernel': ('v2h_fused_kernel (CUDA-core path, pooling > 1)' if pooled else
+                                          'v2h_mma_kernel<KS=%d, STAT_P|STAT_Q> (positive-phase launch)' % ((M + 3) // 4)),
+            'achieved': tf, 'peak': tpeak[0], 'unit': 'TFLOP/s', 'frac': (tf / tpeak[0]) if tf else None, 'traffic': None,
+            'peak_source': tpeak[1], 'launch_us': pos_us, 'algorithmic_flops_per_launch': alg_flops,
+            'note': 'dense-equivalent flops of the one-hot contractions (x, x\', and the P, P\', Q statistics); the bf16x3 / '
+                    'bf16x2 operand splits and tile padding are overhead, not counted. At 100 x 200 bp per step the launch is '
+                    'latency/issue bound (ncu: profiles/), not throughput bound.',
+            'hbm_frac': (alg_bytes / (pos_us * 1e-6) / 1e9 / hbm_peak) if pos_us else None,
+            'gather_adds_per_launch': adds,
+            'fp32_add_frac': (adds / (pos_us * 1e-6) / (148 * 128 * sm_max * 1e6)) if pos_us else None}
         if not args.no_scan:
             line['scan'] = bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src)
         if not args.no_e2e:
@@ -253,45 +270,42 @@ def main():
 
 
 def time_step_kernels(model, data, B, dev):
-    """Device time of each phase of one training step, eager launches bracketed by CUDA events (warm)."""
+    """Device time of the phases of one training step. Each phase is captured 20x back to back in a CUDA graph and the
+    graph is timed with CUDA events on the launching stream, so host launch latency is excluded. The positive-phase
+    kernel is obtained as (accumulate) - (accumulate with an empty minibatch): the latter launches everything but it."""
     import torch
     from crbm_b200 import _lib
     lib = _lib.load()
+    reps, rounds = 20, 5
+    full = model._fill_args(data.words.data_ptr(), data.row_words, B, data.L)
+    empty = model._fill_args(data.words.data_ptr(), data.row_words, 0, data.L)
+
+    def timed(fn):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(rounds):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / (reps * rounds)
+
     out = {}
-    a = model._fill_args(data.words.data_ptr(), data.row_words, B, data.L)
-    s = _lib.stream_handle()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-    reps = 50
-    for _ in range(5):
-        lib.crbm_train_accumulate(a, s); lib.crbm_train_apply(a, s)
-    torch.cuda.synchronize()
-    ev[0].record()
-    for _ in range(reps):
-        lib.crbm_train_accumulate(a, s)
-    ev[1].record()
-    for _ in range(reps):
-        lib.crbm_train_apply(a, s)
-    ev[2].record()
-    torch.cuda.synchronize()
-    out['accumulate_eager'] = ev[0].elapsed_time(ev[1]) * 1e3 / reps
-    out['apply_eager'] = ev[1].elapsed_time(ev[2]) * 1e3 / reps
-    # positive phase alone: n_data rows, cd_k sweeps cannot be switched off, so time via the free-standing entry
-    # points that launch exactly one fused kernel: crbm_free_energy (F_FE variant) is not the same kernel, hence
-    # the positive-phase kernel is timed by differencing accumulate with an empty minibatch.
-    a0 = model._fill_args(data.words.data_ptr(), data.row_words, 0, data.L)
-    for _ in range(5):
-        lib.crbm_train_accumulate(a0, s)
-    torch.cuda.synchronize()
-    ev[0].record()
-    for _ in range(reps):
-        lib.crbm_train_accumulate(a0, s)
-    ev[1].record()
-    torch.cuda.synchronize()
-    out['accumulate_without_positive_phase'] = ev[0].elapsed_time(ev[1]) * 1e3 / reps
-    out['positive_phase_fused'] = max(0.0, out['accumulate_eager'] - out['accumulate_without_positive_phase'])
-    K, M = model.num_motifs, model.motif_length
-    mw = 3 * ((M + 2) // 3)
-    out['_partial_bytes'] = ((K + 31) // 32) * max(1, 148 // ((K + 31) // 32)) * (8 * mw + 4) * 32 * 4
+    out['accumulate'] = timed(lambda: _lib.check(lib.crbm_train_accumulate(full, _lib.stream_handle())))
+    out['accumulate_without_positive_phase'] = timed(lambda: _lib.check(lib.crbm_train_accumulate(empty, _lib.stream_handle())))
+    out['apply'] = timed(lambda: _lib.check(lib.crbm_train_apply(full, _lib.stream_handle())))
+    out['positive_phase_kernel'] = max(0.0, out['accumulate'] - out['accumulate_without_positive_phase'])
     return out
 
 

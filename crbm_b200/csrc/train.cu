@@ -4,6 +4,7 @@
 //   h2v_bits_kernel     A5+A6: sparse hidden bit planes -> visible activity -> 4-way softmax -> sampled packed V
 //   reduce_partials     per-CTA register accumulators -> the rank's `stats` vector
 //   apply_update        A11 sparsity factor + A12 momentum update of W, b, c
+#include <stdlib.h>
 #include "v2h_mma.cuh"
 
 namespace crbm {
@@ -78,6 +79,13 @@ static Tiling make_tiling(int K, int M, int pooling, int Lh, int n_rows) {
     if (t.gy > per_tile) t.gy = per_tile;
     if (t.gy < 1) t.gy = 1;
     return t;
+}
+// tensor-pipe kernels: one CTA per (16-motif m-tile, slice of the position blocks), two CTAs per SM
+static int mma_gy(int K, int n_items) {
+    const int mtiles = ceil_div(K, 16);
+    int gy = ceil_div(n_items, 8);
+    const int cap = (2 * num_sms()) / mtiles > 0 ? (2 * num_sms()) / mtiles : 1;
+    return gy > cap ? cap : (gy < 1 ? 1 : gy);
 }
 static int max_gy(int K) { const int kt = ceil_div(K, KTILE); return num_sms() / kt > 0 ? num_sms() / kt : 1; }
 
@@ -283,18 +291,19 @@ __global__ void __launch_bounds__(128) reduce_partials_kernel(const ReduceParams
     if (warp != 0) return;
     v = (sh[0][lane] + sh[1][lane]) + (sh[2][lane] + sh[3][lane]);
     if (p.mma) {
-        // fragment order (v2h_mma.cuh): register o of lane (g,q) = motif 16mt + 8(r>>1) + g, column 8t + 2q + (r&1) = 4m + a
+        // fragment order (v2h_mma.cuh), kt = m-tile of 16 motifs: slot t*4+r of lane (g,q) = motif 16kt + 8(r>>1) + g,
+        // column 8t + 2q + (r&1) = 4m + a; then sum_p[h], sum_pr[h], sum_q[h] on the q == 0 lanes
         const int g = lane >> 2, q = lane & 3;
         if (o < S.np + S.nq) {
             const bool isq = o >= S.np;
             const int oo = isq ? o - S.np : o;
-            const int r = oo & 3, t = (oo >> 2) % (2 * p.KS), mt = oo / (8 * p.KS);
-            const int k = kt * KTILE + 16 * mt + 8 * (r >> 1) + g;
+            const int r = oo & 3, t = oo >> 2;
+            const int k = kt * 16 + 8 * (r >> 1) + g;
             const int col = 8 * t + 2 * q + (r & 1), m = col >> 2, a = col & 3;
             if (k < p.K && m < p.M) (isq ? S.vh_q : S.vh_p)[((size_t)k * 4 + a) * p.M + m] = v;
         } else if (q == 0) {
-            const int w = o - S.np - S.nq, which = w >> 2, r4 = w & 3;
-            const int k = kt * KTILE + 16 * (r4 >> 1) + 8 * (r4 & 1) + g;
+            const int w = o - S.np - S.nq, which = w >> 1, h = w & 1;
+            const int k = kt * 16 + 8 * h + g;
             if (k < p.K) {
                 if (which == 0) { if (S.h_fwd) S.h_fwd[k] = v; if (S.h_sum) atomicAdd(S.h_sum + k, v); }
                 else if (which == 1) { if (S.h_sum) atomicAdd(S.h_sum + k, v); }
@@ -392,9 +401,10 @@ __global__ void fe_finish_kernel(const uint32_t *__restrict__ packed, int row_wo
 
 static size_t partial_floats(int K, int M) {
     const int MW = 3 * ceil_div(M, 3);
-    const size_t nacc_cc = 8 * (size_t)MW + 4, nacc_mma = 32 * (size_t)ceil_div(M, 4) + 12;
-    const size_t nacc = nacc_cc > nacc_mma ? nacc_cc : nacc_mma;
-    return (size_t)ceil_div(K, KTILE) * max_gy(K) * nacc * 32;
+    const size_t cc = (size_t)ceil_div(K, KTILE) * max_gy(K) * (8 * (size_t)MW + 4) * 32;
+    const int mtiles = ceil_div(K, 16);
+    const size_t mma = (size_t)mtiles * ((2 * num_sms()) / mtiles + 1) * (16 * (size_t)ceil_div(M, 4) + 6) * 32;
+    return cc > mma ? cc : mma;
 }
 
 static void fill_layout(int K, int M, crbm_stats_layout *l) {
@@ -449,11 +459,12 @@ int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const fl
     Tiling t = make_tiling(K, M, pool, Lh, N);
     DenseParams p{packed, row_words, N, L, Lh, W, b, K, M, pool, strand_mode, out_kind, t.bv, t.nblk, t.n_items, out};
     if (pool == 1) {
-        // tensor-pipe kernel, three CTAs per SM: size the grid to one full wave
+        // tensor-pipe kernel: CTAs of one 16-motif m-tile, three per SM: size the grid to one full wave
+        const int mtiles = ceil_div(K, 16);
         int gy = ceil_div(t.n_items, 8);
-        const int cap = (3 * num_sms()) / t.ktiles > 0 ? (3 * num_sms()) / t.ktiles : 1;
+        const int cap = (3 * num_sms()) / mtiles > 0 ? (3 * num_sms()) / mtiles : 1;
         if (gy > cap) gy = cap;
-        return dispatch_dense_mma(ceil_div(M, 4), p, dim3(t.ktiles, gy), (cudaStream_t)stream);
+        return dispatch_dense_mma(ceil_div(M, 4), p, dim3(mtiles, gy), (cudaStream_t)stream);
     }
     return dispatch_dense(t.MW, p, dim3(t.ktiles, t.gy), (cudaStream_t)stream);
 }
@@ -514,15 +525,17 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     const bool mma = P == 1;
     const int KS = ceil_div(M, 4);
     auto run_fused = [&](int flags, const V2HParams &p, const Tiling &t) -> int {
-        return mma ? dispatch_mma(KS, flags, p, dim3(t.ktiles, t.gy), s) : dispatch_fused(t.MW, flags, p, dim3(t.ktiles, t.gy), s);
+        return mma ? dispatch_mma(KS, flags, p, dim3(ceil_div(K, 16), mma_gy(K, t.n_items)), s)
+                   : dispatch_fused(t.MW, flags, p, dim3(t.ktiles, t.gy), s);
     };
     ReduceParams red{};
-    red.ktiles = ceil_div(K, KTILE); red.MW = 3 * ceil_div(M, 3); red.KS = KS; red.mma = mma ? 1 : 0; red.M = M; red.K = K;
+    red.ktiles = mma ? ceil_div(K, 16) : ceil_div(K, KTILE);        // tiles of the partial buffers: m-tiles / k-tiles
+    red.MW = 3 * ceil_div(M, 3); red.KS = KS; red.mma = mma ? 1 : 0; red.M = M; red.K = K;
     auto add_set = [&](const float *partial, const Tiling &t, bool has_p, bool has_q) -> ReduceSet & {
         ReduceSet &S = red.set[red.nsets];
-        const int per = mma ? 16 * KS : 4 * t.MW;
-        S.partial = partial; S.gy = t.gy;
-        S.np = has_p ? per : 0; S.nq = has_q ? per : 0; S.nacc = S.np + S.nq + (mma ? 12 : 4);
+        const int per = mma ? 8 * KS : 4 * t.MW;
+        S.partial = partial; S.gy = mma ? mma_gy(K, t.n_items) : t.gy;
+        S.np = has_p ? per : 0; S.nq = has_q ? per : 0; S.nacc = S.np + S.nq + (mma ? 6 : 4);
         red.block_start[red.nsets + 1] = red.block_start[red.nsets] + red.ktiles * S.nacc;
         ++red.nsets;
         return S;

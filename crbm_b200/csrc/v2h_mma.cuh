@@ -24,25 +24,27 @@
 
 namespace crbm {
 
+constexpr int MTILE = 16;                                       // motifs per CTA of the tensor-pipe kernels (one MMA m-tile)
+
 template <int KS> struct MmaShape {
     static constexpr int NT2 = 2 * KS;                          // 8-column tiles over c = 4*m + a  (16*KS columns)
-    static constexpr int FRAGS = 2 * 3 * 2 * KS;                // [strand][split][mt][ks]
+    static constexpr int FRAGS = 2 * 3 * KS;                    // [strand][split][ks]
     static constexpr size_t wimg_bytes = (size_t)FRAGS * 512;   // 32 lanes x 16 bytes per fragment
-    static constexpr size_t wtile_bytes = (size_t)KTILE * 4 * CRBM_MAX_MOTIF_LEN * sizeof(float);
+    static constexpr size_t wtile_bytes = (size_t)MTILE * 4 * CRBM_MAX_MOTIF_LEN * sizeof(float);
     static constexpr size_t smem_bytes = wimg_bytes + wtile_bytes + 16;
 };
 template <int KS, int FLAGS> constexpr size_t mma_smem_bytes() {
     // W fragments + staging tile, or the scratch of the final 8-warp tree reduction, whichever is larger
     const size_t a = MmaShape<KS>::smem_bytes;
-    const size_t nacc = ((FLAGS & F_STAT_P) ? 16 * KS : 0) + ((FLAGS & F_STAT_Q) ? 16 * KS : 0) + 12;
+    const size_t nacc = ((FLAGS & F_STAT_P) ? 8 * KS : 0) + ((FLAGS & F_STAT_Q) ? 8 * KS : 0) + 6;
     const size_t b = 4 * nacc * 32 * sizeof(float);
     return a > b ? a : b;
 }
 
 template <int KS, int FLAGS> struct MmaAcc {
-    static constexpr int NP = (FLAGS & F_STAT_P) ? 16 * KS : 0;      // registers per thread
-    static constexpr int NQ = (FLAGS & F_STAT_Q) ? 16 * KS : 0;
-    static constexpr int NACC = NP + NQ + 12;                        // + sumP, sumPr, sumQ for the thread's 4 motif rows
+    static constexpr int NP = (FLAGS & F_STAT_P) ? 8 * KS : 0;       // registers per thread
+    static constexpr int NQ = (FLAGS & F_STAT_Q) ? 8 * KS : 0;
+    static constexpr int NACC = NP + NQ + 6;                         // + sumP, sumPr, sumQ for the thread's 2 motif rows
 };
 
 __device__ __forceinline__ void hmma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -67,14 +69,14 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t &hi, uint32_
     mid = pack_bf16x2(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xffff0000u));
 }
 
-// W tile (32 motifs x 4 x M, fp32, staged by the TMA engine) -> three bf16 images in MMA A-fragment order, both strands.
-// Element (row r, column c) of the (mt, ks) fragment is Wx[16*mt + r][16*ks + c]; forward strand Wx[k][4m+a] = W[k][a][m],
+// W tile (16 motifs x 4 x M, fp32, staged by the TMA engine) -> three bf16 images in MMA A-fragment order, both strands.
+// Element (row r, column c) of the ks-th fragment is Wx[r][16*ks + c]; forward strand Wx[k][4m+a] = W[k][a][m],
 // reverse strand Wx[k][4m+a] = W[k][3-a][M-1-m] (convRBM.py:241 with filter_flip=True); zero beyond M.
 template <int KS>
 __device__ __forceinline__ void build_w_fragments(uint32_t *wimg, float *wtile, uint64_t *bar,
-                                                  const float *__restrict__ W, int K, int M, int kt) {
-    const int k0 = kt * KTILE;
-    const int nk = min(KTILE, K - k0);
+                                                  const float *__restrict__ W, int K, int M, int mtile) {
+    const int k0 = mtile * MTILE;
+    const int nk = min(MTILE, K - k0);
     const uint32_t bytes = (uint32_t)nk * 4u * (uint32_t)M * 4u;
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
@@ -83,13 +85,13 @@ __device__ __forceinline__ void build_w_fragments(uint32_t *wimg, float *wtile, 
         tma_load_1d(wtile, W + (size_t)k0 * 4 * M, bytes, bar);
     }
     mbar_wait(bar, 0);
-    // one work unit = one 32-bit register of one fragment: (strand, mt, ks, lane, reg)
-    const int units = 2 * 2 * KS * 32 * 4;
+    // one work unit = one 32-bit register of one fragment: (strand, ks, lane, reg)
+    const int units = 2 * KS * 32 * 4;
     for (int u = threadIdx.x; u < units; u += blockDim.x) {
         const int reg = u & 3, lane = (u >> 2) & 31, rest = u >> 7;
-        const int ks = rest % KS, mt = (rest / KS) & 1, strand = rest / (2 * KS);
+        const int ks = rest % KS, strand = rest / KS;
         const int g = lane >> 2, q = lane & 3;
-        const int row = 16 * mt + g + 8 * (reg & 1);
+        const int row = g + 8 * (reg & 1);
         float v[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -104,11 +106,10 @@ __device__ __forceinline__ void build_w_fragments(uint32_t *wimg, float *wtile, 
         const float r0 = (v[0] - __uint_as_float(hi << 16)) - __uint_as_float(mid << 16);
         const float r1 = (v[1] - __uint_as_float(hi & 0xffff0000u)) - __uint_as_float(mid & 0xffff0000u);
         lo = pack_bf16x2(r0, r1);
-        const int f0 = ((strand * 3 + 0) * 2 + mt) * KS + ks;
-        const int stride = 2 * KS;                                   // fragments between consecutive splits
+        const int f0 = (strand * 3 + 0) * KS + ks;                   // fragment index [strand][split][ks]
         wimg[(f0 * 32 + lane) * 4 + reg] = hi;
-        wimg[((f0 + stride) * 32 + lane) * 4 + reg] = mid;
-        wimg[((f0 + 2 * stride) * 32 + lane) * 4 + reg] = lo;
+        wimg[((f0 + KS) * 32 + lane) * 4 + reg] = mid;
+        wimg[((f0 + 2 * KS) * 32 + lane) * 4 + reg] = lo;
     }
     __syncthreads();
 }
@@ -119,8 +120,11 @@ __device__ __forceinline__ uint32_t onehot_pair(uint32_t two_bases /*4 bits*/, u
     return ((t & 3u) ? 0u : 0x3F80u) | ((t & 12u) ? 0u : 0x3F800000u);
 }
 
+// grid (m-tiles of 16 motifs, CTAs), 256 threads, two CTAs per SM: every warp owns the CTA's m-tile for a stream of
+// 16-position blocks. (ncu on the first version with 32-motif warps: 254 registers, 8 warps/SM, one wave of 4.05 blocks
+// per warp on average but 5 at most; 16-motif warps need <= 128 registers, and m-tiles beyond K are not launched.)
 template <int KS, int FLAGS>
-__global__ void __launch_bounds__(256, 1) v2h_mma_kernel(const V2HParams p) {
+__global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
     using Sh = MmaShape<KS>;
     using Ac = MmaAcc<KS, FLAGS>;
     constexpr int NT2 = Sh::NT2;
@@ -130,29 +134,28 @@ __global__ void __launch_bounds__(256, 1) v2h_mma_kernel(const V2HParams p) {
     float *wtile = reinterpret_cast<float *>(smem + Sh::wimg_bytes);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + Sh::wimg_bytes + Sh::wtile_bytes);
 
-    const int kt = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int mtile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
-    build_w_fragments<KS>(wimg, wtile, bar, p.W, p.K, p.M, kt);
+    build_w_fragments<KS>(wimg, wtile, bar, p.W, p.K, p.M, mtile);
     const uint4 *wfrag = reinterpret_cast<const uint4 *>(wimg) + lane;
 
-    // the thread's four motif rows: r4 = 2*mt + h  ->  k = 32*kt + 16*mt + 8*h + g
-    float bias[4];
-    bool kval[4];
+    // the thread's two motif rows: h = 0, 1  ->  k = 16*mtile + 8*h + g
+    float bias[2];
+    bool kval[2];
 #pragma unroll
-    for (int r4 = 0; r4 < 4; ++r4) {
-        const int k = kt * KTILE + 16 * (r4 >> 1) + 8 * (r4 & 1) + g;
-        kval[r4] = k < p.K;
-        bias[r4] = kval[r4] ? __ldg(p.b + k) : 0.f;
+    for (int h = 0; h < 2; ++h) {
+        const int k = mtile * MTILE + 8 * h + g;
+        kval[h] = k < p.K;
+        bias[h] = kval[h] ? __ldg(p.b + k) : 0.f;
     }
+    const bool all_k = (mtile + 1) * MTILE <= p.K;
 
-    float accp[2][NT2][4], accq[2][NT2][4];
+    float accp[NT2][4], accq[NT2][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+    for (int t = 0; t < NT2; ++t)
 #pragma unroll
-        for (int t = 0; t < NT2; ++t)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) { accp[mt][t][r] = 0.f; accq[mt][t][r] = 0.f; }
-    float sum_p[4] = {0.f, 0.f, 0.f, 0.f}, sum_pr[4] = {0.f, 0.f, 0.f, 0.f}, sum_q[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int r = 0; r < 4; ++r) { accp[t][r] = 0.f; accq[t][r] = 0.f; }
+    float sum_p[2] = {0.f, 0.f}, sum_pr[2] = {0.f, 0.f}, sum_q[2] = {0.f, 0.f};
 
     // lane-dependent parts of the base offsets (see the derivations in the header comment of each stage)
     const int lo1 = g + (q >> 1);                       // up-pass B: base j0 + 8nt + g + 4ks + q/2 (+2)
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256, 1) v2h_mma_kernel(const V2HParams p) {
     const uint32_t code_f = (uint32_t)(g & 3) * 5u, code_r = (uint32_t)(3 - (g & 3)) * 5u;
     const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
     const uint32_t ctr_hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) * 64u : 0u);
-    const int ktiles = gridDim.x;
+    const int ktiles = (p.K + KTILE - 1) / KTILE;
     const int njb = (p.Lh + 15) >> 4;
 
     const uint32_t *packed = p.packed + (p.batch_index ? (size_t)(*p.batch_index) * p.n_rows * p.row_words : 0);
@@ -175,15 +178,13 @@ __global__ void __launch_bounds__(256, 1) v2h_mma_kernel(const V2HParams p) {
         for (int i = 0; i < 5; ++i) wd[i] = __ldg(row + i);
 
         // ---- x = W (x) X on the tensor pipe, both strands ------------------------------------------------------
-        float d1[2][2][2][4];                                  // [strand][mt][nt][reg]
+        float d1[2][2][4];                                     // [strand][nt][reg]
 #pragma unroll
         for (int s = 0; s < 2; ++s)
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) d1[s][mt][nt][r] = 0.f;
+                for (int r = 0; r < 4; ++r) d1[s][nt][r] = 0.f;
         {
             uint32_t v[3];
 #pragma unroll
@@ -202,33 +203,35 @@ __global__ void __launch_bounds__(256, 1) v2h_mma_kernel(const V2HParams p) {
                 for (int s = 0; s < 2; ++s) {
                     if (s == 1 && !p.ds) continue;
 #pragma unroll
-                    for (int sp = 0; sp < 3; ++sp)
-#pragma unroll
-                        for (int mt = 0; mt < 2; ++mt) {
-                            const uint4 a = wfrag[(((s * 3 + sp) * 2 + mt) * KS + ks) * 32];
-                            hmma_bf16(d1[s][mt][0], a, bx[0][0], bx[0][1]);
-                            hmma_bf16(d1[s][mt][1], a, bx[1][0], bx[1][1]);
-                        }
+                    for (int sp = 0; sp < 3; ++sp) {
+                        const uint4 a = wfrag[((s * 3 + sp) * KS + ks) * 32];
+                        hmma_bf16(d1[s][0], a, bx[0][0], bx[0][1]);
+                        hmma_bf16(d1[s][1], a, bx[1][0], bx[1][1]);
+                    }
                 }
             }
         }
         // ---- sigmoid epilogue, sampling -------------------------------------------------------------------------
-        // d1[s][mt][nt][r]: motif row r4 = 2*mt + (r>>1), position j0 + 8*nt + 2*q + (r&1)
+        // d1[s][nt][r]: motif row h = r>>1, position j0 + 8*nt + 2*q + (r&1)
         const int jrem = p.Lh - j0 - 2 * q;                   // position valid iff 8*nt + (r&1) < jrem
+        const bool full = all_k && (j0 + 16 <= p.Lh);         // warp-uniform: no masking needed
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             if (s == 1 && !p.ds) continue;
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float x = d1[s][nt][r] + bias[r >> 1];
+                    d1[s][nt][r] = __fdividef(1.0f, 1.0f + __expf(-x));
+                }
+            if (!full) {
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int r4 = 2 * mt + (r >> 1);
-                        const bool ok = kval[r4] && (8 * nt + (r & 1) < jrem);
-                        const float x = d1[s][mt][nt][r] + bias[r4];
-                        d1[s][mt][nt][r] = ok ? __fdividef(1.0f, 1.0f + __expf(-x)) : 0.f;
-                    }
+                    for (int r = 0; r < 4; ++r)
+                        if (!(kval[r >> 1] && (8 * nt + (r & 1) < jrem))) d1[s][nt][r] = 0.f;
+            }
         }
         if (SAMPLE) {
 #pragma unroll
@@ -237,12 +240,11 @@ __global__ void __launch_bounds__(256, 1) v2h_mma_kernel(const V2HParams p) {
                 const float *inj = s == 0 ? p.u_fwd : p.u_rc;
                 uint32_t mine = 0u;
 #pragma unroll
-                for (int r4 = 0; r4 < 4; ++r4) {
-                    const int mt = r4 >> 1, h = r4 & 1;
-                    const int k = kt * KTILE + 16 * mt + 8 * h + g;
+                for (int h = 0; h < 2; ++h) {
+                    const int k = mtile * MTILE + 8 * h + g;
                     float u[4];                                  // positions (nt, e): index 2*nt + e
                     if (inj) {
-                        const float *up = inj + (size_t)(n * p.K + (kval[r4] ? k : 0)) * p.Lh + j0 + 2 * q;
+                        const float *up = inj + (size_t)(n * p.K + (kval[h] ? k : 0)) * p.Lh + j0 + 2 * q;
 #pragma unroll
                         for (int i = 0; i < 4; ++i) u[i] = (8 * (i >> 1) + (i & 1) < jrem) ? up[8 * (i >> 1) + (i & 1)] : 1.f;
                     } else {
@@ -254,43 +256,42 @@ __global__ void __launch_bounds__(256, 1) v2h_mma_kernel(const V2HParams p) {
                     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const bool hit = d1[s][mt][nt][2 * h + e] > u[2 * nt + e];
+                            const bool hit = d1[s][nt][2 * h + e] > u[2 * nt + e];
                             const uint32_t word = __ballot_sync(0xffffffffu, hit);
-                            if (lane == ((r4 * 2 + nt) * 2 + e)) mine = word;
+                            if (lane == ((h * 2 + nt) * 2 + e)) mine = word;
                         }
                 }
-                if (lane < 16)
-                    p.bits[(((size_t)s * p.n_rows + n) * ktiles + kt) * (njb * 16) + jb * 16 + lane] = mine;
+                // the 8 words of this m-tile: word index ((mt*2+h)*2+nt)*2+e with mt = mtile & 1, k-tile = mtile >> 1
+                if (lane < 8)
+                    p.bits[(((size_t)s * p.n_rows + n) * ktiles + (mtile >> 1)) * (njb * 16) + jb * 16 + (mtile & 1) * 8 + lane] = mine;
             }
         }
         // ---- statistics on the tensor pipe ----------------------------------------------------------------------
         if (STAT_P || STAT_Q) {
             // A fragments (16 motifs x 16 positions) straight from the accumulator layout of the first MMA
-            uint32_t ap[2][2][4], apr[2][2][4], aq[2][2][4];           // [split][mt][reg]
+            uint32_t ap[2][4], apr[2][4], aq[2][4];           // [split][reg]
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
+            for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int reg = 2 * nt + h, r4 = 2 * mt + h;
-                        const float p0 = d1[0][mt][nt][2 * h], p1 = d1[0][mt][nt][2 * h + 1];
-                        if (STAT_P) {
-                            split2(p0, p1, ap[0][mt][reg], ap[1][mt][reg]);
-                            sum_p[r4] += p0 + p1;
-                            if (p.ds) {
-                                const float s0 = d1[1][mt][nt][2 * h], s1 = d1[1][mt][nt][2 * h + 1];
-                                split2(s0, s1, apr[0][mt][reg], apr[1][mt][reg]);
-                                sum_pr[r4] += s0 + s1;
-                            }
-                        }
-                        if (STAT_Q) {
-                            const float q0 = p0 * (1.f - p0), q1 = p1 * (1.f - p1);
-                            split2(q0, q1, aq[0][mt][reg], aq[1][mt][reg]);
-                            sum_q[r4] += q0 + q1;
-                            if (!STAT_P) sum_p[r4] += p0 + p1;
+                for (int h = 0; h < 2; ++h) {
+                    const int reg = 2 * nt + h;
+                    const float p0 = d1[0][nt][2 * h], p1 = d1[0][nt][2 * h + 1];
+                    if (STAT_P) {
+                        split2(p0, p1, ap[0][reg], ap[1][reg]);
+                        sum_p[h] += p0 + p1;
+                        if (p.ds) {
+                            const float s0 = d1[1][nt][2 * h], s1 = d1[1][nt][2 * h + 1];
+                            split2(s0, s1, apr[0][reg], apr[1][reg]);
+                            sum_pr[h] += s0 + s1;
                         }
                     }
+                    if (STAT_Q) {
+                        const float q0 = p0 * (1.f - p0), q1 = p1 * (1.f - p1);
+                        split2(q0, q1, aq[0][reg], aq[1][reg]);
+                        sum_q[h] += q0 + q1;
+                        if (!STAT_P) sum_p[h] += p0 + p1;
+                    }
+                }
             uint32_t uf[3], ur[3];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
@@ -303,105 +304,78 @@ __global__ void __launch_bounds__(256, 1) v2h_mma_kernel(const V2HParams p) {
                 // column c = 8t + g -> (a_c, m_c) = (g&3, 2t + g/4); K rows = positions 2q, 2q+1 | 2q+8, 2q+9
                 const uint32_t bf0 = onehot_pair(window_bits<2, 3>(uf, 2 * t), code_f);
                 const uint32_t bf1 = onehot_pair(window_bits<2, 3>(uf, 2 * t + 8), code_f);
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    if (STAT_P) {
-                        hmma_bf16(accp[mt][t], ap[0][mt], bf0, bf1);
-                        hmma_bf16(accp[mt][t], ap[1][mt], bf0, bf1);
-                    }
-                    if (STAT_Q) {
-                        hmma_bf16(accq[mt][t], aq[0][mt], bf0, bf1);
-                        hmma_bf16(accq[mt][t], aq[1][mt], bf0, bf1);
-                    }
+                if (STAT_P) {
+                    hmma_bf16(accp[t], ap[0], bf0, bf1);
+                    hmma_bf16(accp[t], ap[1], bf0, bf1);
+                }
+                if (STAT_Q) {
+                    hmma_bf16(accq[t], aq[0], bf0, bf1);
+                    hmma_bf16(accq[t], aq[1], bf0, bf1);
                 }
                 if (STAT_P && p.ds) {
                     // strand fold (convRBM.py:367): column (a_c, m_c) also collects p'[j] [base(j + M-1-m_c) == 3-a_c];
                     // with t' = NT2-1-t the base offset is static: 2*t' (+8) from a window starting at j0 + lo3 + M - 4*KS
                     const uint32_t br0 = onehot_pair(window_bits<2, 3>(ur, 2 * (NT2 - 1 - t)), code_r);
                     const uint32_t br1 = onehot_pair(window_bits<2, 3>(ur, 2 * (NT2 - 1 - t) + 8), code_r);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        hmma_bf16(accp[mt][t], apr[0][mt], br0, br1);
-                        hmma_bf16(accp[mt][t], apr[1][mt], br0, br1);
-                    }
+                    hmma_bf16(accp[t], apr[0], br0, br1);
+                    hmma_bf16(accp[t], apr[1], br0, br1);
                 }
             }
         }
     }
 
     // ---- reduce over the warps of the CTA, write the CTA partial ------------------------------------------------------
+    // Partial layout (per CTA): [NACC][32]: slot t*4 + r of statistic P, then of Q, then sum_p[2], sum_pr[2], sum_q[2].
     if (STAT_P || STAT_Q) {
         constexpr int NACC = Ac::NACC;
-        // per-motif sums: add the four lanes of a quad (they hold different positions of the same motif rows)
 #pragma unroll
-        for (int r4 = 0; r4 < 4; ++r4) {
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
             for (int o = 1; o <= 2; o <<= 1) {
-                sum_p[r4] += __shfl_xor_sync(0xffffffffu, sum_p[r4], o);
-                sum_pr[r4] += __shfl_xor_sync(0xffffffffu, sum_pr[r4], o);
-                sum_q[r4] += __shfl_xor_sync(0xffffffffu, sum_q[r4], o);
+                sum_p[h] += __shfl_xor_sync(0xffffffffu, sum_p[h], o);
+                sum_pr[h] += __shfl_xor_sync(0xffffffffu, sum_pr[h], o);
+                sum_q[h] += __shfl_xor_sync(0xffffffffu, sum_q[h], o);
             }
-            if (q != 0) { sum_p[r4] = 0.f; sum_pr[r4] = 0.f; sum_q[r4] = 0.f; }
+            if (q != 0) { sum_p[h] = 0.f; sum_pr[h] = 0.f; sum_q[h] = 0.f; }
         }
         __syncthreads();
         float *scr = reinterpret_cast<float *>(smem);
-        auto put = [&](float *dst) {
-            int o = 0;
+        auto visit = [&](auto &&f) {
             if (STAT_P) {
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                for (int t = 0; t < NT2; ++t)
 #pragma unroll
-                    for (int t = 0; t < NT2; ++t)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) dst[(o++) * 32] = accp[mt][t][r];
+                    for (int r = 0; r < 4; ++r) f(t * 4 + r, accp[t][r]);
             }
             if (STAT_Q) {
 #pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
+                for (int t = 0; t < NT2; ++t)
 #pragma unroll
-                    for (int t = 0; t < NT2; ++t)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) dst[(o++) * 32] = accq[mt][t][r];
+                    for (int r = 0; r < 4; ++r) f(Ac::NP + t * 4 + r, accq[t][r]);
             }
 #pragma unroll
-            for (int r4 = 0; r4 < 4; ++r4) dst[(o++) * 32] = sum_p[r4];
-#pragma unroll
-            for (int r4 = 0; r4 < 4; ++r4) dst[(o++) * 32] = sum_pr[r4];
-#pragma unroll
-            for (int r4 = 0; r4 < 4; ++r4) dst[(o++) * 32] = sum_q[r4];
-        };
-        auto add = [&](const float *src) {
-            int o = 0;
-            if (STAT_P) {
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int t = 0; t < NT2; ++t)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) accp[mt][t][r] += src[(o++) * 32];
+            for (int h = 0; h < 2; ++h) {
+                f(Ac::NP + Ac::NQ + h, sum_p[h]);
+                f(Ac::NP + Ac::NQ + 2 + h, sum_pr[h]);
+                f(Ac::NP + Ac::NQ + 4 + h, sum_q[h]);
             }
-            if (STAT_Q) {
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-                    for (int t = 0; t < NT2; ++t)
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) accq[mt][t][r] += src[(o++) * 32];
-            }
-#pragma unroll
-            for (int r4 = 0; r4 < 4; ++r4) sum_p[r4] += src[(o++) * 32];
-#pragma unroll
-            for (int r4 = 0; r4 < 4; ++r4) sum_pr[r4] += src[(o++) * 32];
-#pragma unroll
-            for (int r4 = 0; r4 < 4; ++r4) sum_q[r4] += src[(o++) * 32];
         };
         for (int half = nwarps >> 1; half >= 1; half >>= 1) {
-            if (warp >= half && warp < 2 * half) put(scr + (size_t)(warp - half) * NACC * 32 + lane);
+            if (warp >= half && warp < 2 * half) {
+                float *dst = scr + (size_t)(warp - half) * NACC * 32 + lane;
+                visit([&](int o, float &v) { dst[o * 32] = v; });
+            }
             __syncthreads();
-            if (warp < half) add(scr + (size_t)warp * NACC * 32 + lane);
+            if (warp < half) {
+                const float *src = scr + (size_t)warp * NACC * 32 + lane;
+                visit([&](int o, float &v) { v += src[o * 32]; });
+            }
             __syncthreads();
         }
-        if (warp == 0) put(p.partial + ((size_t)(kt * gridDim.y + blockIdx.y) * NACC) * 32 + lane);
+        if (warp == 0) {
+            float *dst = p.partial + ((size_t)(mtile * gridDim.y + blockIdx.y) * NACC) * 32 + lane;
+            visit([&](int o, float &v) { dst[o * 32] = v; });
+        }
     }
 }
 
@@ -418,26 +392,24 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
     uint32_t *wimg = reinterpret_cast<uint32_t *>(smem);
     float *wtile = reinterpret_cast<float *>(smem + Sh::wimg_bytes);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + Sh::wimg_bytes + Sh::wtile_bytes);
-    const int kt = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int mtile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
-    build_w_fragments<KS>(wimg, wtile, bar, p.W, p.K, p.M, kt);
+    build_w_fragments<KS>(wimg, wtile, bar, p.W, p.K, p.M, mtile);
     const uint4 *wfrag = reinterpret_cast<const uint4 *>(wimg) + lane;
     const bool want_f = p.strand_mode != CRBM_STRAND_RC, want_r = p.strand_mode != CRBM_STRAND_FWD;
     const float bscale = p.strand_mode == CRBM_STRAND_SUM ? 2.f : 1.f;        // both activities carry the bias (convRBM.py:513)
-    float bias[4];
-    bool kval[4];
+    float bias[2];
+    bool kval[2];
 #pragma unroll
-    for (int r4 = 0; r4 < 4; ++r4) {
-        const int k = kt * KTILE + 16 * (r4 >> 1) + 8 * (r4 & 1) + g;
-        kval[r4] = k < p.K;
-        bias[r4] = kval[r4] ? bscale * __ldg(p.b + k) : 0.f;
+    for (int h = 0; h < 2; ++h) {
+        const int k = mtile * MTILE + 8 * h + g;
+        kval[h] = k < p.K;
+        bias[h] = kval[h] ? bscale * __ldg(p.b + k) : 0.f;
     }
-    const bool mt_on[2] = {kt * KTILE < p.K, kt * KTILE + 16 < p.K};
     const int lo1 = g + (q >> 1);
     const uint32_t qodd = q & 1;
     const bool prob = p.out_kind == CRBM_OUT_PROBABILITY;
-    // Lh even and 8-byte aligned rows allow float2 stores
-    const bool vec2 = (p.Lh & 1) == 0;
+    const bool vec2 = (p.Lh & 1) == 0;                       // rows then start 8-byte aligned: float2 stores
 
     for (int item = blockIdx.y * nwarps + warp; item < p.n_items; item += gridDim.y * nwarps) {
         const int n = item / p.nblk, jb = item - n * p.nblk, j0 = jb * 16;
@@ -445,13 +417,11 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
         uint32_t wd[5];
 #pragma unroll
         for (int i = 0; i < 5; ++i) wd[i] = __ldg(row + i);
-        float d1[2][2][4];                                  // [mt][nt][reg]
+        float d1[2][4];                                      // [nt][reg]
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) d1[mt][nt][r] = 0.f;
+            for (int r = 0; r < 4; ++r) d1[nt][r] = 0.f;
         uint32_t v[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(wd[1 + i], wd[2 + i], 2 * lo1);
@@ -469,38 +439,30 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
             for (int s = 0; s < 2; ++s) {
                 if (s == 0 ? !want_f : !want_r) continue;
 #pragma unroll
-                for (int sp = 0; sp < 3; ++sp)
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        if (!mt_on[mt]) continue;
-                        const uint4 a = wfrag[(((s * 3 + sp) * 2 + mt) * KS + ks) * 32];
-                        hmma_bf16(d1[mt][0], a, bx[0][0], bx[0][1]);
-                        hmma_bf16(d1[mt][1], a, bx[1][0], bx[1][1]);
-                    }
+                for (int sp = 0; sp < 3; ++sp) {
+                    const uint4 a = wfrag[((s * 3 + sp) * KS + ks) * 32];
+                    hmma_bf16(d1[0], a, bx[0][0], bx[0][1]);
+                    hmma_bf16(d1[1], a, bx[1][0], bx[1][1]);
+                }
             }
         }
         const int jrem = p.Lh - j0 - 2 * q;
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            if (!mt_on[mt]) continue;
+        for (int h = 0; h < 2; ++h) {
+            if (!kval[h]) continue;
+            float *orow = p.out + ((size_t)n * p.K + mtile * MTILE + 8 * h + g) * p.Lh + j0 + 2 * q;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int r4 = 2 * mt + h;
-                if (!kval[r4]) continue;
-                float *orow = p.out + ((size_t)n * p.K + kt * KTILE + 16 * mt + 8 * h + g) * p.Lh + j0 + 2 * q;
-#pragma unroll
-                for (int nt = 0; nt < 2; ++nt) {
-                    float x0 = d1[mt][nt][2 * h] + bias[r4], x1 = d1[mt][nt][2 * h + 1] + bias[r4];
-                    if (prob) {
-                        x0 = __fdividef(1.0f, 1.0f + __expf(-x0));
-                        x1 = __fdividef(1.0f, 1.0f + __expf(-x1));
-                    }
-                    if (vec2 && 8 * nt + 1 < jrem) {
-                        __stcs(reinterpret_cast<float2 *>(orow + 8 * nt), make_float2(x0, x1));
-                    } else {
-                        if (8 * nt < jrem) __stcs(orow + 8 * nt, x0);
-                        if (8 * nt + 1 < jrem) __stcs(orow + 8 * nt + 1, x1);
-                    }
+            for (int nt = 0; nt < 2; ++nt) {
+                float x0 = d1[nt][2 * h] + bias[h], x1 = d1[nt][2 * h + 1] + bias[h];
+                if (prob) {
+                    x0 = __fdividef(1.0f, 1.0f + __expf(-x0));
+                    x1 = __fdividef(1.0f, 1.0f + __expf(-x1));
+                }
+                if (vec2 && 8 * nt + 1 < jrem) {
+                    __stcs(reinterpret_cast<float2 *>(orow + 8 * nt), make_float2(x0, x1));
+                } else {
+                    if (8 * nt < jrem) __stcs(orow + 8 * nt, x0);
+                    if (8 * nt + 1 < jrem) __stcs(orow + 8 * nt + 1, x1);
                 }
             }
         }

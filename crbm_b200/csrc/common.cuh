@@ -8,7 +8,7 @@
 namespace crbm {
 
 constexpr int FRONT_PAD_WORDS = 1;      // word 0 of every packed row is zero padding (16 bases)
-constexpr int BACK_PAD_WORDS  = 6;      // blocks read up to 16+33+2 bases past their first hidden position
+constexpr int BACK_PAD_WORDS  = 7;      // kernels read up to 6 words starting at the word before a block's first position
 constexpr int FANTASY_LEN     = CRBM_FANTASY_LEN;
 constexpr int BLOCK_POS       = 16;     // hidden positions a warp processes per work item
 constexpr int KTILE           = 32;     // motifs per k-tile: one lane per motif

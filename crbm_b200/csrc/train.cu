@@ -461,7 +461,7 @@ int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const fl
     if (pool == 1) {
         // tensor-pipe kernel: CTAs of one 16-motif m-tile, three per SM: size the grid to one full wave
         const int mtiles = ceil_div(K, 16);
-        int gy = ceil_div(t.n_items, 8);
+        int gy = ceil_div(ceil_div(t.n_items, 2), 8);             // items of 32 positions, 8 warps per CTA
         const int cap = (3 * num_sms()) / mtiles > 0 ? (3 * num_sms()) / mtiles : 1;
         if (gy > cap) gy = cap;
         return dispatch_dense_mma(ceil_div(M, 4), p, dim3(mtiles, gy), (cudaStream_t)stream);
@@ -524,9 +524,20 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     // pooling == 1: both contractions on the tensor pipe (v2h_mma.cuh); otherwise the CUDA-core kernel (v2h.cuh)
     const bool mma = P == 1;
     const int KS = ceil_div(M, 4);
+    // The positive phase (minibatch) and the negative phase (persistent chain) only meet in the reduction: the positive
+    // kernels go to a side stream (forked/joined with events, which stream capture records as graph edges), so their
+    // ramp-up and tail overlap h2v and the negative-phase kernel instead of serialising with them.
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (!side) {
+        CRBM_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+        CRBM_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CRBM_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t cur = s;                                  // stream the fused kernels are launched on
     auto run_fused = [&](int flags, const V2HParams &p, const Tiling &t) -> int {
-        return mma ? dispatch_mma(KS, flags, p, dim3(ceil_div(K, 16), mma_gy(K, t.n_items)), s)
-                   : dispatch_fused(t.MW, flags, p, dim3(t.ktiles, t.gy), s);
+        return mma ? dispatch_mma(KS, flags, p, dim3(ceil_div(K, 16), mma_gy(K, t.n_items)), cur)
+                   : dispatch_fused(t.MW, flags, p, dim3(t.ktiles, t.gy), cur);
     };
     ReduceParams red{};
     red.ktiles = mma ? ceil_div(K, 16) : ceil_div(K, KTILE);        // tiles of the partial buffers: m-tiles / k-tiles
@@ -549,6 +560,11 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     p.bv = t.bv; p.nblk = t.nblk; p.n_items = t.n_items;
     p.batch_index = a->batch_index_dev;
     const bool combined = mma ? KS <= 4 : t.MW <= 15;
+    if (a->n_data > 0) {
+        CRBM_CHECK_CUDA(cudaEventRecord(ev_fork, s));       // after the memset of stats
+        CRBM_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+        cur = side;
+    }
     if (a->n_data == 0) {
         // a data-parallel rank whose shard of a short batch is empty contributes zeros
     } else if (combined) {
@@ -567,6 +583,9 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
         ReduceSet &Sq = add_set(part2, t, false, true);
         Sq.vh_q = st + lay.vh_q; Sq.h_q = st + lay.h_q;
     }
+    if (a->n_data > 0) CRBM_CHECK_CUDA(cudaEventRecord(ev_join, side));
+    cur = s;
+
     // ---- negative phase: cd_k Gibbs sweeps of the persistent chain (convRBM.py:391-413) -----------------------------
     Tiling tn = make_tiling(K, M, P, FANTASY_LEN, a->batchsize);
     const size_t n_u_v = (size_t)a->batchsize * Lv, n_u_h = (size_t)a->batchsize * K * (FANTASY_LEN / P);
@@ -607,6 +626,7 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
         if (!mma) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));   // CUDA-core sampler ORs its hits in
         if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
     }
+    if (a->n_data > 0) CRBM_CHECK_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
     ReduceSet &Sn = add_set(part1, tn, true, false);
     Sn.vh_p = st + lay.vh_model; Sn.h_sum = st + lay.h_model;
     red.counts = st + lay.n_hidden_data;

@@ -385,6 +385,10 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
 // bytes of one motif row; the two n-tiles of a block complete a 64-byte run). HBM-write bound by design: 4*K bytes
 // per nucleotide against 0.25 bytes read.
 // ----------------------------------------------------------------------------------------------------------
+// Store shape (scratch/store_pattern.cu, no arithmetic, same out[n][k][j] layout): accumulator fragments written
+// directly = 32-byte pieces of 8 rows per instruction -> 1.4 TB/s; 128 contiguous bytes of one row per instruction
+// -> 3.4 TB/s. So a warp computes 16 motifs x 32 positions, transposes the tile through a private 2 KB shared-memory
+// buffer and writes one row piece (32 floats) per instruction.
 template <int KS>
 __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams p) {
     using Sh = MmaShape<KS>;
@@ -392,6 +396,7 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
     uint32_t *wimg = reinterpret_cast<uint32_t *>(smem);
     float *wtile = reinterpret_cast<float *>(smem + Sh::wimg_bytes);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + Sh::wimg_bytes + Sh::wtile_bytes);
+    float *stage_all = reinterpret_cast<float *>(smem + Sh::wimg_bytes + Sh::wtile_bytes + 16);    // [warp][16][34]
     const int mtile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     build_w_fragments<KS>(wimg, wtile, bar, p.W, p.K, p.M, mtile);
@@ -399,40 +404,43 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
     const bool want_f = p.strand_mode != CRBM_STRAND_RC, want_r = p.strand_mode != CRBM_STRAND_FWD;
     const float bscale = p.strand_mode == CRBM_STRAND_SUM ? 2.f : 1.f;        // both activities carry the bias (convRBM.py:513)
     float bias[2];
-    bool kval[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const int k = mtile * MTILE + 8 * h + g;
-        kval[h] = k < p.K;
-        bias[h] = kval[h] ? bscale * __ldg(p.b + k) : 0.f;
+        bias[h] = k < p.K ? bscale * __ldg(p.b + k) : 0.f;
     }
+    const int nrows = min(MTILE, p.K - mtile * MTILE);
     const int lo1 = g + (q >> 1);
     const uint32_t qodd = q & 1;
     const bool prob = p.out_kind == CRBM_OUT_PROBABILITY;
-    const bool vec2 = (p.Lh & 1) == 0;                       // rows then start 8-byte aligned: float2 stores
+    constexpr int SS = 34;                                   // stage row stride (floats): conflict-free float2 writes
+    float *stage = stage_all + warp * (MTILE * SS);
+    const int nblk2 = (p.nblk + 1) >> 1, n_items2 = p.n_rows * nblk2;
 
-    for (int item = blockIdx.y * nwarps + warp; item < p.n_items; item += gridDim.y * nwarps) {
-        const int n = item / p.nblk, jb = item - n * p.nblk, j0 = jb * 16;
+    for (int item = blockIdx.y * nwarps + warp; item < n_items2; item += gridDim.y * nwarps) {
+        const int n = item / nblk2, jb2 = item - n * nblk2, j0 = jb2 * 32;
         const uint32_t *row = p.packed + (size_t)n * p.row_words + (j0 >> 4);
-        uint32_t wd[5];
+        uint32_t wd[6];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) wd[i] = __ldg(row + i);
-        float d1[2][4];                                      // [nt][reg]
+        for (int i = 0; i < 6; ++i) wd[i] = __ldg(row + i);
+        float d1[4][4];                                      // [nt][reg], nt = 8-position tile of the 32-position item
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int r = 0; r < 4; ++r) d1[nt][r] = 0.f;
-        uint32_t v[3];
+        uint32_t v[2][3];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(wd[1 + i], wd[2 + i], 2 * lo1);
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v[half][i] = __funnelshift_r(wd[1 + half + i], wd[2 + half + i], 2 * lo1);
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-            uint32_t bx[2][2];
+            uint32_t bx[4][2];
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
+            for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb) {
-                    const uint32_t bb = window_bits<1, 3>(v, 8 * nt + 4 * ks + 2 * hb);
+                    const uint32_t bb = window_bits<1, 3>(v[nt >> 1], 8 * (nt & 1) + 4 * ks + 2 * hb);
                     bx[nt][hb] = ((bb >> 1) == qodd) ? (0x3F80u << ((bb & 1u) << 4)) : 0u;
                 }
 #pragma unroll
@@ -441,31 +449,30 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
 #pragma unroll
                 for (int sp = 0; sp < 3; ++sp) {
                     const uint4 a = wfrag[((s * 3 + sp) * KS + ks) * 32];
-                    hmma_bf16(d1[0], a, bx[0][0], bx[0][1]);
-                    hmma_bf16(d1[1], a, bx[1][0], bx[1][1]);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) hmma_bf16(d1[nt], a, bx[nt][0], bx[nt][1]);
                 }
             }
         }
-        const int jrem = p.Lh - j0 - 2 * q;
+        // epilogue -> stage[row][position]
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (!kval[h]) continue;
-            float *orow = p.out + ((size_t)n * p.K + mtile * MTILE + 8 * h + g) * p.Lh + j0 + 2 * q;
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-            for (int nt = 0; nt < 2; ++nt) {
+            for (int nt = 0; nt < 4; ++nt) {
                 float x0 = d1[nt][2 * h] + bias[h], x1 = d1[nt][2 * h + 1] + bias[h];
                 if (prob) {
                     x0 = __fdividef(1.0f, 1.0f + __expf(-x0));
                     x1 = __fdividef(1.0f, 1.0f + __expf(-x1));
                 }
-                if (vec2 && 8 * nt + 1 < jrem) {
-                    __stcs(reinterpret_cast<float2 *>(orow + 8 * nt), make_float2(x0, x1));
-                } else {
-                    if (8 * nt < jrem) __stcs(orow + 8 * nt, x0);
-                    if (8 * nt + 1 < jrem) __stcs(orow + 8 * nt + 1, x1);
-                }
+                *reinterpret_cast<float2 *>(stage + (8 * h + g) * SS + 8 * nt + 2 * q) = make_float2(x0, x1);
             }
-        }
+        __syncwarp();
+        const int jn = min(32, p.Lh - j0);                   // valid positions of this item
+        float *obase = p.out + ((size_t)n * p.K + mtile * MTILE) * p.Lh + j0 + lane;
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r)
+            if (lane < jn) __stcs(obase + (size_t)r * p.Lh, stage[r * SS + lane]);
+        __syncwarp();
     }
 }
 

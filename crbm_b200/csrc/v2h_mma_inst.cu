@@ -39,7 +39,7 @@ int launch_v2h_mma<CRBM_KS>(int flags, const V2HParams &p, dim3 grid, cudaStream
 template <>
 int launch_v2h_dense_mma<CRBM_KS>(const DenseParams &p, dim3 grid, cudaStream_t stream) {
     static bool configured = false;
-    constexpr size_t smem = MmaShape<CRBM_KS>::smem_bytes;
+    constexpr size_t smem = MmaShape<CRBM_KS>::smem_bytes + 8 * MTILE * 34 * sizeof(float);
     if (!configured) {
         CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_dense_mma_kernel<CRBM_KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;

@@ -337,7 +337,27 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
     ms = e0.elapsed_time(e1) / reps
     nt = n * Lt
     alg = n * (Lt / 4.0) + 4.0 * n * K * Lh
-    return {'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
+    # fused reductions (max / argmax / mean over positions per sequence and motif): nothing but (N,K) results is written
+    mx = torch.empty((n, K), dtype=torch.float32, device=dev)
+    am = torch.empty((n, K), dtype=torch.int32, device=dev)
+    mean = torch.empty((n, K), dtype=torch.float32, device=dev)
+
+    def go_red():
+        _lib.check(lib.crbm_scan_reduce(_lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias),
+                                        K, M, model.pooling, _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am),
+                                        _lib.ptr(mean), s), 'scan_reduce')
+    for _ in range(3):
+        go_red()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        go_red()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_red = e0.elapsed_time(e1) / reps
+    return {'fused_reductions': {'metric': 'motif-scan nt/s, max/argmax/mean over positions fused (no dense output)',
+                                 'value': nt / (ms_red * 1e-3), 'unit': 'nt/s', 'ms': ms_red},
+            'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
             'sequences': n, 'ms': ms, 'output_GB': 4.0 * n * K * Lh / 1e9,
             'roofline': {'bound': 'hbm', 'kernel': 'v2h_dense_kernel', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
                          'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None,

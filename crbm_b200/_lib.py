@@ -59,6 +59,8 @@ SIGNATURES = {
     'crbm_random_bases': (c_int, [c_void_p, c_int, c_int, c_int, c_u64, c_void_p]),
     'crbm_v2h_dense': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p]),
+    'crbm_scan_reduce': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     'crbm_pool_probability': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'crbm_sample_hidden': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_u64, c_u64, c_void_p, c_void_p]),
     'crbm_h2v_dense': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

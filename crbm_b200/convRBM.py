@@ -342,6 +342,23 @@ class CRBM(object):
         mode = _lib.STRAND_FWD if self.doublestranded else _lib.STRAND_SUM
         return self._v2h(data, mode, _lib.OUT_PROBABILITY)
 
+    def motifHitSummary(self, data):
+        """Per sequence and motif: max over positions of motifHitProbs, its position and the mean over positions —
+        the reductions secomo.utils applies to motifHitProbs (utils.py:155,245-247,306) — computed inside the scan kernel,
+        so the (N,K,1,Lh) tensor is never materialised. Returns dict(max=(N,K) float32, argmax=(N,K) int32, mean=(N,K))."""
+        lib = self._require_cuda()
+        torch = _torch()
+        seqs = self._as_packed(data)
+        K, M = self.num_motifs, self.motif_length
+        mx = torch.empty((seqs.N, K), dtype=torch.float32, device=self._device)
+        am = torch.empty((seqs.N, K), dtype=torch.int32, device=self._device)
+        mean = torch.empty((seqs.N, K), dtype=torch.float32, device=self._device)
+        mode = _lib.STRAND_FWD if self.doublestranded else _lib.STRAND_SUM
+        _lib.check(lib.crbm_scan_reduce(_lib.ptr(seqs.words), seqs.row_words, seqs.N, seqs.L, _lib.ptr(self._t_W),
+                                        _lib.ptr(self._t_bias), K, M, self.pooling, mode, _lib.OUT_PROBABILITY,
+                                        _lib.ptr(mx), _lib.ptr(am), _lib.ptr(mean), _lib.stream_handle()), 'scan_reduce')
+        return dict(max=mx.cpu().numpy(), argmax=am.cpu().numpy(), mean=mean.cpu().numpy())
+
     def _free_energy_device(self, seqs, want_seq, want_motif, want_count, uniforms=None):
         lib = self._require_cuda()
         torch = _torch()

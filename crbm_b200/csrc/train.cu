@@ -27,7 +27,8 @@ static int dispatch_fused(int MW, int flags, const V2HParams &p, dim3 grid, cuda
 }
 #define CRBM_FOR_EACH_KS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 #define CRBM_DECLARE_KS(KSV) template <> int launch_v2h_mma<KSV>(int, const V2HParams &, dim3, cudaStream_t); \
-    template <> int launch_v2h_dense_mma<KSV>(const DenseParams &, dim3, cudaStream_t);
+    template <> int launch_v2h_dense_mma<KSV>(const DenseParams &, dim3, cudaStream_t); \
+    template <> int launch_v2h_scan_reduce<KSV>(const ScanReduceParams &, cudaStream_t);
 CRBM_FOR_EACH_KS(CRBM_DECLARE_KS)
 #undef CRBM_DECLARE_KS
 static int dispatch_mma(int KS, int flags, const V2HParams &p, dim3 grid, cudaStream_t s) {
@@ -42,6 +43,15 @@ static int dispatch_mma(int KS, int flags, const V2HParams &p, dim3 grid, cudaSt
 static int dispatch_dense_mma(int KS, const DenseParams &p, dim3 grid, cudaStream_t s) {
     switch (KS) {
 #define CRBM_CASE(KSV) case KSV: return launch_v2h_dense_mma<KSV>(p, grid, s);
+        CRBM_FOR_EACH_KS(CRBM_CASE)
+#undef CRBM_CASE
+    }
+    set_error("MMA k-step bucket %d not built", KS);
+    return CRBM_ERR_UNSUPPORTED;
+}
+static int dispatch_scan_reduce(int KS, const ScanReduceParams &p, cudaStream_t s) {
+    switch (KS) {
+#define CRBM_CASE(KSV) case KSV: return launch_v2h_scan_reduce<KSV>(p, s);
         CRBM_FOR_EACH_KS(CRBM_CASE)
 #undef CRBM_CASE
     }
@@ -467,6 +477,26 @@ int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const fl
         return dispatch_dense_mma(ceil_div(M, 4), p, dim3(mtiles, gy), (cudaStream_t)stream);
     }
     return dispatch_dense(t.MW, p, dim3(t.ktiles, t.gy), (cudaStream_t)stream);
+}
+
+int crbm_scan_reduce(const uint32_t *packed, int row_words, int N, int L, const float *W, const float *b, int K, int M,
+                     int pooling, int strand_mode, int out_kind, float *out_max, int *out_argmax, float *out_mean, void *stream) {
+    CRBM_CHECK_ARG(packed && W && b && N > 0 && (out_max || out_argmax || out_mean), "crbm_scan_reduce: bad arguments");
+    const int Lh = L - M + 1;
+    int rc = check_shape("crbm_scan_reduce", K, M, pooling, Lh);
+    if (rc) return rc;
+    CRBM_CHECK_ARG(strand_mode >= 0 && strand_mode <= 2 && (out_kind == 0 || out_kind == 1), "crbm_scan_reduce: bad mode");
+    CRBM_CHECK_ARG(row_words >= packed_row_words(L), "crbm_scan_reduce: row_words too small");
+    CRBM_CHECK_ARG(((uintptr_t)W & 15) == 0, "crbm_scan_reduce: W must be 16-byte aligned");
+    if (out_kind == CRBM_OUT_PROBABILITY && pooling != 1) {
+        set_error("crbm_scan_reduce: pooled probabilities (pooling %d) are not built yet; use crbm_v2h_dense", pooling);
+        return CRBM_ERR_UNSUPPORTED;
+    }
+    Tiling t = make_tiling(K, M, 1, Lh, N);
+    ScanReduceParams sp{};
+    sp.d = DenseParams{packed, row_words, N, L, Lh, W, b, K, M, 1, strand_mode, out_kind, t.bv, t.nblk, t.n_items, nullptr};
+    sp.out_max = out_max; sp.out_argmax = out_argmax; sp.out_mean = out_mean;
+    return dispatch_scan_reduce(ceil_div(M, 4), sp, (cudaStream_t)stream);
 }
 
 int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const float *W, const float *b, const float *c,

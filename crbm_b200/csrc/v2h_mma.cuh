@@ -114,10 +114,56 @@ __device__ __forceinline__ void build_w_fragments(uint32_t *wimg, float *wtile, 
     __syncthreads();
 }
 
-// bf16x2 B-fragment register for two consecutive sequence positions against one base code: 1.0 where equal.
-__device__ __forceinline__ uint32_t onehot_pair(uint32_t two_bases /*4 bits*/, uint32_t code_x5) {
-    const uint32_t t = two_bases ^ code_x5;
-    return ((t & 3u) ? 0u : 0x3F80u) | ((t & 12u) ? 0u : 0x3F800000u);
+// ---- one-hot B fragments from packed bases, bit-parallel ---------------------------------------------------------------
+// A B-fragment register is a bf16x2 whose halves are 1.0 (0x3F80) or 0. For a 16-base window word w the comparisons are
+// done for all 16 bases at once (a few LOP3), the two match bits of a register are brought to bits 0 and 16 of an
+// 8-base "group" word, and a register then costs SHF + LOP3 + IMAD:  ((G >> 2i) & 0x00010001) * 0x3F80.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t onehot_reg(uint32_t group, int i /*0,2,4,6: first base inside its 8-base group*/) {
+    return ((group >> (2 * i)) & 0x00010001u) * 0x3F80u;
+}
+// Up-pass operand: for base b at window position i, low half = [b == 2*qodd], high half = [b == 2*qodd + 1].
+// Fills grp[2w], grp[2w+1] for the NW window words.
+template <int NW>
+__device__ __forceinline__ void upass_groups(const uint32_t (&w)[NW], uint32_t qodd_mask /*qodd ? 0 : 0x55555555*/,
+                                             uint32_t (&grp)[2 * NW]) {
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const uint32_t hi = (w[i] >> 1) & 0x55555555u, lo = w[i] & 0x55555555u;
+        const uint32_t m = hi ^ qodd_mask;                   // bit 2i: (base >> 1) == qodd
+        const uint32_t a = m & ~lo, b = m & lo;              // base & 1 == 0 / == 1
+        grp[2 * i] = prmt(a, b, 0x5410u);                    // bases 0-7: a in the low 16 bits, b in the high 16 bits
+        grp[2 * i + 1] = prmt(a, b, 0x7632u);                // bases 8-15
+    }
+}
+// Statistics operand: for bases (i, i+1) against one code: low half = [base_i == code], high half = [base_{i+1} == code].
+template <int NW>
+__device__ __forceinline__ void pair_groups(const uint32_t (&w)[NW], uint32_t code_rep /*code * 0x55555555*/,
+                                            uint32_t (&grp)[2 * NW]) {
+    uint32_t e[NW + 1];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const uint32_t eq = ~(w[i] ^ code_rep);
+        e[i] = eq & (eq >> 1) & 0x55555555u;                 // bit 2i: base i == code
+    }
+    e[NW] = 0u;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+        const uint32_t nxt = __funnelshift_r(e[i], e[i + 1], 2);   // bit 2i: base i+1 == code
+        grp[2 * i] = prmt(e[i], nxt, 0x5410u);
+        grp[2 * i + 1] = prmt(e[i], nxt, 0x7632u);
+    }
+}
+// 1 / (1 + exp(-x)) with the SFU approximations only (ex2.approx: 2 ulp, rcp.approx: 1 ulp; saturates cleanly to 0 / 1)
+__device__ __forceinline__ float fast_sigmoid(float x) {
+    float t, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+    return r;
 }
 
 // grid (m-tiles of 16 motifs, CTAs), 256 threads, two CTAs per SM: every warp owns the CTA's m-tile for a stream of
@@ -162,8 +208,8 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
     const int lo2 = 2 * q + (g >> 2);                   // forward statistics B: base j0 + 2q + m_c (+1) (+8), m_c = 2nt2 + g/4
     const int mshift = p.M - 4 * KS;                    // in [-3, 0]
     const int sh3 = 16 + 2 * q - (g >> 2) + 1 + mshift; // reverse statistics: window starts at base j0 - 16 + sh3
-    const uint32_t qodd = q & 1;
-    const uint32_t code_f = (uint32_t)(g & 3) * 5u, code_r = (uint32_t)(3 - (g & 3)) * 5u;
+    const uint32_t qmask = (q & 1) ? 0u : 0x55555555u;
+    const uint32_t code_f = (uint32_t)(g & 3) * 0x55555555u, code_r = (uint32_t)(3 - (g & 3)) * 0x55555555u;
     const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
     const uint32_t ctr_hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) * 64u : 0u);
     const int ktiles = (p.K + KTILE - 1) / KTILE;
@@ -186,9 +232,10 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) d1[s][nt][r] = 0.f;
         {
-            uint32_t v[3];
+            uint32_t v[3], vg[6];
 #pragma unroll
             for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(wd[1 + i], wd[2 + i], 2 * lo1);
+            upass_groups<3>(v, qmask, vg);
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
                 uint32_t bx[2][2];
@@ -196,8 +243,8 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                     for (int hb = 0; hb < 2; ++hb) {
-                        const uint32_t bb = window_bits<1, 3>(v, 8 * nt + 4 * ks + 2 * hb);
-                        bx[nt][hb] = ((bb >> 1) == qodd) ? (0x3F80u << ((bb & 1u) << 4)) : 0u;
+                        const int off = 8 * nt + 4 * ks + 2 * hb;
+                        bx[nt][hb] = onehot_reg(vg[off >> 3], off & 7);
                     }
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
@@ -223,7 +270,7 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const float x = d1[s][nt][r] + bias[r >> 1];
-                    d1[s][nt][r] = __fdividef(1.0f, 1.0f + __expf(-x));
+                    d1[s][nt][r] = fast_sigmoid(x);
                 }
             if (!full) {
 #pragma unroll
@@ -292,18 +339,20 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
                         if (!STAT_P) sum_p[h] += p0 + p1;
                     }
                 }
-            uint32_t uf[3], ur[3];
+            uint32_t uf[3], ur[3], gf[6], gr[6];
 #pragma unroll
             for (int i = 0; i < 3; ++i) {
                 uf[i] = __funnelshift_r(wd[1 + i], wd[2 + i], 2 * lo2);
                 const uint32_t lo = sh3 >= 16 ? wd[1 + i] : wd[i], hi = sh3 >= 16 ? wd[2 + i] : wd[1 + i];
                 ur[i] = __funnelshift_r(lo, hi, 2 * (sh3 & 15));
             }
+            pair_groups<3>(uf, code_f, gf);
+            if (STAT_P && p.ds) pair_groups<3>(ur, code_r, gr);
 #pragma unroll
             for (int t = 0; t < NT2; ++t) {
                 // column c = 8t + g -> (a_c, m_c) = (g&3, 2t + g/4); K rows = positions 2q, 2q+1 | 2q+8, 2q+9
-                const uint32_t bf0 = onehot_pair(window_bits<2, 3>(uf, 2 * t), code_f);
-                const uint32_t bf1 = onehot_pair(window_bits<2, 3>(uf, 2 * t + 8), code_f);
+                const uint32_t bf0 = onehot_reg(gf[(2 * t) >> 3], (2 * t) & 7);
+                const uint32_t bf1 = onehot_reg(gf[(2 * t + 8) >> 3], (2 * t + 8) & 7);
                 if (STAT_P) {
                     hmma_bf16(accp[t], ap[0], bf0, bf1);
                     hmma_bf16(accp[t], ap[1], bf0, bf1);
@@ -315,8 +364,8 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
                 if (STAT_P && p.ds) {
                     // strand fold (convRBM.py:367): column (a_c, m_c) also collects p'[j] [base(j + M-1-m_c) == 3-a_c];
                     // with t' = NT2-1-t the base offset is static: 2*t' (+8) from a window starting at j0 + lo3 + M - 4*KS
-                    const uint32_t br0 = onehot_pair(window_bits<2, 3>(ur, 2 * (NT2 - 1 - t)), code_r);
-                    const uint32_t br1 = onehot_pair(window_bits<2, 3>(ur, 2 * (NT2 - 1 - t) + 8), code_r);
+                    const uint32_t br0 = onehot_reg(gr[(2 * (NT2 - 1 - t)) >> 3], (2 * (NT2 - 1 - t)) & 7);
+                    const uint32_t br1 = onehot_reg(gr[(2 * (NT2 - 1 - t) + 8) >> 3], (2 * (NT2 - 1 - t) + 8) & 7);
                     hmma_bf16(accp[t], apr[0], br0, br1);
                     hmma_bf16(accp[t], apr[1], br0, br1);
                 }
@@ -411,7 +460,7 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
     }
     const int nrows = min(MTILE, p.K - mtile * MTILE);
     const int lo1 = g + (q >> 1);
-    const uint32_t qodd = q & 1;
+    const uint32_t qmask = (q & 1) ? 0u : 0x55555555u;
     const bool prob = p.out_kind == CRBM_OUT_PROBABILITY;
     constexpr int SS = 34;                                   // stage row stride (floats): conflict-free float2 writes
     float *stage = stage_all + warp * (MTILE * SS);
@@ -428,11 +477,14 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int r = 0; r < 4; ++r) d1[nt][r] = 0.f;
-        uint32_t v[2][3];
+        uint32_t vg[2][6];
 #pragma unroll
-        for (int half = 0; half < 2; ++half)
+        for (int half = 0; half < 2; ++half) {
+            uint32_t v[3];
 #pragma unroll
-            for (int i = 0; i < 3; ++i) v[half][i] = __funnelshift_r(wd[1 + half + i], wd[2 + half + i], 2 * lo1);
+            for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(wd[1 + half + i], wd[2 + half + i], 2 * lo1);
+            upass_groups<3>(v, qmask, vg[half]);
+        }
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             uint32_t bx[4][2];
@@ -440,8 +492,8 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb) {
-                    const uint32_t bb = window_bits<1, 3>(v[nt >> 1], 8 * (nt & 1) + 4 * ks + 2 * hb);
-                    bx[nt][hb] = ((bb >> 1) == qodd) ? (0x3F80u << ((bb & 1u) << 4)) : 0u;
+                    const int off = 8 * (nt & 1) + 4 * ks + 2 * hb;
+                    bx[nt][hb] = onehot_reg(vg[nt >> 1][off >> 3], off & 7);
                 }
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
@@ -461,8 +513,8 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
             for (int nt = 0; nt < 4; ++nt) {
                 float x0 = d1[nt][2 * h] + bias[h], x1 = d1[nt][2 * h + 1] + bias[h];
                 if (prob) {
-                    x0 = __fdividef(1.0f, 1.0f + __expf(-x0));
-                    x1 = __fdividef(1.0f, 1.0f + __expf(-x1));
+                    x0 = fast_sigmoid(x0);
+                    x1 = fast_sigmoid(x1);
                 }
                 *reinterpret_cast<float2 *>(stage + (8 * h + g) * SS + 8 * nt + 2 * q) = make_float2(x0, x1);
             }
@@ -476,7 +528,121 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// Motif scan with the reductions its callers apply fused in (reference secomo/utils.py:155,245-247 take
+// the max over positions of motifHitProbs, :306 the mean): per sequence and motif the maximum hit probability, its
+// position (first maximum, like numpy.argmax) and the mean over positions. The 4*K bytes/nt of output never reach HBM,
+// which turns the scan from HBM-write bound into compute bound and makes genome-scale inputs fit.
+// One warp walks all position blocks of one sequence for the CTA's m-tile and keeps running (max, argmax, sum) in
+// registers; the four lanes of a quad hold different positions of the same motif rows and are combined by shuffles.
+// ----------------------------------------------------------------------------------------------------------
+struct ScanReduceParams {
+    DenseParams d;
+    float *out_max, *out_mean;     // (N,K) each, may be null
+    int *out_argmax;               // (N,K), may be null
+};
+
+template <int KS>
+__global__ void __launch_bounds__(256, 3) v2h_scan_reduce_kernel(const ScanReduceParams sp) {
+    using Sh = MmaShape<KS>;
+    const DenseParams &p = sp.d;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t *wimg = reinterpret_cast<uint32_t *>(smem);
+    float *wtile = reinterpret_cast<float *>(smem + Sh::wimg_bytes);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + Sh::wimg_bytes + Sh::wtile_bytes);
+    const int mtile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    build_w_fragments<KS>(wimg, wtile, bar, p.W, p.K, p.M, mtile);
+    const uint4 *wfrag = reinterpret_cast<const uint4 *>(wimg) + lane;
+    const bool want_f = p.strand_mode != CRBM_STRAND_RC, want_r = p.strand_mode != CRBM_STRAND_FWD;
+    const float bscale = p.strand_mode == CRBM_STRAND_SUM ? 2.f : 1.f;
+    float bias[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int k = mtile * MTILE + 8 * h + g;
+        bias[h] = k < p.K ? bscale * __ldg(p.b + k) : 0.f;
+    }
+    const int lo1 = g + (q >> 1);
+    const uint32_t qmask = (q & 1) ? 0u : 0x55555555u;
+    const bool prob = p.out_kind == CRBM_OUT_PROBABILITY;
+
+    for (int n = blockIdx.y * nwarps + warp; n < p.n_rows; n += gridDim.y * nwarps) {
+        float best[2] = {-INFINITY, -INFINITY}, sum[2] = {0.f, 0.f};
+        int bpos[2] = {0, 0};
+        const uint32_t *row0 = p.packed + (size_t)n * p.row_words;
+        for (int jb = 0; jb < p.nblk; ++jb) {
+            const int j0 = jb * 16;
+            uint32_t wd[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) wd[i] = __ldg(row0 + jb + i);
+            float d1[2][4];
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) d1[nt][r] = 0.f;
+            uint32_t v[3], vg[6];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(wd[1 + i], wd[2 + i], 2 * lo1);
+            upass_groups<3>(v, qmask, vg);
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                uint32_t bx[2][2];
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int hb = 0; hb < 2; ++hb) {
+                        const int off = 8 * nt + 4 * ks + 2 * hb;
+                        bx[nt][hb] = onehot_reg(vg[off >> 3], off & 7);
+                    }
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if (s == 0 ? !want_f : !want_r) continue;
+#pragma unroll
+                    for (int spl = 0; spl < 3; ++spl) {
+                        const uint4 a = wfrag[((s * 3 + spl) * KS + ks) * 32];
+                        hmma_bf16(d1[0], a, bx[0][0], bx[0][1]);
+                        hmma_bf16(d1[1], a, bx[1][0], bx[1][1]);
+                    }
+                }
+            }
+            const int jrem = p.Lh - j0 - 2 * q;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (8 * nt + e < jrem) {
+                            float x = d1[nt][2 * h + e] + bias[h];
+                            if (prob) x = fast_sigmoid(x);
+                            sum[h] += x;
+                            if (x > best[h]) { best[h] = x; bpos[h] = j0 + 8 * nt + 2 * q + e; }   // ascending positions: first max kept
+                        }
+                    }
+        }
+        // combine the four lanes of the quad (same motif rows, interleaved positions): max with smallest position on ties
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const float ob = __shfl_xor_sync(0xffffffffu, best[h], o);
+                const int op = __shfl_xor_sync(0xffffffffu, bpos[h], o);
+                sum[h] += __shfl_xor_sync(0xffffffffu, sum[h], o);
+                if (ob > best[h] || (ob == best[h] && op < bpos[h])) { best[h] = ob; bpos[h] = op; }
+            }
+            const int k = mtile * MTILE + 8 * h + g;
+            if (q == 0 && k < p.K) {
+                const size_t o = (size_t)n * p.K + k;
+                if (sp.out_max) sp.out_max[o] = best[h];
+                if (sp.out_argmax) sp.out_argmax[o] = bpos[h];
+                if (sp.out_mean) sp.out_mean[o] = sum[h] / (float)p.Lh;
+            }
+        }
+    }
+}
+
 template <int KS> int launch_v2h_mma(int flags, const V2HParams &p, dim3 grid, cudaStream_t stream);
+template <int KS> int launch_v2h_scan_reduce(const ScanReduceParams &p, cudaStream_t stream);
 template <int KS> int launch_v2h_dense_mma(const DenseParams &p, dim3 grid, cudaStream_t stream);
 
 }  // namespace crbm

@@ -49,4 +49,21 @@ int launch_v2h_dense_mma<CRBM_KS>(const DenseParams &p, dim3 grid, cudaStream_t 
     return CRBM_OK;
 }
 
+template <>
+int launch_v2h_scan_reduce<CRBM_KS>(const ScanReduceParams &sp, cudaStream_t stream) {
+    static bool configured = false;
+    constexpr size_t smem = MmaShape<CRBM_KS>::smem_bytes;
+    if (!configured) {
+        CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_scan_reduce_kernel<CRBM_KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const int mtiles = (sp.d.K + MTILE - 1) / MTILE;
+    int gy = (sp.d.n_rows + 7) / 8;
+    const int cap = (3 * num_sms()) / mtiles > 0 ? (3 * num_sms()) / mtiles : 1;
+    if (gy > cap) gy = cap;
+    v2h_scan_reduce_kernel<CRBM_KS><<<dim3(mtiles, gy), 256, smem, stream>>>(sp);
+    CRBM_CHECK_LAUNCH();
+    return CRBM_OK;
+}
+
 }  // namespace crbm

@@ -73,6 +73,14 @@ int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L,
                    const float *W, const float *b, int K, int M, int pooling,
                    int strand_mode, int out_kind, float *out, void *stream);
 
+/* ---- A7 with the callers' reductions fused in (reference secomo/utils.py:155,245-247 max over positions, :306 mean) -- */
+/* Per sequence and motif: maximum of the activity / hit probability over positions, the position of the first maximum
+ * (numpy.argmax semantics) and the mean over positions; each output is (N,K) and may be NULL. The (N,K,1,Lh) tensor is
+ * never written. pooling must be 1 for out_kind = PROBABILITY. */
+int crbm_scan_reduce(const uint32_t *packed, int row_words, int N, int L,
+                     const float *W, const float *b, int K, int M, int pooling,
+                     int strand_mode, int out_kind, float *out_max, int *out_argmax, float *out_mean, void *stream);
+
 /* ---- A2 on a given activity tensor (eager `_bottomUpProbability(activities)`) --------------------------- */
 int crbm_pool_probability(const float *act, int N, int K, int Lh, int pooling, float *prob, void *stream);
 

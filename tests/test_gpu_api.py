@@ -149,3 +149,20 @@ def test_statistics_vector_is_additive_across_shards(data):
         np.testing.assert_allclose(m.c.get_value(), full.c.get_value(), rtol=1e-5, atol=2e-6)
     got = np.concatenate([shards[0][0].fantasy_h.get_value(), shards[1][0].fantasy_h.get_value()])
     np.testing.assert_array_equal(got, full.fantasy_h.get_value())
+
+
+@pytest.mark.parametrize('K,M,L,ds', [(100, 15, 200, True), (33, 9, 77, False), (16, 25, 500, True)])
+def test_fused_scan_reductions_match_dense_scan(K, M, L, ds):
+    """max / argmax / mean over positions computed inside the scan kernel == the same reductions of the
+    dense motifHitProbs tensor (argmax bit-exact, numpy first-maximum semantics)."""
+    import crbm_b200
+    rs = np.random.RandomState(K + L)
+    m = crbm_b200.CRBM(K, M, doublestranded=ds, seed=1)
+    m.motifs.set_value((0.4 * rs.randn(K, 1, 4, M)).astype(np.float32))
+    m.bias.set_value((-3 + rs.randn(1, K)).astype(np.float32))
+    seqs = crbm_b200.PackedSequences.random(37, L, seed=3)
+    dense = m.motifHitProbs(seqs)[:, :, 0, :]
+    got = m.motifHitSummary(seqs)
+    np.testing.assert_array_equal(got['max'], dense.max(axis=2))
+    np.testing.assert_array_equal(got['argmax'], dense.argmax(axis=2))
+    np.testing.assert_allclose(got['mean'], dense.mean(axis=2), rtol=1e-5, atol=1e-7)

@@ -39,6 +39,7 @@ class _SharedParam(object):
         return getattr(self._owner, '_t_' + self.name)
 
     def get_value(self, borrow=False):
+        self._owner._check_deferred()
         return self._tensor().detach().cpu().numpy().reshape(self._shape).copy()
 
     def set_value(self, value, borrow=False):
@@ -201,6 +202,7 @@ class CRBM(object):
 
     def _as_packed(self, data):
         self._require_cuda()
+        self._check_deferred()
         if isinstance(data, PackedSequences):
             return data
         data = np.asarray(data) if not hasattr(data, 'shape') else data
@@ -553,9 +555,77 @@ class CRBM(object):
 
     def _trainingFct(self, data, uniforms=None, local_shard=False):
         """Train on one mini-batch (reference :524-526 -> theano_trainingFct). Under data parallelism `data` is the
-        global minibatch (every rank passes the same array) unless local_shard=True (this rank's rows only)."""
+        global minibatch (every rank passes the same array) unless local_shard=True (this rank's rows only).
+
+        One-hot input (NumPy or torch, host or device) takes the streamlined path: the batch is copied into a persistent
+        staging buffer and one CUDA graph (pack -> accumulate -> apply) is replayed, so a step costs one copy and one
+        graph launch on the host. Its one-hot validation result is checked at the next call / synchronisation point."""
+        if (uniforms is None and self._world == 1 and self._use_graphs and not isinstance(data, PackedSequences)
+                and getattr(data, 'ndim', 0) == 4):
+            return self._train_step_onehot(data)
         seqs = self._as_packed(data)
         self._train_packed(seqs, 0, seqs.N, uniforms, local_shard)
+
+    def _check_deferred(self):
+        """Raise if the one-hot validation of an earlier streamlined training call failed."""
+        eng = getattr(self, '_onehot_engine', None)
+        if eng is not None and eng.get('pending'):
+            eng['event'].synchronize()
+            eng['pending'] = False
+            if int(eng['bad_host'][0]) != 0:
+                raise ValueError("input is not one-hot at %d positions (expected exactly one 1 among A,C,G,T)"
+                                 % int(eng['bad_host'][0]))
+
+    def _train_step_onehot(self, data):
+        lib = self._require_cuda()
+        torch = _torch()
+        self._check_deferred()
+        n, L = int(data.shape[0]), int(data.shape[3])
+        if tuple(data.shape[1:3]) != (1, 4):
+            raise ValueError("expected one-hot data of shape (N,1,4,L), got %r" % (tuple(data.shape),))
+        eng = getattr(self, '_onehot_engine', None)
+        if eng is None or eng['key'] != (n, L):
+            rw = lib.crbm_packed_row_words(L)
+            eng = dict(key=(n, L), graph=None, pending=False)
+            eng['staging'] = torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device)
+            eng['words'] = torch.zeros((n, rw), dtype=torch.int32, device=self._device)
+            eng['bad'] = torch.zeros(1, dtype=torch.int32, device=self._device)
+            eng['bad_host'] = torch.zeros(1, dtype=torch.int32).pin_memory()
+            eng['event'] = torch.cuda.Event()
+            eng['step_dev'] = torch.zeros(1, dtype=torch.int64, device=self._device)
+            a = self._fill_args(eng['words'].data_ptr(), rw, n, L)
+            a.step_dev = eng['step_dev'].data_ptr()
+            eng['args'], eng['rw'] = a, rw
+            self._onehot_engine = eng
+        src = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)) if isinstance(data, np.ndarray) else data
+        eng['staging'].copy_(src, non_blocking=True)
+        eng['step_dev'].fill_(self._step)
+
+        def body():
+            s = _lib.stream_handle()
+            _lib.check(lib.crbm_pack_onehot(_lib.ptr(eng['staging']), n, L, _lib.ptr(eng['words']), eng['rw'],
+                                            _lib.ptr(eng['bad']), s), 'pack_onehot')
+            _lib.check(lib.crbm_train_accumulate(eng['args'], s), 'train_accumulate')
+            _lib.check(lib.crbm_train_apply(eng['args'], s), 'train_apply')
+
+        if eng['graph'] is None:
+            body()                                   # first call eagerly (one-time kernel attribute setup), then capture
+            torch.cuda.synchronize(self._device)
+            g = torch.cuda.CUDAGraph()
+            saved = [t.clone() for t in (self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
+                                         self._t_fantasy, eng['step_dev'])]
+            with torch.cuda.graph(g):
+                body()
+            for t, v in zip((self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
+                             self._t_fantasy, eng['step_dev']), saved):
+                t.copy_(v)
+            eng['graph'] = g
+        else:
+            eng['graph'].replay()
+        eng['bad_host'].copy_(eng['bad'], non_blocking=True)
+        eng['event'].record()
+        eng['pending'] = True
+        self._step += 1
 
     def _evaluateData(self, data, uniforms=None):
         """[mean free energy, mean of a sampled forward-strand H] (reference :466-472, 517-522)."""

@@ -166,3 +166,30 @@ def test_fused_scan_reductions_match_dense_scan(K, M, L, ds):
     np.testing.assert_array_equal(got['max'], dense.max(axis=2))
     np.testing.assert_array_equal(got['argmax'], dense.argmax(axis=2))
     np.testing.assert_allclose(got['mean'], dense.mean(axis=2), rtol=1e-5, atol=1e-7)
+
+
+def test_streamlined_onehot_step_equals_packed_step_and_validates(data):
+    """`_trainingFct(one-hot array)` (staging copy + graph replay) gives the same parameters as the explicit packed path,
+    and rejects non-one-hot input (reported at the next synchronisation point)."""
+    import crbm_b200
+    from crbm_b200 import CRBM
+    out = []
+    for fast in (True, False):
+        np.random.seed(3)
+        m = CRBM(num_motifs=12, motif_length=9, cd_k=1, seed=5, batchsize=20)
+        for i in range(5):
+            batch = data[20 * i:20 * (i + 1)]
+            if fast:
+                m._trainingFct(batch)
+            else:
+                m._train_packed(crbm_b200.PackedSequences.from_onehot(batch), 0, 20)
+        out.append((m.motifs.get_value(), m.bias.get_value(), m.c.get_value(), m.fantasy_h.get_value()))
+    for a, b in zip(*out):
+        np.testing.assert_array_equal(a, b)
+    m = CRBM(num_motifs=4, motif_length=5, seed=1, batchsize=20)
+    bad = data[:20].copy()
+    bad[3, 0, :, 7] = 0.0
+    m._trainingFct(data[:20])
+    m._trainingFct(bad)
+    with pytest.raises(ValueError):
+        m.motifs.get_value()

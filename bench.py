@@ -305,6 +305,7 @@ def time_step_kernels(model, data, B, dev):
     out['accumulate'] = timed(lambda: _lib.check(lib.crbm_train_accumulate(full, _lib.stream_handle())))
     out['accumulate_without_positive_phase'] = timed(lambda: _lib.check(lib.crbm_train_accumulate(empty, _lib.stream_handle())))
     out['apply'] = timed(lambda: _lib.check(lib.crbm_train_apply(full, _lib.stream_handle())))
+    out['fused_step'] = timed(lambda: _lib.check(lib.crbm_train_step(full, _lib.stream_handle())))
     out['positive_phase_kernel'] = max(0.0, out['accumulate'] - out['accumulate_without_positive_phase'])
     return out
 

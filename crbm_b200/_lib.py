@@ -71,6 +71,7 @@ SIGNATURES = {
     'crbm_train_workspace_bytes': (c_size_t, [c_int, c_int]),
     'crbm_train_accumulate': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_apply': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
+    'crbm_train_step': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_stats_layout': (c_int, [c_int, c_int, ctypes.POINTER(StatsLayout)]),
     'crbm_hidden_bits_to_dense': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'crbm_hidden_dense_to_bits': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -437,11 +437,13 @@ class CRBM(object):
         row_bytes = seqs.row_words * 4
         a = self._fill_args(seqs.words.data_ptr() + start * row_bytes, seqs.row_words, end - start, seqs.L, u_v, u_h, u_hp)
         s = _lib.stream_handle()
-        _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
         if self._world > 1:
             import torch.distributed as dist
+            _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
             dist.all_reduce(self._train_state['stats'])
-        _lib.check(lib.crbm_train_apply(a, s), 'train_apply')
+            _lib.check(lib.crbm_train_apply(a, s), 'train_apply')
+        else:
+            _lib.check(lib.crbm_train_step(a, s), 'train_step')
         self._step += 1
 
     # ---- CUDA-graph replay of whole training steps ------------------------------------------------------------------
@@ -478,6 +480,9 @@ class CRBM(object):
         lib = _lib.load()
         s = _lib.stream_handle()
         a = eng['args']
+        if part == 'both' and self._world == 1:
+            _lib.check(lib.crbm_train_step(a, s), 'train_step')
+            return
         if part in ('both', 'accumulate'):
             _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
         if part == 'both' and self._world > 1:
@@ -605,8 +610,7 @@ class CRBM(object):
             s = _lib.stream_handle()
             _lib.check(lib.crbm_pack_onehot(_lib.ptr(eng['staging']), n, L, _lib.ptr(eng['words']), eng['rw'],
                                             _lib.ptr(eng['bad']), s), 'pack_onehot')
-            _lib.check(lib.crbm_train_accumulate(eng['args'], s), 'train_accumulate')
-            _lib.check(lib.crbm_train_apply(eng['args'], s), 'train_apply')
+            _lib.check(lib.crbm_train_step(eng['args'], s), 'train_step')
 
         if eng['graph'] is None:
             body()                                   # first call eagerly (one-time kernel attribute setup), then capture

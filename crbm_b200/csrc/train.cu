@@ -526,7 +526,8 @@ int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const 
     return CRBM_OK;
 }
 
-int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
+extern "C" int crbm_train_apply(const crbm_train_args *a, void *stream);
+static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fuse_apply) {
     CRBM_CHECK_ARG(a && a->W && a->b && a->c && a->data && a->fantasy_bits && a->v_model && a->stats && a->workspace,
                    "crbm_train_accumulate: null pointer in args");
     const int K = a->K, M = a->M, P = a->pooling, Lh = a->L - M + 1;
@@ -668,7 +669,15 @@ int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     red.cnt_out[0] = st + lay.v_data; red.cnt_out[1] = st + lay.v_model;
     reduce_partials_kernel<<<red.block_start[red.nsets] + 2, 128, 0, s>>>(red);
     CRBM_CHECK_LAUNCH();
+    if (fuse_apply) return crbm_train_apply(a, stream);
     return CRBM_OK;
+}
+
+int crbm_train_accumulate(const crbm_train_args *a, void *stream) { return train_accumulate_impl(a, stream, false); }
+
+int crbm_train_step(const crbm_train_args *a, void *stream) {
+    CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc, "crbm_train_step: null pointer in args");
+    return train_accumulate_impl(a, stream, true);
 }
 
 int crbm_train_apply(const crbm_train_args *a, void *stream) {

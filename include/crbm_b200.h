@@ -148,6 +148,9 @@ size_t crbm_train_workspace_bytes(int K, int M);
 int crbm_train_accumulate(const crbm_train_args *args, void *stream);
 /* sparsity factor, momentum update of W,b,c from (all-reduced) args->stats. */
 int crbm_train_apply(const crbm_train_args *args, void *stream);
+/* accumulate followed by apply, for a single rank (no exchange in between). (A fused reduce+update kernel was measured
+ * and was not faster than the two small launches; see DESIGN.md.) */
+int crbm_train_step(const crbm_train_args *args, void *stream);
 
 /* layout of `stats` (offsets in floats), for hosts that want to inspect gradients */
 typedef struct crbm_stats_layout {

@@ -246,7 +246,9 @@ def main():
         line['roofline'] = {
             'bound': 'tensor', 'kernel': ('v2h_fused_kernel (CUDA-core path, pooling > 1)' if pooled else
                                           'v2h_mma_kernel<KS=%d, STAT_P|STAT_Q> (positive-phase launch)' % ((M + 3) // 4)),
-            'achieved': tf, 'peak': tpeak[0], 'unit': 'TFLOP/s', 'frac': (tf / tpeak[0]) if tf else None, 'traffic': None,
+            'achieved': tf, 'peak': tpeak[0], 'unit': 'TFLOP/s', 'frac': (tf / tpeak[0]) if tf else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01_ncu_metrics_final.md)
+            'traffic': 60416 if (args.workload == 'c2' and not pooled) else None,
             'peak_source': tpeak[1], 'launch_us': pos_us, 'algorithmic_flops_per_launch': alg_flops,
             'note': 'dense-equivalent flops of the one-hot contractions (x, x\', and the P, P\', Q statistics); the bf16x3 / '
                     'bf16x2 operand splits and tile padding are overhead, not counted. At 100 x 200 bp per step the launch is '
@@ -360,8 +362,10 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
                                  'value': nt / (ms_red * 1e-3), 'unit': 'nt/s', 'ms': ms_red},
             'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
             'sequences': n, 'ms': ms, 'output_GB': 4.0 * n * K * Lh / 1e9,
-            'roofline': {'bound': 'hbm', 'kernel': 'v2h_dense_kernel', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
-                         'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
+            'roofline': {'bound': 'hbm', 'kernel': 'v2h_dense_mma_kernel', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
+                         'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak,
+                         # ncu --set full on this launch (107 526 x 200 bp, K=100): 8.29 GB written + 0.33 GB read
+                         'traffic': 8.62e9 if (n == 107526 and K == 100) else None, 'algorithmic_bytes': alg,
                          'peak_source': peak_src, 'bytes_per_nt': alg / nt}}
 
 

@@ -39,6 +39,16 @@ class TrainArgs(ctypes.Structure):
     ]
 
 
+MAX_PEERS = 8
+
+
+class P2PArgs(ctypes.Structure):
+    """struct crbm_p2p_args."""
+    _fields_ = [('n_ranks', c_int), ('rank', c_int), ('parity', c_int), ('sequence', ctypes.c_ulonglong),
+                ('peer_stats', c_void_p * MAX_PEERS), ('peer_flags', c_void_p * MAX_PEERS), ('stats_stride', c_size_t),
+                ('error_flag', c_void_p), ('ticket', c_void_p)]
+
+
 class StatsLayout(ctypes.Structure):
     """struct crbm_stats_layout."""
     _fields_ = [(n, c_int) for n in (
@@ -72,6 +82,8 @@ SIGNATURES = {
     'crbm_train_accumulate': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_apply': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_step': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
+    'crbm_train_accumulate_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
+    'crbm_train_apply_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
     'crbm_train_stats_layout': (c_int, [c_int, c_int, ctypes.POINTER(StatsLayout)]),
     'crbm_hidden_bits_to_dense': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'crbm_hidden_dense_to_bits': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -184,6 +184,8 @@ class CRBM(object):
         self._train_state = None
         self._engine = None
         self._use_graphs = True
+        self._p2p = None            # peer-memory all-reduce state (data parallel), set up lazily
+        self._dp_seq = 0            # number of data-parallel training steps done (identical on every rank)
         self.theano_getHitProbs = self.motifHitProbs      # the attribute the north star calls getHitProbs (:508)
         self.getHitProbs = self.motifHitProbs
         self.theano_freeEnergy = lambda data: self.freeEnergy(data)
@@ -420,6 +422,63 @@ class CRBM(object):
         a.stats, a.workspace, a.workspace_bytes = st['stats'].data_ptr(), st['workspace'].data_ptr(), st['ws_bytes']
         return a
 
+    # ---- data parallel: one-shot all-reduce over NVLink peer memory, fused into the update --------------------------------
+    def _p2p_setup(self):
+        """Expose this rank's double-buffered statistics vector + flags to the peers (torch symmetric memory = CUDA VMM /
+        IPC handles exchanged through the process group). Returns None (-> NCCL all-reduce) if that is not possible."""
+        if self._p2p is not None:
+            return self._p2p or None
+        import os
+        self._p2p = False
+        if self._world == 1 or self._world > _lib.MAX_PEERS or os.environ.get('CRBM_DP', 'p2p') != 'p2p':
+            return None
+        torch = _torch()
+        lib = _lib.load()
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            st = self._ensure_train_state()
+            nfl = int(lib.crbm_train_stats_floats(self.num_motifs, self.motif_length))
+            stride = (nfl + 63) // 64 * 64
+            buf = symm_mem.empty(2 * stride + 64, dtype=torch.float32, device=self._device)
+            buf.zero_()
+            torch.cuda.synchronize(self._device)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD.group_name)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            assert len(ptrs) == self._world and ptrs[self._rank] == buf.data_ptr()
+            flag_off = 2 * stride * 4
+            p = dict(buf=buf, hdl=hdl, stride=stride, peer_stats=ptrs, peer_flags=[x + flag_off for x in ptrs],
+                     ticket=torch.zeros(1, dtype=torch.int32, device=self._device),
+                     error=torch.zeros(1, dtype=torch.int32, device=self._device), local_stats=buf.data_ptr())
+            dist.barrier()
+            self._p2p = p
+            return p
+        except Exception as e:                              # pragma: no cover - depends on the machine
+            warnings.warn("crbm_b200: peer-memory all-reduce unavailable (%s); falling back to NCCL all_reduce" % (e,))
+            return None
+
+    def _p2p_args(self, p, parity, sequence):
+        a = _lib.P2PArgs()
+        a.n_ranks, a.rank, a.parity, a.sequence = self._world, self._rank, parity, sequence
+        for r in range(self._world):
+            a.peer_stats[r], a.peer_flags[r] = p['peer_stats'][r], p['peer_flags'][r]
+        a.stats_stride, a.error_flag, a.ticket = p['stride'], p['error'].data_ptr(), p['ticket'].data_ptr()
+        return a
+
+    def _p2p_step(self, args, p, parity, sequence):
+        """accumulate into buffer `parity`, publish, then the fused all-reduce + update (both on the current stream)."""
+        lib = _lib.load()
+        s = _lib.stream_handle()
+        args.stats = p['local_stats'] + parity * p['stride'] * 4
+        pa = self._p2p_args(p, parity, sequence)
+        _lib.check(lib.crbm_train_accumulate_p2p(args, pa, s), 'train_accumulate_p2p')
+        _lib.check(lib.crbm_train_apply_p2p(args, pa, s), 'train_apply_p2p')
+
+    def _p2p_check(self):
+        p = self._p2p
+        if p and int(p['error'].item()) != 0:
+            raise RuntimeError("crbm_b200: a data-parallel peer did not publish its statistics in time")
+
     def _train_packed(self, seqs, start, end, uniforms=None, local_shard=False):
         """One training step on rows [start,end) of `seqs` (this rank's shard is cut here unless `local_shard`)."""
         lib = self._require_cuda()
@@ -438,10 +497,16 @@ class CRBM(object):
         a = self._fill_args(seqs.words.data_ptr() + start * row_bytes, seqs.row_words, end - start, seqs.L, u_v, u_h, u_hp)
         s = _lib.stream_handle()
         if self._world > 1:
-            import torch.distributed as dist
-            _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
-            dist.all_reduce(self._train_state['stats'])
-            _lib.check(lib.crbm_train_apply(a, s), 'train_apply')
+            p = self._p2p_setup()
+            if p is not None:
+                a.step = self._dp_seq
+                self._p2p_step(a, p, self._dp_seq & 1, self._dp_seq + 1)
+            else:
+                import torch.distributed as dist
+                _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
+                dist.all_reduce(self._train_state['stats'])
+                _lib.check(lib.crbm_train_apply(a, s), 'train_apply')
+            self._dp_seq += 1
         else:
             _lib.check(lib.crbm_train_step(a, s), 'train_step')
         self._step += 1
@@ -483,6 +548,9 @@ class CRBM(object):
         if part == 'both' and self._world == 1:
             _lib.check(lib.crbm_train_step(a, s), 'train_step')
             return
+        if part.startswith('p2p'):
+            self._p2p_step(a, self._p2p, int(part[3:]), 0)       # sequence comes from *step_dev inside the kernels
+            return
         if part in ('both', 'accumulate'):
             _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
         if part == 'both' and self._world > 1:
@@ -503,7 +571,8 @@ class CRBM(object):
             side = torch.cuda.Stream(device=self._device)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._run_steps_once(eng, part)
+                if part != 'p2p':                     # (p2p kernels were warmed up by the eager alignment steps)
+                    self._run_steps_once(eng, part)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize(self._device)
             for t, v in zip(tensors, saved):
@@ -511,8 +580,8 @@ class CRBM(object):
             g = torch.cuda.CUDAGraph()
             c0 = _lib.load().crbm_launch_count()
             with torch.cuda.graph(g):
-                for _ in range(nsteps):
-                    self._run_steps_once(eng, part)
+                for i in range(nsteps):
+                    self._run_steps_once(eng, ('p2p%d' % (i & 1)) if part == 'p2p' else part)
             if part in ('both', 'accumulate'):
                 eng['launches_per_step'] = int(_lib.load().crbm_launch_count() - c0) // nsteps + (1 if part == 'accumulate' else 0)
             eng['graphs'][key] = g
@@ -525,6 +594,36 @@ class CRBM(object):
         if count <= 0:
             return
         eng = self._graph_engine(seqs, steps_per_graph)
+        p = self._p2p_setup() if self._world > 1 else None
+        if p is not None:
+            # whole steps (accumulate -> publish -> peer all-reduce + update) replayed as graphs of an even number of
+            # steps starting at an even sequence number, so that the buffer parity of every graph node is static
+            lb, rw = self._local_batch, seqs.row_words
+            done = 0
+
+            def eager(nsteps):
+                nonlocal done
+                for _ in range(nsteps):
+                    a = self._fill_args(eng['shard'].data_ptr() + (first_batch + done) * lb * rw * 4, rw, lb, seqs.L)
+                    a.step = self._dp_seq
+                    self._p2p_step(a, p, self._dp_seq & 1, self._dp_seq + 1)
+                    self._dp_seq += 1
+                    done += 1
+            spg = steps_per_graph - (steps_per_graph & 1)
+            eager(min(count, (self._dp_seq & 1) + (0 if ('p2p_warm' in eng) else 2)))
+            eng['p2p_warm'] = True
+            if spg >= 2 and count - done >= spg:
+                eng['step_dev'].fill_(self._dp_seq)
+                eng['batch_dev'].fill_(first_batch + done)
+                g = self._graph_for(eng, spg, 'p2p')
+                nrep = (count - done) // spg
+                for _ in range(nrep):
+                    g.replay()
+                self._dp_seq += nrep * spg
+                done += nrep * spg
+            eager(count - done)
+            self._step += count
+            return
         eng['step_dev'].fill_(self._step)
         eng['batch_dev'].fill_(first_batch)
         if self._world > 1:

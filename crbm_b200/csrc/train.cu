@@ -246,6 +246,12 @@ struct ReduceParams {
     int cnt_row_words[2], cnt_n[2], cnt_L[2];
     const int *batch_index;
     float *cnt_out[2];      // 4 floats each
+    // data-parallel p2p mode: the last CTA to finish publishes `sequence` (system scope) in the flag arrays of all peers
+    unsigned int *ticket;   // device counter, zero between launches
+    unsigned long long *peer_flags[CRBM_MAX_PEERS];   // every rank's flag array [n_ranks][2]; entry [rank][parity] is ours
+    int n_ranks, rank, parity;
+    unsigned long long sequence;
+    const unsigned long long *sequence_dev;   // if set: sequence = *sequence_dev + 1
 };
 
 // Counts of the four base codes over n rows of L packed bases; one CTA, result written (not accumulated).
@@ -273,7 +279,31 @@ __device__ void count_bases_block(const uint32_t *__restrict__ rows, int row_wor
     __syncthreads();
     if (threadIdx.x < 4) out[threadIdx.x] = (float)tot[threadIdx.x];
 }
+__device__ __forceinline__ void reduce_partials_body(const ReduceParams &p);
+__device__ __forceinline__ void reduce_publish(const ReduceParams &p) {
+    if (!p.n_ranks) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(p.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *p.ticket = 0u;
+            __threadfence_system();
+            const unsigned long long seq = p.sequence_dev ? *p.sequence_dev + 1ull : p.sequence;
+            // one-way stores over NVLink: every peer polls its own memory
+            for (int r = 0; r < p.n_ranks; ++r)
+                *reinterpret_cast<volatile unsigned long long *>(p.peer_flags[r] + 2 * p.rank + p.parity) = seq;
+            __threadfence_system();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const ReduceParams p) {
+    reduce_partials_body(p);
+    reduce_publish(p);
+}
+
+__device__ __forceinline__ void reduce_partials_body(const ReduceParams &p) {
     __shared__ float sh[4][32];
     if ((int)blockIdx.x >= p.block_start[p.nsets]) {
         const int w = blockIdx.x - p.block_start[p.nsets];
@@ -384,6 +414,102 @@ __global__ void apply_update_kernel(const ApplyParams p) {
     } else if (gid == nW + p.K + 4) {
         if (p.step_dev) *p.step_dev += 1ull;
         if (p.batch_index_dev) { const int nb = *p.batch_index_dev + 1; *p.batch_index_dev = nb >= p.n_batches ? 0 : nb; }
+    }
+}
+
+// ---- A11 + A12 fused with a one-shot all-reduce over peer memory (data parallel) ------------------------------------------
+// Every rank's statistics buffer is mapped into every other rank's address space (NVLink). A thread block first waits
+// until all ranks have published this step's sequence number (their reduce kernels finished), then each thread adds its
+// entries over the ranks in rank order — the sums are bit-identical on every rank, so the replicas stay identical — and
+// applies the update. 18 420 floats x 8 ranks = 0.6 MB of remote reads per rank per step at C2.
+struct ApplyP2PParams {
+    ApplyParams ap;
+    int n_ranks, parity;
+    const float *peer_stats[CRBM_MAX_PEERS];      // every rank's statistics double buffer (peer-mapped)
+    const unsigned long long *local_flags;        // this rank's flag array [n_ranks][2], written by the peers
+    size_t stats_stride;
+    unsigned long long sequence;
+    const unsigned long long *sequence_dev;
+    int *error_flag;
+    unsigned int *ticket;   // zero between launches (shared with the reduce kernel, which has finished by then)
+};
+// Sums of NI statistics entries over the ranks, in rank order. All NI * n_ranks loads are issued before the first add, so
+// the thread pays one NVLink round trip, not one per term.
+template <int NI>
+__device__ __forceinline__ void p2p_sums(const ApplyP2PParams &p, const int (&idx)[NI], float (&out)[NI]) {
+    float x[NI][CRBM_MAX_PEERS];
+    const size_t off = (size_t)p.parity * p.stats_stride;
+#pragma unroll
+    for (int r = 0; r < CRBM_MAX_PEERS; ++r) {
+        if (r < p.n_ranks) {
+            const float *base = p.peer_stats[r] + off;
+#pragma unroll
+            for (int i = 0; i < NI; ++i) x[i][r] = __ldcv(base + idx[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        float v = 0.f;
+#pragma unroll
+        for (int r = 0; r < CRBM_MAX_PEERS; ++r) if (r < p.n_ranks) v += x[i][r];
+        out[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) apply_update_p2p_kernel(const ApplyP2PParams p) {
+    const ApplyParams &ap = p.ap;
+    if (threadIdx.x < p.n_ranks) {
+        const unsigned long long want = p.sequence_dev ? *p.sequence_dev + 1ull : p.sequence;
+        const volatile unsigned long long *f = p.local_flags + 2 * threadIdx.x + p.parity;
+        long long spins = 0;
+        while (*f < want) {
+            if (++spins > (1ll << 25)) { *p.error_flag = 1; break; }       // ~2 s: a peer is gone; do not hang the GPU
+            __nanosleep(32);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nW = ap.K * 4 * ap.M;
+    const crbm_stats_layout &lay = ap.lay;
+    const float strands = ap.ds ? 2.f : 1.f;
+    if (gid < nW + ap.K) {
+        const bool isW = gid < nW;
+        const int k = isW ? gid / (4 * ap.M) : gid - nW;
+        const int idx[6] = {lay.n_hidden_data, lay.n_hidden_model, lay.h_fwd + k,
+                            isW ? lay.vh_data + gid : lay.h_data + k, isW ? lay.vh_model + gid : lay.h_model + k,
+                            isW ? lay.vh_q + gid : lay.h_q + k};
+        float s[6];
+        p2p_sums<6>(p, idx, s);
+        const float nhd = s[0], nhm = s[1];
+        const float pk = s[2] / nhd;
+        const float gk = -(ap.rho / pk - (1.f - ap.rho) / (1.f - pk)) / ((float)ap.K * nhd);
+        const float gd = s[3] / (strands * nhd);
+        const float gm = s[4] / (strands * nhm);
+        const float reg = gk * s[5];
+        float *vel = isW ? ap.vW + gid : ap.vb + k, *par = isW ? ap.W + gid : ap.b + k;
+        const float v = ap.mu * *vel + ap.lr * (gd - gm - ap.lam * reg);
+        *vel = v;
+        *par += v;
+    } else if (gid < nW + ap.K + 4) {
+        const int a = gid - nW - ap.K;
+        const int idx[6] = {lay.n_vis_data, lay.n_vis_model, lay.v_data + a, lay.v_data + 3 - a, lay.v_model + a, lay.v_model + 3 - a};
+        float s[6];
+        p2p_sums<6>(p, idx, s);
+        const float gd = (s[2] + s[3]) / s[0];
+        const float gm = (s[4] + s[5]) / s[1];
+        const float v = ap.mu * ap.vc[a] + ap.lr * (gd - gm);
+        ap.vc[a] = v;
+        ap.c[a] += v;
+    }
+    // the step / minibatch counters are advanced by the last block to finish: every block has read *sequence_dev by then
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(p.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *p.ticket = 0u;
+            if (ap.step_dev) *ap.step_dev += 1ull;
+            if (ap.batch_index_dev) { const int nb = *ap.batch_index_dev + 1; *ap.batch_index_dev = nb >= ap.n_batches ? 0 : nb; }
+        }
     }
 }
 
@@ -527,7 +653,7 @@ int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const 
 }
 
 extern "C" int crbm_train_apply(const crbm_train_args *a, void *stream);
-static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fuse_apply) {
+static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fuse_apply, const crbm_p2p_args *p2p = nullptr) {
     CRBM_CHECK_ARG(a && a->W && a->b && a->c && a->data && a->fantasy_bits && a->v_model && a->stats && a->workspace,
                    "crbm_train_accumulate: null pointer in args");
     const int K = a->K, M = a->M, P = a->pooling, Lh = a->L - M + 1;
@@ -667,6 +793,11 @@ static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fu
     red.cnt_rows[1] = a->v_model; red.cnt_row_words[1] = a->v_row_words; red.cnt_n[1] = a->batchsize; red.cnt_L[1] = Lv;
     red.batch_index = a->batch_index_dev;
     red.cnt_out[0] = st + lay.v_data; red.cnt_out[1] = st + lay.v_model;
+    if (p2p) {
+        red.ticket = p2p->ticket; red.n_ranks = p2p->n_ranks; red.rank = p2p->rank; red.parity = p2p->parity;
+        for (int r = 0; r < p2p->n_ranks; ++r) red.peer_flags[r] = p2p->peer_flags[r];
+        red.sequence = p2p->sequence; red.sequence_dev = a->step_dev;
+    }
     reduce_partials_kernel<<<red.block_start[red.nsets] + 2, 128, 0, s>>>(red);
     CRBM_CHECK_LAUNCH();
     if (fuse_apply) return crbm_train_apply(a, stream);
@@ -674,6 +805,36 @@ static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fu
 }
 
 int crbm_train_accumulate(const crbm_train_args *a, void *stream) { return train_accumulate_impl(a, stream, false); }
+
+int crbm_train_accumulate_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, void *stream) {
+    CRBM_CHECK_ARG(p2p && p2p->n_ranks > 0 && p2p->n_ranks <= CRBM_MAX_PEERS && p2p->rank >= 0 && p2p->rank < p2p->n_ranks &&
+                   p2p->ticket && (p2p->parity == 0 || p2p->parity == 1), "crbm_train_accumulate_p2p: bad p2p arguments");
+    for (int r = 0; r < p2p->n_ranks; ++r) CRBM_CHECK_ARG(p2p->peer_flags[r], "crbm_train_accumulate_p2p: null peer flag pointer");
+    return train_accumulate_impl(a, stream, false, p2p);
+}
+
+int crbm_train_apply_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, void *stream) {
+    CRBM_CHECK_ARG(a && a->W && a->b && a->c && a->vW && a->vb && a->vc, "crbm_train_apply_p2p: null pointer in args");
+    CRBM_CHECK_ARG(p2p && p2p->n_ranks > 0 && p2p->n_ranks <= CRBM_MAX_PEERS && p2p->rank >= 0 && p2p->rank < p2p->n_ranks &&
+                   p2p->error_flag && p2p->ticket && (p2p->parity == 0 || p2p->parity == 1), "crbm_train_apply_p2p: bad p2p arguments");
+    for (int r = 0; r < p2p->n_ranks; ++r) CRBM_CHECK_ARG(p2p->peer_stats[r] && p2p->peer_flags[r], "crbm_train_apply_p2p: null peer pointer");
+    ApplyP2PParams p{};
+    ApplyParams &ap = p.ap;
+    ap.W = a->W; ap.b = a->b; ap.c = a->c; ap.vW = a->vW; ap.vb = a->vb; ap.vc = a->vc; ap.stats = nullptr;
+    fill_layout(a->K, a->M, &ap.lay);
+    ap.K = a->K; ap.M = a->M; ap.ds = a->doublestranded ? 1 : 0;
+    ap.lr = a->learning_rate; ap.mu = a->momentum; ap.rho = a->rho; ap.lam = a->lambda_rate;
+    ap.step_dev = a->step_dev; ap.batch_index_dev = a->batch_index_dev; ap.n_batches = a->n_batches;
+    p.n_ranks = p2p->n_ranks; p.parity = p2p->parity;
+    for (int r = 0; r < p2p->n_ranks; ++r) p.peer_stats[r] = p2p->peer_stats[r];
+    p.local_flags = p2p->peer_flags[p2p->rank];
+    p.stats_stride = p2p->stats_stride; p.sequence = p2p->sequence; p.sequence_dev = a->step_dev; p.error_flag = p2p->error_flag;
+    p.ticket = p2p->ticket;
+    const int n = a->K * 4 * a->M + a->K + 4;
+    apply_update_p2p_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    CRBM_CHECK_LAUNCH();
+    return CRBM_OK;
+}
 
 int crbm_train_step(const crbm_train_args *a, void *stream) {
     CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc, "crbm_train_step: null pointer in args");

@@ -152,6 +152,29 @@ int crbm_train_apply(const crbm_train_args *args, void *stream);
  * and was not faster than the two small launches; see DESIGN.md.) */
 int crbm_train_step(const crbm_train_args *args, void *stream);
 
+/* ---- data-parallel update without a separate collective: one-shot all-reduce over NVLink peer memory, fused into the update
+ * Every rank exposes, in peer-mapped memory (CUDA IPC / VMM; torch symmetric memory on the Python host), a double-buffered
+ * statistics vector and a flag array [n_ranks][2]. crbm_train_accumulate_p2p is crbm_train_accumulate writing into buffer
+ * `parity` (args->stats must point at it) and then, from the last CTA of the reduction, storing `sequence` into entry
+ * [rank][parity] of EVERY rank's flag array (one-way NVLink stores after a system-scope fence). crbm_train_apply_p2p polls
+ * its own flag array until all ranks carry `sequence`, then every thread loads its statistics entries from all ranks'
+ * buffers at once (one NVLink round trip), adds them in rank order (bit-identical sums on every rank, so the replicas stay
+ * identical) and applies the update: no NCCL launch, no extra kernel, and whole steps sit in one CUDA graph.
+ * The wait is bounded (~2 s); on expiry *error_flag is set to 1. `sequence` must increase by one per step on every rank and
+ * consecutive steps must alternate `parity`; when args->step_dev is set the sequence is *step_dev + 1. */
+#define CRBM_MAX_PEERS 8
+typedef struct crbm_p2p_args {
+    int n_ranks, rank, parity;
+    unsigned long long sequence;
+    float *peer_stats[CRBM_MAX_PEERS];               /* each rank's stats double buffer: 2 * stats_stride floats */
+    unsigned long long *peer_flags[CRBM_MAX_PEERS];  /* each rank's flag array: n_ranks * 2 entries, zero-initialised */
+    size_t stats_stride;                             /* floats between the two buffers (>= crbm_train_stats_floats) */
+    int *error_flag;                                 /* device int, set to 1 if a peer never showed up */
+    unsigned int *ticket;                            /* device counter (zero-initialised) electing the last CTA */
+} crbm_p2p_args;
+int crbm_train_accumulate_p2p(const crbm_train_args *args, const crbm_p2p_args *p2p, void *stream);
+int crbm_train_apply_p2p(const crbm_train_args *args, const crbm_p2p_args *p2p, void *stream);
+
 /* layout of `stats` (offsets in floats), for hosts that want to inspect gradients */
 typedef struct crbm_stats_layout {
     int vh_data, vh_model, vh_q;   /* each K*4*M: sum P(x)V folded over strands; same for the model; sum Q(x)V */

@@ -16,6 +16,13 @@ namespace crbm {
 CRBM_FOR_EACH_MW(CRBM_DECLARE)
 #undef CRBM_DECLARE
 
+int launch_v2h_dense_tc(const DenseParams &, cudaStream_t);          // scan_tc.cu: tcgen05 / TMEM scan kernel
+static bool scan_uses_tcgen05() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CRBM_SCAN_KERNEL"); v = (e && e[0] == 'm') ? 0 : 1; }   // "mma" -> mma.sync kernel
+    return v == 1;
+}
+
 static int dispatch_fused(int MW, int flags, const V2HParams &p, dim3 grid, cudaStream_t s) {
     switch (MW) {
 #define CRBM_CASE(MWV) case MWV: return launch_v2h_fused<MWV>(flags, p, grid, s);
@@ -594,8 +601,9 @@ int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const fl
     else pool = 1;
     Tiling t = make_tiling(K, M, pool, Lh, N);
     DenseParams p{packed, row_words, N, L, Lh, W, b, K, M, pool, strand_mode, out_kind, t.bv, t.nblk, t.n_items, out};
+    if (pool == 1 && scan_uses_tcgen05()) return launch_v2h_dense_tc(p, (cudaStream_t)stream);
     if (pool == 1) {
-        // tensor-pipe kernel: CTAs of one 16-motif m-tile, three per SM: size the grid to one full wave
+        // mma.sync tensor-pipe kernel (kept for comparison: CRBM_SCAN_KERNEL=mma): CTAs of one 16-motif m-tile, three per SM: size the grid to one full wave
         const int mtiles = ceil_div(K, 16);
         int gy = ceil_div(ceil_div(t.n_items, 2), 8);             // items of 32 positions, 8 warps per CTA
         const int cap = (3 * num_sms()) / mtiles > 0 ? (3 * num_sms()) / mtiles : 1;

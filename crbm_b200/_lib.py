@@ -69,6 +69,8 @@ SIGNATURES = {
     'crbm_random_bases': (c_int, [c_void_p, c_int, c_int, c_int, c_u64, c_void_p]),
     'crbm_v2h_dense': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p]),
+    'crbm_v2h_dense_strided': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p, ctypes.c_longlong, c_void_p]),
     'crbm_scan_reduce': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
     'crbm_pool_probability': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

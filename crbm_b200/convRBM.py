@@ -237,23 +237,39 @@ class CRBM(object):
         return obj
 
     # ---- bottom-up builders (reference :238-275), eager ------------------------------------------------------------
-    def _v2h(self, data, strand_mode, out_kind, max_chunk_bytes=1 << 30):
+    def _v2h_device(self, seqs, strand_mode, out_kind, start=0, end=None):
+        """(end-start, K, 1, Lh) device tensor of activities / probabilities of rows [start, end) of `seqs`.
+        With pooling 1 it is a view of a buffer whose rows are padded to a multiple of 8 floats: the tcgen05 scan kernel
+        then writes whole 32-byte sectors only; the values are those of the contiguous layout."""
         lib = self._require_cuda()
         torch = _torch()
+        K, M = self.num_motifs, self.motif_length
+        Lh = seqs.L - M + 1
+        if Lh <= 0:
+            raise ValueError("sequences of length %d are shorter than the motif (%d)" % (seqs.L, M))
+        end = seqs.N if end is None else end
+        n = end - start
+        pooled = self.pooling != 1 and out_kind == _lib.OUT_PROBABILITY
+        pitch = Lh if pooled else (Lh + 7) // 8 * 8
+        buf = torch.empty((n, K, 1, pitch), dtype=torch.float32, device=self._device)
+        _lib.check(lib.crbm_v2h_dense_strided(_lib.ptr(seqs.words[start:]), seqs.row_words, n, seqs.L, _lib.ptr(self._t_W),
+                                              _lib.ptr(self._t_bias), K, M, self.pooling, strand_mode, out_kind,
+                                              _lib.ptr(buf), pitch, _lib.stream_handle()), 'v2h_dense')
+        return buf[:, :, :, :Lh]
+
+    def _v2h(self, data, strand_mode, out_kind, max_chunk_bytes=1 << 30):
         seqs = self._as_packed(data)
         K, M = self.num_motifs, self.motif_length
         Lh = seqs.L - M + 1
         if Lh <= 0:
             raise ValueError("sequences of length %d are shorter than the motif (%d)" % (seqs.L, M))
+        torch = _torch()
         out = np.empty((seqs.N, K, 1, Lh), dtype=np.float32)
+        host = torch.from_numpy(out)
         rows = max(1, int(max_chunk_bytes // (4 * K * Lh)))
         for s in range(0, seqs.N, rows):
             e = min(seqs.N, s + rows)
-            dev = torch.empty((e - s, K, 1, Lh), dtype=torch.float32, device=self._device)
-            _lib.check(lib.crbm_v2h_dense(_lib.ptr(seqs.words[s:]), seqs.row_words, e - s, seqs.L, _lib.ptr(self._t_W),
-                                          _lib.ptr(self._t_bias), K, M, self.pooling, strand_mode, out_kind,
-                                          _lib.ptr(dev), _lib.stream_handle()), 'v2h_dense')
-            out[s:e] = dev.cpu().numpy()
+            host[s:e].copy_(self._v2h_device(seqs, strand_mode, out_kind, s, e))
         return out
 
     def _bottomUpActivity(self, data, flip_motif=False):

@@ -20,6 +20,7 @@
 // One CTA per SM slot (two per SM when N <= 128), persistent over tiles, one __syncthreads per tile.
 // Bound: HBM write (4*K bytes per hidden position); tensor pipe ~20-30 % busy, MUFU (two per output) ~70 %.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "v2h.cuh"
 
 namespace crbm {
@@ -29,10 +30,16 @@ struct TcParams {
     int NT;            // motifs per CTA (multiple of 16, <= 256)
     int ksteps;        // Kdim / 16
     int n_atoms;       // ceil(Kdim / 64): 128-byte swizzle atoms along K
-    int tmem_stride;   // columns between the two accumulator buffers (power of two >= NT)
-    int tmem_cols;     // 2 * tmem_stride
-    int n_tiles;       // ceil(total / 128)
+    int tmem_stride;   // columns between accumulator buffers (power of two >= max(NT, 128))
+    int nbuf;          // accumulator buffers in the 512 TMEM columns: 4 (NT <= 128) or 2
+    int a_stages;      // one-hot A tiles in the shared-memory ring (2 or 3)
+    int store_len;     // positions written per row: Lh, or the padded row (aligned mode: the pad floats are written too, so
+                       // that no 32-byte sector is left partially written -> no read-modify-write in DRAM)
+    int n_tiles;       // ceil(n_rows * LhV / 128)
     float scale;       // -log2(e) for probabilities, 1 for activities
+    int LhV;           // virtual hidden length the tiles are cut from: Lh, or Lh rounded up to 32 when the output rows are
+                       // sector aligned (then every warp of a tile sits inside one sequence at a multiple of 32 positions)
+    long long row_stride;   // floats between consecutive (n,k) rows of the output (Lh for the reference's contiguous layout)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -67,7 +74,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// after tmem_ld_wait(): pins the uses of v behind the wait (the compiler sees no data dependence on the wait itself)
+__device__ __forceinline__ void tmem_ld_fence8(uint32_t (&v)[8]) {
+    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
+}
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes, 8-row groups
 // 1024 bytes apart (stride byte offset), 16-byte chunks XOR-swizzled with the row index inside a group.
@@ -85,17 +101,22 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((chunk ^ r) & 7) << 4));
 }
 
-constexpr int TC_THREADS = 256;
 constexpr int TC_TILE = 128;
 constexpr int A_ATOM_BYTES = TC_TILE * 128;
+constexpr int TC_PRODUCER_WARPS = 4;                      // build the one-hot A tiles, one thread issues the MMAs
+constexpr int TC_EPILOGUE_WARPS = 16;                     // four warpgroups draining accumulator buffers
+constexpr int TC_THREADS = 32 * (TC_PRODUCER_WARPS + TC_EPILOGUE_WARPS);
+constexpr int TC_TMEM_COLS = 512;                         // the CTA owns the SM: all of tensor memory
+constexpr int TC_MAX_A_STAGES = 3;
 
-__host__ __device__ inline size_t tc_smem_bytes(int NT, int n_atoms) {
-    return 1024 /*alignment slack*/ + (size_t)n_atoms * A_ATOM_BYTES + 2 * (size_t)n_atoms * NT * 128 + (size_t)NT * 4 + 64;
+__host__ __device__ inline size_t tc_smem_bytes(int NT, int n_atoms, int a_stages) {
+    return 1024 /*alignment slack*/ + (size_t)a_stages * n_atoms * A_ATOM_BYTES + 2 * (size_t)n_atoms * NT * 128 + (size_t)NT * 4 + 256;
 }
 
 // (sequence, hidden position) of the first row of a tile; tiles advance by a fixed stride, so no 64-bit division is needed
 struct TilePos {
     int n0, j0;
+    __device__ __forceinline__ void init(int first_pos, int Lh) { n0 = first_pos / Lh; j0 = first_pos - n0 * Lh; }
     __device__ __forceinline__ void advance(int positions, int Lh) {
         const int jj = j0 + positions;
         const int dn = jj / Lh;
@@ -109,35 +130,40 @@ struct TilePos {
     }
 };
 
-// One-hot A tile of the 128 hidden positions starting at `tp`: thread t builds the even (t < 128) or odd chunks of row t & 127.
-__device__ __forceinline__ void tc_build_a(const TcParams &p, unsigned char *A, const TilePos &tp) {
-    const DenseParams &d = p.d;
-    const int r = threadIdx.x & 127, half = threadIdx.x >> 7;
-    uint32_t v[3] = {0u, 0u, 0u};
-    int mlim = 0;
-    int n, j;
-    tp.row(r, d.Lh, n, j);
-    if (n < d.n_rows) {
-        const uint32_t *row = d.packed + (size_t)n * d.row_words;
-        const int bit = 2 * (j + 16 * FRONT_PAD_WORDS);
-        const uint32_t *w = row + (bit >> 5);
-        const int sh = bit & 31;
-        const uint32_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
-        v[0] = __funnelshift_r(w0, w1, sh);               // bases j .. j+15
-        v[1] = __funnelshift_r(w1, w2, sh);               // bases j+16 .. j+31
-        v[2] = __funnelshift_r(w2, w3, sh);               // bases j+32 .. j+47
-        mlim = d.M;
-    }
-    const int nch = 2 * p.ksteps;                         // 16-byte chunks per row: chunk ch holds m = 2ch, 2ch+1
+// the packed words under hidden position row `r` of a tile: three 16-base windows starting at the position's first base
+struct RowBases {
+    uint32_t w[4];
+    int sh, mlim;
+    __device__ __forceinline__ void load(const TcParams &p, const TilePos &tp, int r) {
+        const DenseParams &d = p.d;
+        int n, j;
+        tp.row(r, p.LhV, n, j);
+        mlim = 0; sh = 0;
+        w[0] = w[1] = w[2] = w[3] = 0u;
+        if (n < d.n_rows && j < d.Lh) {
+            const int bit = 2 * (j + 16 * FRONT_PAD_WORDS);
+            const uint32_t *src = d.packed + (size_t)n * d.row_words + (bit >> 5);
+            sh = bit & 31;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        const int ch = 2 * i + half;
+            for (int i = 0; i < 4; ++i) w[i] = __ldg(src + i);
+            mlim = d.M;
+        }
+    }
+};
+
+// One-hot row `r` of an A tile: 16-byte chunk ch holds the eight fp16 [base(j+2ch) == 0..3], [base(j+2ch+1) == 0..3].
+__device__ __forceinline__ void tc_build_row(const TcParams &p, unsigned char *A, int r, const RowBases &rb) {
+    uint32_t v[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(rb.w[i], rb.w[i + 1], rb.sh);     // bases j+16i .. j+16i+15
+    const int nch = 2 * p.ksteps;
+#pragma unroll
+    for (int ch = 0; ch < 18; ++ch) {
         if (ch < nch) {
-            // bases 2ch, 2ch+1 sit in window (2ch >> 4) == (i >> 2) at bit 2 * (2ch & 15)
-            const uint32_t bits = (v[i >> 2] >> (2 * ((4 * i) & 15))) >> (4 * half);
+            const uint32_t bits = v[ch >> 3] >> (4 * (ch & 7));
             const int b0 = bits & 3, b1 = (bits >> 2) & 3, m0 = 2 * ch;
-            const uint32_t h0 = (m0 < mlim) ? (0x3C00u << (16 * (b0 & 1))) : 0u;      // fp16 1.0 in the half selected by the base
-            const uint32_t h1 = (m0 + 1 < mlim) ? (0x3C00u << (16 * (b1 & 1))) : 0u;
+            const uint32_t h0 = (m0 < rb.mlim) ? (0x3C00u << (16 * (b0 & 1))) : 0u;   // fp16 1.0 in the half selected by the base
+            const uint32_t h1 = (m0 + 1 < rb.mlim) ? (0x3C00u << (16 * (b1 & 1))) : 0u;
             uint4 q;
             q.x = (b0 & 2) ? 0u : h0; q.y = (b0 & 2) ? h0 : 0u;
             q.z = (b1 & 2) ? 0u : h1; q.w = (b1 & 2) ? h1 : 0u;
@@ -147,7 +173,7 @@ __device__ __forceinline__ void tc_build_a(const TcParams &p, unsigned char *A, 
 }
 
 __device__ __forceinline__ void tc_issue_mma(const TcParams &p, uint32_t a_addr, uint32_t bhi_addr, uint32_t blo_addr,
-                                             uint32_t tmem_d, uint32_t idesc, uint64_t *bar) {
+                                             uint32_t tmem_d, uint32_t idesc) {
     const uint32_t b_atom = (uint32_t)p.NT * 128u;
     for (int s = 0; s < p.ksteps; ++s) {
         const uint32_t atom = s >> 2, koff = (s & 3) * 32;            // 16 fp16 = 32 bytes per k-step inside the 128-byte row
@@ -155,27 +181,44 @@ __device__ __forceinline__ void tc_issue_mma(const TcParams &p, uint32_t a_addr,
         umma_f16(tmem_d, ad, umma_desc_sw128(bhi_addr + atom * b_atom + koff), idesc, s > 0 ? 1u : 0u);
         umma_f16(tmem_d, ad, umma_desc_sw128(blo_addr + atom * b_atom + koff), idesc, 1u);
     }
-    umma_commit(bar);
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_PRODUCER_WARPS) : "memory"); }
 
-__global__ void __launch_bounds__(TC_THREADS, 2) v2h_dense_tc_kernel(const TcParams p) {
+// Warp-specialised, persistent, one CTA per SM:
+//   warps 0-3   producers: thread r builds row r of the next one-hot A tile (ring of a_stages tiles; the packed words of the
+//               tile after that are already in flight), then thread 0 issues the tile's MMAs into accumulator buffer i % nbuf
+//               and commits to full[buf] and a_free[stage]
+//   warps 4-19  four epilogue warpgroups: group g drains buffer g % nbuf (when nbuf < 4 the groups sharing a buffer take
+//               alternate 8-motif chunks): wait full[buf] -> tcgen05.ld -> bias, sigmoid -> 128-byte row stores -> arrive empty[buf]
+template <bool PROB>
+__global__ void __launch_bounds__(TC_THREADS, 1) v2h_dense_tc_kernel(const TcParams p) {
     const DenseParams &d = p.d;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char *smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    const size_t a_tile_bytes = (size_t)p.n_atoms * A_ATOM_BYTES;
     unsigned char *A = smem;
-    unsigned char *Bhi = A + (size_t)p.n_atoms * A_ATOM_BYTES;
+    unsigned char *Bhi = A + (size_t)p.a_stages * a_tile_bytes;
     unsigned char *Blo = Bhi + (size_t)p.n_atoms * p.NT * 128;
     float *bias_s = reinterpret_cast<float *>(Blo + (size_t)p.n_atoms * p.NT * 128);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + p.NT);       // NT multiple of 16 -> 8-byte aligned
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2);
+    uint64_t *full = reinterpret_cast<uint64_t *>(bias_s + p.NT);       // NT multiple of 16 -> 8-byte aligned
+    uint64_t *empty = full + 4;
+    uint64_t *a_free = empty + 4;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_free + TC_MAX_A_STAGES);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kbase = blockIdx.y * p.NT;
     const int Kdim = 16 * p.ksteps;
+    const int nbuf = p.nbuf, groups_per_buf = 4 / nbuf;
 
-    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    if (tid == 32) { mbar_init(bars, 1); mbar_init(bars + 1, 1); }
+    if (warp == 0) tmem_alloc(tmem_slot, (uint32_t)TC_TMEM_COLS);
+    if (tid == 32) {
+        for (int i = 0; i < 4; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 4 * groups_per_buf); }
+        for (int i = 0; i < TC_MAX_A_STAGES; ++i) mbar_init(a_free + i, 1);
+    }
 
     // ---- B: W (strand-selected, scaled) -> fp16 hi / lo, K-major SWIZZLE_128B ------------------------------------------------
     for (int idx = tid; idx < p.NT * Kdim; idx += TC_THREADS) {
@@ -198,84 +241,122 @@ __global__ void __launch_bounds__(TC_THREADS, 2) v2h_dense_tc_kernel(const TcPar
         const float bs = d.strand_mode == CRBM_STRAND_SUM ? 2.f : 1.f;       // both activities carry the bias (convRBM.py:513)
         bias_s[i] = k < d.K ? bs * p.scale * __ldg(d.b + k) : 0.f;
     }
-
-    int tile = blockIdx.x;
-    const int stride_pos = TC_TILE * (int)gridDim.x;
-    TilePos cur;                                                     // first row of `tile`
-    cur.n0 = (tile * TC_TILE) / d.Lh;
-    cur.j0 = tile * TC_TILE - cur.n0 * d.Lh;
-    if (tile < p.n_tiles) tc_build_a(p, A, cur);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t a_addr = smem_u32(A), bhi_addr = smem_u32(Bhi), blo_addr = smem_u32(Blo);
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, N = NT, M = 128
-    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
-    if (tid == 0 && tile < p.n_tiles) tc_issue_mma(p, a_addr, bhi_addr, blo_addr, tmem_base, idesc, bars);
+    const int stride_pos = TC_TILE * (int)gridDim.x;                  // positions between consecutive tiles of this CTA
+    // number of tiles this CTA processes: tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int my_tiles = ((int)blockIdx.x < p.n_tiles) ? (p.n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    const bool prob = d.out_kind == CRBM_OUT_PROBABILITY;
-    const int q = warp & 3, chalf = warp >> 2;
-    const int nchunks = p.NT >> 4;
-    for (int it = 0; tile < p.n_tiles; ++it, tile += (int)gridDim.x) {
-        const int buf = it & 1;
-        mbar_wait(bars + buf, (uint32_t)((it >> 1) & 1));           // MMAs of this tile are done: A is free, D[buf] is full
-        tc_fence_after();
-        const int next = tile + (int)gridDim.x;
-        TilePos nxt = cur;
-        nxt.advance(stride_pos, d.Lh);
-        if (next < p.n_tiles) {
-            tc_build_a(p, A, nxt);
+    if (warp < TC_PRODUCER_WARPS) {
+        // ================================================= producers ===================================================
+        const uint32_t a_addr = smem_u32(A), bhi_addr = smem_u32(Bhi), blo_addr = smem_u32(Blo);
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B fp16, both K-major, N = NT, M = 128
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);
+        TilePos tp;
+        tp.init((int)blockIdx.x * TC_TILE, p.LhV);
+        RowBases cur, nxt;
+        if (my_tiles > 0) cur.load(p, tp, tid);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int stage = i % p.a_stages, use = i / p.a_stages;
+            tp.advance(stride_pos, p.LhV);
+            if (i + 1 < my_tiles) nxt.load(p, tp, tid);                              // in flight while this tile is built
+            if (use > 0) mbar_wait(a_free + stage, (uint32_t)((use - 1) & 1));       // the MMAs that read this stage are done
+            tc_build_row(p, A + (size_t)stage * a_tile_bytes, tid, cur);
             fence_async_smem();
-        }
-        tc_fence_before();
-        __syncthreads();                                             // also: everyone has drained D[buf ^ 1] (previous tile)
-        if (tid == 0 && next < p.n_tiles) {
-            tc_fence_after();
-            tc_issue_mma(p, a_addr, bhi_addr, blo_addr, tmem_base + (uint32_t)((buf ^ 1) * p.tmem_stride), idesc, bars + (buf ^ 1));
-        }
-        // ---- epilogue of `tile` from D[buf]: this thread owns position row 32q + lane ------------------------------------------
-        int n, j;
-        cur.row(32 * q + lane, d.Lh, n, j);
-        const bool valid = n < d.n_rows;
-        float *orow = d.out + ((size_t)n * d.K + kbase) * d.Lh + j;
-        const uint32_t trow = tmem_base + (uint32_t)(buf * p.tmem_stride) + ((uint32_t)(32 * q) << 16);
-        for (int ch = chalf; ch < nchunks; ch += 2) {
-            uint32_t v[16];
-            tmem_ld16(trow + ch * 16, v);
-            tmem_ld_wait();
-            const int krem = d.K - kbase - ch * 16;                  // valid motifs in this chunk (warp-uniform)
-            const float4 *bs4 = reinterpret_cast<const float4 *>(bias_s + ch * 16);
-            float *o = orow + (size_t)(ch * 16) * d.Lh;
-#pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-                const float4 b4 = bs4[c4];
-                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = 4 * c4 + e;
-                    float x = __uint_as_float(v[c]) + bb[e];
-                    if (prob) {
-                        float t, rr;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x));
-                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(1.0f + t));
-                        x = rr;
-                    }
-                    if (valid && c < krem) __stcs(o + (size_t)c * d.Lh, x);
-                }
+            producer_bar_sync();
+            if (tid == 0) {
+                const int buf = i % nbuf, u = i / nbuf;
+                if (u > 0) mbar_wait(empty + buf, (uint32_t)((u - 1) & 1));          // the epilogue has drained this accumulator
+                tc_fence_after();
+                tc_issue_mma(p, a_addr + (uint32_t)(stage * a_tile_bytes), bhi_addr, blo_addr,
+                             tmem_base + (uint32_t)(buf * p.tmem_stride), idesc);
+                umma_commit(full + buf);
+                umma_commit(a_free + stage);
             }
+            cur = nxt;
         }
-        cur = nxt;
+    } else {
+        // ================================================= epilogue ====================================================
+        const int ew = warp - TC_PRODUCER_WARPS;           // 0..15
+        const int q = warp & 3;                            // TMEM lane quarter this warp may read: lanes 32q .. 32q+31
+        const int grp = ew >> 2;                           // warpgroup 0..3
+        const int buf = grp % nbuf, sub = grp / nbuf;      // accumulator buffer and chunk phase of this group
+        const size_t stride8 = 8 * (size_t)p.row_stride;
+        const int kvalid = min(p.NT, d.K - kbase);
+        const int nch8 = (kvalid + 7) >> 3;
+        const uint32_t trow = tmem_base + (uint32_t)(buf * p.tmem_stride) + ((uint32_t)(32 * q) << 16);
+        TilePos tp;
+        tp.init(((int)blockIdx.x + buf * (int)gridDim.x) * TC_TILE, p.LhV);
+        for (int i = buf, u = 0; i < my_tiles; i += nbuf, ++u) {
+            int n, j;
+            tp.row(32 * q + lane, p.LhV, n, j);
+            tp.advance(stride_pos * nbuf, p.LhV);
+            const bool valid = n < d.n_rows && j < p.store_len;
+            float *orow = d.out + ((size_t)n * d.K + kbase) * (size_t)p.row_stride + j;
+            mbar_wait(full + buf, (uint32_t)(u & 1));
+            tc_fence_after();
+            auto finish = [&](uint32_t (&v)[8], int ch) {
+                tmem_ld_fence8(v);
+                const float4 b0 = reinterpret_cast<const float4 *>(bias_s)[2 * ch], b1 = reinterpret_cast<const float4 *>(bias_s)[2 * ch + 1];
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float x[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    x[c] = __uint_as_float(v[c]) + bb[c];
+                    if (PROB) {
+                        float t;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x[c]));
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x[c]) : "f"(1.0f + t));
+                    }
+                }
+                // one pointer per motif row, advanced by the row stride: the stores are predicated, never branched around
+                float *o = orow + (size_t)ch * stride8;
+                const int krem = kvalid - ch * 8;                        // valid motifs in this chunk (warp-uniform)
+                if (krem >= 8) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (valid) __stcs(o, x[c]);
+                        o += p.row_stride;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (valid && c < krem) __stcs(o, x[c]);
+                        o += p.row_stride;
+                    }
+                }
+            };
+            // the TMEM load of the next chunk is in flight while the current one is finished
+            uint32_t va[8], vb[8];
+            int ch = sub;
+            if (ch < nch8) tmem_ld8(trow + ch * 8, va);
+            while (ch < nch8) {
+                tmem_ld_wait();
+                if (ch + groups_per_buf < nch8) tmem_ld8(trow + (ch + groups_per_buf) * 8, vb);
+                finish(va, ch);
+                ch += groups_per_buf;
+                if (ch >= nch8) break;
+                tmem_ld_wait();
+                if (ch + groups_per_buf < nch8) tmem_ld8(trow + (ch + groups_per_buf) * 8, va);
+                finish(vb, ch);
+                ch += groups_per_buf;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + buf);
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (warp == 0) tmem_dealloc(tmem_base, (uint32_t)TC_TMEM_COLS);
 }
 
 static int pow2_at_least(int x, int lo) { int v = lo; while (v < x) v <<= 1; return v; }
 
-int launch_v2h_dense_tc(const DenseParams &d, cudaStream_t stream) {
+int launch_v2h_dense_tc(const DenseParams &d, long long row_stride, cudaStream_t stream) {
     TcParams p{};
     p.d = d;
     const int Kdim = 16 * ceil_div(4 * d.M, 16);
@@ -283,34 +364,42 @@ int launch_v2h_dense_tc(const DenseParams &d, cudaStream_t stream) {
     p.n_atoms = ceil_div(Kdim, 64);
     const int Kpad = 16 * ceil_div(d.K, 16);
     // motifs per CTA: as many as fit in shared memory (B resident for the whole kernel) and in one MMA (N <= 256)
+    const size_t smem_cap = 220 * 1024;
     int n_mtiles = ceil_div(Kpad, 256);
     int NT = 16 * ceil_div(ceil_div(Kpad, n_mtiles), 16);
-    while (tc_smem_bytes(NT, p.n_atoms) > 200 * 1024 && NT > 16) {
+    while (tc_smem_bytes(NT, p.n_atoms, 2) > smem_cap && NT > 16) {
         ++n_mtiles;
         NT = 16 * ceil_div(ceil_div(Kpad, n_mtiles), 16);
     }
     p.NT = NT;
     n_mtiles = ceil_div(d.K, NT);
-    p.tmem_stride = pow2_at_least(NT, 32);
-    p.tmem_cols = 2 * p.tmem_stride;
-    const long long total = (long long)d.n_rows * d.Lh;             // hidden positions
-    CRBM_CHECK_ARG((total + TC_TILE - 1) / TC_TILE < (1ll << 30), "v2h_dense_tc: more than 2^37 hidden positions in one call");
+    p.a_stages = tc_smem_bytes(NT, p.n_atoms, TC_MAX_A_STAGES) <= smem_cap ? TC_MAX_A_STAGES : 2;
+    p.tmem_stride = pow2_at_least(NT, 128);
+    p.nbuf = TC_TMEM_COLS / p.tmem_stride;                           // 4 accumulator buffers (N <= 128) or 2
+    // sector-aligned output rows (32-byte multiples): cut the tiles from rows padded to 32 positions, so that every warp
+    // store is 128 contiguous bytes starting on a sector boundary (scratch/store_align.cu: 5.9 TB/s vs 3.5 TB/s otherwise)
+    p.row_stride = row_stride;
+    const bool aligned = (row_stride % 8 == 0) && (((uintptr_t)d.out & 31) == 0);
+    p.LhV = aligned ? 32 * ceil_div(d.Lh, 32) : d.Lh;
+    p.store_len = aligned ? (int)(row_stride < p.LhV ? row_stride : p.LhV) : d.Lh;
+    const long long total = (long long)d.n_rows * p.LhV;            // (virtual) hidden positions
+    CRBM_CHECK_ARG((total + TC_TILE - 1) / TC_TILE < (1ll << 24), "v2h_dense_tc: more than 2^31 hidden positions in one call");
     p.n_tiles = (int)((total + TC_TILE - 1) / TC_TILE);
     p.scale = d.out_kind == CRBM_OUT_PROBABILITY ? -1.4426950408889634f : 1.0f;
-    const size_t smem = tc_smem_bytes(NT, p.n_atoms);
-    static size_t configured = 0;
-    if (smem > configured) {
-        CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    // the CTA allocates all 512 TMEM columns: ask for more than half of the shared memory so that two CTAs never share an SM
+    const size_t smem = tc_smem_bytes(NT, p.n_atoms, p.a_stages) > 120 * 1024 ? tc_smem_bytes(NT, p.n_atoms, p.a_stages) : 120 * 1024;
+    const bool prob = d.out_kind == CRBM_OUT_PROBABILITY;
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[prob]) {
+        CRBM_CHECK_CUDA(prob ? cudaFuncSetAttribute(v2h_dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                             : cudaFuncSetAttribute(v2h_dense_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[prob] = smem;
     }
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
-    if (per_sm > 2) per_sm = 2;
-    if (per_sm < 1) per_sm = 1;
-    int gx = (per_sm * num_sms()) / n_mtiles;
+    int gx = num_sms() / n_mtiles;
     if (gx < 1) gx = 1;
     if (gx > p.n_tiles) gx = p.n_tiles;
-    v2h_dense_tc_kernel<<<dim3(gx, n_mtiles), TC_THREADS, smem, stream>>>(p);
+    if (prob) v2h_dense_tc_kernel<true><<<dim3(gx, n_mtiles), TC_THREADS, smem, stream>>>(p);
+    else v2h_dense_tc_kernel<false><<<dim3(gx, n_mtiles), TC_THREADS, smem, stream>>>(p);
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }

@@ -16,7 +16,7 @@ namespace crbm {
 CRBM_FOR_EACH_MW(CRBM_DECLARE)
 #undef CRBM_DECLARE
 
-int launch_v2h_dense_tc(const DenseParams &, cudaStream_t);          // scan_tc.cu: tcgen05 / TMEM scan kernel
+int launch_v2h_dense_tc(const DenseParams &, long long row_stride, cudaStream_t);          // scan_tc.cu: tcgen05 / TMEM scan kernel
 static bool scan_uses_tcgen05() {
     static int v = -1;
     if (v < 0) { const char *e = getenv("CRBM_SCAN_KERNEL"); v = (e && e[0] == 'm') ? 0 : 1; }   // "mma" -> mma.sync kernel
@@ -586,10 +586,11 @@ size_t crbm_train_workspace_bytes(int K, int M) {
     return 3 * partial_floats(K, M) * sizeof(float) + 256;
 }
 
-int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const float *W, const float *b, int K, int M,
-                   int pooling, int strand_mode, int out_kind, float *out, void *stream) {
+int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L, const float *W, const float *b, int K, int M,
+                           int pooling, int strand_mode, int out_kind, float *out, long long out_row_stride, void *stream) {
     CRBM_CHECK_ARG(packed && W && b && out && N > 0, "crbm_v2h_dense: bad arguments");
     const int Lh = L - M + 1;
+    CRBM_CHECK_ARG(out_row_stride >= Lh, "crbm_v2h_dense: output row stride %lld < hidden length %d", out_row_stride, Lh);
     int rc = check_shape("crbm_v2h_dense", K, M, pooling, Lh);
     if (rc) return rc;
     CRBM_CHECK_ARG(strand_mode >= 0 && strand_mode <= 2 && (out_kind == 0 || out_kind == 1), "crbm_v2h_dense: bad mode");
@@ -601,7 +602,8 @@ int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const fl
     else pool = 1;
     Tiling t = make_tiling(K, M, pool, Lh, N);
     DenseParams p{packed, row_words, N, L, Lh, W, b, K, M, pool, strand_mode, out_kind, t.bv, t.nblk, t.n_items, out};
-    if (pool == 1 && scan_uses_tcgen05()) return launch_v2h_dense_tc(p, (cudaStream_t)stream);
+    if (pool == 1 && scan_uses_tcgen05()) return launch_v2h_dense_tc(p, out_row_stride, (cudaStream_t)stream);
+    if (out_row_stride != Lh) { set_error("crbm_v2h_dense: a padded output row stride needs pooling == 1"); return CRBM_ERR_UNSUPPORTED; }
     if (pool == 1) {
         // mma.sync tensor-pipe kernel (kept for comparison: CRBM_SCAN_KERNEL=mma): CTAs of one 16-motif m-tile, three per SM: size the grid to one full wave
         const int mtiles = ceil_div(K, 16);
@@ -611,6 +613,11 @@ int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const fl
         return dispatch_dense_mma(ceil_div(M, 4), p, dim3(mtiles, gy), (cudaStream_t)stream);
     }
     return dispatch_dense(t.MW, p, dim3(t.ktiles, t.gy), (cudaStream_t)stream);
+}
+
+int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const float *W, const float *b, int K, int M,
+                   int pooling, int strand_mode, int out_kind, float *out, void *stream) {
+    return crbm_v2h_dense_strided(packed, row_words, N, L, W, b, K, M, pooling, strand_mode, out_kind, out, (long long)(L - M + 1), stream);
 }
 
 int crbm_scan_reduce(const uint32_t *packed, int row_words, int N, int L, const float *W, const float *b, int K, int M,

@@ -72,6 +72,13 @@ int crbm_random_bases(uint32_t *packed, int row_words, int N, int L, uint64_t se
 int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L,
                    const float *W, const float *b, int K, int M, int pooling,
                    int strand_mode, int out_kind, float *out, void *stream);
+/* Same with padded output rows: row (n,k) starts at out + (n*K + k) * out_row_stride floats (out_row_stride >= Lh; the pad
+ * floats hold unspecified finite values). With out 32-byte aligned and out_row_stride a multiple of 8 every store of the tcgen05 scan
+ * kernel covers whole 32-byte sectors, which is what HBM write bandwidth needs (partial-sector writes cost ~1.7x:
+ * scratch/store_align.cu). out_row_stride == Lh is the reference's contiguous layout. Padded rows need pooling == 1. */
+int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L,
+                           const float *W, const float *b, int K, int M, int pooling,
+                           int strand_mode, int out_kind, float *out, long long out_row_stride, void *stream);
 
 /* ---- A7 with the callers' reductions fused in (reference secomo/utils.py:155,245-247 max over positions, :306 mean) -- */
 /* Per sequence and motif: maximum of the activity / hit probability over positions, the position of the first maximum

@@ -37,6 +37,7 @@ WORKLOADS = {
                batch=128, L=500, n_seq=65536, default_steps=512),
 }
 METRIC = 'CD-1 train nt/s'
+SCAN_TRAFFIC = None      # dram__bytes_read.sum + dram__bytes_write.sum of the scan launch (profiles/), filled in after the ncu capture
 
 
 def peaks():
@@ -313,7 +314,10 @@ def time_step_kernels(model, data, B, dev):
 
 
 def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
-    """getHitProbs kernel with fp32 output materialised in HBM; input and output larger than L2."""
+    """getHitProbs kernel (tcgen05 / TMEM, csrc/scan_tc.cu) with fp32 output materialised in HBM; input and output larger
+    than L2. Timed in the layout CRBM.motifHitProbs uses on the device (rows padded to a multiple of 8 floats, so every store
+    covers whole 32-byte sectors) and in the reference's contiguous (N,K,1,Lh) layout. Algorithmic bytes count Lh floats
+    per row in both cases."""
     import torch
     import crbm_b200
     from crbm_b200 import _lib
@@ -321,51 +325,50 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
     Lh = Lt - M + 1
     n = max(1024, min(200000, int(8e9 // (4 * K * Lh))))
     seqs = crbm_b200.PackedSequences.random(n, Lt, seed=99, device=dev)
-    out = torch.empty((n, K, 1, Lh), dtype=torch.float32, device=dev)
     s = _lib.stream_handle()
-
-    def go():
-        _lib.check(lib.crbm_v2h_dense(_lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias),
-                                      K, M, model.pooling, _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(out), s), 'scan')
-    for _ in range(3):
-        go()
-    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
-    e0.record()
-    for _ in range(reps):
-        go()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    ms_by_pitch = {}
+    for pitch in ((Lh + 7) // 8 * 8, Lh):
+        out = torch.empty((n, K, 1, pitch), dtype=torch.float32, device=dev)
+        ms_by_pitch[pitch] = timed(lambda: _lib.check(lib.crbm_v2h_dense_strided(
+            _lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias), K, M, model.pooling,
+            _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(out), pitch, s), 'scan'))
+        del out
+    pitch = (Lh + 7) // 8 * 8
+    ms = ms_by_pitch[pitch]
     nt = n * Lt
     alg = n * (Lt / 4.0) + 4.0 * n * K * Lh
     # fused reductions (max / argmax / mean over positions per sequence and motif): nothing but (N,K) results is written
     mx = torch.empty((n, K), dtype=torch.float32, device=dev)
     am = torch.empty((n, K), dtype=torch.int32, device=dev)
     mean = torch.empty((n, K), dtype=torch.float32, device=dev)
-
-    def go_red():
-        _lib.check(lib.crbm_scan_reduce(_lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias),
-                                        K, M, model.pooling, _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am),
-                                        _lib.ptr(mean), s), 'scan_reduce')
-    for _ in range(3):
-        go_red()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(reps):
-        go_red()
-    e1.record()
-    torch.cuda.synchronize()
-    ms_red = e0.elapsed_time(e1) / reps
+    ms_red = timed(lambda: _lib.check(lib.crbm_scan_reduce(
+        _lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias), K, M, model.pooling,
+        _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am), _lib.ptr(mean), s), 'scan_reduce'))
     return {'fused_reductions': {'metric': 'motif-scan nt/s, max/argmax/mean over positions fused (no dense output)',
                                  'value': nt / (ms_red * 1e-3), 'unit': 'nt/s', 'ms': ms_red},
             'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
             'sequences': n, 'ms': ms, 'output_GB': 4.0 * n * K * Lh / 1e9,
-            'roofline': {'bound': 'hbm', 'kernel': 'v2h_dense_mma_kernel', 'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
+            'layout': 'output rows padded from %d to %d floats (32-byte sectors); contiguous (N,K,1,Lh) layout: %.3f ms = %.3e nt/s'
+                      % (Lh, pitch, ms_by_pitch[Lh], nt / (ms_by_pitch[Lh] * 1e-3)),
+            'roofline': {'bound': 'hbm', 'kernel': 'v2h_dense_tc_kernel<PROB> (tcgen05.mma, TMEM accumulators)',
+                         'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
                          'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak,
-                         # ncu --set full on this launch (107 526 x 200 bp, K=100): 8.29 GB written + 0.33 GB read
-                         'traffic': 8.62e9 if (n == 107526 and K == 100) else None, 'algorithmic_bytes': alg,
+                         # ncu --set full on this launch (107 526 x 200 bp, K=100, padded rows): dram written + read
+                         'traffic': SCAN_TRAFFIC if (n == 107526 and K == 100) else None, 'algorithmic_bytes': alg,
                          'peak_source': peak_src, 'bytes_per_nt': alg / nt}}
 
 

@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) v2h_dense_tc_kernel(const TcPar
     uint64_t *a_free = empty + 4;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_free + TC_MAX_A_STAGES);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);         // warp-uniform for the compiler: uniform registers / branches
     const int kbase = blockIdx.y * p.NT;
     const int Kdim = 16 * p.ksteps;
     const int nbuf = p.nbuf, groups_per_buf = 4 / nbuf;
@@ -291,11 +292,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) v2h_dense_tc_kernel(const TcPar
         TilePos tp;
         tp.init(((int)blockIdx.x + buf * (int)gridDim.x) * TC_TILE, p.LhV);
         for (int i = buf, u = 0; i < my_tiles; i += nbuf, ++u) {
+            // output address = warp-uniform 64-bit row base (sequence tp.n0, motif kbase + 8 ch) + per-thread 32-bit byte offset
+            // (its sequence relative to tp.n0, its position, the motif inside the chunk): one STG per value, no 64-bit math
             int n, j;
             tp.row(32 * q + lane, p.LhV, n, j);
-            tp.advance(stride_pos * nbuf, p.LhV);
             const bool valid = n < d.n_rows && j < p.store_len;
-            float *orow = d.out + ((size_t)n * d.K + kbase) * (size_t)p.row_stride + j;
+            const uint32_t rs4 = (uint32_t)p.row_stride * 4u;
+            const uint32_t off0 = (uint32_t)(n - tp.n0) * (uint32_t)d.K * rs4 + (uint32_t)j * 4u;
+            uint32_t offc[8];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) offc[c] = off0 + (uint32_t)c * rs4;
+            char *ub_tile = reinterpret_cast<char *>(d.out) + ((size_t)tp.n0 * d.K + kbase) * (size_t)p.row_stride * 4;
+            tp.advance(stride_pos * nbuf, p.LhV);
             mbar_wait(full + buf, (uint32_t)(u & 1));
             tc_fence_after();
             auto finish = [&](uint32_t (&v)[8], int ch) {
@@ -304,29 +312,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) v2h_dense_tc_kernel(const TcPar
                 const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                 float x[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    x[c] = __uint_as_float(v[c]) + bb[c];
-                    if (PROB) {
-                        float t;
-                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x[c]));
-                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x[c]) : "f"(1.0f + t));
+                for (int c = 0; c < 8; ++c) x[c] = __uint_as_float(v[c]) + bb[c];
+                if (PROB) {
+                    // p = 1 / (1 + 2^x) with x = -log2(e) * activity. The MUFU pipe is the busiest unit of this kernel
+                    // (two ops per output), so two outputs share one reciprocal: r = 1 / ((1+e0)(1+e1)), p0 = r (1+e1),
+                    // p1 = r (1+e0). x is clamped to 60 so that the product stays finite (p < 1e-18 is unaffected at 1e-5).
+#pragma unroll
+                    for (int c = 0; c < 8; c += 2) {
+                        float e0, e1, r;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(x[c], 60.f)));
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(x[c + 1], 60.f)));
+                        const float a0 = 1.0f + e0, a1 = 1.0f + e1;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a0 * a1));
+                        x[c] = r * a1;
+                        x[c + 1] = r * a0;
                     }
                 }
-                // one pointer per motif row, advanced by the row stride: the stores are predicated, never branched around
-                float *o = orow + (size_t)ch * stride8;
+                char *ub = ub_tile + (size_t)ch * stride8 * 4;
                 const int krem = kvalid - ch * 8;                        // valid motifs in this chunk (warp-uniform)
                 if (krem >= 8) {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        if (valid) __stcs(o, x[c]);
-                        o += p.row_stride;
-                    }
+                    for (int c = 0; c < 8; ++c)
+                        if (valid) __stcs(reinterpret_cast<float *>(ub + offc[c]), x[c]);
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        if (valid && c < krem) __stcs(o, x[c]);
-                        o += p.row_stride;
-                    }
+                    for (int c = 0; c < 8; ++c)
+                        if (valid && c < krem) __stcs(reinterpret_cast<float *>(ub + offc[c]), x[c]);
                 }
             };
             // the TMEM load of the next chunk is in flight while the current one is finished
@@ -383,6 +394,7 @@ int launch_v2h_dense_tc(const DenseParams &d, long long row_stride, cudaStream_t
     p.LhV = aligned ? 32 * ceil_div(d.Lh, 32) : d.Lh;
     p.store_len = aligned ? (int)(row_stride < p.LhV ? row_stride : p.LhV) : d.Lh;
     const long long total = (long long)d.n_rows * p.LhV;            // (virtual) hidden positions
+    CRBM_CHECK_ARG((long long)d.K * row_stride * (TC_TILE / p.LhV + 3) < (1ll << 29), "v2h_dense_tc: K * row stride too large for 32-bit tile offsets");
     CRBM_CHECK_ARG((total + TC_TILE - 1) / TC_TILE < (1ll << 24), "v2h_dense_tc: more than 2^31 hidden positions in one call");
     p.n_tiles = (int)((total + TC_TILE - 1) / TC_TILE);
     p.scale = d.out_kind == CRBM_OUT_PROBABILITY ? -1.4426950408889634f : 1.0f;

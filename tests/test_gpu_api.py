@@ -154,7 +154,7 @@ def test_statistics_vector_is_additive_across_shards(data):
 @pytest.mark.parametrize('K,M,L,ds', [(100, 15, 200, True), (33, 9, 77, False), (16, 25, 500, True)])
 def test_fused_scan_reductions_match_dense_scan(K, M, L, ds):
     """max / argmax / mean over positions computed inside the scan kernel == the same reductions of the
-    dense motifHitProbs tensor (argmax bit-exact, numpy first-maximum semantics)."""
+    dense motifHitProbs tensor (argmax exact wherever the maximum is unique at fp32 resolution, numpy first-maximum semantics)."""
     import crbm_b200
     rs = np.random.RandomState(K + L)
     m = crbm_b200.CRBM(K, M, doublestranded=ds, seed=1)
@@ -163,8 +163,15 @@ def test_fused_scan_reductions_match_dense_scan(K, M, L, ds):
     seqs = crbm_b200.PackedSequences.random(37, L, seed=3)
     dense = m.motifHitProbs(seqs)[:, :, 0, :]
     got = m.motifHitSummary(seqs)
-    np.testing.assert_array_equal(got['max'], dense.max(axis=2))
-    np.testing.assert_array_equal(got['argmax'], dense.argmax(axis=2))
+    # the dense scan runs on tcgen05 (fp16 hi/lo split of W), the fused reductions on mma.sync (bf16 x3 split): the two agree
+    # to fp32 rounding, so the maxima are compared at 2e-6 and the hit position wherever the maximum is not a near-tie
+    np.testing.assert_allclose(got['max'], dense.max(axis=2), rtol=2e-6, atol=2e-7)
+    srt = np.sort(dense, axis=2)
+    clear = (srt[:, :, -1] - srt[:, :, -2]) > 4e-6 * np.maximum(srt[:, :, -1], 1e-3)
+    assert clear.mean() > 0.95
+    np.testing.assert_array_equal(got['argmax'][clear], dense.argmax(axis=2)[clear])
+    at = np.take_along_axis(dense, got['argmax'][:, :, None].astype(np.int64), axis=2)[:, :, 0]
+    np.testing.assert_allclose(at, dense.max(axis=2), rtol=4e-6, atol=4e-7)     # near-ties: the reported position is a maximum
     np.testing.assert_allclose(got['mean'], dense.mean(axis=2), rtol=1e-5, atol=1e-7)
 
 

@@ -341,13 +341,14 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
         return e0.elapsed_time(e1) / reps
 
     ms_by_pitch = {}
-    for pitch in ((Lh + 7) // 8 * 8, Lh):
+    pitch_fast = (Lh + 7) // 8 * 8 if model.pooling == 1 else Lh     # pooled probabilities: CUDA-core kernel, contiguous rows only
+    for pitch in sorted({pitch_fast, Lh}, reverse=True):
         out = torch.empty((n, K, 1, pitch), dtype=torch.float32, device=dev)
         ms_by_pitch[pitch] = timed(lambda: _lib.check(lib.crbm_v2h_dense_strided(
             _lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias), K, M, model.pooling,
             _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(out), pitch, s), 'scan'))
         del out
-    pitch = (Lh + 7) // 8 * 8
+    pitch = pitch_fast
     ms = ms_by_pitch[pitch]
     nt = n * Lt
     alg = n * (Lt / 4.0) + 4.0 * n * K * Lh
@@ -364,7 +365,8 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
             'sequences': n, 'ms': ms, 'output_GB': 4.0 * n * K * Lh / 1e9,
             'layout': 'output rows padded from %d to %d floats (32-byte sectors); contiguous (N,K,1,Lh) layout: %.3f ms = %.3e nt/s'
                       % (Lh, pitch, ms_by_pitch[Lh], nt / (ms_by_pitch[Lh] * 1e-3)),
-            'roofline': {'bound': 'hbm', 'kernel': 'v2h_dense_tc_kernel<PROB> (tcgen05.mma, TMEM accumulators)',
+            'roofline': {'bound': 'hbm', 'kernel': ('v2h_dense_tc_kernel<PROB> (tcgen05.mma, TMEM accumulators)' if model.pooling == 1 else
+                                                 'v2h_dense_kernel (CUDA cores, pooling > 1)'),
                          'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
                          'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak,
                          # ncu --set full on this launch (107 526 x 200 bp, K=100, padded rows): dram written + read

@@ -64,6 +64,7 @@ SIGNATURES = {
     'crbm_hidden_words': (c_int, [c_int]),
     'crbm_fantasy_words': (c_int, []),
     'crbm_pack_onehot': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    'crbm_pack_onehot_accumulate': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'crbm_pack_codes': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     'crbm_unpack_onehot': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     'crbm_random_bases': (c_int, [c_void_p, c_int, c_int, c_int, c_u64, c_void_p]),

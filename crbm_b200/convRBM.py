@@ -687,31 +687,30 @@ class CRBM(object):
         self._train_packed(seqs, 0, seqs.N, uniforms, local_shard)
 
     def _check_deferred(self):
-        """Raise if the one-hot validation of an earlier streamlined training call failed."""
+        """Raise if the one-hot validation of an earlier streamlined training call failed (the kernels keep a running
+        count on the device; it is read here, at the synchronisation points of the API, not once per minibatch)."""
         eng = getattr(self, '_onehot_engine', None)
         if eng is not None and eng.get('pending'):
-            eng['event'].synchronize()
             eng['pending'] = False
-            if int(eng['bad_host'][0]) != 0:
-                raise ValueError("input is not one-hot at %d positions (expected exactly one 1 among A,C,G,T)"
-                                 % int(eng['bad_host'][0]))
+            nbad = int(eng['bad'].item())
+            if nbad != 0:
+                eng['bad'].zero_()
+                raise ValueError("input is not one-hot at %d positions (expected exactly one 1 among A,C,G,T)" % nbad)
 
     def _train_step_onehot(self, data):
         lib = self._require_cuda()
         torch = _torch()
-        self._check_deferred()
         n, L = int(data.shape[0]), int(data.shape[3])
         if tuple(data.shape[1:3]) != (1, 4):
             raise ValueError("expected one-hot data of shape (N,1,4,L), got %r" % (tuple(data.shape),))
         eng = getattr(self, '_onehot_engine', None)
         if eng is None or eng['key'] != (n, L):
+            self._check_deferred()
             rw = lib.crbm_packed_row_words(L)
-            eng = dict(key=(n, L), graph=None, pending=False)
+            eng = dict(key=(n, L), graph=None, pending=False, dev_step=-1)
             eng['staging'] = torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device)
             eng['words'] = torch.zeros((n, rw), dtype=torch.int32, device=self._device)
             eng['bad'] = torch.zeros(1, dtype=torch.int32, device=self._device)
-            eng['bad_host'] = torch.zeros(1, dtype=torch.int32).pin_memory()
-            eng['event'] = torch.cuda.Event()
             eng['step_dev'] = torch.zeros(1, dtype=torch.int64, device=self._device)
             a = self._fill_args(eng['words'].data_ptr(), rw, n, L)
             a.step_dev = eng['step_dev'].data_ptr()
@@ -719,32 +718,32 @@ class CRBM(object):
             self._onehot_engine = eng
         src = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)) if isinstance(data, np.ndarray) else data
         eng['staging'].copy_(src, non_blocking=True)
-        eng['step_dev'].fill_(self._step)
+        if eng['dev_step'] != self._step:             # the update kernel advances the device-side step counter itself
+            eng['step_dev'].fill_(self._step)
 
         def body():
             s = _lib.stream_handle()
-            _lib.check(lib.crbm_pack_onehot(_lib.ptr(eng['staging']), n, L, _lib.ptr(eng['words']), eng['rw'],
-                                            _lib.ptr(eng['bad']), s), 'pack_onehot')
+            _lib.check(lib.crbm_pack_onehot_accumulate(_lib.ptr(eng['staging']), n, L, _lib.ptr(eng['words']), eng['rw'],
+                                                       _lib.ptr(eng['bad']), s), 'pack_onehot')
             _lib.check(lib.crbm_train_step(eng['args'], s), 'train_step')
 
         if eng['graph'] is None:
             body()                                   # first call eagerly (one-time kernel attribute setup), then capture
             torch.cuda.synchronize(self._device)
             g = torch.cuda.CUDAGraph()
-            saved = [t.clone() for t in (self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
-                                         self._t_fantasy, eng['step_dev'])]
+            tensors = (self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc, self._t_fantasy, eng['step_dev'],
+                       eng['bad'])
+            saved = [t.clone() for t in tensors]
             with torch.cuda.graph(g):
                 body()
-            for t, v in zip((self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
-                             self._t_fantasy, eng['step_dev']), saved):
+            for t, v in zip(tensors, saved):
                 t.copy_(v)
             eng['graph'] = g
         else:
             eng['graph'].replay()
-        eng['bad_host'].copy_(eng['bad'], non_blocking=True)
-        eng['event'].record()
         eng['pending'] = True
         self._step += 1
+        eng['dev_step'] = self._step
 
     def _evaluateData(self, data, uniforms=None):
         """[mean free energy, mean of a sampled forward-strand H] (reference :466-472, 517-522)."""

@@ -222,14 +222,21 @@ using namespace crbm;
 
 extern "C" {
 
-int crbm_pack_onehot(const float *onehot, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream) {
+static int pack_onehot_impl(const float *onehot, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream, bool reset) {
     CRBM_CHECK_ARG(onehot && packed && bad_count && N > 0 && L > 0, "crbm_pack_onehot: bad arguments");
     CRBM_CHECK_ARG(row_words >= packed_row_words(L), "crbm_pack_onehot: row_words %d < %d", row_words, packed_row_words(L));
     cudaStream_t s = (cudaStream_t)stream;
-    CRBM_CHECK_CUDA(cudaMemsetAsync(bad_count, 0, sizeof(int), s));
+    if (reset) CRBM_CHECK_CUDA(cudaMemsetAsync(bad_count, 0, sizeof(int), s));
     pack_onehot_kernel<<<blocks_for((long long)N * row_words, 256), 256, 0, s>>>(onehot, N, L, packed, row_words, bad_count);
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
+}
+
+int crbm_pack_onehot(const float *onehot, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream) {
+    return pack_onehot_impl(onehot, N, L, packed, row_words, bad_count, stream, true);
+}
+int crbm_pack_onehot_accumulate(const float *onehot, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream) {
+    return pack_onehot_impl(onehot, N, L, packed, row_words, bad_count, stream, false);
 }
 
 int crbm_pack_codes(const uint8_t *codes, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream) {

@@ -59,6 +59,9 @@ int         crbm_fantasy_words(void);              /* uint32 words per (strand, 
 /* one-hot (N,1,4,L) fp32 -> packed rows. *bad_count (device int, zeroed by the callee) receives the number of
  * positions that are not exactly one-hot. */
 int crbm_pack_onehot(const float *onehot, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream);
+/* same, but *bad_count is added to instead of being reset: a host that validates lazily (once per synchronisation point,
+ * not once per minibatch) keeps one running counter */
+int crbm_pack_onehot_accumulate(const float *onehot, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream);
 /* base codes (N,L) uint8 in {0,1,2,3} -> packed rows; codes > 3 are counted in *bad_count. */
 int crbm_pack_codes(const uint8_t *codes, int N, int L, uint32_t *packed, int row_words, int *bad_count, void *stream);
 /* packed rows -> one-hot (N,1,4,L) fp32 */

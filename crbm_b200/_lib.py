@@ -20,6 +20,7 @@ MAX_MOTIF_LEN = 33
 MAX_POOLING = 16
 STRAND_FWD, STRAND_RC, STRAND_SUM = 0, 1, 2
 OUT_ACTIVITY, OUT_PROBABILITY = 0, 1
+PHASE_NEGATIVE, PHASE_POSITIVE, PHASE_REDUCE, PHASE_APPLY = 1, 2, 4, 8
 
 
 class TrainArgs(ctypes.Structure):
@@ -85,6 +86,7 @@ SIGNATURES = {
     'crbm_train_accumulate': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_apply': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_step': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
+    'crbm_train_phases': (c_int, [ctypes.POINTER(TrainArgs), c_int, c_void_p]),
     'crbm_train_accumulate_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
     'crbm_train_apply_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
     'crbm_train_stats_layout': (c_int, [c_int, c_int, ctypes.POINTER(StatsLayout)]),

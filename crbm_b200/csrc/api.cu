@@ -1,5 +1,6 @@
 // Error plumbing, device queries and the trivial entry points of the C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include "common.cuh"
 
@@ -15,6 +16,12 @@ void set_error(const char *fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CRBM_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 
 int num_sms() {
     static int sms = 0;

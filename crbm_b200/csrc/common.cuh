@@ -23,6 +23,25 @@ void count_launch(int n = 1);
 #define CRBM_CHECK_LAUNCH() do { crbm::count_launch(); CRBM_CHECK_CUDA(cudaPeekAtLastError()); } while (0)
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// The kernels of a training step form a chain (h2v -> v2h -> reduce -> update -> next h2v ...). Launched with the
+// programmatic-stream-serialization attribute, a kernel may start as soon as every CTA of its predecessor has executed
+// griddepcontrol.launch_dependents; it runs its prologue (staging W, building fragments) and blocks in griddepcontrol.wait
+// until the predecessor has completed and flushed. Stream capture records this as a programmatic graph edge.
+// CRBM_PDL=0 turns the attribute off (the device-side instructions are then no-ops).
+bool pdl_enabled();
+template <typename P>
+inline cudaError_t launch_chain(void (*kernel)(P), dim3 grid, dim3 block, size_t smem, cudaStream_t s, const P &params, bool pdl = true) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, params);
+}
 inline int packed_row_words(int L) { return 4 * ceil_div(FRONT_PAD_WORDS + ceil_div(L, 16) + BACK_PAD_WORDS, 4); }
 int num_sms();
 
@@ -60,6 +79,9 @@ __host__ __device__ inline float u01(uint32_t x) { return (float)(x >> 8) * (1.0
 enum : uint32_t { RNG_BASES = 1, RNG_HIDDEN = 2, RNG_HIDDEN_RC = 3, RNG_VISIBLE = 4, RNG_EVAL = 5, RNG_API = 6 };
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- packed 2-bit sequence access -----------------------------------------------------------------------------
 // Base i (i >= -16) of a row sits at bit 2*(i+16).
 __device__ __forceinline__ int base_at(const uint32_t *__restrict__ row, int i) {

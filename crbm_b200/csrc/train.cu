@@ -131,6 +131,9 @@ constexpr int H2V_LIST = 1024 + 4;     // a round holds at most 32 words x 32 bi
 __global__ void __launch_bounds__(512) h2v_bits_kernel(const H2VParams p) {
     extern __shared__ __align__(128) unsigned char h2v_smem[];
     const int M = p.M, Lv = FANTASY_LEN + M - 1;
+    // programmatic dependent launch: W (update kernel) and the bit planes (previous sweep) come from the predecessors
+    pdl_wait();
+    pdl_launch_dependents();
     // the motif bank is staged once per CTA by the TMA engine: L1 is cold at kernel start, and every hit reads two
     // short rows of W, so fetching them one miss at a time would serialise L2 round trips
     const float *Wsm = p.W;
@@ -306,12 +309,14 @@ __device__ __forceinline__ void reduce_publish(const ReduceParams &p) {
 }
 
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const ReduceParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
     reduce_partials_body(p);
     reduce_publish(p);
 }
 
 __device__ __forceinline__ void reduce_partials_body(const ReduceParams &p) {
-    __shared__ float sh[4][32];
+    __shared__ float sh[4][32], shr[4][32];
     if ((int)blockIdx.x >= p.block_start[p.nsets]) {
         const int w = blockIdx.x - p.block_start[p.nsets];
         if (p.cnt_n[w] > 0) {
@@ -330,13 +335,23 @@ __device__ __forceinline__ void reduce_partials_body(const ReduceParams &p) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.counts) {
         p.counts[0] = p.c0; p.counts[1] = p.c1; p.counts[2] = p.c2; p.counts[3] = p.c3;
     }
+    // h_sum = sum_p + sum_pr is written once, by the CTA of the sum_p slot, which also adds the partials of the matching
+    // sum_pr slot (`pair` slots further); the CTA of the sum_pr slot has nothing left to do. No atomics, no zeroing.
+    const int tail = o - S.np - S.nq, pair = p.mma ? 2 : 1;
+    if (tail >= pair && tail < 2 * pair) return;
+    const bool with_rc = tail >= 0 && tail < pair;
     const float *src = S.partial + ((size_t)kt * S.gy * S.nacc + o) * 32 + lane;
-    float v = 0.f;
-    for (int c = warp; c < S.gy; c += 4) v += src[(size_t)c * S.nacc * 32];
+    float v = 0.f, vr = 0.f;
+    for (int c = warp; c < S.gy; c += 4) {
+        v += src[(size_t)c * S.nacc * 32];
+        if (with_rc) vr += src[((size_t)c * S.nacc + pair) * 32];
+    }
     sh[warp][lane] = v;
+    shr[warp][lane] = vr;
     __syncthreads();
     if (warp != 0) return;
     v = (sh[0][lane] + sh[1][lane]) + (sh[2][lane] + sh[3][lane]);
+    vr = (shr[0][lane] + shr[1][lane]) + (shr[2][lane] + shr[3][lane]);
     if (p.mma) {
         // fragment order (v2h_mma.cuh), kt = m-tile of 16 motifs: slot t*4+r of lane (g,q) = motif 16kt + 8(r>>1) + g,
         // column 8t + 2q + (r&1) = 4m + a; then sum_p[h], sum_pr[h], sum_q[h] on the q == 0 lanes
@@ -352,9 +367,8 @@ __device__ __forceinline__ void reduce_partials_body(const ReduceParams &p) {
             const int w = o - S.np - S.nq, which = w >> 1, h = w & 1;
             const int k = kt * 16 + 8 * h + g;
             if (k < p.K) {
-                if (which == 0) { if (S.h_fwd) S.h_fwd[k] = v; if (S.h_sum) atomicAdd(S.h_sum + k, v); }
-                else if (which == 1) { if (S.h_sum) atomicAdd(S.h_sum + k, v); }
-                else if (S.h_q) S.h_q[k] = v;
+                if (which == 0) { if (S.h_fwd) S.h_fwd[k] = v; if (S.h_sum) S.h_sum[k] = v + vr; }
+                else if (which == 2 && S.h_q) S.h_q[k] = v;
             }
         }
     } else {
@@ -367,8 +381,7 @@ __device__ __forceinline__ void reduce_partials_body(const ReduceParams &p) {
             if (m < p.M) (isq ? S.vh_q : S.vh_p)[((size_t)k * 4 + a) * p.M + m] = v;
         } else {
             const int w = o - S.np - S.nq;
-            if (w == 0) { if (S.h_fwd) S.h_fwd[k] = v; if (S.h_sum) atomicAdd(S.h_sum + k, v); }
-            else if (w == 1) { if (S.h_sum) atomicAdd(S.h_sum + k, v); }
+            if (w == 0) { if (S.h_fwd) S.h_fwd[k] = v; if (S.h_sum) S.h_sum[k] = v + vr; }
             else if (w == 2) { if (S.h_q) S.h_q[k] = v; }
         }
     }
@@ -386,6 +399,8 @@ struct ApplyParams {
     int n_batches;
 };
 __global__ void apply_update_kernel(const ApplyParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nW = p.K * 4 * p.M;
     const float *st = p.stats;
@@ -463,6 +478,8 @@ __device__ __forceinline__ void p2p_sums(const ApplyP2PParams &p, const int (&id
     }
 }
 __global__ void __launch_bounds__(256) apply_update_p2p_kernel(const ApplyP2PParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
     const ApplyParams &ap = p.ap;
     if (threadIdx.x < p.n_ranks) {
         const unsigned long long want = p.sequence_dev ? *p.sequence_dev + 1ull : p.sequence;
@@ -668,7 +685,16 @@ int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const 
 }
 
 extern "C" int crbm_train_apply(const crbm_train_args *a, void *stream);
-static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fuse_apply, const crbm_p2p_args *p2p = nullptr) {
+// One training step as a chain of launches on ONE stream, in the order
+//     h2v -> v2h(chain, sample) [x cd_k]  ->  v2h(minibatch: P, Q statistics)  ->  reduce  ->  update
+// every kernel launched as a programmatic dependent of the one before it (common.cuh: launch_chain): the next grid's CTAs move in
+// while the previous grid drains, run their prologue, and block in griddepcontrol.wait. The positive phase is independent of the chain
+// sweeps and only waits before it exits (V2HParams::pdl_late), so it also overlaps their tail. (An earlier version forked the
+// positive phase to a side stream; the two v2h grids each fill the register files, so they never ran side by side: measured
+// `accumulate` - `accumulate without positive phase` = the positive kernel's stand-alone time.)
+// `phases` selects which part is launched; the partial-sum buffers in the workspace are fixed, so the parts may be issued by
+// separate calls (e.g. the chain sweeps while the next minibatch is still being copied in).
+static int train_phases_impl(const crbm_train_args *a, int phases, void *stream, const crbm_p2p_args *p2p = nullptr) {
     CRBM_CHECK_ARG(a && a->W && a->b && a->c && a->data && a->fantasy_bits && a->v_model && a->stats && a->workspace,
                    "crbm_train_accumulate: null pointer in args");
     const int K = a->K, M = a->M, P = a->pooling, Lh = a->L - M + 1;
@@ -687,7 +713,6 @@ static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fu
     crbm_stats_layout lay;
     fill_layout(K, M, &lay);
     float *st = a->stats;
-    CRBM_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(float) * lay.total, s));
     const int kw = ceil_div(K, 32);
     const int ds = a->doublestranded ? 1 : 0;
     float *part0 = reinterpret_cast<float *>(a->workspace);
@@ -696,20 +721,9 @@ static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fu
     // pooling == 1: both contractions on the tensor pipe (v2h_mma.cuh); otherwise the CUDA-core kernel (v2h.cuh)
     const bool mma = P == 1;
     const int KS = ceil_div(M, 4);
-    // The positive phase (minibatch) and the negative phase (persistent chain) only meet in the reduction: the positive
-    // kernels go to a side stream (forked/joined with events, which stream capture records as graph edges), so their
-    // ramp-up and tail overlap h2v and the negative-phase kernel instead of serialising with them.
-    static cudaStream_t side = nullptr;
-    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    if (!side) {
-        CRBM_CHECK_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-        CRBM_CHECK_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-        CRBM_CHECK_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    }
-    cudaStream_t cur = s;                                  // stream the fused kernels are launched on
     auto run_fused = [&](int flags, const V2HParams &p, const Tiling &t) -> int {
-        return mma ? dispatch_mma(KS, flags, p, dim3(ceil_div(K, 16), mma_gy(K, t.n_items)), cur)
-                   : dispatch_fused(t.MW, flags, p, dim3(t.ktiles, t.gy), cur);
+        return mma ? dispatch_mma(KS, flags, p, dim3(ceil_div(K, 16), mma_gy(K, t.n_items)), s)
+                   : dispatch_fused(t.MW, flags, p, dim3(t.ktiles, t.gy), s);
     };
     ReduceParams red{};
     red.ktiles = mma ? ceil_div(K, 16) : ceil_div(K, KTILE);        // tiles of the partial buffers: m-tiles / k-tiles
@@ -724,6 +738,49 @@ static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fu
         return S;
     };
 
+    // ---- negative phase: cd_k Gibbs sweeps of the persistent chain (convRBM.py:391-413) -----------------------------
+    Tiling tn = make_tiling(K, M, P, FANTASY_LEN, a->batchsize);
+    if (phases & CRBM_PHASE_NEGATIVE) {
+        const size_t n_u_v = (size_t)a->batchsize * Lv, n_u_h = (size_t)a->batchsize * K * (FANTASY_LEN / P);
+        const size_t bits_bytes = (size_t)2 * a->batchsize * kw * FANTASY_WORDS * sizeof(uint32_t);
+        const size_t w_bytes = (size_t)K * 16 * M;
+        const int h2v_items = a->batchsize * ceil_div(Lv, 16);
+        int h2v_nw = ceil_div(h2v_items, num_sms());
+        h2v_nw = h2v_nw < 2 ? 2 : h2v_nw > 16 ? 16 : h2v_nw;
+        const size_t list_bytes = (size_t)h2v_nw * H2V_LIST * sizeof(uint32_t);
+        const int w_in_smem = w_bytes + 16 + list_bytes <= 200 * 1024;
+        const size_t list_offset = w_in_smem ? w_bytes + 16 : 16;
+        const size_t h2v_smem = list_offset + list_bytes;
+        static size_t h2v_smem_configured = 48 * 1024;
+        if (h2v_smem > h2v_smem_configured) {
+            CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h2v_smem));
+            h2v_smem_configured = h2v_smem;
+        }
+        for (int it = 0; it < a->cd_k; ++it) {
+            const bool last = it == a->cd_k - 1;
+            H2VParams h{};
+            h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.kw = kw; h.M = M; h.ds = ds; h.w_in_smem = w_in_smem; h.words_per_row = ceil_div(Lv, 16); h.list_offset = (int)list_offset;
+            h.W = a->W; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words;
+            h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
+            h.seed = a->seed; h.step_dev = a->step_dev;
+            h.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
+            CRBM_CHECK_CUDA(launch_chain(h2v_bits_kernel, dim3(ceil_div(h2v_items, h2v_nw)), dim3(32 * h2v_nw), h2v_smem, s, h));
+            CRBM_CHECK_LAUNCH();
+
+            V2HParams q{};
+            q.packed = a->v_model; q.row_words = a->v_row_words; q.n_rows = a->batchsize; q.L = Lv; q.Lh = FANTASY_LEN;
+            q.W = a->W; q.b = a->b; q.K = K; q.M = M; q.pooling = P; q.ds = ds;
+            q.bv = tn.bv; q.nblk = tn.nblk; q.n_items = tn.n_items;
+            q.partial = part1; q.bits = a->fantasy_bits;
+            q.u_fwd = a->u_h ? a->u_h + it * n_u_h : nullptr;
+            q.u_rc = a->u_hp ? a->u_hp + it * n_u_h : nullptr;
+            q.seed = a->seed; q.step_dev = a->step_dev;
+            q.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
+            if (!mma) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));   // CUDA-core sampler ORs its hits in
+            if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
+        }
+    }
+
     // ---- positive phase on the minibatch (convRBM.py:377-388) and the sparsity statistic (:440-451) ----------
     Tiling t = make_tiling(K, M, P, Lh, a->n_data);
     V2HParams p{};
@@ -731,101 +788,67 @@ static int train_accumulate_impl(const crbm_train_args *a, void *stream, bool fu
     p.W = a->W; p.b = a->b; p.K = K; p.M = M; p.pooling = P; p.ds = ds;
     p.bv = t.bv; p.nblk = t.nblk; p.n_items = t.n_items;
     p.batch_index = a->batch_index_dev;
+    p.pdl_late = 1;
     const bool combined = mma ? KS <= 4 : t.MW <= 15;
-    if (a->n_data > 0) {
-        CRBM_CHECK_CUDA(cudaEventRecord(ev_fork, s));       // after the memset of stats
-        CRBM_CHECK_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-        cur = side;
-    }
+    const bool pos = (phases & CRBM_PHASE_POSITIVE) != 0;
     if (a->n_data == 0) {
-        // a data-parallel rank whose shard of a short batch is empty contributes zeros
+        // a data-parallel rank whose shard of a short batch is empty contributes zeros (its statistics are not written below)
+        if (phases & CRBM_PHASE_REDUCE) CRBM_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(float) * lay.total, s));
     } else if (combined) {
         p.partial = part0;
-        if ((rc = run_fused(F_STAT_P | F_STAT_Q, p, t))) return rc;
+        if (pos && (rc = run_fused(F_STAT_P | F_STAT_Q, p, t))) return rc;
         ReduceSet &S = add_set(part0, t, true, true);
         S.vh_p = st + lay.vh_data; S.vh_q = st + lay.vh_q;
         S.h_sum = st + lay.h_data; S.h_fwd = st + lay.h_fwd; S.h_q = st + lay.h_q;
     } else {
         p.partial = part0;
-        if ((rc = run_fused(F_STAT_P, p, t))) return rc;
+        if (pos && (rc = run_fused(F_STAT_P, p, t))) return rc;
         ReduceSet &S = add_set(part0, t, true, false);
         S.vh_p = st + lay.vh_data; S.h_sum = st + lay.h_data; S.h_fwd = st + lay.h_fwd;
         p.partial = part2;
-        if ((rc = run_fused(F_STAT_Q, p, t))) return rc;
+        if (pos && (rc = run_fused(F_STAT_Q, p, t))) return rc;
         ReduceSet &Sq = add_set(part2, t, false, true);
         Sq.vh_q = st + lay.vh_q; Sq.h_q = st + lay.h_q;
     }
-    if (a->n_data > 0) CRBM_CHECK_CUDA(cudaEventRecord(ev_join, side));
-    cur = s;
 
-    // ---- negative phase: cd_k Gibbs sweeps of the persistent chain (convRBM.py:391-413) -----------------------------
-    Tiling tn = make_tiling(K, M, P, FANTASY_LEN, a->batchsize);
-    const size_t n_u_v = (size_t)a->batchsize * Lv, n_u_h = (size_t)a->batchsize * K * (FANTASY_LEN / P);
-    const size_t bits_bytes = (size_t)2 * a->batchsize * kw * FANTASY_WORDS * sizeof(uint32_t);
-    const size_t w_bytes = (size_t)K * 16 * M;
-    const int h2v_items = a->batchsize * ceil_div(Lv, 16);
-    int h2v_nw = ceil_div(h2v_items, num_sms());
-    h2v_nw = h2v_nw < 2 ? 2 : h2v_nw > 16 ? 16 : h2v_nw;
-    const size_t list_bytes = (size_t)h2v_nw * H2V_LIST * sizeof(uint32_t);
-    const int w_in_smem = w_bytes + 16 + list_bytes <= 200 * 1024;
-    const size_t list_offset = w_in_smem ? w_bytes + 16 : 16;
-    const size_t h2v_smem = list_offset + list_bytes;
-    static size_t h2v_smem_configured = 48 * 1024;
-    if (h2v_smem > h2v_smem_configured) {
-        CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h2v_smem));
-        h2v_smem_configured = h2v_smem;
-    }
-    for (int it = 0; it < a->cd_k; ++it) {
-        const bool last = it == a->cd_k - 1;
-        H2VParams h{};
-        h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.kw = kw; h.M = M; h.ds = ds; h.w_in_smem = w_in_smem; h.words_per_row = ceil_div(Lv, 16); h.list_offset = (int)list_offset;
-        h.W = a->W; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words;
-        h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
-        h.seed = a->seed; h.step_dev = a->step_dev;
-        h.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
-        h2v_bits_kernel<<<ceil_div(h2v_items, h2v_nw), 32 * h2v_nw, h2v_smem, s>>>(h);
+    // ---- per-CTA partial sums of both phases -> statistics vector ---------------------------------------------------------
+    if (phases & CRBM_PHASE_REDUCE) {
+        ReduceSet &Sn = add_set(part1, tn, true, false);
+        Sn.vh_p = st + lay.vh_model; Sn.h_sum = st + lay.h_model;
+        red.counts = st + lay.n_hidden_data;
+        red.c0 = (float)a->n_data * Lh; red.c1 = (float)a->batchsize * FANTASY_LEN;
+        red.c2 = (float)a->n_data * a->L; red.c3 = (float)a->batchsize * Lv;
+        red.cnt_rows[0] = a->data; red.cnt_row_words[0] = a->data_row_words; red.cnt_n[0] = a->n_data; red.cnt_L[0] = a->L;
+        red.cnt_rows[1] = a->v_model; red.cnt_row_words[1] = a->v_row_words; red.cnt_n[1] = a->batchsize; red.cnt_L[1] = Lv;
+        red.batch_index = a->batch_index_dev;
+        red.cnt_out[0] = st + lay.v_data; red.cnt_out[1] = st + lay.v_model;
+        if (p2p) {
+            red.ticket = p2p->ticket; red.n_ranks = p2p->n_ranks; red.rank = p2p->rank; red.parity = p2p->parity;
+            for (int r = 0; r < p2p->n_ranks; ++r) red.peer_flags[r] = p2p->peer_flags[r];
+            red.sequence = p2p->sequence; red.sequence_dev = a->step_dev;
+        }
+        CRBM_CHECK_CUDA(launch_chain(reduce_partials_kernel, dim3(red.block_start[red.nsets] + 2), dim3(128), 0, s, red));
         CRBM_CHECK_LAUNCH();
-
-        V2HParams q{};
-        q.packed = a->v_model; q.row_words = a->v_row_words; q.n_rows = a->batchsize; q.L = Lv; q.Lh = FANTASY_LEN;
-        q.W = a->W; q.b = a->b; q.K = K; q.M = M; q.pooling = P; q.ds = ds;
-        q.bv = tn.bv; q.nblk = tn.nblk; q.n_items = tn.n_items;
-        q.partial = part1; q.bits = a->fantasy_bits;
-        q.u_fwd = a->u_h ? a->u_h + it * n_u_h : nullptr;
-        q.u_rc = a->u_hp ? a->u_hp + it * n_u_h : nullptr;
-        q.seed = a->seed; q.step_dev = a->step_dev;
-        q.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
-        if (!mma) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));   // CUDA-core sampler ORs its hits in
-        if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
     }
-    if (a->n_data > 0) CRBM_CHECK_CUDA(cudaStreamWaitEvent(s, ev_join, 0));
-    ReduceSet &Sn = add_set(part1, tn, true, false);
-    Sn.vh_p = st + lay.vh_model; Sn.h_sum = st + lay.h_model;
-    red.counts = st + lay.n_hidden_data;
-    red.c0 = (float)a->n_data * Lh; red.c1 = (float)a->batchsize * FANTASY_LEN;
-    red.c2 = (float)a->n_data * a->L; red.c3 = (float)a->batchsize * Lv;
-    red.cnt_rows[0] = a->data; red.cnt_row_words[0] = a->data_row_words; red.cnt_n[0] = a->n_data; red.cnt_L[0] = a->L;
-    red.cnt_rows[1] = a->v_model; red.cnt_row_words[1] = a->v_row_words; red.cnt_n[1] = a->batchsize; red.cnt_L[1] = Lv;
-    red.batch_index = a->batch_index_dev;
-    red.cnt_out[0] = st + lay.v_data; red.cnt_out[1] = st + lay.v_model;
-    if (p2p) {
-        red.ticket = p2p->ticket; red.n_ranks = p2p->n_ranks; red.rank = p2p->rank; red.parity = p2p->parity;
-        for (int r = 0; r < p2p->n_ranks; ++r) red.peer_flags[r] = p2p->peer_flags[r];
-        red.sequence = p2p->sequence; red.sequence_dev = a->step_dev;
-    }
-    reduce_partials_kernel<<<red.block_start[red.nsets] + 2, 128, 0, s>>>(red);
-    CRBM_CHECK_LAUNCH();
-    if (fuse_apply) return crbm_train_apply(a, stream);
+    if (phases & CRBM_PHASE_APPLY) return crbm_train_apply(a, stream);
     return CRBM_OK;
 }
 
-int crbm_train_accumulate(const crbm_train_args *a, void *stream) { return train_accumulate_impl(a, stream, false); }
+int crbm_train_phases(const crbm_train_args *a, int phases, void *stream) {
+    CRBM_CHECK_ARG(phases > 0 && phases < 16, "crbm_train_phases: bad phase mask 0x%x", phases);
+    if (phases & CRBM_PHASE_APPLY) CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc, "crbm_train_phases: null velocity pointer in args");
+    return train_phases_impl(a, phases, stream);
+}
+
+int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
+    return train_phases_impl(a, CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE, stream);
+}
 
 int crbm_train_accumulate_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, void *stream) {
     CRBM_CHECK_ARG(p2p && p2p->n_ranks > 0 && p2p->n_ranks <= CRBM_MAX_PEERS && p2p->rank >= 0 && p2p->rank < p2p->n_ranks &&
                    p2p->ticket && (p2p->parity == 0 || p2p->parity == 1), "crbm_train_accumulate_p2p: bad p2p arguments");
     for (int r = 0; r < p2p->n_ranks; ++r) CRBM_CHECK_ARG(p2p->peer_flags[r], "crbm_train_accumulate_p2p: null peer flag pointer");
-    return train_accumulate_impl(a, stream, false, p2p);
+    return train_phases_impl(a, CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE, stream, p2p);
 }
 
 int crbm_train_apply_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, void *stream) {
@@ -846,14 +869,14 @@ int crbm_train_apply_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, voi
     p.stats_stride = p2p->stats_stride; p.sequence = p2p->sequence; p.sequence_dev = a->step_dev; p.error_flag = p2p->error_flag;
     p.ticket = p2p->ticket;
     const int n = a->K * 4 * a->M + a->K + 4;
-    apply_update_p2p_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    CRBM_CHECK_CUDA(launch_chain(apply_update_p2p_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, p));
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }
 
 int crbm_train_step(const crbm_train_args *a, void *stream) {
     CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc, "crbm_train_step: null pointer in args");
-    return train_accumulate_impl(a, stream, true);
+    return train_phases_impl(a, CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE | CRBM_PHASE_APPLY, stream);
 }
 
 int crbm_train_apply(const crbm_train_args *a, void *stream) {
@@ -865,7 +888,7 @@ int crbm_train_apply(const crbm_train_args *a, void *stream) {
     p.lr = a->learning_rate; p.mu = a->momentum; p.rho = a->rho; p.lam = a->lambda_rate;
     p.step_dev = a->step_dev; p.batch_index_dev = a->batch_index_dev; p.n_batches = a->n_batches;
     const int n = a->K * 4 * a->M + a->K + 5;
-    apply_update_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(p);
+    CRBM_CHECK_CUDA(launch_chain(apply_update_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, p));
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }

@@ -46,6 +46,9 @@ struct V2HParams {
     // device-resident cursors (CUDA-graph replay): minibatch index into `packed`, training step
     const int *batch_index;
     const unsigned long long *step_dev;
+    // programmatic dependent launch (common.cuh): 0 = wait for the predecessor grid before the main loop (the kernel reads
+    // what it wrote); 1 = only before exit (independent of the predecessor: keeps stream order transitive, overlaps its tail)
+    int pdl_late;
 };
 
 template <int MW> struct V2HShape {

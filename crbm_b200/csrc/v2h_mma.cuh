@@ -216,6 +216,13 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
     const int njb = (p.Lh + 15) >> 4;
 
     const uint32_t *packed = p.packed + (p.batch_index ? (size_t)(*p.batch_index) * p.n_rows * p.row_words : 0);
+    // Programmatic dependent launch: everything above reads only W, b and the step / minibatch cursors, which the update
+    // kernel of the previous step wrote and which were complete before the predecessor grid could let this one start
+    // (every kernel of the chain triggers its dependents only after its own wait). The sequence rows and the bit planes
+    // belong to the predecessor (h2v) for the chain sweeps; the positive phase depends on nothing in flight and only
+    // waits before it exits, so that "this grid has completed" still implies "everything before it has".
+    if (!p.pdl_late) pdl_wait();
+    pdl_launch_dependents();
     for (int item = blockIdx.y * nwarps + warp; item < p.n_items; item += gridDim.y * nwarps) {
         const int n = item / p.nblk, jb = item - n * p.nblk, j0 = jb * 16;
         const uint32_t *row = packed + (size_t)n * p.row_words + (j0 >> 4);     // word holding bases j0-16 .. j0-1
@@ -426,6 +433,7 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
             visit([&](int o, float &v) { dst[o * 32] = v; });
         }
     }
+    if (p.pdl_late) pdl_wait();
 }
 
 // ----------------------------------------------------------------------------------------------------------

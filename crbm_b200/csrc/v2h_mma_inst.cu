@@ -15,7 +15,7 @@ static int launch_mma_variant(const V2HParams &p, dim3 grid, cudaStream_t stream
         CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_mma_kernel<KS, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    v2h_mma_kernel<KS, FLAGS><<<grid, 256, smem, stream>>>(p);
+    CRBM_CHECK_CUDA(launch_chain(v2h_mma_kernel<KS, FLAGS>, grid, dim3(256), smem, stream, p));
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }

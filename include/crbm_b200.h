@@ -161,6 +161,15 @@ int crbm_train_apply(const crbm_train_args *args, void *stream);
 /* accumulate followed by apply, for a single rank (no exchange in between). (A fused reduce+update kernel was measured
  * and was not faster than the two small launches; see DESIGN.md.) */
 int crbm_train_step(const crbm_train_args *args, void *stream);
+/* The same step issued in parts (bit mask), for hosts that overlap the host->device copy of the next minibatch with the
+ * chain sweeps: NEGATIVE does not read args->data. The parts of one step must be issued in this order on one stream (or on
+ * streams ordered by events); REDUCE needs both NEGATIVE and POSITIVE of the same step. All kernels are launched as
+ * programmatic dependents of their predecessor in the stream (CRBM_PDL=0 in the environment turns that off). */
+#define CRBM_PHASE_NEGATIVE 1   /* cd_k Gibbs sweeps of the persistent chain (convRBM.py:391-408) -> partial sums */
+#define CRBM_PHASE_POSITIVE 2   /* P(h|data), sparsity statistic (convRBM.py:377-388, 440-451) -> partial sums */
+#define CRBM_PHASE_REDUCE   4   /* partial sums -> args->stats */
+#define CRBM_PHASE_APPLY    8   /* crbm_train_apply */
+int crbm_train_phases(const crbm_train_args *args, int phases, void *stream);
 
 /* ---- data-parallel update without a separate collective: one-shot all-reduce over NVLink peer memory, fused into the update
  * Every rank exposes, in peer-mapped memory (CUDA IPC / VMM; torch symmetric memory on the Python host), a double-buffered

@@ -37,7 +37,7 @@ WORKLOADS = {
                batch=128, L=500, n_seq=65536, default_steps=512),
 }
 METRIC = 'CD-1 train nt/s'
-SCAN_TRAFFIC = None      # dram__bytes_read.sum + dram__bytes_write.sum of the scan launch (profiles/), filled in after the ncu capture
+SCAN_TRAFFIC = 8209885000   # dram__bytes_read.sum + dram__bytes_write.sum of the scan launch (profiles/r01_ncu_metrics_f.md), padded rows, 107 526 x 200 bp, K=100
 
 
 def peaks():
@@ -258,15 +258,19 @@ def main():
             'gather_adds_per_launch': adds,
             'fp32_add_frac': (adds / (pos_us * 1e-6) / (148 * 128 * sm_max * 1e6)) if pos_us else None}
         if not args.no_scan:
-            line['scan'] = bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src)
+            line['scan'] = bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src, world, rank)
         if not args.no_e2e:
             line['e2e'] = bench_e2e(model, B, Lt, world, dev, min(args.steps, 2000))
         if not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_sample(wl)
         line['clocks'] = clocks
         print(json.dumps(line))
-    elif not args.no_e2e:
-        bench_e2e(model, B, Lt, world, dev, min(args.steps, 2000))
+    else:
+        # the other ranks scan their own shard (no communication on the data path) and feed their own minibatches
+        if not args.no_scan:
+            bench_scan(model, K, M, Lt, dev, 1.0, '', world, rank)
+        if not args.no_e2e:
+            bench_e2e(model, B, Lt, world, dev, min(args.steps, 2000))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -313,7 +317,7 @@ def time_step_kernels(model, data, B, dev):
     return out
 
 
-def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
+def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src, world=1, rank=0):
     """getHitProbs kernel (tcgen05 / TMEM, csrc/scan_tc.cu) with fp32 output materialised in HBM; input and output larger
     than L2. Timed in the layout CRBM.motifHitProbs uses on the device (rows padded to a multiple of 8 floats, so every store
     covers whole 32-byte sectors) and in the reference's contiguous (N,K,1,Lh) layout. Algorithmic bytes count Lh floats
@@ -324,7 +328,7 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
     lib = _lib.load()
     Lh = Lt - M + 1
     n = max(1024, min(200000, int(8e9 // (4 * K * Lh))))
-    seqs = crbm_b200.PackedSequences.random(n, Lt, seed=99, device=dev)
+    seqs = crbm_b200.PackedSequences.random(n, Lt, seed=99 + rank, device=dev)      # this rank's shard of the sequences
     s = _lib.stream_handle()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 5
@@ -333,12 +337,21 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
         e0.record()
         for _ in range(reps):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / reps
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:                               # whole job = all shards; time = slowest rank
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     ms_by_pitch = {}
     pitch_fast = (Lh + 7) // 8 * 8 if model.pooling == 1 else Lh     # pooled probabilities: CUDA-core kernel, contiguous rows only
@@ -350,28 +363,32 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src):
         del out
     pitch = pitch_fast
     ms = ms_by_pitch[pitch]
-    nt = n * Lt
-    alg = n * (Lt / 4.0) + 4.0 * n * K * Lh
+    nt = n * Lt * world                          # whole job
+    alg = n * (Lt / 4.0) + 4.0 * n * K * Lh      # per GPU (the roofline is per device)
     # fused reductions (max / argmax / mean over positions per sequence and motif): nothing but (N,K) results is written
     mx = torch.empty((n, K), dtype=torch.float32, device=dev)
     am = torch.empty((n, K), dtype=torch.int32, device=dev)
     mean = torch.empty((n, K), dtype=torch.float32, device=dev)
-    ms_red = timed(lambda: _lib.check(lib.crbm_scan_reduce(
-        _lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias), K, M, model.pooling,
-        _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am), _lib.ptr(mean), s), 'scan_reduce'))
-    return {'fused_reductions': {'metric': 'motif-scan nt/s, max/argmax/mean over positions fused (no dense output)',
-                                 'value': nt / (ms_red * 1e-3), 'unit': 'nt/s', 'ms': ms_red},
+    fused = None
+    if model.pooling == 1:                      # (the fused reductions of pooled probabilities are not built)
+        ms_red = timed(lambda: _lib.check(lib.crbm_scan_reduce(
+            _lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias), K, M, model.pooling,
+            _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am), _lib.ptr(mean), s), 'scan_reduce'))
+        fused = {'metric': 'motif-scan nt/s, max/argmax/mean over positions fused (no dense output)',
+                 'value': nt / (ms_red * 1e-3), 'unit': 'nt/s', 'ms': ms_red}
+    return {'fused_reductions': fused,
             'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
-            'sequences': n, 'ms': ms, 'output_GB': 4.0 * n * K * Lh / 1e9,
+            'sequences_per_gpu': n, 'n_gpus': world, 'ms': ms, 'output_GB_per_gpu': 4.0 * n * K * Lh / 1e9,
             'layout': 'output rows padded from %d to %d floats (32-byte sectors); contiguous (N,K,1,Lh) layout: %.3f ms = %.3e nt/s'
                       % (Lh, pitch, ms_by_pitch[Lh], nt / (ms_by_pitch[Lh] * 1e-3)),
+            'sharding': 'sequences sharded across ranks, weights replicated, no collective on the data path',
             'roofline': {'bound': 'hbm', 'kernel': ('v2h_dense_tc_kernel<PROB> (tcgen05.mma, TMEM accumulators)' if model.pooling == 1 else
                                                  'v2h_dense_kernel (CUDA cores, pooling > 1)'),
                          'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
                          'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak,
                          # ncu --set full on this launch (107 526 x 200 bp, K=100, padded rows): dram written + read
                          'traffic': SCAN_TRAFFIC if (n == 107526 and K == 100) else None, 'algorithmic_bytes': alg,
-                         'peak_source': peak_src, 'bytes_per_nt': alg / nt}}
+                         'peak_source': peak_src, 'bytes_per_nt': alg / (n * Lt)}}
 
 
 def bench_e2e(model, B, Lt, world, dev, steps):

@@ -16,6 +16,8 @@ Differences a caller can observe (all documented in DESIGN.md):
 import time
 import warnings
 
+import ctypes
+
 import numpy as np
 
 from . import _lib
@@ -677,9 +679,9 @@ class CRBM(object):
         """Train on one mini-batch (reference :524-526 -> theano_trainingFct). Under data parallelism `data` is the
         global minibatch (every rank passes the same array) unless local_shard=True (this rank's rows only).
 
-        One-hot input (NumPy or torch, host or device) takes the streamlined path: two CUDA graphs per step. The chain
-        sweeps (h2v -> v2h of the persistent particles) are replayed first; meanwhile the batch is copied into a persistent
-        staging buffer and packed on a second stream; then positive phase -> reduction -> update. The one-hot validation
+        One-hot input (NumPy or torch, host or device) takes the streamlined path: one call into the library issues the
+        chain sweeps (h2v -> v2h of the persistent particles), copies the batch into a persistent staging buffer and packs it
+        on a second stream meanwhile, then positive phase -> reduction -> update. The one-hot validation
         result is checked at the next call / synchronisation point."""
         if (uniforms is None and self._world == 1 and self._use_graphs and not isinstance(data, PackedSequences)
                 and getattr(data, 'ndim', 0) == 4):
@@ -708,7 +710,7 @@ class CRBM(object):
         if eng is None or eng['key'] != (n, L):
             self._check_deferred()
             rw = lib.crbm_packed_row_words(L)
-            eng = dict(key=(n, L), graphs=None, pending=False, dev_step=-1)
+            eng = dict(key=(n, L), side=None, pending=False, dev_step=-1)
             eng['staging'] = torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device)
             eng['words'] = torch.zeros((n, rw), dtype=torch.int32, device=self._device)
             eng['bad'] = torch.zeros(1, dtype=torch.int32, device=self._device)
@@ -718,52 +720,22 @@ class CRBM(object):
             eng['args'], eng['rw'] = a, rw
             self._onehot_engine = eng
         src = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)) if isinstance(data, np.ndarray) else data
+        if src.dtype != torch.float32 or not src.is_contiguous():
+            src = src.to(torch.float32).contiguous()
         if eng['dev_step'] != self._step:             # the update kernel advances the device-side step counter itself
             eng['step_dev'].fill_(self._step)
-        NEG, REST = _lib.PHASE_NEGATIVE, _lib.PHASE_POSITIVE | _lib.PHASE_REDUCE | _lib.PHASE_APPLY
         main = torch.cuda.current_stream(self._device)
-
-        def feed():
-            # input side, on its own stream: host -> device copy of the one-hot batch, then 2-bit packing + validation.
-            # It overlaps the chain sweeps (which do not read the minibatch); the previous step's positive phase has
-            # finished reading the packed buffer (`done`).
-            side = eng['side']
-            side.wait_event(eng['done'])
-            with torch.cuda.stream(side):
-                eng['staging'].copy_(src, non_blocking=True)
-                _lib.check(lib.crbm_pack_onehot_accumulate(_lib.ptr(eng['staging']), n, L, _lib.ptr(eng['words']), eng['rw'],
-                                                           _lib.ptr(eng['bad']), _lib.stream_handle()), 'pack_onehot')
-                eng['ready'].record(side)
-
-        def part(phases):
-            _lib.check(lib.crbm_train_phases(eng['args'], phases, _lib.stream_handle()), 'train_phases')
-
-        if eng['graphs'] is None:
+        if eng['side'] is None:
             eng['side'] = torch.cuda.Stream(device=self._device)
             eng['ready'], eng['done'] = torch.cuda.Event(), torch.cuda.Event()
+            eng['ready'].record(eng['side'])
             eng['done'].record(main)
-            feed()
-            main.wait_event(eng['ready'])
-            part(NEG)                                # first call eagerly (one-time kernel attribute setup), then capture
-            part(REST)
-            torch.cuda.synchronize(self._device)
-            tensors = (self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc, self._t_fantasy, eng['step_dev'])
-            saved = [t.clone() for t in tensors]
-            graphs = []
-            for phases in (NEG, REST):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    part(phases)
-                graphs.append(g)
-            for t, v in zip(tensors, saved):
-                t.copy_(v)
-            eng['graphs'] = graphs
-        else:
-            eng['graphs'][0].replay()                # chain sweeps start at once ...
-            feed()                                   # ... while the minibatch is copied in and packed
-            main.wait_event(eng['ready'])
-            eng['graphs'][1].replay()                # positive phase, reduction, update
-        eng['done'].record(main)
+        # One C call issues the whole step (crbm_train_step_onehot): chain sweeps on the current stream; copy of the batch into
+        # the staging buffer + packing + validation on the side stream, overlapping them; then positive phase, reduction, update.
+        _lib.check(lib.crbm_train_step_onehot(eng['args'], ctypes.c_void_p(src.data_ptr()), _lib.ptr(eng['staging']), _lib.ptr(eng['bad']),
+                                              ctypes.c_void_p(eng['side'].cuda_stream), ctypes.c_void_p(eng['done'].cuda_event),
+                                              ctypes.c_void_p(eng['ready'].cuda_event), ctypes.c_void_p(main.cuda_stream)),
+                   'train_step_onehot')
         eng['pending'] = True
         self._step += 1
         eng['dev_step'] = self._step

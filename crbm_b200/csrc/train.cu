@@ -840,6 +840,28 @@ int crbm_train_phases(const crbm_train_args *a, int phases, void *stream) {
     return train_phases_impl(a, phases, stream);
 }
 
+int crbm_train_step_onehot(const crbm_train_args *a, const float *host_onehot, float *staging, int *bad_count,
+                           void *copy_stream, void *consumed_event, void *ready_event, void *stream) {
+    CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc && host_onehot && staging && bad_count && copy_stream && consumed_event && ready_event,
+                   "crbm_train_step_onehot: null argument");
+    CRBM_CHECK_ARG(a->n_data > 0 && !a->batch_index_dev, "crbm_train_step_onehot: needs a non-empty minibatch addressed directly");
+    cudaStream_t s = (cudaStream_t)stream, cs = (cudaStream_t)copy_stream;
+    cudaEvent_t consumed = (cudaEvent_t)consumed_event, ready = (cudaEvent_t)ready_event;
+    // chain sweeps first: they do not read the minibatch, so the device is busy while the batch crosses PCIe
+    int rc = train_phases_impl(a, CRBM_PHASE_NEGATIVE, stream);
+    if (rc) return rc;
+    CRBM_CHECK_CUDA(cudaStreamWaitEvent(cs, consumed, 0));      // previous step's positive phase has read the packed rows
+    CRBM_CHECK_CUDA(cudaMemcpyAsync(staging, host_onehot, sizeof(float) * 4 * (size_t)a->n_data * a->L, cudaMemcpyDefault, cs));
+    rc = crbm_pack_onehot_accumulate(staging, a->n_data, a->L, const_cast<uint32_t *>(a->data), a->data_row_words, bad_count, copy_stream);
+    if (rc) return rc;
+    CRBM_CHECK_CUDA(cudaEventRecord(ready, cs));
+    CRBM_CHECK_CUDA(cudaStreamWaitEvent(s, ready, 0));
+    rc = train_phases_impl(a, CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE | CRBM_PHASE_APPLY, stream);
+    if (rc) return rc;
+    CRBM_CHECK_CUDA(cudaEventRecord(consumed, s));
+    return CRBM_OK;
+}
+
 int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     return train_phases_impl(a, CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE, stream);
 }

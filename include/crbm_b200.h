@@ -170,6 +170,14 @@ int crbm_train_step(const crbm_train_args *args, void *stream);
 #define CRBM_PHASE_REDUCE   4   /* partial sums -> args->stats */
 #define CRBM_PHASE_APPLY    8   /* crbm_train_apply */
 int crbm_train_phases(const crbm_train_args *args, int phases, void *stream);
+/* One whole step fed from HOST memory (what `theano_trainingFct(one-hot batch)` is, convRBM.py:459,524-526): launches NEGATIVE on
+ * `stream`; on `copy_stream` waits for `consumed_event`, copies host_onehot ((n_data,1,4,L) fp32, pinned for an asynchronous
+ * copy) into `staging` (device, same size), packs it into args->data (crbm_pack_onehot_accumulate, *bad_count running) and
+ * records `ready_event`; `stream` waits for it, then POSITIVE | REDUCE | APPLY, then records `consumed_event` on `stream`.
+ * Events are cudaEvent_t handles owned by the caller; `consumed_event` must have been recorded once before the first call.
+ * args->batch_index_dev must be NULL. Returns without synchronising. */
+int crbm_train_step_onehot(const crbm_train_args *args, const float *host_onehot, float *staging, int *bad_count,
+                           void *copy_stream, void *consumed_event, void *ready_event, void *stream);
 
 /* ---- data-parallel update without a separate collective: one-shot all-reduce over NVLink peer memory, fused into the update
  * Every rank exposes, in peer-mapped memory (CUDA IPC / VMM; torch symmetric memory on the Python host), a double-buffered

@@ -23,6 +23,12 @@ static bool scan_uses_tcgen05() {
     return v == 1;
 }
 
+static bool pool_uses_mma() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CRBM_POOL_KERNEL"); v = (e && e[0] == 'c') ? 0 : 1; }      // "cuda" -> CUDA-core kernel
+    return v == 1;
+}
+
 static int dispatch_fused(int MW, int flags, const V2HParams &p, dim3 grid, cudaStream_t s) {
     switch (MW) {
 #define CRBM_CASE(MWV) case MWV: return launch_v2h_fused<MWV>(flags, p, grid, s);
@@ -718,8 +724,8 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     float *part0 = reinterpret_cast<float *>(a->workspace);
     float *part1 = part0 + partial_floats(K, M);
     float *part2 = part1 + partial_floats(K, M);
-    // pooling == 1: both contractions on the tensor pipe (v2h_mma.cuh); otherwise the CUDA-core kernel (v2h.cuh)
-    const bool mma = P == 1;
+    // both contractions on the tensor pipe (v2h_mma.cuh); CRBM_POOL_KERNEL=cuda keeps pooling > 1 on the CUDA-core kernel (v2h.cuh)
+    const bool mma = P == 1 || pool_uses_mma();
     const int KS = ceil_div(M, 4);
     auto run_fused = [&](int flags, const V2HParams &p, const Tiling &t) -> int {
         return mma ? dispatch_mma(KS, flags, p, dim3(ceil_div(K, 16), mma_gy(K, t.n_items)), s)
@@ -776,7 +782,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
             q.u_rc = a->u_hp ? a->u_hp + it * n_u_h : nullptr;
             q.seed = a->seed; q.step_dev = a->step_dev;
             q.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
-            if (!mma) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));   // CUDA-core sampler ORs its hits in
+            if (P != 1) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));  // the pooled samplers OR their hits in
             if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
         }
     }

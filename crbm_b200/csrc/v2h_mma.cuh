@@ -169,7 +169,7 @@ __device__ __forceinline__ float fast_sigmoid(float x) {
 // grid (m-tiles of 16 motifs, CTAs), 256 threads, two CTAs per SM: every warp owns the CTA's m-tile for a stream of
 // 16-position blocks. (ncu on the first version with 32-motif warps: 254 registers, 8 warps/SM, one wave of 4.05 blocks
 // per warp on average but 5 at most; 16-motif warps need <= 128 registers, and m-tiles beyond K are not launched.)
-template <int KS, int FLAGS>
+template <int KS, int FLAGS, bool POOL>
 __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
     using Sh = MmaShape<KS>;
     using Ac = MmaAcc<KS, FLAGS>;
@@ -215,6 +215,19 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
     const int ktiles = (p.K + KTILE - 1) / KTILE;
     const int njb = (p.Lh + 15) >> 4;
 
+    // pooling > 1 (POOL): blocks of bv = (16 / P) * P positions, so that pool groups never straddle blocks; the MMA tile still
+    // spans 16 positions from j0 = blk * bv and the tail is masked. The thread's four positions 8nt + 2q + e of a motif row
+    // belong to the groups gidx[2nt + e]; group sums are quad reductions (the four lanes of a quad hold one motif row).
+    const float fpool = (float)p.pooling;
+    const int ng = POOL ? p.bv / p.pooling : 0;
+    const int groups_per_seq = p.Lh / p.pooling;
+    int gidx[4] = {0, 0, 0, 0};
+    PoolMasks mk{0u, 0u, 0u};
+    if (POOL) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gidx[i] = (8 * (i >> 1) + 2 * q + (i & 1)) / p.pooling;
+        mk = make_pool_masks(p.pooling);
+    }
     const uint32_t *packed = p.packed + (p.batch_index ? (size_t)(*p.batch_index) * p.n_rows * p.row_words : 0);
     // Programmatic dependent launch: everything above reads only W, b and the step / minibatch cursors, which the update
     // kernel of the previous step wrote and which were complete before the predecessor grid could let this one start
@@ -224,11 +237,20 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
     if (!p.pdl_late) pdl_wait();
     pdl_launch_dependents();
     for (int item = blockIdx.y * nwarps + warp; item < p.n_items; item += gridDim.y * nwarps) {
-        const int n = item / p.nblk, jb = item - n * p.nblk, j0 = jb * 16;
-        const uint32_t *row = packed + (size_t)n * p.row_words + (j0 >> 4);     // word holding bases j0-16 .. j0-1
-        uint32_t wd[5];
+        const int n = item / p.nblk, jb = item - n * p.nblk, j0 = POOL ? jb * p.bv : jb * 16;
+        const uint32_t *row = packed + (size_t)n * p.row_words + (j0 >> 4);     // word holding bases j0-16 .. j0-1 (j0 % 16 == 0)
+        uint32_t wd[5];                                                        // wd[i]: bases j0-16+16i .. j0-1+16i
+        if (POOL) {
+            uint32_t raw[6];
 #pragma unroll
-        for (int i = 0; i < 5; ++i) wd[i] = __ldg(row + i);
+            for (int i = 0; i < 6; ++i) raw[i] = __ldg(row + i);
+            const int sh = 2 * (j0 & 15);                                      // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 5; ++i) wd[i] = __funnelshift_r(raw[i], raw[i + 1], sh);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) wd[i] = __ldg(row + i);
+        }
 
         // ---- x = W (x) X on the tensor pipe, both strands ------------------------------------------------------
         float d1[2][2][4];                                     // [strand][nt][reg]
@@ -269,25 +291,112 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
         // d1[s][nt][r]: motif row h = r>>1, position j0 + 8*nt + 2*q + (r&1)
         const int jrem = p.Lh - j0 - 2 * q;                   // position valid iff 8*nt + (r&1) < jrem
         const bool full = all_k && (j0 + 16 <= p.Lh);         // warp-uniform: no masking needed
+        float qv[2][4];                                       // POOL: Q = p (1 - sum_group p) of the forward strand
+        if (!POOL) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            if (s == 1 && !p.ds) continue;
-#pragma unroll
-            for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    const float x = d1[s][nt][r] + bias[r >> 1];
-                    d1[s][nt][r] = fast_sigmoid(x);
-                }
-            if (!full) {
+            for (int s = 0; s < 2; ++s) {
+                if (s == 1 && !p.ds) continue;
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-                    for (int r = 0; r < 4; ++r)
-                        if (!(kval[r >> 1] && (8 * nt + (r & 1) < jrem))) d1[s][nt][r] = 0.f;
+                    for (int r = 0; r < 4; ++r) {
+                        const float x = d1[s][nt][r] + bias[r >> 1];
+                        d1[s][nt][r] = fast_sigmoid(x);
+                    }
+                if (!full) {
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r)
+                            if (!(kval[r >> 1] && (8 * nt + (r & 1) < jrem))) d1[s][nt][r] = 0.f;
+                }
+            }
+        } else {
+            // p = exp(x) / (P + sum_group exp(x)) (convRBM.py:252). x is clamped at 60 instead of subtracting the group maximum
+            // (identical unless a weight bank has diverged; e^60 * 16 is finite in fp32).
+            const uint32_t validbits = valid_mask(p.bv, j0, p.Lh);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s == 1 && !p.ds) continue;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float e[4], inv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int pos = 8 * (i >> 1) + 2 * q + (i & 1);
+                        const float x = fminf(d1[s][i >> 1][2 * h + (i & 1)] + bias[h], 60.f);
+                        float t;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 1.4426950408889634f));
+                        e[i] = (kval[h] && ((validbits >> pos) & 1u)) ? t : 0.f;
+                        inv[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int gI = 0; gI < BLOCK_POS / 2; ++gI) {
+                        if (gI < ng) {                         // warp-uniform
+                            float part = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part += gidx[i] == gI ? e[i] : 0.f;
+                            part += __shfl_xor_sync(0xffffffffu, part, 1);
+                            part += __shfl_xor_sync(0xffffffffu, part, 2);
+                            float r;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fpool + part));
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) inv[i] = gidx[i] == gI ? r : inv[i];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float pr = e[i] * inv[i];
+                        d1[s][i >> 1][2 * h + (i & 1)] = pr;
+                        if (s == 0) qv[i >> 1][2 * h + (i & 1)] = pr * (fpool * inv[i]);
+                    }
+                }
             }
         }
-        if (SAMPLE) {
+        if (SAMPLE && POOL) {
+            // one uniform per pool group (convRBM.py:259-267): every lane of a quad gathers the 16 probabilities of its motif
+            // row and walks them in position order exactly like the CUDA-core kernel (v2h.cuh sample_block); lane q == 0
+            // sets the bits (the planes were zeroed before the launch; hits are rare).
+            mk.valid = valid_mask(p.bv, j0, p.Lh);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (s == 1 && !p.ds) continue;
+                const float *inj = s == 0 ? p.u_fwd : p.u_rc;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = mtile * MTILE + 8 * h + g;
+                    float pv[BLOCK_POS];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq)
+                            pv[8 * (i >> 1) + 2 * qq + (i & 1)] = __shfl_sync(0xffffffffu, d1[s][i >> 1][2 * h + (i & 1)], (lane & 28) | qq);
+                    GroupUniforms gu;
+                    gu.inj = inj ? inj + (size_t)(n * p.K + (kval[h] ? k : 0)) * groups_per_seq : nullptr;
+                    gu.key = key; gu.row = (uint32_t)(n * p.K + k); gu.tag = s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC; gu.hi = ctr_hi;
+                    gu.cached_q = -1;
+                    uint32_t bits = 0u;
+                    bool done = false;
+                    float u = 0.f, run = 0.f;
+                    int grp = j0 / p.pooling - 1;
+#pragma unroll
+                    for (int r = 0; r < BLOCK_POS; ++r) {
+                        if ((mk.start >> r) & 1u) {
+                            ++grp; done = false; run = 0.f;
+                            if ((mk.valid >> r) & 1u) u = gu.get(grp);
+                        }
+                        run += pv[r];
+                        const bool hit = ((mk.valid >> r) & 1u) && !done && (run > u);
+                        done = done || hit;
+                        if (hit) bits |= 1u << r;
+                    }
+                    if (q == 0 && kval[h])
+                        scatter_sample_bits(p.bits + ((size_t)(s * p.n_rows + n) * ktiles + (mtile >> 1)) * FANTASY_WORDS, bits, j0,
+                                            (mtile & 1) * 16 + 8 * h + g);
+                }
+            }
+        }
+        if (SAMPLE && !POOL) {
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (s == 1 && !p.ds) continue;
@@ -340,7 +449,7 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
                         }
                     }
                     if (STAT_Q) {
-                        const float q0 = p0 * (1.f - p0), q1 = p1 * (1.f - p1);
+                        const float q0 = POOL ? qv[nt][2 * h] : p0 * (1.f - p0), q1 = POOL ? qv[nt][2 * h + 1] : p1 * (1.f - p1);
                         split2(q0, q1, aq[0][reg], aq[1][reg]);
                         sum_q[h] += q0 + q1;
                         if (!STAT_P) sum_p[h] += p0 + p1;

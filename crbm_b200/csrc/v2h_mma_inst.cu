@@ -7,17 +7,21 @@
 
 namespace crbm {
 
-template <int KS, int FLAGS>
-static int launch_mma_variant(const V2HParams &p, dim3 grid, cudaStream_t stream) {
+template <int KS, int FLAGS, bool POOL>
+static int launch_mma_pool(const V2HParams &p, dim3 grid, cudaStream_t stream) {
     static bool configured = false;
     constexpr size_t smem = mma_smem_bytes<KS, FLAGS>();
     if (!configured) {
-        CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_mma_kernel<KS, FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_mma_kernel<KS, FLAGS, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    CRBM_CHECK_CUDA(launch_chain(v2h_mma_kernel<KS, FLAGS>, grid, dim3(256), smem, stream, p));
+    CRBM_CHECK_CUDA(launch_chain(v2h_mma_kernel<KS, FLAGS, POOL>, grid, dim3(256), smem, stream, p));
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
+}
+template <int KS, int FLAGS>
+static int launch_mma_variant(const V2HParams &p, dim3 grid, cudaStream_t stream) {
+    return p.pooling == 1 ? launch_mma_pool<KS, FLAGS, false>(p, grid, stream) : launch_mma_pool<KS, FLAGS, true>(p, grid, stream);
 }
 
 template <>

@@ -245,8 +245,7 @@ def main():
         tpeak = tensor_peak()
         pooled = P != 1
         line['roofline'] = {
-            'bound': 'tensor', 'kernel': ('v2h_fused_kernel (CUDA-core path, pooling > 1)' if pooled else
-                                          'v2h_mma_kernel<KS=%d, STAT_P|STAT_Q> (positive-phase launch)' % ((M + 3) // 4)),
+            'bound': 'tensor', 'kernel': ('v2h_mma_kernel<KS=%d, %s%s> (positive-phase launch%s)' % ((M + 3) // 4, 'STAT_P|STAT_Q' if M <= 16 else 'STAT_P> + <STAT_Q', ', POOL' if pooled else '', '' if M <= 16 else 'es')),
             'achieved': tf, 'peak': tpeak[0], 'unit': 'TFLOP/s', 'frac': (tf / tpeak[0]) if tf else None,
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01_ncu_metrics_final.md)
             'traffic': 60416 if (args.workload == 'c2' and not pooled) else None,
@@ -354,7 +353,7 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src, world=1, rank=0):
         return ms
 
     ms_by_pitch = {}
-    pitch_fast = (Lh + 7) // 8 * 8 if model.pooling == 1 else Lh     # pooled probabilities: CUDA-core kernel, contiguous rows only
+    pitch_fast = (Lh + 7) // 8 * 8
     for pitch in sorted({pitch_fast, Lh}, reverse=True):
         out = torch.empty((n, K, 1, pitch), dtype=torch.float32, device=dev)
         ms_by_pitch[pitch] = timed(lambda: _lib.check(lib.crbm_v2h_dense_strided(
@@ -383,7 +382,7 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src, world=1, rank=0):
                       % (Lh, pitch, ms_by_pitch[Lh], nt / (ms_by_pitch[Lh] * 1e-3)),
             'sharding': 'sequences sharded across ranks, weights replicated, no collective on the data path',
             'roofline': {'bound': 'hbm', 'kernel': ('v2h_dense_tc_kernel<PROB> (tcgen05.mma, TMEM accumulators)' if model.pooling == 1 else
-                                                 'v2h_dense_kernel (CUDA cores, pooling > 1)'),
+                                                 'v2h_dense_tc_kernel<PROB, POOL> (tcgen05.mma, TMEM accumulators, pool groups summed by warp shuffles)'),
                          'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
                          'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak,
                          # ncu --set full on this launch (107 526 x 200 bp, K=100, padded rows): dram written + read

@@ -13,10 +13,10 @@ Differences a caller can observe (all documented in DESIGN.md):
   * under torch.distributed (one process per GPU) `fit` is data-parallel: every minibatch and the persistent chain
     are sharded across ranks and one all-reduce of the statistics vector per step keeps all replicas identical.
 """
+import ctypes
+import os
 import time
 import warnings
-
-import ctypes
 
 import numpy as np
 
@@ -241,8 +241,8 @@ class CRBM(object):
     # ---- bottom-up builders (reference :238-275), eager ------------------------------------------------------------
     def _v2h_device(self, seqs, strand_mode, out_kind, start=0, end=None):
         """(end-start, K, 1, Lh) device tensor of activities / probabilities of rows [start, end) of `seqs`.
-        With pooling 1 it is a view of a buffer whose rows are padded to a multiple of 8 floats: the tcgen05 scan kernel
-        then writes whole 32-byte sectors only; the values are those of the contiguous layout."""
+        It is a view of a buffer whose rows are padded to a multiple of 8 floats: the tcgen05 scan kernel then writes
+        whole 32-byte sectors only; the values are those of the contiguous layout."""
         lib = self._require_cuda()
         torch = _torch()
         K, M = self.num_motifs, self.motif_length
@@ -252,7 +252,7 @@ class CRBM(object):
         end = seqs.N if end is None else end
         n = end - start
         pooled = self.pooling != 1 and out_kind == _lib.OUT_PROBABILITY
-        pitch = Lh if pooled else (Lh + 7) // 8 * 8
+        pitch = Lh if (pooled and os.environ.get('CRBM_POOL_KERNEL', '')[:1] == 'c') else (Lh + 7) // 8 * 8
         buf = torch.empty((n, K, 1, pitch), dtype=torch.float32, device=self._device)
         _lib.check(lib.crbm_v2h_dense_strided(_lib.ptr(seqs.words[start:]), seqs.row_words, n, seqs.L, _lib.ptr(self._t_W),
                                               _lib.ptr(self._t_bias), K, M, self.pooling, strand_mode, out_kind,

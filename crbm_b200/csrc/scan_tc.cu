@@ -40,6 +40,9 @@ struct TcParams {
     int LhV;           // virtual hidden length the tiles are cut from: Lh, or Lh rounded up to 32 when the output rows are
                        // sector aligned (then every warp of a tile sits inside one sequence at a multiple of 32 positions)
     long long row_stride;   // floats between consecutive (n,k) rows of the output (Lh for the reference's contiguous layout)
+    int P;             // pooling factor of the probabilities (1: sigmoid)
+    int VP;            // real positions per warp of a tile: 32, or (32 / P) * P so that pool groups never straddle warps. Virtual
+                       // position v of a sequence <-> real position (v / 32) * VP + v % 32, valid iff v % 32 < VP
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
@@ -128,6 +131,12 @@ struct TilePos {
         n = n0 + dn;
         j = jj - dn * Lh;
     }
+    // same with the virtual -> real position map of pooled tiles (TcParams::VP); ok = the row is a real position of its warp
+    __device__ __forceinline__ void row(int r, int Lh, int VP, int &n, int &j, bool &ok) const {
+        row(r, Lh, n, j);
+        ok = (j & 31) < VP;
+        j = (j >> 5) * VP + (j & 31);
+    }
 };
 
 // the packed words under hidden position row `r` of a tile: three 16-base windows starting at the position's first base
@@ -137,10 +146,11 @@ struct RowBases {
     __device__ __forceinline__ void load(const TcParams &p, const TilePos &tp, int r) {
         const DenseParams &d = p.d;
         int n, j;
-        tp.row(r, p.LhV, n, j);
+        bool ok;
+        tp.row(r, p.LhV, p.VP, n, j, ok);
         mlim = 0; sh = 0;
         w[0] = w[1] = w[2] = w[3] = 0u;
-        if (n < d.n_rows && j < d.Lh) {
+        if (ok && n < d.n_rows && j < d.Lh) {
             const int bit = 2 * (j + 16 * FRONT_PAD_WORDS);
             const uint32_t *src = d.packed + (size_t)n * d.row_words + (bit >> 5);
             sh = bit & 31;
@@ -193,7 +203,30 @@ __device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, 
 //               and commits to full[buf] and a_free[stage]
 //   warps 4-19  four epilogue warpgroups: group g drains buffer g % nbuf (when nbuf < 4 the groups sharing a buffer take
 //               alternate 8-motif chunks): wait full[buf] -> tcgen05.ld -> bias, sigmoid -> 128-byte row stores -> arrive empty[buf]
-template <bool PROB>
+// Sum of v over the pool group of P consecutive lanes that contains this lane (groups start at lanes that are multiples of P;
+// gs = this lane's group start). Window sums of length 1, 2, 4, ... by doubling, P composed from its binary digits, then the
+// value of the group's first lane is broadcast: popcount(P) + floor(log2 P) shuffles instead of P.
+__device__ __forceinline__ float pool_group_sum(float v, int P, int gs) {
+    float w[5];
+    w[0] = v;
+#pragma unroll
+    for (int b = 1; b < 5; ++b) {
+        w[b] = w[b - 1];
+        if ((1 << b) <= P) w[b] = w[b - 1] + __shfl_down_sync(0xffffffffu, w[b - 1], 1 << (b - 1));     // warp-uniform branch
+    }
+    float acc = 0.f;
+    int off = 0;
+#pragma unroll
+    for (int b = 4; b >= 0; --b) {
+        if (P & (1 << b)) {
+            acc += off ? __shfl_down_sync(0xffffffffu, w[b], off) : w[b];
+            off += 1 << b;
+        }
+    }
+    return __shfl_sync(0xffffffffu, acc, gs);
+}
+
+template <bool PROB, bool POOL>
 __global__ void __launch_bounds__(TC_THREADS, 1) v2h_dense_tc_kernel(const TcParams p) {
     const DenseParams &d = p.d;
     extern __shared__ unsigned char smem_raw[];
@@ -295,8 +328,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) v2h_dense_tc_kernel(const TcPar
             // output address = warp-uniform 64-bit row base (sequence tp.n0, motif kbase + 8 ch) + per-thread 32-bit byte offset
             // (its sequence relative to tp.n0, its position, the motif inside the chunk): one STG per value, no 64-bit math
             int n, j;
-            tp.row(32 * q + lane, p.LhV, n, j);
-            const bool valid = n < d.n_rows && j < p.store_len;
+            bool ok;
+            tp.row(32 * q + lane, p.LhV, p.VP, n, j, ok);
+            const bool valid = ok && n < d.n_rows && j < p.store_len;
             const uint32_t rs4 = (uint32_t)p.row_stride * 4u;
             const uint32_t off0 = (uint32_t)(n - tp.n0) * (uint32_t)d.K * rs4 + (uint32_t)j * 4u;
             uint32_t offc[8];
@@ -313,7 +347,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) v2h_dense_tc_kernel(const TcPar
                 float x[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) x[c] = __uint_as_float(v[c]) + bb[c];
-                if (PROB) {
+                if (PROB && POOL) {
+                    // p = exp(a) / (P + sum_group exp(a)) (convRBM.py:252) with x = -log2(e) a; a group is P consecutive lanes of
+                    // this warp. a is clamped at 40 so that the paired reciprocal below stays finite ((16 e^40)^2 < FLT_MAX).
+                    const float fpool = (float)p.P;
+                    const int gs = lane - lane % p.P;
+                    float e[8], t[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[c]) : "f"(fminf(-x[c], 57.7f)));
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) t[c] = fpool + pool_group_sum(e[c], p.P, gs);
+#pragma unroll
+                    for (int c = 0; c < 8; c += 2) {
+                        float r;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t[c] * t[c + 1]));
+                        x[c] = e[c] * (r * t[c + 1]);
+                        x[c + 1] = e[c + 1] * (r * t[c]);
+                    }
+                } else if (PROB) {
                     // p = 1 / (1 + 2^x) with x = -log2(e) * activity. The MUFU pipe is the busiest unit of this kernel
                     // (two ops per output), so two outputs share one reciprocal: r = 1 / ((1+e0)(1+e1)), p0 = r (1+e1),
                     // p1 = r (1+e0). x is clamped to 60 so that the product stays finite (p < 1e-18 is unaffected at 1e-5).
@@ -391,8 +442,14 @@ int launch_v2h_dense_tc(const DenseParams &d, long long row_stride, cudaStream_t
     // store is 128 contiguous bytes starting on a sector boundary (scratch/store_align.cu: 5.9 TB/s vs 3.5 TB/s otherwise)
     p.row_stride = row_stride;
     const bool aligned = (row_stride % 8 == 0) && (((uintptr_t)d.out & 31) == 0);
-    p.LhV = aligned ? 32 * ceil_div(d.Lh, 32) : d.Lh;
-    p.store_len = aligned ? (int)(row_stride < p.LhV ? row_stride : p.LhV) : d.Lh;
+    const bool prob = d.out_kind == CRBM_OUT_PROBABILITY;
+    const bool pool = prob && d.pooling > 1;
+    p.P = pool ? d.pooling : 1;
+    p.VP = pool ? (32 / p.P) * p.P : 32;
+    // pooled: every warp must hold whole pool groups of one sequence, so the tiles are always cut from the virtual rows
+    p.LhV = (aligned || pool) ? 32 * ceil_div(d.Lh, p.VP) : d.Lh;
+    const int covered = (p.LhV / 32) * p.VP;                       // real positions the virtual row covers (>= Lh)
+    p.store_len = aligned ? (int)(row_stride < covered ? row_stride : covered) : d.Lh;
     const long long total = (long long)d.n_rows * p.LhV;            // (virtual) hidden positions
     CRBM_CHECK_ARG((long long)d.K * row_stride * (TC_TILE / p.LhV + 3) < (1ll << 29), "v2h_dense_tc: K * row stride too large for 32-bit tile offsets");
     CRBM_CHECK_ARG((total + TC_TILE - 1) / TC_TILE < (1ll << 24), "v2h_dense_tc: more than 2^31 hidden positions in one call");
@@ -400,18 +457,18 @@ int launch_v2h_dense_tc(const DenseParams &d, long long row_stride, cudaStream_t
     p.scale = d.out_kind == CRBM_OUT_PROBABILITY ? -1.4426950408889634f : 1.0f;
     // the CTA allocates all 512 TMEM columns: ask for more than half of the shared memory so that two CTAs never share an SM
     const size_t smem = tc_smem_bytes(NT, p.n_atoms, p.a_stages) > 120 * 1024 ? tc_smem_bytes(NT, p.n_atoms, p.a_stages) : 120 * 1024;
-    const bool prob = d.out_kind == CRBM_OUT_PROBABILITY;
-    static size_t configured[2] = {0, 0};
-    if (smem > configured[prob]) {
-        CRBM_CHECK_CUDA(prob ? cudaFuncSetAttribute(v2h_dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                             : cudaFuncSetAttribute(v2h_dense_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[prob] = smem;
+    const int variant = pool ? 2 : prob ? 1 : 0;
+    void (*kernel)(const TcParams) = variant == 2 ? v2h_dense_tc_kernel<true, true> : variant == 1 ? v2h_dense_tc_kernel<true, false>
+                                                                                                  : v2h_dense_tc_kernel<false, false>;
+    static size_t configured[3] = {0, 0, 0};
+    if (smem > configured[variant]) {
+        CRBM_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[variant] = smem;
     }
     int gx = num_sms() / n_mtiles;
     if (gx < 1) gx = 1;
     if (gx > p.n_tiles) gx = p.n_tiles;
-    if (prob) v2h_dense_tc_kernel<true><<<dim3(gx, n_mtiles), TC_THREADS, smem, stream>>>(p);
-    else v2h_dense_tc_kernel<false><<<dim3(gx, n_mtiles), TC_THREADS, smem, stream>>>(p);
+    kernel<<<dim3(gx, n_mtiles), TC_THREADS, smem, stream>>>(p);
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }

@@ -625,7 +625,7 @@ int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L, 
     else pool = 1;
     Tiling t = make_tiling(K, M, pool, Lh, N);
     DenseParams p{packed, row_words, N, L, Lh, W, b, K, M, pool, strand_mode, out_kind, t.bv, t.nblk, t.n_items, out};
-    if (pool == 1 && scan_uses_tcgen05()) return launch_v2h_dense_tc(p, out_row_stride, (cudaStream_t)stream);
+    if ((pool == 1 || pool_uses_mma()) && scan_uses_tcgen05()) return launch_v2h_dense_tc(p, out_row_stride, (cudaStream_t)stream);
     if (out_row_stride != Lh) { set_error("crbm_v2h_dense: a padded output row stride needs pooling == 1"); return CRBM_ERR_UNSUPPORTED; }
     if (pool == 1) {
         // mma.sync tensor-pipe kernel (kept for comparison: CRBM_SCAN_KERNEL=mma): CTAs of one 16-motif m-tile, three per SM: size the grid to one full wave

@@ -205,7 +205,8 @@ def test_train_steps_match_reference(crbm, name):
 # ---- oracle parity on fresh seeded inputs, shapes the fixtures do not cover ------------------------------------------------
 @pytest.mark.parametrize('K,M,P,L,ds', [(100, 15, 1, 200, True), (128, 20, 5, 999, True), (64, 25, 1, 120, False),
                                         (3, 1, 1, 9, True), (35, 33, 2, 96, True), (10, 15, 8, 94, True),
-                                        (1, 3, 16, 50, False)])
+                                        (1, 3, 16, 50, False), (16, 10, 3, 69, True), (16, 6, 7, 75, False),
+                                        (24, 12, 6, 83, True), (130, 9, 5, 2008, True)])
 def test_scan_and_free_energy_match_oracle(crbm, O, K, M, P, L, ds):
     rs = np.random.RandomState(K * 7 + M)
     N = 3

@@ -116,7 +116,7 @@ def run_reference(args, wl, rank, world):
                              'sample': '%d train steps of %d x %d bp (torch-CPU restatement of the Theano graph; Theano not '
                                        'installable offline)' % (steps, wl['batch'], Lt)},
             'e2e': {'value': nts, 'unit': 'nt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_sample(wl, budget_s=12.0):
@@ -139,6 +139,10 @@ def cpu_baseline_sample(wl, budget_s=12.0):
 
 
 def main():
+    # exactly one line on stdout: libraries that print there (NCCL's version banner) are sent to stderr
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None)
@@ -263,7 +267,7 @@ def main():
         if not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_sample(wl)
         line['clocks'] = clocks
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     else:
         # the other ranks scan their own shard (no communication on the data path) and feed their own minibatches
         if not args.no_scan:

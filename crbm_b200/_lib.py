@@ -87,7 +87,7 @@ SIGNATURES = {
     'crbm_train_apply': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_step': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_phases': (c_int, [ctypes.POINTER(TrainArgs), c_int, c_void_p]),
-    'crbm_train_step_onehot': (c_int, [ctypes.POINTER(TrainArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'crbm_train_step_onehot': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'crbm_train_accumulate_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
     'crbm_train_apply_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
     'crbm_train_stats_layout': (c_int, [c_int, c_int, ctypes.POINTER(StatsLayout)]),

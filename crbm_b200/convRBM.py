@@ -600,7 +600,7 @@ class CRBM(object):
             with torch.cuda.graph(g):
                 for i in range(nsteps):
                     self._run_steps_once(eng, ('p2p%d' % (i & 1)) if part == 'p2p' else part)
-            if part in ('both', 'accumulate'):
+            if part in ('both', 'accumulate', 'p2p'):
                 eng['launches_per_step'] = int(_lib.load().crbm_launch_count() - c0) // nsteps + (1 if part == 'accumulate' else 0)
             eng['graphs'][key] = g
         return g
@@ -683,9 +683,15 @@ class CRBM(object):
         chain sweeps (h2v -> v2h of the persistent particles), copies the batch into a persistent staging buffer and packs it
         on a second stream meanwhile, then positive phase -> reduction -> update. The one-hot validation
         result is checked at the next call / synchronisation point."""
-        if (uniforms is None and self._world == 1 and self._use_graphs and not isinstance(data, PackedSequences)
-                and getattr(data, 'ndim', 0) == 4):
-            return self._train_step_onehot(data)
+        if (uniforms is None and self._use_graphs and not isinstance(data, PackedSequences) and getattr(data, 'ndim', 0) == 4
+                and (self._world == 1 or self._p2p_setup() is not None)):
+            if self._world > 1 and not local_shard:         # this rank's rows of the global minibatch
+                n = int(data.shape[0])
+                per = (n + self._world - 1) // self._world
+                lo = min(n, self._rank * per)
+                data = data[lo:min(n, lo + per)]
+            if int(data.shape[0]) > 0:
+                return self._train_step_onehot(data)
         seqs = self._as_packed(data)
         self._train_packed(seqs, 0, seqs.N, uniforms, local_shard)
 
@@ -710,35 +716,40 @@ class CRBM(object):
         if eng is None or eng['key'] != (n, L):
             self._check_deferred()
             rw = lib.crbm_packed_row_words(L)
-            eng = dict(key=(n, L), side=None, pending=False, dev_step=-1)
+            eng = dict(key=(n, L), side=None, pending=False)
             eng['staging'] = torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device)
             eng['words'] = torch.zeros((n, rw), dtype=torch.int32, device=self._device)
             eng['bad'] = torch.zeros(1, dtype=torch.int32, device=self._device)
-            eng['step_dev'] = torch.zeros(1, dtype=torch.int64, device=self._device)
             a = self._fill_args(eng['words'].data_ptr(), rw, n, L)
-            a.step_dev = eng['step_dev'].data_ptr()
             eng['args'], eng['rw'] = a, rw
             self._onehot_engine = eng
         src = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)) if isinstance(data, np.ndarray) else data
         if src.dtype != torch.float32 or not src.is_contiguous():
             src = src.to(torch.float32).contiguous()
-        if eng['dev_step'] != self._step:             # the update kernel advances the device-side step counter itself
-            eng['step_dev'].fill_(self._step)
         main = torch.cuda.current_stream(self._device)
         if eng['side'] is None:
             eng['side'] = torch.cuda.Stream(device=self._device)
             eng['ready'], eng['done'] = torch.cuda.Event(), torch.cuda.Event()
             eng['ready'].record(eng['side'])
             eng['done'].record(main)
+        a, pa = eng['args'], None
+        if self._world > 1:
+            # data parallel: statistics into buffer `parity` of the peer-mapped double buffer, sequence number per step
+            p = self._p2p
+            a.step = self._dp_seq
+            a.stats = p['local_stats'] + (self._dp_seq & 1) * p['stride'] * 4
+            pa = self._p2p_args(p, self._dp_seq & 1, self._dp_seq + 1)
+            self._dp_seq += 1
+        else:
+            a.step = self._step
         # One C call issues the whole step (crbm_train_step_onehot): chain sweeps on the current stream; copy of the batch into
         # the staging buffer + packing + validation on the side stream, overlapping them; then positive phase, reduction, update.
-        _lib.check(lib.crbm_train_step_onehot(eng['args'], ctypes.c_void_p(src.data_ptr()), _lib.ptr(eng['staging']), _lib.ptr(eng['bad']),
+        _lib.check(lib.crbm_train_step_onehot(a, pa, ctypes.c_void_p(src.data_ptr()), _lib.ptr(eng['staging']), _lib.ptr(eng['bad']),
                                               ctypes.c_void_p(eng['side'].cuda_stream), ctypes.c_void_p(eng['done'].cuda_event),
                                               ctypes.c_void_p(eng['ready'].cuda_event), ctypes.c_void_p(main.cuda_stream)),
                    'train_step_onehot')
         eng['pending'] = True
         self._step += 1
-        eng['dev_step'] = self._step
 
     def _evaluateData(self, data, uniforms=None):
         """[mean free energy, mean of a sampled forward-strand H] (reference :466-472, 517-522)."""

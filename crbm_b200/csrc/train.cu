@@ -812,6 +812,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
         ReduceSet &S = add_set(part0, t, true, false);
         S.vh_p = st + lay.vh_data; S.h_sum = st + lay.h_data; S.h_fwd = st + lay.h_fwd;
         p.partial = part2;
+        p.ds = 0;                                   // the sparsity statistic uses the forward strand only (convRBM.py:443)
         if (pos && (rc = run_fused(F_STAT_Q, p, t))) return rc;
         ReduceSet &Sq = add_set(part2, t, false, true);
         Sq.vh_q = st + lay.vh_q; Sq.h_q = st + lay.h_q;
@@ -846,7 +847,8 @@ int crbm_train_phases(const crbm_train_args *a, int phases, void *stream) {
     return train_phases_impl(a, phases, stream);
 }
 
-int crbm_train_step_onehot(const crbm_train_args *a, const float *host_onehot, float *staging, int *bad_count,
+extern "C" int crbm_train_apply_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, void *stream);
+int crbm_train_step_onehot(const crbm_train_args *a, const crbm_p2p_args *p2p, const float *host_onehot, float *staging, int *bad_count,
                            void *copy_stream, void *consumed_event, void *ready_event, void *stream) {
     CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc && host_onehot && staging && bad_count && copy_stream && consumed_event && ready_event,
                    "crbm_train_step_onehot: null argument");
@@ -862,7 +864,15 @@ int crbm_train_step_onehot(const crbm_train_args *a, const float *host_onehot, f
     if (rc) return rc;
     CRBM_CHECK_CUDA(cudaEventRecord(ready, cs));
     CRBM_CHECK_CUDA(cudaStreamWaitEvent(s, ready, 0));
-    rc = train_phases_impl(a, CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE | CRBM_PHASE_APPLY, stream);
+    if (p2p) {
+        // data parallel: this rank's shard; the reduction publishes the statistics to the peers, the update sums them over NVLink
+        CRBM_CHECK_ARG(p2p->n_ranks > 0 && p2p->n_ranks <= CRBM_MAX_PEERS && p2p->rank >= 0 && p2p->rank < p2p->n_ranks && p2p->ticket &&
+                       (p2p->parity == 0 || p2p->parity == 1), "crbm_train_step_onehot: bad p2p arguments");
+        rc = train_phases_impl(a, CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE, stream, p2p);
+        if (!rc) rc = crbm_train_apply_p2p(a, p2p, stream);
+    } else {
+        rc = train_phases_impl(a, CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE | CRBM_PHASE_APPLY, stream);
+    }
     if (rc) return rc;
     CRBM_CHECK_CUDA(cudaEventRecord(consumed, s));
     return CRBM_OK;

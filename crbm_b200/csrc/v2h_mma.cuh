@@ -158,6 +158,9 @@ __device__ __forceinline__ void pair_groups(const uint32_t (&w)[NW], uint32_t co
         grp[2 * i + 1] = prmt(e[i], nxt, 0x7632u);
     }
 }
+// out-of-line copy of the generator for call sites inside heavily unrolled code
+static __device__ __noinline__ uint4 philox4x32_call(uint4 ctr, uint2 key) { return philox4x32(ctr, key); }
+
 // 1 / (1 + exp(-x)) with the SFU approximations only (ex2.approx: 2 ulp, rcp.approx: 1 ulp; saturates cleanly to 0 / 1)
 __device__ __forceinline__ float fast_sigmoid(float x) {
     float t, r;
@@ -371,19 +374,36 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
 #pragma unroll
                         for (int qq = 0; qq < 4; ++qq)
                             pv[8 * (i >> 1) + 2 * qq + (i & 1)] = __shfl_sync(0xffffffffu, d1[s][i >> 1][2 * h + (i & 1)], (lane & 28) | qq);
-                    GroupUniforms gu;
-                    gu.inj = inj ? inj + (size_t)(n * p.K + (kval[h] ? k : 0)) * groups_per_seq : nullptr;
-                    gu.key = key; gu.row = (uint32_t)(n * p.K + k); gu.tag = s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC; gu.hi = ctr_hi;
-                    gu.cached_q = -1;
+                    // the block's group uniforms: injected, or one / two Philox draws per (motif row, block) — taken before the
+                    // position loop so that the unrolled loop holds no copy of the generator (the first version inlined one per
+                    // position: 126 us per launch at C3, the instruction cache thrashing)
+                    const int g0 = j0 / p.pooling;
+                    float ug[BLOCK_POS / 2];
+                    if (inj) {
+                        const float *ur = inj + (size_t)(n * p.K + (kval[h] ? k : 0)) * groups_per_seq + g0;
+#pragma unroll
+                        for (int i = 0; i < BLOCK_POS / 2; ++i) ug[i] = (i < ng && g0 + i < groups_per_seq) ? ur[i] : 1.f;
+                    } else {
+                        const uint32_t tag = s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC;
+                        const uint4 r0 = philox4x32_call(make_uint4((uint32_t)(n * p.K + k), (uint32_t)(2 * jb), ctr_hi, tag), key);
+                        ug[0] = u01(r0.x); ug[1] = u01(r0.y); ug[2] = u01(r0.z); ug[3] = u01(r0.w);
+                        ug[4] = ug[5] = ug[6] = ug[7] = 1.f;
+                        if (ng > 4) {                          // warp-uniform
+                            const uint4 r1 = philox4x32_call(make_uint4((uint32_t)(n * p.K + k), (uint32_t)(2 * jb + 1), ctr_hi, tag), key);
+                            ug[4] = u01(r1.x); ug[5] = u01(r1.y); ug[6] = u01(r1.z); ug[7] = u01(r1.w);
+                        }
+                    }
                     uint32_t bits = 0u;
                     bool done = false;
                     float u = 0.f, run = 0.f;
-                    int grp = j0 / p.pooling - 1;
+                    int gi = -1;
 #pragma unroll
                     for (int r = 0; r < BLOCK_POS; ++r) {
-                        if ((mk.start >> r) & 1u) {
-                            ++grp; done = false; run = 0.f;
-                            if ((mk.valid >> r) & 1u) u = gu.get(grp);
+                        if ((mk.start >> r) & 1u) {            // warp-uniform
+                            ++gi; done = false; run = 0.f;
+                            u = ug[0];
+#pragma unroll
+                            for (int i = 1; i < BLOCK_POS / 2; ++i) u = gi == i ? ug[i] : u;
                         }
                         run += pv[r];
                         const bool hit = ((mk.valid >> r) & 1u) && !done && (run > u);

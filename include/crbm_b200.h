@@ -175,9 +175,12 @@ int crbm_train_phases(const crbm_train_args *args, int phases, void *stream);
  * copy) into `staging` (device, same size), packs it into args->data (crbm_pack_onehot_accumulate, *bad_count running) and
  * records `ready_event`; `stream` waits for it, then POSITIVE | REDUCE | APPLY, then records `consumed_event` on `stream`.
  * Events are cudaEvent_t handles owned by the caller; `consumed_event` must have been recorded once before the first call.
- * args->batch_index_dev must be NULL. Returns without synchronising. */
-int crbm_train_step_onehot(const crbm_train_args *args, const float *host_onehot, float *staging, int *bad_count,
-                           void *copy_stream, void *consumed_event, void *ready_event, void *stream);
+ * args->batch_index_dev must be NULL. host_onehot may also be a device pointer (the copy is cudaMemcpyDefault). With p2p != NULL
+ * (data parallel, see below) the minibatch is this rank's shard, args->stats points at buffer `parity`, and the last two phases
+ * are crbm_train_accumulate_p2p's publishing reduction and crbm_train_apply_p2p. Returns without synchronising. */
+struct crbm_p2p_args;
+int crbm_train_step_onehot(const crbm_train_args *args, const struct crbm_p2p_args *p2p, const float *host_onehot, float *staging,
+                           int *bad_count, void *copy_stream, void *consumed_event, void *ready_event, void *stream);
 
 /* ---- data-parallel update without a separate collective: one-shot all-reduce over NVLink peer memory, fused into the update
  * Every rank exposes, in peer-mapped memory (CUDA IPC / VMM; torch symmetric memory on the Python host), a double-buffered

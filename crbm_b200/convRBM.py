@@ -707,31 +707,15 @@ class CRBM(object):
                 raise ValueError("input is not one-hot at %d positions (expected exactly one 1 among A,C,G,T)" % nbad)
 
     def _train_step_onehot(self, data):
-        lib = self._require_cuda()
-        torch = _torch()
-        n, L = int(data.shape[0]), int(data.shape[3])
-        if tuple(data.shape[1:3]) != (1, 4):
-            raise ValueError("expected one-hot data of shape (N,1,4,L), got %r" % (tuple(data.shape),))
+        shape = data.shape
+        n, L = int(shape[0]), int(shape[3])
         eng = getattr(self, '_onehot_engine', None)
         if eng is None or eng['key'] != (n, L):
-            self._check_deferred()
-            rw = lib.crbm_packed_row_words(L)
-            eng = dict(key=(n, L), side=None, pending=False)
-            eng['staging'] = torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device)
-            eng['words'] = torch.zeros((n, rw), dtype=torch.int32, device=self._device)
-            eng['bad'] = torch.zeros(1, dtype=torch.int32, device=self._device)
-            a = self._fill_args(eng['words'].data_ptr(), rw, n, L)
-            eng['args'], eng['rw'] = a, rw
-            self._onehot_engine = eng
+            eng = self._onehot_engine_for(data, n, L)
+        torch = eng['torch']
         src = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)) if isinstance(data, np.ndarray) else data
         if src.dtype != torch.float32 or not src.is_contiguous():
             src = src.to(torch.float32).contiguous()
-        main = torch.cuda.current_stream(self._device)
-        if eng['side'] is None:
-            eng['side'] = torch.cuda.Stream(device=self._device)
-            eng['ready'], eng['done'] = torch.cuda.Event(), torch.cuda.Event()
-            eng['ready'].record(eng['side'])
-            eng['done'].record(main)
         a, pa = eng['args'], None
         if self._world > 1:
             # data parallel: statistics into buffer `parity` of the peer-mapped double buffer, sequence number per step
@@ -744,12 +728,35 @@ class CRBM(object):
             a.step = self._step
         # One C call issues the whole step (crbm_train_step_onehot): chain sweeps on the current stream; copy of the batch into
         # the staging buffer + packing + validation on the side stream, overlapping them; then positive phase, reduction, update.
-        _lib.check(lib.crbm_train_step_onehot(a, pa, ctypes.c_void_p(src.data_ptr()), _lib.ptr(eng['staging']), _lib.ptr(eng['bad']),
-                                              ctypes.c_void_p(eng['side'].cuda_stream), ctypes.c_void_p(eng['done'].cuda_event),
-                                              ctypes.c_void_p(eng['ready'].cuda_event), ctypes.c_void_p(main.cuda_stream)),
-                   'train_step_onehot')
+        rc = eng['fn'](a, pa, src.data_ptr(), eng['c_staging'], eng['c_bad'], eng['c_side'], eng['c_done'], eng['c_ready'],
+                       torch.cuda.current_stream(self._device).cuda_stream)
+        if rc != _lib.OK:
+            _lib.check(rc, 'train_step_onehot')
         eng['pending'] = True
         self._step += 1
+
+    def _onehot_engine_for(self, data, n, L):
+        """Persistent buffers, side stream and events of the streamlined one-hot training call for batches of (n, L)."""
+        lib = self._require_cuda()
+        torch = _torch()
+        if tuple(data.shape[1:3]) != (1, 4):
+            raise ValueError("expected one-hot data of shape (N,1,4,L), got %r" % (tuple(data.shape),))
+        self._check_deferred()
+        rw = lib.crbm_packed_row_words(L)
+        eng = dict(key=(n, L), pending=False, torch=torch, fn=lib.crbm_train_step_onehot, rw=rw)
+        eng['staging'] = torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device)
+        eng['words'] = torch.zeros((n, rw), dtype=torch.int32, device=self._device)
+        eng['bad'] = torch.zeros(1, dtype=torch.int32, device=self._device)
+        eng['args'] = self._fill_args(eng['words'].data_ptr(), rw, n, L)
+        main = torch.cuda.current_stream(self._device)
+        eng['side'] = torch.cuda.Stream(device=self._device)
+        eng['ready'], eng['done'] = torch.cuda.Event(), torch.cuda.Event()
+        eng['ready'].record(eng['side'])
+        eng['done'].record(main)
+        eng['c_staging'], eng['c_bad'] = eng['staging'].data_ptr(), eng['bad'].data_ptr()
+        eng['c_side'], eng['c_done'], eng['c_ready'] = eng['side'].cuda_stream, eng['done'].cuda_event, eng['ready'].cuda_event
+        self._onehot_engine = eng
+        return eng
 
     def _evaluateData(self, data, uniforms=None):
         """[mean free energy, mean of a sampled forward-strand H] (reference :466-472, 517-522)."""

@@ -652,13 +652,14 @@ int crbm_scan_reduce(const uint32_t *packed, int row_words, int N, int L, const 
     CRBM_CHECK_ARG(strand_mode >= 0 && strand_mode <= 2 && (out_kind == 0 || out_kind == 1), "crbm_scan_reduce: bad mode");
     CRBM_CHECK_ARG(row_words >= packed_row_words(L), "crbm_scan_reduce: row_words too small");
     CRBM_CHECK_ARG(((uintptr_t)W & 15) == 0, "crbm_scan_reduce: W must be 16-byte aligned");
-    if (out_kind == CRBM_OUT_PROBABILITY && pooling != 1) {
-        set_error("crbm_scan_reduce: pooled probabilities (pooling %d) are not built yet; use crbm_v2h_dense", pooling);
-        return CRBM_ERR_UNSUPPORTED;
+    int pool = 1;
+    if (out_kind == CRBM_OUT_PROBABILITY) {
+        CRBM_CHECK_ARG(Lh % pooling == 0, "crbm_scan_reduce: hidden length %d not divisible by pooling %d", Lh, pooling);
+        pool = pooling;
     }
-    Tiling t = make_tiling(K, M, 1, Lh, N);
+    Tiling t = make_tiling(K, M, pool, Lh, N);
     ScanReduceParams sp{};
-    sp.d = DenseParams{packed, row_words, N, L, Lh, W, b, K, M, 1, strand_mode, out_kind, t.bv, t.nblk, t.n_items, nullptr};
+    sp.d = DenseParams{packed, row_words, N, L, Lh, W, b, K, M, pool, strand_mode, out_kind, t.bv, t.nblk, t.n_items, nullptr};
     sp.out_max = out_max; sp.out_argmax = out_argmax; sp.out_mean = out_mean;
     return dispatch_scan_reduce(ceil_div(M, 4), sp, (cudaStream_t)stream);
 }

@@ -20,15 +20,17 @@
 // positions of one sequence and keeps its accumulators for the whole kernel; one tree reduction per CTA at the end.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "v2h.cuh"
 
 namespace crbm {
 
 constexpr int MTILE = 16;                                       // motifs per CTA of the tensor-pipe kernels (one MMA m-tile)
+constexpr int NSPLIT = 2;                                       // W = hi + lo in fp16 (11 + 11 significand bits; three bf16 terms in the first version)
 
 template <int KS> struct MmaShape {
     static constexpr int NT2 = 2 * KS;                          // 8-column tiles over c = 4*m + a  (16*KS columns)
-    static constexpr int FRAGS = 2 * 3 * KS;                    // [strand][split][ks]
+    static constexpr int FRAGS = 2 * NSPLIT * KS;               // [strand][split][ks]
     static constexpr size_t wimg_bytes = (size_t)FRAGS * 512;   // 32 lanes x 16 bytes per fragment
     static constexpr size_t wtile_bytes = (size_t)MTILE * 4 * CRBM_MAX_MOTIF_LEN * sizeof(float);
     static constexpr size_t smem_bytes = wimg_bytes + wtile_bytes + 16;
@@ -56,6 +58,15 @@ __device__ __forceinline__ void hmma_bf16(float (&d)[4], uint32_t a0, uint32_t a
 __device__ __forceinline__ void hmma_bf16(float (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1) {
     hmma_bf16(d, a.x, a.y, a.z, a.w, b0, b1);
 }
+__device__ __forceinline__ void hmma_f16(float (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
 __device__ __forceinline__ void hmma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     hmma_bf16(d, a[0], a[1], a[2], a[3], b0, b1);
 }
@@ -69,7 +80,7 @@ __device__ __forceinline__ void split2(float v0, float v1, uint32_t &hi, uint32_
     mid = pack_bf16x2(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xffff0000u));
 }
 
-// W tile (16 motifs x 4 x M, fp32, staged by the TMA engine) -> three bf16 images in MMA A-fragment order, both strands.
+// W tile (16 motifs x 4 x M, fp32, staged by the TMA engine) -> two fp16 images (hi, lo) in MMA A-fragment order, both strands.
 // Element (row r, column c) of the ks-th fragment is Wx[r][16*ks + c]; forward strand Wx[k][4m+a] = W[k][a][m],
 // reverse strand Wx[k][4m+a] = W[k][3-a][M-1-m] (convRBM.py:241 with filter_flip=True); zero beyond M.
 template <int KS>
@@ -101,15 +112,13 @@ __device__ __forceinline__ void build_w_fragments(uint32_t *wimg, float *wtile, 
             if (m < M && row < nk) w = strand == 0 ? wtile[(row * 4 + a) * M + m] : wtile[(row * 4 + 3 - a) * M + (M - 1 - m)];
             v[e] = w;
         }
-        uint32_t hi, mid, lo;
-        split2(v[0], v[1], hi, mid);
-        const float r0 = (v[0] - __uint_as_float(hi << 16)) - __uint_as_float(mid << 16);
-        const float r1 = (v[1] - __uint_as_float(hi & 0xffff0000u)) - __uint_as_float(mid & 0xffff0000u);
-        lo = pack_bf16x2(r0, r1);
-        const int f0 = (strand * 3 + 0) * KS + ks;                   // fragment index [strand][split][ks]
+        // W = hi + lo, both fp16: |W - hi - lo| <= 2^-22 |W| (3e-8 absolute below the fp16 normal range), as in scan_tc.cu
+        const uint32_t hi = pack_half2(v[0], v[1]);
+        const __half2 hh = *reinterpret_cast<const __half2 *>(&hi);
+        const uint32_t lo = pack_half2(v[0] - __low2float(hh), v[1] - __high2float(hh));
+        const int f0 = (strand * NSPLIT + 0) * KS + ks;              // fragment index [strand][split][ks]
         wimg[(f0 * 32 + lane) * 4 + reg] = hi;
-        wimg[((f0 + KS) * 32 + lane) * 4 + reg] = mid;
-        wimg[((f0 + 2 * KS) * 32 + lane) * 4 + reg] = lo;
+        wimg[((f0 + KS) * 32 + lane) * 4 + reg] = lo;
     }
     __syncthreads();
 }
@@ -125,6 +134,10 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 __device__ __forceinline__ uint32_t onehot_reg(uint32_t group, int i /*0,2,4,6: first base inside its 8-base group*/) {
     return ((group >> (2 * i)) & 0x00010001u) * 0x3F80u;
+}
+// same with fp16 ones (0x3C00): B operand of the up-pass, whose A operand (W) is fp16
+__device__ __forceinline__ uint32_t onehot_reg_h(uint32_t group, int i) {
+    return ((group >> (2 * i)) & 0x00010001u) * 0x3C00u;
 }
 // Up-pass operand: for base b at window position i, low half = [b == 2*qodd], high half = [b == 2*qodd + 1].
 // Fills grp[2w], grp[2w+1] for the NW window words.
@@ -276,16 +289,16 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
 #pragma unroll
                     for (int hb = 0; hb < 2; ++hb) {
                         const int off = 8 * nt + 4 * ks + 2 * hb;
-                        bx[nt][hb] = onehot_reg(vg[off >> 3], off & 7);
+                        bx[nt][hb] = onehot_reg_h(vg[off >> 3], off & 7);
                     }
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     if (s == 1 && !p.ds) continue;
 #pragma unroll
-                    for (int sp = 0; sp < 3; ++sp) {
-                        const uint4 a = wfrag[((s * 3 + sp) * KS + ks) * 32];
-                        hmma_bf16(d1[s][0], a, bx[0][0], bx[0][1]);
-                        hmma_bf16(d1[s][1], a, bx[1][0], bx[1][1]);
+                    for (int sp = 0; sp < NSPLIT; ++sp) {
+                        const uint4 a = wfrag[((s * NSPLIT + sp) * KS + ks) * 32];
+                        hmma_f16(d1[s][0], a, bx[0][0], bx[0][1]);
+                        hmma_f16(d1[s][1], a, bx[1][0], bx[1][1]);
                     }
                 }
             }
@@ -630,16 +643,16 @@ __global__ void __launch_bounds__(256, 3) v2h_dense_mma_kernel(const DenseParams
 #pragma unroll
                 for (int hb = 0; hb < 2; ++hb) {
                     const int off = 8 * (nt & 1) + 4 * ks + 2 * hb;
-                    bx[nt][hb] = onehot_reg(vg[nt >> 1][off >> 3], off & 7);
+                    bx[nt][hb] = onehot_reg_h(vg[nt >> 1][off >> 3], off & 7);
                 }
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (s == 0 ? !want_f : !want_r) continue;
 #pragma unroll
-                for (int sp = 0; sp < 3; ++sp) {
-                    const uint4 a = wfrag[((s * 3 + sp) * KS + ks) * 32];
+                for (int sp = 0; sp < NSPLIT; ++sp) {
+                    const uint4 a = wfrag[((s * NSPLIT + sp) * KS + ks) * 32];
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) hmma_bf16(d1[nt], a, bx[nt][0], bx[nt][1]);
+                    for (int nt = 0; nt < 4; ++nt) hmma_f16(d1[nt], a, bx[nt][0], bx[nt][1]);
                 }
             }
         }
@@ -702,16 +715,29 @@ __global__ void __launch_bounds__(256, 3) v2h_scan_reduce_kernel(const ScanReduc
     const int lo1 = g + (q >> 1);
     const uint32_t qmask = (q & 1) ? 0u : 0x55555555u;
     const bool prob = p.out_kind == CRBM_OUT_PROBABILITY;
+    // pooled probabilities: blocks of bv = (16 / P) * P positions and quad-reduced group sums, as in v2h_mma_kernel<POOL>
+    const bool pooled = prob && p.pooling > 1;
+    const int bstep = pooled ? p.bv : 16, ng = pooled ? p.bv / p.pooling : 0;
+    const float fpool = (float)p.pooling;
+    int gidx[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gidx[i] = (8 * (i >> 1) + 2 * q + (i & 1)) / p.pooling;
 
     for (int n = blockIdx.y * nwarps + warp; n < p.n_rows; n += gridDim.y * nwarps) {
         float best[2] = {-INFINITY, -INFINITY}, sum[2] = {0.f, 0.f};
         int bpos[2] = {0, 0};
         const uint32_t *row0 = p.packed + (size_t)n * p.row_words;
         for (int jb = 0; jb < p.nblk; ++jb) {
-            const int j0 = jb * 16;
+            const int j0 = jb * bstep;
             uint32_t wd[5];
+            {
+                uint32_t rawd[6];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) wd[i] = __ldg(row0 + jb + i);
+                for (int i = 0; i < 6; ++i) rawd[i] = __ldg(row0 + (j0 >> 4) + i);
+                const int shw = 2 * (j0 & 15);                                  // warp-uniform; 0 unless pooled
+#pragma unroll
+                for (int i = 0; i < 5; ++i) wd[i] = __funnelshift_r(rawd[i], rawd[i + 1], shw);
+            }
             float d1[2][4];
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt)
@@ -729,20 +755,50 @@ __global__ void __launch_bounds__(256, 3) v2h_scan_reduce_kernel(const ScanReduc
 #pragma unroll
                     for (int hb = 0; hb < 2; ++hb) {
                         const int off = 8 * nt + 4 * ks + 2 * hb;
-                        bx[nt][hb] = onehot_reg(vg[off >> 3], off & 7);
+                        bx[nt][hb] = onehot_reg_h(vg[off >> 3], off & 7);
                     }
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     if (s == 0 ? !want_f : !want_r) continue;
 #pragma unroll
-                    for (int spl = 0; spl < 3; ++spl) {
-                        const uint4 a = wfrag[((s * 3 + spl) * KS + ks) * 32];
-                        hmma_bf16(d1[0], a, bx[0][0], bx[0][1]);
-                        hmma_bf16(d1[1], a, bx[1][0], bx[1][1]);
+                    for (int spl = 0; spl < NSPLIT; ++spl) {
+                        const uint4 a = wfrag[((s * NSPLIT + spl) * KS + ks) * 32];
+                        hmma_f16(d1[0], a, bx[0][0], bx[0][1]);
+                        hmma_f16(d1[1], a, bx[1][0], bx[1][1]);
                     }
                 }
             }
-            const int jrem = p.Lh - j0 - 2 * q;
+            const int jrem = min(p.Lh - j0, bstep) - 2 * q;      // position 8nt + 2q + e of the block is real iff 8nt + e < jrem
+            if (pooled) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float ev[4], inv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float x = fminf(d1[i >> 1][2 * h + (i & 1)] + bias[h], 60.f);
+                        float t;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * 1.4426950408889634f));
+                        ev[i] = (8 * (i >> 1) + (i & 1) < jrem) ? t : 0.f;
+                        inv[i] = 0.f;
+                    }
+#pragma unroll
+                    for (int gI = 0; gI < BLOCK_POS / 2; ++gI) {
+                        if (gI < ng) {                         // warp-uniform
+                            float part = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) part += gidx[i] == gI ? ev[i] : 0.f;
+                            part += __shfl_xor_sync(0xffffffffu, part, 1);
+                            part += __shfl_xor_sync(0xffffffffu, part, 2);
+                            float r;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fpool + part));
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) inv[i] = gidx[i] == gI ? r : inv[i];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d1[i >> 1][2 * h + (i & 1)] = ev[i] * inv[i];
+                }
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -750,8 +806,11 @@ __global__ void __launch_bounds__(256, 3) v2h_scan_reduce_kernel(const ScanReduc
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         if (8 * nt + e < jrem) {
-                            float x = d1[nt][2 * h + e] + bias[h];
-                            if (prob) x = fast_sigmoid(x);
+                            float x = d1[nt][2 * h + e];
+                            if (!pooled) {
+                                x += bias[h];
+                                if (prob) x = fast_sigmoid(x);
+                            }
                             sum[h] += x;
                             if (x > best[h]) { best[h] = x; bpos[h] = j0 + 8 * nt + 2 * q + e; }   // ascending positions: first max kept
                         }

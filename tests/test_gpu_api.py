@@ -151,13 +151,14 @@ def test_statistics_vector_is_additive_across_shards(data):
     np.testing.assert_array_equal(got, full.fantasy_h.get_value())
 
 
-@pytest.mark.parametrize('K,M,L,ds', [(100, 15, 200, True), (33, 9, 77, False), (16, 25, 500, True)])
-def test_fused_scan_reductions_match_dense_scan(K, M, L, ds):
+@pytest.mark.parametrize('K,M,L,ds,P', [(100, 15, 200, True, 1), (33, 9, 77, False, 1), (16, 25, 500, True, 1),
+                                        (128, 20, 999, True, 5), (24, 12, 83, True, 6), (20, 8, 71, False, 4)])
+def test_fused_scan_reductions_match_dense_scan(K, M, L, ds, P):
     """max / argmax / mean over positions computed inside the scan kernel == the same reductions of the
     dense motifHitProbs tensor (argmax exact wherever the maximum is unique at fp32 resolution, numpy first-maximum semantics)."""
     import crbm_b200
     rs = np.random.RandomState(K + L)
-    m = crbm_b200.CRBM(K, M, doublestranded=ds, seed=1)
+    m = crbm_b200.CRBM(K, M, doublestranded=ds, pooling=P, seed=1)
     m.motifs.set_value((0.4 * rs.randn(K, 1, 4, M)).astype(np.float32))
     m.bias.set_value((-3 + rs.randn(1, K)).astype(np.float32))
     seqs = crbm_b200.PackedSequences.random(37, L, seed=3)

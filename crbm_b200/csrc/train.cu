@@ -122,7 +122,7 @@ static int max_gy(int K) { const int kt = ceil_div(K, KTILE); return num_sms() /
 // 2-bit codes into the packed word.
 struct H2VParams {
     const uint32_t *bits;     // [2][B][kw][FANTASY_WORDS]
-    int Bn, K, kw, M, ds, w_in_smem, words_per_row, list_offset;
+    int Bn, K, kw, M, ds, w_in_smem, words_per_row, list_offset, split, split_log2;
     const float *W, *c;
     uint32_t *v_packed;       // rows of Lv bases
     int v_row_words;
@@ -156,9 +156,14 @@ __global__ void __launch_bounds__(512) h2v_bits_kernel(const H2VParams p) {
         mbar_wait(bar, 0);
         Wsm = wbuf;
     }
-    // work item = (particle n, 16-position word w); one item per warp, CTAs sized so that one wave covers the SMs
-    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (item >= p.Bn * p.words_per_row) return;
+    // work item = (particle n, 16-position word w), shared by `split` adjacent warps of the CTA (a power of two): warp `part`
+    // scans the k-tiles part, part + split, ...; the partial activities are combined through shared memory in a fixed order.
+    // (One warp per item left 10-13 warps per SM walking 2 * kw * 2 rounds each: latency bound, 83 us per launch at K = 512.)
+    const int wslot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int part = wslot & (p.split - 1);
+    const int item_raw = wslot >> p.split_log2;
+    const bool live = item_raw < p.Bn * p.words_per_row;
+    const int item = live ? item_raw : 0;
     const int n = item / p.words_per_row, w = item - n * p.words_per_row, lane = threadIdx.x & 31;
     const int pidx = lane & 15, ah = lane >> 4;
     const int i = 16 * w + pidx;
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(512) h2v_bits_kernel(const H2VParams p) {
     for (int s = 0; s < strands; ++s) {
         const float *Wbase = s == 0 ? Wsm + (size_t)(2 * ah) * M : Wsm + (size_t)(3 - 2 * ah) * M;
         const int dir = s == 0 ? M : -M;                     // second base row: +M (forward) / -M (reverse)
-        for (int t = 0; t < p.kw; ++t) {
+        for (int t = live ? part : p.kw; t < p.kw; t += p.split) {
             const uint32_t *tile = p.bits + (((size_t)s * p.Bn + n) * p.kw + t) * FANTASY_WORDS;
             for (int jb0 = jb_lo; jb0 <= jb_hi; jb0 += 2) {
                 const int jbl = jb0 + (lane >> 4), f = lane & 15;
@@ -216,6 +221,20 @@ __global__ void __launch_bounds__(512) h2v_bits_kernel(const H2VParams p) {
             }
         }
     }
+    if (p.split > 1) {
+        // the list area of a warp is free now: it carries the warp's partial sums to the item's first warp
+        float2 *mine = reinterpret_cast<float2 *>(list);
+        mine[lane] = make_float2(acc0, acc1);
+        __syncthreads();
+        if (part == 0) {
+            for (int i = 1; i < p.split; ++i) {
+                const float2 o = reinterpret_cast<const float2 *>(list + (size_t)i * H2V_LIST)[lane];
+                acc0 += o.x;
+                acc1 += o.y;
+            }
+        }
+    }
+    if (part != 0 || !live) return;
     // lanes (p, 0) and (p, 1) hold bases {A,C} and {G,T} of position i
     const float o0 = __shfl_xor_sync(0xffffffffu, acc0, 16), o1 = __shfl_xor_sync(0xffffffffu, acc1, 16);
     const bool active = ah == 0 && i < Lv;
@@ -752,8 +771,17 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
         const size_t bits_bytes = (size_t)2 * a->batchsize * kw * FANTASY_WORDS * sizeof(uint32_t);
         const size_t w_bytes = (size_t)K * 16 * M;
         const int h2v_items = a->batchsize * ceil_div(Lv, 16);
-        int h2v_nw = ceil_div(h2v_items, num_sms());
-        h2v_nw = h2v_nw < 2 ? 2 : h2v_nw > 16 ? 16 : h2v_nw;
+        // warps per item: at most 4, at least two k-tiles per warp, at most ~64 warps per SM
+        // (measured: C2, kw = 4: 1 / 2 / 4 warps -> 47.5 / 46.9 / 49.0 us per step; C4, kw = 16: 1 / 4 warps -> 1515 / 1135 us)
+        int split_log2 = 0;
+        while (split_log2 < 2 && (4 << split_log2) <= kw && (long long)h2v_items * (2 << split_log2) <= 64ll * num_sms()) ++split_log2;
+        if (const char *e = getenv("CRBM_H2V_SPLIT")) split_log2 = atoi(e) <= 1 ? 0 : atoi(e) == 2 ? 1 : 2;
+        while ((1 << split_log2) > kw) --split_log2;
+        const int h2v_split = 1 << split_log2;
+        const int h2v_slots = h2v_items * h2v_split;
+        int h2v_nw = ceil_div(h2v_slots, num_sms());
+        h2v_nw = h2v_nw < 4 ? 4 : h2v_nw > 16 ? 16 : h2v_nw;
+        h2v_nw = ceil_div(h2v_nw, h2v_split) * h2v_split;                // the warps of an item sit in one CTA
         const size_t list_bytes = (size_t)h2v_nw * H2V_LIST * sizeof(uint32_t);
         const int w_in_smem = w_bytes + 16 + list_bytes <= 200 * 1024;
         const size_t list_offset = w_in_smem ? w_bytes + 16 : 16;
@@ -767,11 +795,12 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
             const bool last = it == a->cd_k - 1;
             H2VParams h{};
             h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.kw = kw; h.M = M; h.ds = ds; h.w_in_smem = w_in_smem; h.words_per_row = ceil_div(Lv, 16); h.list_offset = (int)list_offset;
+            h.split = h2v_split; h.split_log2 = split_log2;
             h.W = a->W; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words;
             h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
             h.seed = a->seed; h.step_dev = a->step_dev;
             h.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
-            CRBM_CHECK_CUDA(launch_chain(h2v_bits_kernel, dim3(ceil_div(h2v_items, h2v_nw)), dim3(32 * h2v_nw), h2v_smem, s, h));
+            CRBM_CHECK_CUDA(launch_chain(h2v_bits_kernel, dim3(ceil_div(h2v_slots, h2v_nw)), dim3(32 * h2v_nw), h2v_smem, s, h));
             CRBM_CHECK_LAUNCH();
 
             V2HParams q{};

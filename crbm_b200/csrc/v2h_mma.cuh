@@ -435,28 +435,54 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
                 if (s == 1 && !p.ds) continue;
                 const float *inj = s == 0 ? p.u_fwd : p.u_rc;
                 uint32_t mine = 0u;
+                bool hit[8];                                     // index 4*h + 2*nt + e
+                if (inj) {
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int k = mtile * MTILE + 8 * h + g;
-                    float u[4];                                  // positions (nt, e): index 2*nt + e
-                    if (inj) {
+                    for (int h = 0; h < 2; ++h) {
+                        const int k = mtile * MTILE + 8 * h + g;
                         const float *up = inj + (size_t)(n * p.K + (kval[h] ? k : 0)) * p.Lh + j0 + 2 * q;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) u[i] = (8 * (i >> 1) + (i & 1) < jrem) ? up[8 * (i >> 1) + (i & 1)] : 1.f;
-                    } else {
-                        const uint4 rnd = philox4x32(make_uint4((uint32_t)(n * p.K + k), (uint32_t)(jb * 4 + q), ctr_hi,
-                                                                s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC), key);
-                        u[0] = u01(rnd.x); u[1] = u01(rnd.y); u[2] = u01(rnd.z); u[3] = u01(rnd.w);
+                        for (int i = 0; i < 4; ++i) {
+                            const float u = (8 * (i >> 1) + (i & 1) < jrem) ? up[8 * (i >> 1) + (i & 1)] : 1.f;
+                            hit[4 * h + i] = d1[s][i >> 1][2 * h + (i & 1)] > u;
+                        }
                     }
+                } else {
+                    // One Philox draw per lane and strand = eight 16-bit uniforms for its 2 motifs x 4 positions. A sample is
+                    // decided by floor(65536 p) against its 16 bits; only when the two are equal (probability 2^-16 per
+                    // sample) does the warp take a second draw and compare the fraction: exact Bernoulli(p) to 2^-32, at
+                    // half the generator work of one 24-bit uniform per sample (the generator was a third of this kernel).
+                    const uint32_t tag = s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC;
+                    const uint4 ctr = make_uint4((uint32_t)(n * p.K + mtile * MTILE + g), (uint32_t)(jb * 4 + q), ctr_hi, tag);
+                    const uint4 rnd = philox4x32(ctr, key);
+                    const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
+                    float fr[8];
+                    bool amb = false;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float t = d1[s][(i >> 1) & 1][2 * (i >> 2) + (i & 1)] * 65536.f;
+                        const int ti = (int)t, u16 = (int)((rw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                        fr[i] = ti == u16 ? t - (float)ti : -1.f;
+                        hit[i] = ti > u16;
+                        amb = amb || ti == u16;
+                    }
+                    if (__any_sync(0xffffffffu, amb)) {          // rare: ~1 % of the blocks
+                        const uint4 r2 = philox4x32_call(make_uint4(ctr.x, ctr.y, ctr.z, tag + 16u), key);
+                        const uint32_t r2w[4] = {r2.x, r2.y, r2.z, r2.w};
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            if (fr[i] >= 0.f) hit[i] = fr[i] * 65536.f > (float)((r2w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
                         for (int e = 0; e < 2; ++e) {
-                            const bool hit = d1[s][nt][2 * h + e] > u[2 * nt + e];
-                            const uint32_t word = __ballot_sync(0xffffffffu, hit);
+                            const uint32_t word = __ballot_sync(0xffffffffu, hit[4 * h + 2 * nt + e]);
                             if (lane == ((h * 2 + nt) * 2 + e)) mine = word;
                         }
-                }
                 // the 8 words of this m-tile: word index ((mt*2+h)*2+nt)*2+e with mt = mtile & 1, k-tile = mtile >> 1
                 if (lane < 8)
                     p.bits[(((size_t)s * p.n_rows + n) * ktiles + (mtile >> 1)) * (njb * 16) + jb * 16 + (mtile & 1) * 8 + lane] = mine;

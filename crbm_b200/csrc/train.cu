@@ -367,9 +367,24 @@ __device__ __forceinline__ void reduce_partials_body(const ReduceParams &p) {
     const bool with_rc = tail >= 0 && tail < pair;
     const float *src = S.partial + ((size_t)kt * S.gy * S.nacc + o) * 32 + lane;
     float v = 0.f, vr = 0.f;
-    for (int c = warp; c < S.gy; c += 4) {
-        v += src[(size_t)c * S.nacc * 32];
-        if (with_rc) vr += src[((size_t)c * S.nacc + pair) * 32];
+    {
+        // four independent loads in flight per warp and pass (the partials are L2 resident; the loop is latency bound)
+        const size_t cs = (size_t)S.nacc * 32;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int c = warp; c < S.gy; c += 16) {
+            const float t0 = src[c * cs];
+            const float t1 = c + 4 < S.gy ? src[(c + 4) * cs] : 0.f;
+            const float t2 = c + 8 < S.gy ? src[(c + 8) * cs] : 0.f;
+            const float t3 = c + 12 < S.gy ? src[(c + 12) * cs] : 0.f;
+            a0 += t0; a1 += t1; a2 += t2; a3 += t3;
+            if (with_rc) {
+                vr += src[c * cs + pair * 32];
+                if (c + 4 < S.gy) vr += src[(c + 4) * cs + pair * 32];
+                if (c + 8 < S.gy) vr += src[(c + 8) * cs + pair * 32];
+                if (c + 12 < S.gy) vr += src[(c + 12) * cs + pair * 32];
+            }
+        }
+        v = (a0 + a1) + (a2 + a3);
     }
     sh[warp][lane] = v;
     shr[warp][lane] = vr;

@@ -395,44 +395,57 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src, world=1, rank=0):
 
 
 def bench_e2e(model, B, Lt, world, dev, steps):
-    """Through the reference-facing call with HOST buffers: pinned one-hot fp32 minibatch -> device every step, the
-    step itself, and a device -> host read of the updated visible bias c (16 bytes) every step."""
+    """Through the reference-facing call with HOST buffers, every step: a pinned one-hot fp32 minibatch is copied host -> device
+    inside `CRBM._trainingFct`, the step runs, and the updated visible bias c (16 bytes) is read device -> host.
+    `value`: the read-back is an asynchronous copy into a ring of pinned slots (consumed after a stream synchronisation every
+    `ring` steps), so the host keeps issuing steps while the device works — the way a training loop that logs a metric runs.
+    `blocking_read_value`: the host blocks on every step's read-back before it issues the next step."""
     import numpy as np
     import torch
-    nb = 16
+    nb, ring = 16, 64
     rs = np.random.RandomState(7)
     host = []
     for i in range(nb):
         codes = torch.from_numpy(rs.randint(0, 4, size=(B, Lt)))
         oh = torch.nn.functional.one_hot(codes, 4).permute(0, 2, 1).reshape(B, 1, 4, Lt).to(torch.float32).contiguous()
         host.append(oh.pin_memory())
-    sink = torch.empty(4, dtype=torch.float32).pin_memory()
+    sink = torch.empty((ring, 4), dtype=torch.float32).pin_memory()
+    c_dev = model._t_c.reshape(-1)
 
-    def one(i):
+    def one(i, blocking):
         model._trainingFct(host[i % nb], local_shard=True)          # pinned host one-hot batch in, copied by the call
-        sink.copy_(model._t_c.reshape(-1), non_blocking=False)      # device -> host read of the step's result
+        sink[i % ring].copy_(c_dev, non_blocking=not blocking)      # device -> host read of the step's result
+        if not blocking and i % ring == ring - 1:
+            torch.cuda.current_stream().synchronize()               # the ring is consumed: its slots may be overwritten
 
-    for i in range(5):
-        one(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        one(i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    return {'value': steps * B * Lt * world / (ms * 1e-3), 'unit': 'nt/s', 'h2d_bytes_per_step': B * 4 * Lt * 4,
-            'd2h_bytes_per_step': 16, 'steps': steps,
-            'call': 'CRBM._trainingFct(one-hot fp32 batch in pinned host memory) + read back c'}
+    def run(blocking, n):
+        for i in range(5):
+            one(i, True)
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            one(i, blocking)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return n * B * Lt * world / (ms * 1e-3)
+
+    steps = max(ring, steps // ring * ring)
+    blocking = run(True, min(steps, 1024))
+    value = run(False, steps)
+    return {'value': value, 'unit': 'nt/s', 'h2d_bytes_per_step': B * 4 * Lt * 4, 'd2h_bytes_per_step': 16, 'steps': steps,
+            'blocking_read_value': blocking,
+            'call': 'CRBM._trainingFct(one-hot fp32 batch in pinned host memory) + read back c every step (asynchronous copy into a '
+                    'pinned ring, stream synchronised every %d steps; blocking_read_value: host blocks on every read-back)' % ring}
 
 
 if __name__ == '__main__':

@@ -151,6 +151,8 @@ class CRBM(object):
         if batchsize % self._world != 0:
             raise Exception("batchsize must be divisible by the number of data-parallel ranks.")
         self._local_batch = batchsize // self._world
+        self._p2p_loopback = self._world == 1 and os.environ.get('CRBM_P2P_LOOPBACK', '') == '1'
+        self._dp = self._world > 1 or self._p2p_loopback           # steps go through the data-parallel exchange
 
         x = np.random.randn(num_motifs, 1, input_dims, motif_length).astype(np.float32)        # reference :127
         if not rho:                                                                             # reference :136-140
@@ -446,12 +448,22 @@ class CRBM(object):
         IPC handles exchanged through the process group). Returns None (-> NCCL all-reduce) if that is not possible."""
         if self._p2p is not None:
             return self._p2p or None
-        import os
         self._p2p = False
-        if self._world == 1 or self._world > _lib.MAX_PEERS or os.environ.get('CRBM_DP', 'p2p') != 'p2p':
-            return None
         torch = _torch()
         lib = _lib.load()
+        if self._world == 1 and self._p2p_loopback:
+            # single-rank loop-back (CRBM_P2P_LOOPBACK=1): the peer-memory kernels run with this rank as its only peer, in
+            # ordinary device memory — exercises the publish / poll / rank-ordered sum path on a one-GPU box
+            nfl = int(lib.crbm_train_stats_floats(self.num_motifs, self.motif_length))
+            stride = (nfl + 63) // 64 * 64
+            buf = torch.zeros(2 * stride + 64, dtype=torch.float32, device=self._device)
+            self._ensure_train_state()
+            self._p2p = dict(buf=buf, hdl=None, stride=stride, peer_stats=[buf.data_ptr()], peer_flags=[buf.data_ptr() + 2 * stride * 4],
+                             ticket=torch.zeros(1, dtype=torch.int32, device=self._device),
+                             error=torch.zeros(1, dtype=torch.int32, device=self._device), local_stats=buf.data_ptr())
+            return self._p2p
+        if self._world == 1 or self._world > _lib.MAX_PEERS or os.environ.get('CRBM_DP', 'p2p') != 'p2p':
+            return None
         try:
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm_mem
@@ -514,7 +526,7 @@ class CRBM(object):
         row_bytes = seqs.row_words * 4
         a = self._fill_args(seqs.words.data_ptr() + start * row_bytes, seqs.row_words, end - start, seqs.L, u_v, u_h, u_hp)
         s = _lib.stream_handle()
-        if self._world > 1:
+        if self._dp:
             p = self._p2p_setup()
             if p is not None:
                 a.step = self._dp_seq
@@ -612,7 +624,7 @@ class CRBM(object):
         if count <= 0:
             return
         eng = self._graph_engine(seqs, steps_per_graph)
-        p = self._p2p_setup() if self._world > 1 else None
+        p = self._p2p_setup() if self._dp else None
         if p is not None:
             # whole steps (accumulate -> publish -> peer all-reduce + update) replayed as graphs of an even number of
             # steps starting at an even sequence number, so that the buffer parity of every graph node is static
@@ -684,7 +696,7 @@ class CRBM(object):
         on a second stream meanwhile, then positive phase -> reduction -> update. The one-hot validation
         result is checked at the next call / synchronisation point."""
         if (uniforms is None and self._use_graphs and not isinstance(data, PackedSequences) and getattr(data, 'ndim', 0) == 4
-                and (self._world == 1 or self._p2p_setup() is not None)):
+                and (not self._dp or self._p2p_setup() is not None)):
             if self._world > 1 and not local_shard:         # this rank's rows of the global minibatch
                 n = int(data.shape[0])
                 per = (n + self._world - 1) // self._world
@@ -717,7 +729,7 @@ class CRBM(object):
         if src.dtype != torch.float32 or not src.is_contiguous():
             src = src.to(torch.float32).contiguous()
         a, pa = eng['args'], None
-        if self._world > 1:
+        if self._dp:
             # data parallel: statistics into buffer `parity` of the peer-mapped double buffer, sequence number per step
             p = self._p2p
             a.step = self._dp_seq

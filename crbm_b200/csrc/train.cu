@@ -281,12 +281,6 @@ struct ReduceParams {
     int cnt_row_words[2], cnt_n[2], cnt_L[2];
     const int *batch_index;
     float *cnt_out[2];      // 4 floats each
-    // data-parallel p2p mode: the last CTA to finish publishes `sequence` (system scope) in the flag arrays of all peers
-    unsigned int *ticket;   // device counter, zero between launches
-    unsigned long long *peer_flags[CRBM_MAX_PEERS];   // every rank's flag array [n_ranks][2]; entry [rank][parity] is ours
-    int n_ranks, rank, parity;
-    unsigned long long sequence;
-    const unsigned long long *sequence_dev;   // if set: sequence = *sequence_dev + 1
 };
 
 // Counts of the four base codes over n rows of L packed bases; one CTA, result written (not accumulated).
@@ -315,29 +309,11 @@ __device__ void count_bases_block(const uint32_t *__restrict__ rows, int row_wor
     if (threadIdx.x < 4) out[threadIdx.x] = (float)tot[threadIdx.x];
 }
 __device__ __forceinline__ void reduce_partials_body(const ReduceParams &p);
-__device__ __forceinline__ void reduce_publish(const ReduceParams &p) {
-    if (!p.n_ranks) return;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int t = atomicAdd(p.ticket, 1u);
-        if (t == gridDim.x - 1) {
-            *p.ticket = 0u;
-            __threadfence_system();
-            const unsigned long long seq = p.sequence_dev ? *p.sequence_dev + 1ull : p.sequence;
-            // one-way stores over NVLink: every peer polls its own memory
-            for (int r = 0; r < p.n_ranks; ++r)
-                *reinterpret_cast<volatile unsigned long long *>(p.peer_flags[r] + 2 * p.rank + p.parity) = seq;
-            __threadfence_system();
-        }
-    }
-}
 
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const ReduceParams p) {
     pdl_wait();
     pdl_launch_dependents();
     reduce_partials_body(p);
-    reduce_publish(p);
 }
 
 __device__ __forceinline__ void reduce_partials_body(const ReduceParams &p) {
@@ -438,6 +414,19 @@ struct ApplyParams {
     int *batch_index_dev;
     int n_batches;
 };
+// The update arithmetic, shared by the single-rank and the peer-memory kernel with explicit roundings (no FMA contraction that
+// could differ between the two), so that a one-rank exchange reproduces the plain step bit for bit.
+__device__ __forceinline__ float sparsity_factor(float h_fwd, float nhd, float rho, int K) {
+    const float pk = __fdiv_rn(h_fwd, nhd);
+    const float t = __fsub_rn(__fdiv_rn(rho, pk), __fdiv_rn(__fsub_rn(1.f, rho), __fsub_rn(1.f, pk)));
+    return __fdiv_rn(-t, __fmul_rn((float)K, nhd));
+}
+// v <- mu v + lr (data / nd - model / nm - lam reg)
+__device__ __forceinline__ float next_velocity(float vel, float data, float nd, float model, float nm, float reg, float mu, float lr, float lam) {
+    const float g = __fsub_rn(__fsub_rn(__fdiv_rn(data, nd), __fdiv_rn(model, nm)), __fmul_rn(lam, reg));
+    return __fadd_rn(__fmul_rn(mu, vel), __fmul_rn(lr, g));
+}
+
 __global__ void apply_update_kernel(const ApplyParams p) {
     pdl_wait();
     pdl_launch_dependents();
@@ -448,31 +437,26 @@ __global__ void apply_update_kernel(const ApplyParams p) {
     const float strands = p.ds ? 2.f : 1.f;
     if (gid < nW + p.K) {
         const int k = gid < nW ? gid / (4 * p.M) : gid - nW;
-        const float pk = st[p.lay.h_fwd + k] / nhd;
-        const float gk = -(p.rho / pk - (1.f - p.rho) / (1.f - pk)) / ((float)p.K * nhd);
+        const float gk = sparsity_factor(st[p.lay.h_fwd + k], nhd, p.rho, p.K);
+        const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
         if (gid < nW) {
-            const float gd = st[p.lay.vh_data + gid] / (strands * nhd);
-            const float gm = st[p.lay.vh_model + gid] / (strands * nhm);
-            const float reg = gk * st[p.lay.vh_q + gid];
-            const float v = p.mu * p.vW[gid] + p.lr * (gd - gm - p.lam * reg);
+            const float v = next_velocity(p.vW[gid], st[p.lay.vh_data + gid], nd, st[p.lay.vh_model + gid], nm,
+                                          __fmul_rn(gk, st[p.lay.vh_q + gid]), p.mu, p.lr, p.lam);
             p.vW[gid] = v;
-            p.W[gid] += v;
+            p.W[gid] = __fadd_rn(p.W[gid], v);
         } else {
-            const float gd = st[p.lay.h_data + k] / (strands * nhd);
-            const float gm = st[p.lay.h_model + k] / (strands * nhm);
-            const float reg = gk * st[p.lay.h_q + k];
-            const float v = p.mu * p.vb[k] + p.lr * (gd - gm - p.lam * reg);
+            const float v = next_velocity(p.vb[k], st[p.lay.h_data + k], nd, st[p.lay.h_model + k], nm,
+                                          __fmul_rn(gk, st[p.lay.h_q + k]), p.mu, p.lr, p.lam);
             p.vb[k] = v;
-            p.b[k] += v;
+            p.b[k] = __fadd_rn(p.b[k], v);
         }
     } else if (gid < nW + p.K + 4) {
         const int a = gid - nW - p.K;
-        const float nvd = st[p.lay.n_vis_data], nvm = st[p.lay.n_vis_model];
-        const float gd = (st[p.lay.v_data + a] + st[p.lay.v_data + 3 - a]) / nvd;      // f_a + f_{3-a}, convRBM.py:345
-        const float gm = (st[p.lay.v_model + a] + st[p.lay.v_model + 3 - a]) / nvm;
-        const float v = p.mu * p.vc[a] + p.lr * (gd - gm);
+        // f_a + f_{3-a}, convRBM.py:345
+        const float v = next_velocity(p.vc[a], __fadd_rn(st[p.lay.v_data + a], st[p.lay.v_data + 3 - a]), st[p.lay.n_vis_data],
+                                      __fadd_rn(st[p.lay.v_model + a], st[p.lay.v_model + 3 - a]), st[p.lay.n_vis_model], 0.f, p.mu, p.lr, 0.f);
         p.vc[a] = v;
-        p.c[a] += v;
+        p.c[a] = __fadd_rn(p.c[a], v);
     } else if (gid == nW + p.K + 4) {
         if (p.step_dev) *p.step_dev += 1ull;
         if (p.batch_index_dev) { const int nb = *p.batch_index_dev + 1; *p.batch_index_dev = nb >= p.n_batches ? 0 : nb; }
@@ -489,6 +473,8 @@ struct ApplyP2PParams {
     int n_ranks, parity;
     const float *peer_stats[CRBM_MAX_PEERS];      // every rank's statistics double buffer (peer-mapped)
     const unsigned long long *local_flags;        // this rank's flag array [n_ranks][2], written by the peers
+    unsigned long long *peer_flags[CRBM_MAX_PEERS]; // every rank's flag array; entry [rank][parity] of each is ours to write
+    int rank;
     size_t stats_stride;
     unsigned long long sequence;
     const unsigned long long *sequence_dev;
@@ -523,13 +509,22 @@ __global__ void __launch_bounds__(256) apply_update_p2p_kernel(const ApplyP2PPar
     const ApplyParams &ap = p.ap;
     if (threadIdx.x < p.n_ranks) {
         const unsigned long long want = p.sequence_dev ? *p.sequence_dev + 1ull : p.sequence;
-        const volatile unsigned long long *f = p.local_flags + 2 * threadIdx.x + p.parity;
+        // publish: this rank's statistics are complete (the reduction is the predecessor grid): one thread per peer stores the
+        // step's sequence number into that peer's flag array (one-way NVLink store; every peer polls its own memory).
+        // (The first version published from the last CTA of the reduction, elected by a ticket all 758 CTAs took after a
+        // fence: measured with one rank as its own peer, the exchange cost 9.2 us per step.)
+        if (blockIdx.x == 0)        // release at system scope: the statistics this thread can see are visible before the flag
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_flags[threadIdx.x] + 2 * p.rank + p.parity), "l"(want) : "memory");
+        // acquire loads instead of a volatile spin + system fence (a MEMBAR.SYS per block was most of the exchange's cost)
+        const unsigned long long *f = p.local_flags + 2 * threadIdx.x + p.parity;
         long long spins = 0;
-        while (*f < want) {
+        for (;;) {
+            unsigned long long seen;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+            if (seen >= want) break;
             if (++spins > (1ll << 25)) { *p.error_flag = 1; break; }       // ~2 s: a peer is gone; do not hang the GPU
             __nanosleep(32);
         }
-        __threadfence_system();
     }
     __syncthreads();
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -545,25 +540,20 @@ __global__ void __launch_bounds__(256) apply_update_p2p_kernel(const ApplyP2PPar
         float s[6];
         p2p_sums<6>(p, idx, s);
         const float nhd = s[0], nhm = s[1];
-        const float pk = s[2] / nhd;
-        const float gk = -(ap.rho / pk - (1.f - ap.rho) / (1.f - pk)) / ((float)ap.K * nhd);
-        const float gd = s[3] / (strands * nhd);
-        const float gm = s[4] / (strands * nhm);
-        const float reg = gk * s[5];
+        const float gk = sparsity_factor(s[2], nhd, ap.rho, ap.K);
+        const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
         float *vel = isW ? ap.vW + gid : ap.vb + k, *par = isW ? ap.W + gid : ap.b + k;
-        const float v = ap.mu * *vel + ap.lr * (gd - gm - ap.lam * reg);
+        const float v = next_velocity(*vel, s[3], nd, s[4], nm, __fmul_rn(gk, s[5]), ap.mu, ap.lr, ap.lam);
         *vel = v;
-        *par += v;
+        *par = __fadd_rn(*par, v);
     } else if (gid < nW + ap.K + 4) {
         const int a = gid - nW - ap.K;
         const int idx[6] = {lay.n_vis_data, lay.n_vis_model, lay.v_data + a, lay.v_data + 3 - a, lay.v_model + a, lay.v_model + 3 - a};
         float s[6];
         p2p_sums<6>(p, idx, s);
-        const float gd = (s[2] + s[3]) / s[0];
-        const float gm = (s[4] + s[5]) / s[1];
-        const float v = ap.mu * ap.vc[a] + ap.lr * (gd - gm);
+        const float v = next_velocity(ap.vc[a], __fadd_rn(s[2], s[3]), s[0], __fadd_rn(s[4], s[5]), s[1], 0.f, ap.mu, ap.lr, 0.f);
         ap.vc[a] = v;
-        ap.c[a] += v;
+        ap.c[a] = __fadd_rn(ap.c[a], v);
     }
     // the step / minibatch counters are advanced by the last block to finish: every block has read *sequence_dev by then
     __syncthreads();
@@ -874,11 +864,6 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
         red.cnt_rows[1] = a->v_model; red.cnt_row_words[1] = a->v_row_words; red.cnt_n[1] = a->batchsize; red.cnt_L[1] = Lv;
         red.batch_index = a->batch_index_dev;
         red.cnt_out[0] = st + lay.v_data; red.cnt_out[1] = st + lay.v_model;
-        if (p2p) {
-            red.ticket = p2p->ticket; red.n_ranks = p2p->n_ranks; red.rank = p2p->rank; red.parity = p2p->parity;
-            for (int r = 0; r < p2p->n_ranks; ++r) red.peer_flags[r] = p2p->peer_flags[r];
-            red.sequence = p2p->sequence; red.sequence_dev = a->step_dev;
-        }
         CRBM_CHECK_CUDA(launch_chain(reduce_partials_kernel, dim3(red.block_start[red.nsets] + 2), dim3(128), 0, s, red));
         CRBM_CHECK_LAUNCH();
     }
@@ -949,6 +934,8 @@ int crbm_train_apply_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, voi
     p.n_ranks = p2p->n_ranks; p.parity = p2p->parity;
     for (int r = 0; r < p2p->n_ranks; ++r) p.peer_stats[r] = p2p->peer_stats[r];
     p.local_flags = p2p->peer_flags[p2p->rank];
+    for (int r = 0; r < p2p->n_ranks; ++r) p.peer_flags[r] = p2p->peer_flags[r];
+    p.rank = p2p->rank;
     p.stats_stride = p2p->stats_stride; p.sequence = p2p->sequence; p.sequence_dev = a->step_dev; p.error_flag = p2p->error_flag;
     p.ticket = p2p->ticket;
     const int n = a->K * 4 * a->M + a->K + 4;

@@ -185,11 +185,13 @@ int crbm_train_step_onehot(const crbm_train_args *args, const struct crbm_p2p_ar
 /* ---- data-parallel update without a separate collective: one-shot all-reduce over NVLink peer memory, fused into the update
  * Every rank exposes, in peer-mapped memory (CUDA IPC / VMM; torch symmetric memory on the Python host), a double-buffered
  * statistics vector and a flag array [n_ranks][2]. crbm_train_accumulate_p2p is crbm_train_accumulate writing into buffer
- * `parity` (args->stats must point at it) and then, from the last CTA of the reduction, storing `sequence` into entry
- * [rank][parity] of EVERY rank's flag array (one-way NVLink stores after a system-scope fence). crbm_train_apply_p2p polls
- * its own flag array until all ranks carry `sequence`, then every thread loads its statistics entries from all ranks'
- * buffers at once (one NVLink round trip), adds them in rank order (bit-identical sums on every rank, so the replicas stay
- * identical) and applies the update: no NCCL launch, no extra kernel, and whole steps sit in one CUDA graph.
+ * `parity` (args->stats must point at it). crbm_train_apply_p2p first stores `sequence` into entry [rank][parity] of EVERY rank's
+ * flag array (one-way NVLink stores after a system-scope fence: this rank's statistics are complete, the reduction being the
+ * predecessor grid), then polls its own flag array until all ranks carry `sequence`, then every thread loads its statistics
+ * entries from all ranks' buffers at once (one NVLink round trip), adds them in rank order (bit-identical sums on every rank, so
+ * the replicas stay identical) and applies the update with the arithmetic of crbm_train_apply: no NCCL launch, no extra kernel,
+ * and whole steps sit in one CUDA graph. With n_ranks == 1 (the rank as its own peer, ordinary device memory) the result is
+ * bit-identical to crbm_train_step.
  * The wait is bounded (~2 s); on expiry *error_flag is set to 1. `sequence` must increase by one per step on every rank and
  * consecutive steps must alternate `parity`; when args->step_dev is set the sequence is *step_dev + 1. */
 #define CRBM_MAX_PEERS 8

@@ -89,6 +89,62 @@ def test_graph_replay_equals_eager_steps(data):
         np.testing.assert_array_equal(a, b)
 
 
+@pytest.mark.parametrize('P,cd_k', [(1, 1), (1, 3), (4, 2)])
+def test_step_issued_in_phases_equals_whole_step(data, P, cd_k):
+    """crbm_train_phases: NEGATIVE, then POSITIVE | REDUCE, then APPLY as three calls == crbm_train_step, bit for bit
+    (the partial-sum buffers are fixed, so the parts of a step may be issued separately)."""
+    import torch
+    import crbm_b200
+    from crbm_b200 import CRBM, _lib
+    lib = _lib.load()
+    Lt = 15 - 1 + (186 // P) * P
+    seqs = crbm_b200.PackedSequences.from_onehot(data[:60, :, :, :Lt])
+    out = []
+    for split in (False, True):
+        np.random.seed(2)
+        m = CRBM(num_motifs=20, motif_length=15, pooling=P, cd_k=cd_k, seed=9, batchsize=20)
+        for i in range(3):
+            a = m._fill_args(seqs.words.data_ptr() + 20 * i * seqs.row_words * 4, seqs.row_words, 20, seqs.L)
+            a.step = i
+            s = _lib.stream_handle()
+            if split:
+                _lib.check(lib.crbm_train_phases(a, _lib.PHASE_NEGATIVE, s))
+                _lib.check(lib.crbm_train_phases(a, _lib.PHASE_POSITIVE | _lib.PHASE_REDUCE, s))
+                _lib.check(lib.crbm_train_phases(a, _lib.PHASE_APPLY, s))
+            else:
+                _lib.check(lib.crbm_train_step(a, s))
+        torch.cuda.synchronize()
+        out.append((m.motifs.get_value(), m.bias.get_value(), m.c.get_value(), m.fantasy_h.get_value(), m.fantasy_h_prime.get_value()))
+    for x, y in zip(*out):
+        np.testing.assert_array_equal(x, y)
+    with pytest.raises(ValueError):
+        _lib.check(lib.crbm_train_phases(a, 0, _lib.stream_handle()))
+
+
+def test_peer_memory_exchange_loopback_equals_plain_step(data, monkeypatch):
+    """The data-parallel kernels (publishing reduction + polling, rank-ordered sum inside the update, csrc/train.cu) with this
+    rank as its only peer (CRBM_P2P_LOOPBACK=1) must reproduce the single-rank step bit for bit — graph replay, eager packed
+    steps and the host-fed one-hot call alike. (The multi-rank check is tests/test_gpu_multi.py.)"""
+    import crbm_b200
+    from crbm_b200 import CRBM
+    seqs = crbm_b200.PackedSequences.from_onehot(data[:20 * 11 + 5])
+    out = []
+    for loopback in ('1', ''):
+        monkeypatch.setenv('CRBM_P2P_LOOPBACK', loopback)
+        np.random.seed(4)
+        m = CRBM(num_motifs=14, motif_length=11, epochs=2, cd_k=2, seed=21)
+        assert m._dp == (loopback == '1')
+        m._train_full_batches(seqs, 0, 11)        # (not fit(): its evaluation pass advances the Philox step of the plain path only)
+        for i in range(3):
+            m._trainingFct(data[20 * i:20 * i + 20])
+        m._train_packed(seqs, 0, 20)
+        out.append((m.motifs.get_value(), m.bias.get_value(), m.c.get_value(), m.fantasy_h.get_value()))
+        if loopback:
+            m._p2p_check()
+    for a, b in zip(*out):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_unsupported_shapes_fail_loudly(data):
     from crbm_b200 import CRBM
     m = CRBM(num_motifs=2, motif_length=34)

@@ -153,3 +153,22 @@ def test_batch_indices_and_truncation():
     m = CRBM(num_motifs=2, motif_length=20, pooling=5, batchsize=20)
     assert m._iterateBatchIndices(45, 20) == [[0, 20], [20, 40], [40, 45]]
     assert m._truncated_length(1000) == 999
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm: oracle/crbm_torch_cpu.py on the host cores) prints exactly one JSON line on
+    stdout with the keys the driver reads; nothing else may reach stdout."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup', '1'],
+                       capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'nt/s' and d['higher_is_better'] is True and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
+    assert d['e2e'] == {'value': d['value'], 'unit': 'nt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert d['config']['workload'].startswith('C2')

@@ -391,7 +391,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) v2h_dense_tc_kernel(const TcPar
                         if (valid && c < krem) __stcs(reinterpret_cast<float *>(ub + offc[c]), x[c]);
                 }
             };
-            // the TMEM load of the next chunk is in flight while the current one is finished
+            // the TMEM load of the next chunk is in flight while the current one is finished (tcgen05.wait::ld waits for every
+            // outstanding load, so the pipeline is one load deep; 16-column loads were measured: 67.7 % instead of 68.6 % of HBM)
             uint32_t va[8], vb[8];
             int ch = sub;
             if (ch < nch8) tmem_ld8(trow + ch * 8, va);

@@ -37,7 +37,7 @@ WORKLOADS = {
                batch=128, L=500, n_seq=65536, default_steps=512),
 }
 METRIC = 'CD-1 train nt/s'
-SCAN_TRAFFIC = 8209836992   # dram__bytes_read.sum + dram__bytes_write.sum of the scan launch (profiles/r01_ncu_metrics_g.md), padded rows, 107 526 x 200 bp, K=100
+SCAN_TRAFFIC = 8209066664   # dram__bytes_read.sum + dram__bytes_write.sum of the scan launch (profiles/r01_ncu_metrics_h.md), padded rows, 107 526 x 200 bp, K=100
 
 
 def peaks():
@@ -251,8 +251,8 @@ def main():
         line['roofline'] = {
             'bound': 'tensor', 'kernel': ('v2h_mma_kernel<KS=%d, %s%s> (positive-phase launch%s)' % ((M + 3) // 4, 'STAT_P|STAT_Q' if M <= 16 else 'STAT_P> + <STAT_Q', ', POOL' if pooled else '', '' if M <= 16 else 'es')),
             'achieved': tf, 'peak': tpeak[0], 'unit': 'TFLOP/s', 'frac': (tf / tpeak[0]) if tf else None,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01_ncu_metrics_g.md)
-            'traffic': 62976 if (args.workload == 'c2' and not pooled) else None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01_ncu_metrics_h.md)
+            'traffic': 62720 if (args.workload == 'c2' and not pooled) else None,
             'peak_source': tpeak[1], 'launch_us': pos_us, 'algorithmic_flops_per_launch': alg_flops,
             'note': 'dense-equivalent flops of the one-hot contractions (x, x\', and the P, P\', Q statistics); the bf16x3 / '
                     'bf16x2 operand splits and tile padding are overhead, not counted. At 100 x 200 bp per step the launch is '

@@ -309,6 +309,22 @@ __device__ void count_bases_block(const uint32_t *__restrict__ rows, int row_wor
     if (threadIdx.x < 4) out[threadIdx.x] = (float)tot[threadIdx.x];
 }
 __device__ __forceinline__ void reduce_partials_body(const ReduceParams &p);
+// This warp's share (CTA partials warp, warp + 4, ...) of accumulator slot `slot` of k-tile `kt`, 32 lanes wide. Four independent loads
+// in flight per pass (the partials are L2 resident; the loop is latency bound). The summation order is part of the contract: the plain
+// reduction and the fused reduce + update kernel use this function and combine the four warps as (w0 + w1) + (w2 + w3).
+__device__ __forceinline__ float warp_partial(const ReduceSet &S, int kt, int slot, int lane, int warp) {
+    const float *src = S.partial + ((size_t)kt * S.gy * S.nacc + slot) * 32 + lane;
+    const size_t cs = (size_t)S.nacc * 32;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int c = warp; c < S.gy; c += 16) {
+        const float t0 = src[c * cs];
+        const float t1 = c + 4 < S.gy ? src[(c + 4) * cs] : 0.f;
+        const float t2 = c + 8 < S.gy ? src[(c + 8) * cs] : 0.f;
+        const float t3 = c + 12 < S.gy ? src[(c + 12) * cs] : 0.f;
+        a0 += t0; a1 += t1; a2 += t2; a3 += t3;
+    }
+    return (a0 + a1) + (a2 + a3);
+}
 
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const ReduceParams p) {
     pdl_wait();
@@ -341,27 +357,8 @@ __device__ __forceinline__ void reduce_partials_body(const ReduceParams &p) {
     const int tail = o - S.np - S.nq, pair = p.mma ? 2 : 1;
     if (tail >= pair && tail < 2 * pair) return;
     const bool with_rc = tail >= 0 && tail < pair;
-    const float *src = S.partial + ((size_t)kt * S.gy * S.nacc + o) * 32 + lane;
-    float v = 0.f, vr = 0.f;
-    {
-        // four independent loads in flight per warp and pass (the partials are L2 resident; the loop is latency bound)
-        const size_t cs = (size_t)S.nacc * 32;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        for (int c = warp; c < S.gy; c += 16) {
-            const float t0 = src[c * cs];
-            const float t1 = c + 4 < S.gy ? src[(c + 4) * cs] : 0.f;
-            const float t2 = c + 8 < S.gy ? src[(c + 8) * cs] : 0.f;
-            const float t3 = c + 12 < S.gy ? src[(c + 12) * cs] : 0.f;
-            a0 += t0; a1 += t1; a2 += t2; a3 += t3;
-            if (with_rc) {
-                vr += src[c * cs + pair * 32];
-                if (c + 4 < S.gy) vr += src[(c + 4) * cs + pair * 32];
-                if (c + 8 < S.gy) vr += src[(c + 8) * cs + pair * 32];
-                if (c + 12 < S.gy) vr += src[(c + 12) * cs + pair * 32];
-            }
-        }
-        v = (a0 + a1) + (a2 + a3);
-    }
+    float v = warp_partial(S, kt, o, lane, warp);
+    float vr = with_rc ? warp_partial(S, kt, o + pair, lane, warp) : 0.f;
     sh[warp][lane] = v;
     shr[warp][lane] = vr;
     __syncthreads();
@@ -460,6 +457,97 @@ __global__ void apply_update_kernel(const ApplyParams p) {
     } else if (gid == nW + p.K + 4) {
         if (p.step_dev) *p.step_dev += 1ull;
         if (p.batch_index_dev) { const int nb = *p.batch_index_dev + 1; *p.batch_index_dev = nb >= p.n_batches ? 0 : nb; }
+    }
+}
+
+// ---- reduction + update in one launch (single rank, tensor-pipe partial layout) ------------------------------------------------
+// The update of W[k,a,m] needs three sums over the CTA partials (data P, data Q, model P) and the forward hidden sum of its motif:
+// one CTA of 16 warps per (m-tile, accumulator slot) reduces those four rows (four warps per row, the summation order of
+// reduce_partials_kernel) and applies the update to its 32 weights; two CTAs per m-tile do the 16 biases, one CTA the base counts, c
+// and the step / minibatch cursors. (With 4 warps per CTA walking the four rows in turn the kernel was slower than the two launches.)
+// Same arithmetic as reduce + apply (warp_partial, sparsity_factor, next_velocity): bit-identical parameters, one launch and one
+// pass over the statistics less; the statistics vector is not written (crbm_train_accumulate still does).
+struct FusedUpdateParams {
+    ReduceParams red;     // the sets of the reduction: data P (| Q), optional separate Q, model
+    ApplyParams ap;
+    int sd, sq, sm;       // indices of the data-P set, of the set holding the Q slots, and of the model set
+    int q_off;            // first Q slot inside set sq
+    int per;              // accumulator slots per statistic (8 * KS)
+};
+__global__ void __launch_bounds__(512) reduce_update_kernel(const FusedUpdateParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ float sh[5][4][32];
+    __shared__ float counts[8];
+    const ReduceParams &R = p.red;
+    const ApplyParams &ap = p.ap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = warp >> 2, sub = warp & 3;            // 16 warps: four per accumulator row, like the CTAs of reduce_partials_kernel
+    const int g = lane >> 2, q = lane & 3;
+    const ReduceSet &D = R.set[p.sd], &Q = R.set[p.sq], &Mo = R.set[p.sm];
+    const float nhd = R.c0, nhm = R.c1;
+    const float strands = ap.ds ? 2.f : 1.f;
+    const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
+    const int n_w = R.ktiles * p.per;
+    auto total = [&](int r) { return (sh[r][0][lane] + sh[r][1][lane]) + (sh[r][2][lane] + sh[r][3][lane]); };
+    if ((int)blockIdx.x < n_w) {
+        const int kt = blockIdx.x / p.per, o = blockIdx.x - kt * p.per;
+        const int r = o & 3, t = o >> 2, h = r >> 1;
+        const ReduceSet &S = row == 0 ? D : row == 1 ? Q : row == 2 ? Mo : D;
+        const int slot = row == 0 ? o : row == 1 ? p.q_off + o : row == 2 ? o : D.np + D.nq + h;   // row 3: sum_p[h], forward hidden sum
+        sh[row][sub][lane] = warp_partial(S, kt, slot, lane, sub);
+        __syncthreads();
+        if (warp != 0) return;
+        const float vd = total(0), vq = total(1), vm = total(2);
+        const float hf = __shfl_sync(0xffffffffu, total(3), lane & 28);      // the sums sit on the q == 0 lanes
+        const int k = kt * 16 + 8 * h + g;
+        const int col = 8 * t + 2 * q + (r & 1), m = col >> 2, a = col & 3;
+        if (k < ap.K && m < ap.M) {
+            const int gid = (k * 4 + a) * ap.M + m;
+            const float gk = sparsity_factor(hf, nhd, ap.rho, ap.K);
+            const float v = next_velocity(ap.vW[gid], vd, nd, vm, nm, __fmul_rn(gk, vq), ap.mu, ap.lr, ap.lam);
+            ap.vW[gid] = v;
+            ap.W[gid] = __fadd_rn(ap.W[gid], v);
+        }
+    } else if ((int)blockIdx.x < n_w + 2 * R.ktiles) {
+        // biases of motifs 16 kt + 8 h + g: rows sum_p, sum_pr (data), sum_p, sum_pr (model), sum_q
+        const int kt = (blockIdx.x - n_w) >> 1, h = (blockIdx.x - n_w) & 1;
+        const int bd = D.np + D.nq, bq = Q.np + Q.nq, bm = Mo.np + Mo.nq;
+        if (row == 0) sh[0][sub][lane] = warp_partial(D, kt, bd + h, lane, sub);
+        else if (row == 1) sh[1][sub][lane] = warp_partial(D, kt, bd + 2 + h, lane, sub);
+        else if (row == 2) sh[2][sub][lane] = warp_partial(Mo, kt, bm + h, lane, sub);
+        else sh[3][sub][lane] = warp_partial(Mo, kt, bm + 2 + h, lane, sub);
+        if (row == 0) sh[4][sub][lane] = warp_partial(Q, kt, bq + 4 + h, lane, sub);
+        __syncthreads();
+        const int k = kt * 16 + 8 * h + g;
+        if (warp != 0 || q != 0 || k >= ap.K) return;
+        const float hf = total(0);
+        const float hdata = hf + total(1), hmodel = total(2) + total(3), hq = total(4);
+        const float gk = sparsity_factor(hf, nhd, ap.rho, ap.K);
+        const float v = next_velocity(ap.vb[k], hdata, nd, hmodel, nm, __fmul_rn(gk, hq), ap.mu, ap.lr, ap.lam);
+        ap.vb[k] = v;
+        ap.b[k] = __fadd_rn(ap.b[k], v);
+    } else {
+        // base counts of the minibatch and of the sampled visible layer (A9), the update of c, the cursors of the next step
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const uint32_t *rows = R.cnt_rows[w];
+            if (w == 0 && R.batch_index) rows += (size_t)(*R.batch_index) * R.cnt_n[0] * R.cnt_row_words[0];
+            count_bases_block(rows, R.cnt_row_words[w], R.cnt_n[w], R.cnt_L[w], counts + 4 * w);
+            __syncthreads();
+        }
+        if (threadIdx.x < 4) {
+            const int a = threadIdx.x;
+            const float v = next_velocity(ap.vc[a], __fadd_rn(counts[a], counts[3 - a]), R.c2, __fadd_rn(counts[4 + a], counts[7 - a]), R.c3,
+                                          0.f, ap.mu, ap.lr, 0.f);
+            ap.vc[a] = v;
+            ap.c[a] = __fadd_rn(ap.c[a], v);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (ap.step_dev) *ap.step_dev += 1ull;
+            if (ap.batch_index_dev) { const int nb = *ap.batch_index_dev + 1; *ap.batch_index_dev = nb >= ap.n_batches ? 0 : nb; }
+        }
     }
 }
 
@@ -716,6 +804,18 @@ int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const 
 }
 
 extern "C" int crbm_train_apply(const crbm_train_args *a, void *stream);
+static void fill_apply_params(const crbm_train_args *a, ApplyParams *p) {
+    p->W = a->W; p->b = a->b; p->c = a->c; p->vW = a->vW; p->vb = a->vb; p->vc = a->vc; p->stats = a->stats;
+    fill_layout(a->K, a->M, &p->lay);
+    p->K = a->K; p->M = a->M; p->ds = a->doublestranded ? 1 : 0;
+    p->lr = a->learning_rate; p->mu = a->momentum; p->rho = a->rho; p->lam = a->lambda_rate;
+    p->step_dev = a->step_dev; p->batch_index_dev = a->batch_index_dev; p->n_batches = a->n_batches;
+}
+static bool fused_update_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CRBM_FUSED_UPDATE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 // One training step as a chain of launches on ONE stream, in the order
 //     h2v -> v2h(chain, sample) [x cd_k]  ->  v2h(minibatch: P, Q statistics)  ->  reduce  ->  update
 // every kernel launched as a programmatic dependent of the one before it (common.cuh: launch_chain): the next grid's CTAs move in
@@ -864,6 +964,17 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
         red.cnt_rows[1] = a->v_model; red.cnt_row_words[1] = a->v_row_words; red.cnt_n[1] = a->batchsize; red.cnt_L[1] = Lv;
         red.batch_index = a->batch_index_dev;
         red.cnt_out[0] = st + lay.v_data; red.cnt_out[1] = st + lay.v_model;
+        // single rank, tensor-pipe layout, update requested in the same call: reduction and update in one launch
+        if ((phases & CRBM_PHASE_APPLY) && mma && !p2p && a->n_data > 0 && fused_update_enabled()) {
+            FusedUpdateParams f{};
+            f.red = red;
+            fill_apply_params(a, &f.ap);
+            f.per = 8 * KS;
+            f.sd = 0; f.sq = combined ? 0 : 1; f.sm = red.nsets - 1; f.q_off = combined ? f.per : 0;
+            CRBM_CHECK_CUDA(launch_chain(reduce_update_kernel, dim3(red.ktiles * (f.per + 2) + 1), dim3(512), 0, s, f));
+            CRBM_CHECK_LAUNCH();
+            return CRBM_OK;
+        }
         CRBM_CHECK_CUDA(launch_chain(reduce_partials_kernel, dim3(red.block_start[red.nsets] + 2), dim3(128), 0, s, red));
         CRBM_CHECK_LAUNCH();
     }
@@ -952,11 +1063,7 @@ int crbm_train_step(const crbm_train_args *a, void *stream) {
 int crbm_train_apply(const crbm_train_args *a, void *stream) {
     CRBM_CHECK_ARG(a && a->W && a->b && a->c && a->vW && a->vb && a->vc && a->stats, "crbm_train_apply: null pointer in args");
     ApplyParams p{};
-    p.W = a->W; p.b = a->b; p.c = a->c; p.vW = a->vW; p.vb = a->vb; p.vc = a->vc; p.stats = a->stats;
-    fill_layout(a->K, a->M, &p.lay);
-    p.K = a->K; p.M = a->M; p.ds = a->doublestranded ? 1 : 0;
-    p.lr = a->learning_rate; p.mu = a->momentum; p.rho = a->rho; p.lam = a->lambda_rate;
-    p.step_dev = a->step_dev; p.batch_index_dev = a->batch_index_dev; p.n_batches = a->n_batches;
+    fill_apply_params(a, &p);
     const int n = a->K * 4 * a->M + a->K + 5;
     CRBM_CHECK_CUDA(launch_chain(apply_update_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, p));
     CRBM_CHECK_LAUNCH();

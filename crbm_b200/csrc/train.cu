@@ -888,7 +888,10 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
         h2v_nw = h2v_nw < 4 ? 4 : h2v_nw > 16 ? 16 : h2v_nw;
         h2v_nw = ceil_div(h2v_nw, h2v_split) * h2v_split;                // the warps of an item sit in one CTA
         const size_t list_bytes = (size_t)h2v_nw * H2V_LIST * sizeof(uint32_t);
-        const int w_in_smem = w_bytes + 16 + list_bytes <= 200 * 1024;
+        // W staged in shared memory by the TMA engine only on request (CRBM_H2V_WSMEM=1): measured at C2 the staging latency at the
+        // head of the kernel costs more (31.3 us for the chain part) than the L1 misses of the first hits it avoids (30.5 us)
+        static const int wsmem_allowed = [] { const char *e = getenv("CRBM_H2V_WSMEM"); return (e && e[0] == '1') ? 1 : 0; }();
+        const int w_in_smem = wsmem_allowed && w_bytes + 16 + list_bytes <= 200 * 1024;
         const size_t list_offset = w_in_smem ? w_bytes + 16 : 16;
         const size_t h2v_smem = list_offset + list_bytes;
         static size_t h2v_smem_configured = 48 * 1024;

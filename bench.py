@@ -258,7 +258,7 @@ def main():
             # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01_ncu_metrics_h.md)
             'traffic': 62720 if (args.workload == 'c2' and not pooled) else None,
             'peak_source': tpeak[1], 'launch_us': pos_us, 'algorithmic_flops_per_launch': alg_flops,
-            'note': 'dense-equivalent flops of the one-hot contractions (x, x\', and the P, P\', Q statistics); the bf16x3 / '
+            'note': 'dense-equivalent flops of the one-hot contractions (x, x\', and the P, P\', Q statistics); the fp16 hi/lo / '
                     'bf16x2 operand splits and tile padding are overhead, not counted. At 100 x 200 bp per step the launch is '
                     'latency/issue bound (ncu: profiles/), not throughput bound.',
             'hbm_frac': (alg_bytes / (pos_us * 1e-6) / 1e9 / hbm_peak) if pos_us else None,

@@ -172,3 +172,32 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
     assert d['e2e'] == {'value': d['value'], 'unit': 'nt/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['config']['workload'].startswith('C2')
+
+
+def test_save_motifs_jaspar_and_pfm(tmpdir):
+    """secomo/utils.py:16-47 `saveMotifs`: one `<name><i>.pfm` per motif in the layout of Bio.motifs.jaspar.write
+    (header `>id name`, rows `A [ ... ]` with %6.2f values); reference tests/testtutorial.py counts the files."""
+    from crbm_b200 import saveMotifs, formatMotif
+
+    class Stub(object):
+        def getPFMs(self):
+            rs = np.random.RandomState(0)
+            out = []
+            for _ in range(3):
+                x = rs.rand(4, 5)
+                out.append(x / x.sum(axis=0, keepdims=True))
+            return out
+
+    d = os.path.join(tmpdir.strpath, 'pfms', 'nested')
+    saveMotifs(Stub(), d)
+    files = sorted(os.listdir(d))
+    assert files == ['mot0.pfm', 'mot1.pfm', 'mot2.pfm']
+    lines = open(os.path.join(d, 'mot1.pfm')).read().splitlines()
+    assert lines[0] == '>mot2 mot2' and [l[0] for l in lines[1:]] == list('ACGT')
+    vals = np.array([[float(v) for v in l[l.index('[') + 1:l.index(']')].split()] for l in lines[1:]])
+    np.testing.assert_allclose(vals, Stub().getPFMs()[1], atol=0.005)
+    np.testing.assert_allclose(vals.sum(axis=0), 1.0, atol=0.02)
+    pfm = formatMotif(Stub().getPFMs()[0], 'x', 'pfm').splitlines()
+    assert len(pfm) == 4 and all(len(r.split()) == 5 for r in pfm)
+    with pytest.raises(ValueError):
+        saveMotifs(Stub(), d, fformat='tab')

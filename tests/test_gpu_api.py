@@ -58,6 +58,19 @@ def test_topdown_full_pipeline_properties(data):
     np.testing.assert_allclose(p, 0.25, rtol=1e-5, atol=1e-5)     # c == 0 at construction
 
 
+def test_tutorial_function(tmpdir):
+    """crbm_b200.tutorial.tutorial == secomo/tutorial.py without the plots (reference tests/testtutorial.py checks the outputs)."""
+    from crbm_b200.tutorial import tutorial
+    path = tmpdir.mkdir('run')
+    out = tutorial(path.strpath)
+    outputs = [o.basename for o in path.listdir()]
+    assert 'oct4_model_params.pkl' in outputs and 'pfms' in outputs and 'motif_hit_summary.npz' in outputs
+    assert len(os.listdir(os.path.join(path.strpath, 'pfms'))) == 10
+    assert out['matches'].shape == (100, 10, 1, 186) and out['summary']['max'].shape == (3997, 10)
+    assert out['positional_density'].shape == (10, 186)
+    np.testing.assert_allclose(out['summary']['max'][:100], out['matches'][:, :, 0, :].max(axis=2), rtol=2e-6, atol=2e-7)
+
+
 def test_tutorial_flow(tmpdir, data):
     """secomo/tutorial.py:13-44 without the plotting calls."""
     from crbm_b200 import CRBM

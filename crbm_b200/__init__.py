@@ -5,9 +5,10 @@ readSeqsFromFasta, load_sample, splitTrainingTest, saveMotifs. The plotting help
 """
 from .convRBM import CRBM
 from .sequences import (seqToOneHot, readSeqsFromFasta, load_sample, splitTrainingTest, PackedSequences,
-                        sample_fasta_path, seqToCodes, codesToOneHot)
+                        sample_fasta_path, seqToCodes, codesToOneHot, packCodesHost, unpackCodesHost, packedRowWords)
 from .utils import saveMotifs, formatMotif
 
 __version__ = '0.1.0'
 __all__ = ['CRBM', 'seqToOneHot', 'readSeqsFromFasta', 'load_sample', 'splitTrainingTest', 'PackedSequences',
-           'sample_fasta_path', 'seqToCodes', 'codesToOneHot', 'saveMotifs', 'formatMotif']
+           'sample_fasta_path', 'seqToCodes', 'codesToOneHot', 'saveMotifs', 'formatMotif', 'packCodesHost', 'unpackCodesHost',
+           'packedRowWords']

@@ -155,6 +155,43 @@ def splitTrainingTest(filename, train_test_ratio, num_top_regions=None, randomiz
                 f.write('>%s\n%s\n' % (seqs[i].description, str(seqs[i].seq)))
 
 
+# ---- the packed row layout on the host (include/crbm_b200.h; csrc/common.cuh packed_row_words) ---------------------------------
+# A row = 1 zero pad word, ceil(L/16) data words (base i at bits 2*(i%16) of word 1 + i/16, A0 C1 G2 T3), >= 7 zero pad words, the
+# stride rounded up to a multiple of 4 words. Packing on the host lets a FASTA collection be streamed to the GPU at 0.25 byte per
+# base (64x less than the fp32 one-hot array of the reference) without ever building the one-hot array.
+_FRONT_PAD_WORDS, _BACK_PAD_WORDS = 1, 7
+
+
+def packedRowWords(L):
+    return 4 * ((_FRONT_PAD_WORDS + (int(L) + 15) // 16 + _BACK_PAD_WORDS + 3) // 4)
+
+
+def packCodesHost(codes):
+    """(N,L) uint8 base codes in {0,1,2,3} -> (N, packedRowWords(L)) uint32 rows in the device layout (NumPy, no GPU)."""
+    codes = np.asarray(codes)
+    if codes.ndim != 2:
+        raise ValueError("expected base codes of shape (N,L), got %r" % (codes.shape,))
+    if codes.size and int(codes.max()) > 3:
+        raise ValueError("base codes must be in {0,1,2,3}")
+    N, Ln = codes.shape
+    nw = (Ln + 15) // 16
+    padded = np.zeros((N, nw * 16), dtype=np.uint32)
+    padded[:, :Ln] = codes
+    words = (padded.reshape(N, nw, 16) << (2 * np.arange(16, dtype=np.uint32))).sum(axis=2, dtype=np.uint32)
+    out = np.zeros((N, packedRowWords(Ln)), dtype=np.uint32)
+    out[:, _FRONT_PAD_WORDS:_FRONT_PAD_WORDS + nw] = words
+    return out
+
+
+def unpackCodesHost(words, L):
+    """Inverse of packCodesHost: (N, row_words) uint32 rows -> (N,L) uint8 base codes."""
+    words = np.asarray(words, dtype=np.uint32)
+    nw = (int(L) + 15) // 16
+    data = words[:, _FRONT_PAD_WORDS:_FRONT_PAD_WORDS + nw]
+    codes = (data[:, :, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3
+    return codes.reshape(words.shape[0], nw * 16)[:, :int(L)].astype(np.uint8)
+
+
 class PackedSequences(object):
     """N sequences of L bases, 2 bits per base, resident in GPU memory in the row layout of include/crbm_b200.h."""
 
@@ -222,6 +259,21 @@ class PackedSequences(object):
         if int(bad.item()):
             raise ValueError("base codes must be in {0,1,2,3}")
         return cls(words, N, Ln)
+
+    @classmethod
+    def from_packed_host(cls, words, L, device='cuda'):
+        """Rows packed on the host (packCodesHost) -> device; 0.25 byte per base crosses PCIe."""
+        import torch
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        if words.ndim != 2 or words.shape[1] != packedRowWords(L):
+            raise ValueError("expected packed rows of %d words for L=%d, got %r" % (packedRowWords(L), L, words.shape))
+        return cls(torch.from_numpy(words.view(np.int32)).to(device), words.shape[0], L)
+
+    @classmethod
+    def from_fasta(cls, filename, device='cuda'):
+        """FASTA file -> packed sequences on the device (records containing N are skipped as readSeqsFromFasta does)."""
+        codes = seqToCodes(readSeqsFromFasta(filename))
+        return cls.from_packed_host(packCodesHost(codes), codes.shape[1], device)
 
     @classmethod
     def random(cls, N, L, seed=1234, device='cuda'):

@@ -58,6 +58,26 @@ def test_topdown_full_pipeline_properties(data):
     np.testing.assert_allclose(p, 0.25, rtol=1e-5, atol=1e-5)     # c == 0 at construction
 
 
+def test_host_packed_rows_and_fasta_ingest_equal_device_packing(tmpdir):
+    """rows packed on the host (packCodesHost) are bit-identical to crbm_pack_codes / crbm_pack_onehot output, and
+    PackedSequences.from_fasta == packing the one-hot array of the same file (N-containing records skipped, case folded)."""
+    import crbm_b200
+    from crbm_b200 import PackedSequences, packCodesHost
+    rs = np.random.RandomState(5)
+    for Ln in (17, 200, 999):
+        codes = rs.randint(0, 4, size=(9, Ln)).astype(np.uint8)
+        dev = PackedSequences.from_codes(codes)
+        host = PackedSequences.from_packed_host(packCodesHost(codes), Ln)
+        np.testing.assert_array_equal(host.words.cpu().numpy(), dev.words.cpu().numpy())
+    path = os.path.join(tmpdir.strpath, 'x.fa')
+    with open(path, 'w') as f:
+        f.write('>a desc\nACGTacgtAC\n>b\nACGTNCGTAC\n>c\nttttGGGGcc\n')
+    got = PackedSequences.from_fasta(path)
+    ref = PackedSequences.from_onehot(crbm_b200.seqToOneHot(crbm_b200.readSeqsFromFasta(path)))
+    assert got.N == 2 and got.L == 10
+    np.testing.assert_array_equal(got.words.cpu().numpy(), ref.words.cpu().numpy())
+
+
 def test_tutorial_function(tmpdir):
     """crbm_b200.tutorial.tutorial == secomo/tutorial.py without the plots (reference tests/testtutorial.py checks the outputs)."""
     from crbm_b200.tutorial import tutorial

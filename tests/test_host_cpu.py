@@ -201,3 +201,24 @@ def test_save_motifs_jaspar_and_pfm(tmpdir):
     assert len(pfm) == 4 and all(len(r.split()) == 5 for r in pfm)
     with pytest.raises(ValueError):
         saveMotifs(Stub(), d, fformat='tab')
+
+
+def test_host_packing_matches_the_device_row_layout():
+    """packCodesHost: 2 bit/base rows in the layout the kernels read (front pad word, data words, zero padding, stride a multiple
+    of 4 words = crbm_packed_row_words); round trip through unpackCodesHost; ragged tail words zero-padded."""
+    from crbm_b200 import packCodesHost, unpackCodesHost, packedRowWords
+    lib = _lib.load()
+    rs = np.random.RandomState(3)
+    for Ln in (1, 15, 16, 17, 200, 999):
+        assert packedRowWords(Ln) == lib.crbm_packed_row_words(Ln)
+        codes = rs.randint(0, 4, size=(5, Ln)).astype(np.uint8)
+        words = packCodesHost(codes)
+        assert words.shape == (5, packedRowWords(Ln)) and words.dtype == np.uint32
+        assert not words[:, 0].any() and not words[:, 1 + (Ln + 15) // 16:].any()
+        for n, i in ((0, 0), (4, Ln - 1), (2, Ln // 2)):
+            assert (int(words[n, 1 + i // 16]) >> (2 * (i % 16))) & 3 == codes[n, i]
+        if Ln % 16:
+            assert int(words[0, (Ln + 15) // 16]) >> (2 * (Ln % 16)) == 0
+        np.testing.assert_array_equal(unpackCodesHost(words, Ln), codes)
+    with pytest.raises(ValueError):
+        packCodesHost(np.array([[0, 4]], dtype=np.uint8))

@@ -1,11 +1,13 @@
-"""The end-to-end demo of the reference (secomo/tutorial.py:6-67), minus the plots.
+"""End-to-end demo on the bundled Oct4 ChIP-seq sample: the call sequence of the reference's secomo/tutorial.py:6-67
+(BASELINE config "tutorial") with every plotting call replaced by the numbers that plot is drawn from.
 
-Same call sequence on the bundled Oct4 ChIP-seq sample: load -> CRBM(10 motifs x 15 bp, 1 epoch) -> fit -> saveModel /
-loadModel -> getPFMs -> saveMotifs -> motifHitProbs. The plotting calls of the reference (sequence logos, positional density,
-t-SNE, violin plots: matplotlib / seaborn / weblogo / sklearn, SURVEY §2 out of scope) are replaced by the numbers they are drawn
-from, computed inside the scan kernel and written to `motif_hit_summary.npz`:
-  * max / argmax / mean of the hit probabilities over positions per sequence and motif (utils.py:155,245-247,306), and
-  * the mean hit probability per motif and position over the sequences (`positionalDensityPlot`, utils.py:116).
+    load_sample -> CRBM(10 motifs x 15 bp, 1 epoch).fit -> saveModel / loadModel -> getPFMs -> saveMotifs -> motifHitProbs
+
+Sequence logos, positional density, t-SNE and violin plots need matplotlib / seaborn / weblogo / sklearn (out of
+scope). What they visualise is written to `motif_hit_summary.npz` instead:
+  * max / argmax / mean of the hit probabilities over positions per (sequence, motif) — computed inside the scan kernel
+    (`CRBM.motifHitSummary`; the reductions of utils.py:155,245-247,306),
+  * the mean hit probability per (motif, position) over the first 100 sequences (utils.py:116).
 """
 import os
 
@@ -16,28 +18,23 @@ from .sequences import load_sample
 from .utils import saveMotifs
 
 
-def tutorial(path):
-    # one-hot (3997, 1, 4, 200) array of the bundled sample
-    onehot = load_sample()
+def tutorial(path, num_motifs=10, motif_length=15, epochs=1):
+    """Runs the demo, writes `oct4_model_params.pkl`, `pfms/` and `motif_hit_summary.npz` under `path`, returns the results."""
+    data = load_sample()                                         # (3997, 1, 4, 200) one-hot
+    trained = CRBM(num_motifs=num_motifs, motif_length=motif_length, epochs=epochs)
+    trained.fit(data)                                            # one epoch: a smoke run, not a converged model
 
-    # Epoch = 1 is not sufficient to train meaningful features, however, it speeds up automatic testing.
-    model = CRBM(num_motifs=10, motif_length=15, epochs=1)
-    model.fit(onehot)
+    params = os.path.join(path, 'oct4_model_params.pkl')
+    trained.saveModel(params)
+    model = CRBM.loadModel(params)                               # round trip through the reference's pickle layout
 
-    # save parameters and hyper-parameters, re-instantiate the model from them
-    model.saveModel(os.path.join(path, 'oct4_model_params.pkl'))
-    model = CRBM.loadModel(os.path.join(path, 'oct4_model_params.pkl'))
-
-    # position frequency matrices, stored (in 'jaspar' format) in <path>/pfms/
     pfms = model.getPFMs()
-    saveMotifs(model, path=os.path.join(path, 'pfms'))
+    saveMotifs(model, path=os.path.join(path, 'pfms'))           # one JASPAR-format file per motif
 
-    # per-position motif match probabilities for the first 100 sequences
-    matches = model.motifHitProbs(onehot[:100])
-
-    # what the reference's plots show, as numbers
-    summary = model.motifHitSummary(onehot)
-    density = matches.mean(axis=(0, 2))                      # (motifs, positions), utils.py:116
+    head = data[:100]
+    matches = model.motifHitProbs(head)                          # (100, K, 1, 186) per-position match probabilities
+    summary = model.motifHitSummary(data)                        # fused reductions over all 3997 sequences
+    density = matches.mean(axis=(0, 2))                          # (K, positions)
     np.savez(os.path.join(path, 'motif_hit_summary.npz'), max=summary['max'], argmax=summary['argmax'], mean=summary['mean'],
              positional_density=density)
     return {'model': model, 'pfms': pfms, 'matches': matches, 'summary': summary, 'positional_density': density}

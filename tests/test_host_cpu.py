@@ -222,3 +222,16 @@ def test_host_packing_matches_the_device_row_layout():
         np.testing.assert_array_equal(unpackCodesHost(words, Ln), codes)
     with pytest.raises(ValueError):
         packCodesHost(np.array([[0, 4]], dtype=np.uint8))
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under crbm_b200/ may import, call or execute anything under oracle/ (and there is
+    no CPU fallback to route to: compute entry points raise without a CUDA device, see test_compute_fails_loudly_without_gpu)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, 'crbm_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(dirpath, fn), errors='replace').read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, re.M), fn
+                assert 'crbm_oracle' not in text and 'crbm_torch_cpu' not in text, fn

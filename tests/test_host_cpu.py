@@ -235,3 +235,21 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn), errors='replace').read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', text, re.M), fn
                 assert 'crbm_oracle' not in text and 'crbm_torch_cpu' not in text, fn
+
+
+def test_header_is_plain_c(tmpdir):
+    """include/crbm_b200.h is the drop-in boundary: it must compile as C99 and as C++ with no CUDA or torch headers."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(tmpdir.strpath, 'hdr.c')
+    with open(src, 'w') as f:
+        f.write('#include "crbm_b200.h"\nint main(void){ crbm_train_args a; crbm_p2p_args p; crbm_stats_layout l; (void)a; (void)p; (void)l;'
+                ' return CRBM_PHASE_APPLY == 8 ? 0 : 1; }\n')
+    inc = os.path.join(root, 'include')
+    if shutil.which('gcc'):
+        r = subprocess.run(['gcc', '-std=c99', '-Wall', '-Wextra', '-pedantic', '-Werror', '-I', inc, '-fsyntax-only', src], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    if shutil.which('g++'):
+        r = subprocess.run(['g++', '-std=c++17', '-Wall', '-I', inc, '-fsyntax-only', '-x', 'c++', src], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr

@@ -3,6 +3,8 @@
 This is what pins the oracle: every compiled function of the reference (convRBM.py:459-514) plus the symbolic
 builders its tests call, replayed with the same injected uniforms. CPU-only.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -70,3 +72,16 @@ def test_evaluation_functions_match_reference(name):
     np.testing.assert_allclose(a, case['td_act_ss'], **TOL)
     np.testing.assert_allclose(O.top_down_probability(a), case['td_prob_ss'], **TOL)
     np.testing.assert_allclose(O.top_down_activity(case['td_h_real'], None, W, c), case['td_act_real'], **TOL)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/secomo'), reason="the reference tree only exists in the build container")
+def test_reference_own_test_suite_passes_on_the_theano_shim():
+    """Pins the shim the golden fixtures were generated through: the reference's UNMODIFIED tests/testcrbm.py and
+    tests/testloadsamples.py (NumPy control loops for conv2d valid / full / filter_flip, sigmoid, 4-way softmax, one-hot
+    sampling; constructor validation; save / load) run from /root/reference on oracle/theano_shim. Skipped where the
+    reference tree is absent (GPU boxes); never reads it at import time."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(['bash', os.path.join(root, 'oracle', 'run_reference_tests.sh')], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert '17 passed' in r.stdout, r.stdout[-500:]

@@ -190,6 +190,7 @@ class CRBM(object):
         self._use_graphs = True
         self._p2p = None            # peer-memory all-reduce state (data parallel), set up lazily
         self._dp_seq = 0            # number of data-parallel training steps done (identical on every rank)
+        self._sync_replicas()                             # data parallel: every rank starts from rank 0's draw of W
         self.theano_getHitProbs = self.motifHitProbs      # the attribute the north star calls getHitProbs (:508)
         self.getHitProbs = self.motifHitProbs
         self.theano_freeEnergy = lambda data: self.freeEnergy(data)
@@ -199,6 +200,16 @@ class CRBM(object):
         self.theano_trainingFct = self._trainingFct
 
     # ------------------------------------------------------------------------------------------------------
+    def _sync_replicas(self):
+        """Data parallel: parameters and velocities of every rank := rank 0's. The reference draws W from the unseeded NumPy
+        generator (:127), so the replicas would otherwise start — and, since every rank applies the same summed update, stay —
+        different. Called by the constructor and at the start of fit() (after any set_value / loadModel of the caller)."""
+        if self._world <= 1:
+            return
+        import torch.distributed as dist
+        for t in (self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc):
+            dist.broadcast(t, 0)
+
     def _require_cuda(self):
         if self._device.type != 'cuda':
             raise RuntimeError("crbm_b200 computes only on a CUDA device (sm_100a); there is no CPU fallback")
@@ -504,10 +515,22 @@ class CRBM(object):
         _lib.check(lib.crbm_train_accumulate_p2p(args, pa, s), 'train_accumulate_p2p')
         _lib.check(lib.crbm_train_apply_p2p(args, pa, s), 'train_apply_p2p')
 
-    def _p2p_check(self):
+    def _p2p_check(self, collective=False):
+        """Raise if the peer-memory exchange of an earlier step timed out on this rank (the kernel then poisons the
+        parameters it could not update with NaN instead of applying a partial sum). Called at every host synchronisation
+        point: get_value / saveModel (local flag) and the end of every epoch (`collective`: the flags of all ranks are
+        combined first, so that every rank raises, not only the ones that waited)."""
         p = self._p2p
-        if p and int(p['error'].item()) != 0:
-            raise RuntimeError("crbm_b200: a data-parallel peer did not publish its statistics in time")
+        if not p:
+            return
+        err = p['error']
+        if collective and self._world > 1:
+            import torch.distributed as dist
+            err = err.clone()
+            dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if int(err.item()) != 0:
+            raise RuntimeError("crbm_b200: a data-parallel peer did not publish its statistics in time; the parameters of the "
+                               "affected step were not updated and are marked invalid (NaN)")
 
     def _train_packed(self, seqs, start, end, uniforms=None, local_shard=False):
         """One training step on rows [start,end) of `seqs` (this rank's shard is cut here unless `local_shard`)."""
@@ -557,12 +580,14 @@ class CRBM(object):
         The minibatch cursor and the Philox step live in device memory, so the same graph is replayed for every step."""
         torch = _torch()
         lib = self._require_cuda()
-        key = (seqs.words.data_ptr(), seqs.N, seqs.L, steps_per_graph)
+        key = (seqs.N, seqs.L, steps_per_graph)
         eng = getattr(self, '_engine', None)
-        if eng is not None and eng['key'] == key:
+        # the engine keeps the sequences it was captured on alive and is matched by identity: a data pointer may be handed
+        # out again by the caching allocator for a different dataset of the same shape (the shard is a copy under DP)
+        if eng is not None and eng['seqs'] is seqs and eng['key'] == key:
             return eng
         shard, n_full = self._local_shard(seqs)
-        eng = dict(key=key, shard=shard, n_full=n_full, graphs={})
+        eng = dict(key=key, seqs=seqs, shard=shard, n_full=n_full, graphs={})
         eng['step_dev'] = torch.zeros(1, dtype=torch.int64, device=self._device)
         eng['batch_dev'] = torch.zeros(1, dtype=torch.int32, device=self._device)
         a = self._fill_args(shard.data_ptr(), seqs.row_words, self._local_batch, seqs.L)
@@ -686,6 +711,7 @@ class CRBM(object):
                 self._train_packed(seqs, i * self.batchsize, (i + 1) * self.batchsize)
         if seqs.N % self.batchsize:
             self._train_packed(seqs, n_full * self.batchsize, seqs.N)
+        self._p2p_check(collective=True)
 
     def _trainingFct(self, data, uniforms=None, local_shard=False):
         """Train on one mini-batch (reference :524-526 -> theano_trainingFct). Under data parallelism `data` is the
@@ -710,6 +736,7 @@ class CRBM(object):
     def _check_deferred(self):
         """Raise if the one-hot validation of an earlier streamlined training call failed (the kernels keep a running
         count on the device; it is read here, at the synchronisation points of the API, not once per minibatch)."""
+        self._p2p_check()
         eng = getattr(self, '_onehot_engine', None)
         if eng is not None and eng.get('pending'):
             eng['pending'] = False
@@ -728,6 +755,14 @@ class CRBM(object):
         src = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)) if isinstance(data, np.ndarray) else data
         if src.dtype != torch.float32 or not src.is_contiguous():
             src = src.to(torch.float32).contiguous()
+        if src.is_cuda:
+            # the library copies `src` on the side stream: order that copy after whatever produced the tensor on the current
+            # stream, and keep its memory from being reused before the copy has run
+            eng['side'].wait_stream(torch.cuda.current_stream(self._device))
+            src.record_stream(eng['side'])
+        # (a pinned HOST tensor is read asynchronously: it must stay unmodified until the step has executed on the device —
+        # after a stream synchronisation, or once a device->host read issued after this call has completed; pageable NumPy
+        # input is copied synchronously by the driver and may be reused at once.)
         a, pa = eng['args'], None
         if self._dp:
             # data parallel: statistics into buffer `parity` of the peer-mapped double buffer, sequence number per step
@@ -816,6 +851,7 @@ class CRBM(object):
     def fit(self, training_data, test_data=None):
         """Fits the cRBM to the provided training sequences (reference :570-634)."""
         self._require_cuda()
+        self._sync_replicas()
         training = self._prepare(training_data)
         test = self._prepare(test_data) if test_data is not None else training
         verbose = self._rank == 0

@@ -128,7 +128,7 @@ struct H2VParams {
     int v_row_words;
     const float *u_v;         // injected uniforms [n*Lv + i] or null
     uint64_t seed;
-    uint32_t ctr_hi;
+    uint32_t ctr_hi, iter;    // training step and Gibbs sweep (see V2HParams)
     const unsigned long long *step_dev;
 };
 
@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(512) h2v_bits_kernel(const H2VParams p) {
         float u;
         if (p.u_v) u = p.u_v[(size_t)n * Lv + i];
         else {
-            const uint32_t hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) * 64u : 0u);
-            u = u01(philox4x32(make_uint4((uint32_t)(n * Lv + i), 0u, hi, RNG_VISIBLE),
+            const uint32_t hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) : 0u);
+            u = u01(philox4x32(make_uint4((uint32_t)(n * Lv + i), 0u, hi, RNG_VISIBLE | (p.iter << 8)),
                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32))).x);
         }
         const float ut = u * tot;
@@ -595,6 +595,9 @@ __global__ void __launch_bounds__(256) apply_update_p2p_kernel(const ApplyP2PPar
     pdl_wait();
     pdl_launch_dependents();
     const ApplyParams &ap = p.ap;
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
     if (threadIdx.x < p.n_ranks) {
         const unsigned long long want = p.sequence_dev ? *p.sequence_dev + 1ull : p.sequence;
         // publish: this rank's statistics are complete (the reduction is the predecessor grid): one thread per peer stores the
@@ -610,7 +613,7 @@ __global__ void __launch_bounds__(256) apply_update_p2p_kernel(const ApplyP2PPar
             unsigned long long seen;
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
             if (seen >= want) break;
-            if (++spins > (1ll << 25)) { *p.error_flag = 1; break; }       // ~2 s: a peer is gone; do not hang the GPU
+            if (++spins > (1ll << 26)) { *p.error_flag = 1; timed_out = 1; break; }   // ~4 s: a peer is gone; do not hang the GPU
             __nanosleep(32);
         }
     }
@@ -619,7 +622,15 @@ __global__ void __launch_bounds__(256) apply_update_p2p_kernel(const ApplyP2PPar
     const int nW = ap.K * 4 * ap.M;
     const crbm_stats_layout &lay = ap.lay;
     const float strands = ap.ds ? 2.f : 1.f;
-    if (gid < nW + ap.K) {
+    if (timed_out) {
+        // A peer's statistics never arrived: applying whatever its buffer holds would silently diverge this replica. The block
+        // marks the parameters it owns invalid instead (NaN propagates into everything computed from them) and the host raises at
+        // its next synchronisation point (error_flag; CRBM._p2p_check).
+        const float nan = __int_as_float(0x7fc00000);
+        if (gid < nW) { ap.W[gid] = nan; ap.vW[gid] = nan; }
+        else if (gid < nW + ap.K) { ap.b[gid - nW] = nan; ap.vb[gid - nW] = nan; }
+        else if (gid < nW + ap.K + 4) { ap.c[gid - nW - ap.K] = nan; ap.vc[gid - nW - ap.K] = nan; }
+    } else if (gid < nW + ap.K) {
         const bool isW = gid < nW;
         const int k = isW ? gid / (4 * ap.M) : gid - nW;
         const int idx[6] = {lay.n_hidden_data, lay.n_hidden_model, lay.h_fwd + k,
@@ -831,7 +842,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     const int K = a->K, M = a->M, P = a->pooling, Lh = a->L - M + 1;
     int rc = check_shape("crbm_train_accumulate", K, M, P, Lh);
     if (rc) return rc;
-    CRBM_CHECK_ARG(a->n_data >= 0 && a->batchsize > 0 && a->cd_k > 0, "crbm_train_accumulate: bad batch / cd_k");
+    CRBM_CHECK_ARG(a->n_data >= 0 && a->batchsize > 0 && a->cd_k > 0 && a->cd_k < (1 << 24), "crbm_train_accumulate: bad batch / cd_k");
     CRBM_CHECK_ARG(Lh % P == 0, "crbm_train_accumulate: hidden length %d not divisible by pooling %d (truncate as fit() does)", Lh, P);
     CRBM_CHECK_ARG(FANTASY_LEN % P == 0, "crbm_train_accumulate: pooling %d does not divide the fantasy length 200 "
                    "(the reference fails on this reshape too)", P);
@@ -894,10 +905,14 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
         const int w_in_smem = wsmem_allowed && w_bytes + 16 + list_bytes <= 200 * 1024;
         const size_t list_offset = w_in_smem ? w_bytes + 16 : 16;
         const size_t h2v_smem = list_offset + list_bytes;
-        static size_t h2v_smem_configured = 48 * 1024;
-        if (h2v_smem > h2v_smem_configured) {
+        static size_t h2v_smem_configured[64];               // per device (the attribute is per device)
+        int dev_id = 0;
+        CRBM_CHECK_CUDA(cudaGetDevice(&dev_id));
+        size_t &configured = h2v_smem_configured[dev_id & 63];
+        if (configured < 48 * 1024) configured = 48 * 1024;
+        if (h2v_smem > configured) {
             CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h2v_smem));
-            h2v_smem_configured = h2v_smem;
+            configured = h2v_smem;
         }
         for (int it = 0; it < a->cd_k; ++it) {
             const bool last = it == a->cd_k - 1;
@@ -907,7 +922,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
             h.W = a->W; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words;
             h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
             h.seed = a->seed; h.step_dev = a->step_dev;
-            h.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
+            h.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; h.iter = (uint32_t)it;
             CRBM_CHECK_CUDA(launch_chain(h2v_bits_kernel, dim3(ceil_div(h2v_slots, h2v_nw)), dim3(32 * h2v_nw), h2v_smem, s, h));
             CRBM_CHECK_LAUNCH();
 
@@ -919,7 +934,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
             q.u_fwd = a->u_h ? a->u_h + it * n_u_h : nullptr;
             q.u_rc = a->u_hp ? a->u_hp + it * n_u_h : nullptr;
             q.seed = a->seed; q.step_dev = a->step_dev;
-            q.ctr_hi = a->step_dev ? (uint32_t)it : (uint32_t)(a->step * 64u + it);
+            q.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; q.iter = (uint32_t)it;
             if (P != 1) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));  // the pooled samplers OR their hits in
             if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
         }

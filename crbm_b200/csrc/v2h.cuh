@@ -42,7 +42,9 @@ struct V2HParams {
     // randomness
     const float *u_fwd, *u_rc; // injected uniforms [(n*K+k)*(Lh/P)+group] or null
     uint64_t seed;
-    uint32_t ctr_hi;          // step / iteration tag mixed into the Philox counter
+    uint32_t ctr_hi;          // training step (or the caller's offset): third word of the Philox counter
+    uint32_t iter;            // Gibbs sweep of the step: bits [8,32) of the counter's tag word (any cd_k; the sweeps of
+                              // consecutive steps never share a counter)
     // device-resident cursors (CUDA-graph replay): minibatch index into `packed`, training step
     const int *batch_index;
     const unsigned long long *step_dev;
@@ -312,9 +314,9 @@ __global__ void __launch_bounds__(256, 1) v2h_fused_kernel(const V2HParams p) {
     GroupUniforms gu_f, gu_r;
     if (SAMPLE || COUNT) {
         gu_f.key = gu_r.key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-        gu_f.hi = gu_r.hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) * 64u : 0u);
-        gu_f.tag = COUNT ? RNG_EVAL : RNG_HIDDEN;
-        gu_r.tag = RNG_HIDDEN_RC;
+        gu_f.hi = gu_r.hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) : 0u);
+        gu_f.tag = (COUNT ? RNG_EVAL : RNG_HIDDEN) | (p.iter << 8);
+        gu_r.tag = RNG_HIDDEN_RC | (p.iter << 8);
     }
 
     const uint32_t *packed = p.packed + (p.batch_index ? (size_t)(*p.batch_index) * p.n_rows * p.row_words : 0);

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
     const uint32_t qmask = (q & 1) ? 0u : 0x55555555u;
     const uint32_t code_f = (uint32_t)(g & 3) * 0x55555555u, code_r = (uint32_t)(3 - (g & 3)) * 0x55555555u;
     const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-    const uint32_t ctr_hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) * 64u : 0u);
+    const uint32_t ctr_hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) : 0u);
     const int ktiles = (p.K + KTILE - 1) / KTILE;
     const int njb = (p.Lh + 15) >> 4;
 
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
 #pragma unroll
                         for (int i = 0; i < BLOCK_POS / 2; ++i) ug[i] = (i < ng && g0 + i < groups_per_seq) ? ur[i] : 1.f;
                     } else {
-                        const uint32_t tag = s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC;
+                        const uint32_t tag = (s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC) | (p.iter << 8);
                         const uint4 r0 = philox4x32_call(make_uint4((uint32_t)(n * p.K + k), (uint32_t)(2 * jb), ctr_hi, tag), key);
                         ug[0] = u01(r0.x); ug[1] = u01(r0.y); ug[2] = u01(r0.z); ug[3] = u01(r0.w);
                         ug[4] = ug[5] = ug[6] = ug[7] = 1.f;
@@ -452,7 +452,7 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
                     // decided by floor(65536 p) against its 16 bits; only when the two are equal (probability 2^-16 per
                     // sample) does the warp take a second draw and compare the fraction: exact Bernoulli(p) to 2^-32, at
                     // half the generator work of one 24-bit uniform per sample (the generator was a third of this kernel).
-                    const uint32_t tag = s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC;
+                    const uint32_t tag = (s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC) | (p.iter << 8);
                     const uint4 ctr = make_uint4((uint32_t)(n * p.K + mtile * MTILE + g), (uint32_t)(jb * 4 + q), ctr_hi, tag);
                     const uint4 rnd = philox4x32(ctr, key);
                     const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};

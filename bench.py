@@ -252,7 +252,7 @@ def main():
     if rank == 0:
         hbm_peak, peak_src, sm_max = peaks()
         # --- per-kernel device time of one step (CUDA events around eager launches on the launching stream) ------------
-        state = (model._t_W, model._t_bias, model._t_c, model._t_vW, model._t_vb, model._t_vc, model._t_fantasy)
+        state = (model._t_W, model._t_bias, model._t_c, model._t_vW, model._t_vb, model._t_vc, model._chain())
         saved = [t.clone() for t in state]
         kern = time_step_kernels(model, data, B, dev)
         for t, v in zip(state, saved):              # the per-phase timing trains this rank alone: keep the replicas identical

@@ -93,6 +93,10 @@ SIGNATURES = {
     'crbm_train_stats_layout': (c_int, [c_int, c_int, ctypes.POINTER(StatsLayout)]),
     'crbm_hidden_bits_to_dense': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'crbm_hidden_dense_to_bits': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'crbm_chain_layout': (c_int, [c_int, c_int, c_int]),
+    'crbm_chain_words': (c_size_t, [c_int, c_int, c_int]),
+    'crbm_chain_to_dense': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'crbm_chain_from_dense': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'crbm_launch_count': (ctypes.c_ulonglong, []),
 }
 

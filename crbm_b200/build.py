@@ -17,6 +17,7 @@ OBJ = os.path.join(CSRC, '_build')
 LIB = os.path.join(HERE, 'libcrbm_b200.so')
 MWS = (3, 6, 9, 12, 15, 18, 21, 24, 27, 30, 33)
 KSS = (1, 2, 3, 4, 5, 6, 7, 8, 9)
+TT_POOLS = (1, 2, 4, 5, 10)       # pooling factors the tcgen05 training kernel is instantiated for
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
 
@@ -42,6 +43,8 @@ def _jobs():
         jobs.append((os.path.join(CSRC, 'v2h_inst.cu'), os.path.join(OBJ, 'v2h_inst_%d.o' % mw), ['-DCRBM_MW=%d' % mw]))
     for ks in KSS:
         jobs.append((os.path.join(CSRC, 'v2h_mma_inst.cu'), os.path.join(OBJ, 'v2h_mma_inst_%d.o' % ks), ['-DCRBM_KS=%d' % ks]))
+    for pp in TT_POOLS:
+        jobs.append((os.path.join(CSRC, 'train_tc_inst.cu'), os.path.join(OBJ, 'train_tc_inst_%d.o' % pp), ['-DCRBM_TT_P=%d' % pp]))
     return jobs
 
 

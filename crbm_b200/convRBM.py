@@ -31,6 +31,10 @@ def _torch():
     return torch
 
 
+def torch_int32():
+    return _torch().int32
+
+
 class _SharedParam(object):
     """Stand-in for a `theano.shared` variable (reference :133,149,152): get_value() / set_value() in host layout."""
 
@@ -64,8 +68,8 @@ class _FantasyParam(object):
         torch = _torch()
         lib = _lib.load()
         dense = torch.empty((o._local_batch, o.num_motifs, 1, FANTASY_LEN), dtype=torch.float32, device=o._device)
-        _lib.check(lib.crbm_hidden_bits_to_dense(_lib.ptr(o._t_fantasy[self._strand]), o._local_batch, o.num_motifs,
-                                                 _lib.ptr(dense), _lib.stream_handle()), 'bits_to_dense')
+        _lib.check(lib.crbm_chain_to_dense(_lib.ptr(o._chain()[self._strand]), o._local_batch, o.num_motifs, o.motif_length,
+                                           o.pooling, _lib.ptr(dense), _lib.stream_handle()), 'chain_to_dense')
         return dense.cpu().numpy()
 
     def set_value(self, value, borrow=False):
@@ -77,8 +81,8 @@ class _FantasyParam(object):
         if value.shape != (o._local_batch, o.num_motifs, 1, FANTASY_LEN):
             raise ValueError("fantasy particles: expected %r" % ((o._local_batch, o.num_motifs, 1, FANTASY_LEN),))
         dense = torch.from_numpy(value).to(o._device)
-        _lib.check(lib.crbm_hidden_dense_to_bits(_lib.ptr(dense), o._local_batch, o.num_motifs,
-                                                 _lib.ptr(o._t_fantasy[self._strand]), _lib.stream_handle()), 'dense_to_bits')
+        _lib.check(lib.crbm_chain_from_dense(_lib.ptr(dense), o._local_batch, o.num_motifs, o.motif_length, o.pooling,
+                                             _lib.ptr(o._chain()[self._strand]), _lib.stream_handle()), 'chain_from_dense')
 
 
 class CRBM(object):
@@ -181,7 +185,7 @@ class CRBM(object):
         self._seed = int(time.time()) if seed is None else int(seed)                           # reference :155
         self._step = 0
         self._kw = (num_motifs + 31) // 32
-        self._t_fantasy = torch.zeros((2, self._local_batch, self._kw, _lib.FANTASY_WORDS), dtype=torch.int32, device=dev)
+        self._t_fantasy = None      # the persistent chain (bit planes), allocated with the first compute call (_chain)
         self.fantasy_h = _FantasyParam(self, 0)
         if doublestranded:
             self.fantasy_h_prime = _FantasyParam(self, 1)
@@ -216,6 +220,15 @@ class CRBM(object):
         if self.input_dims != 4:
             raise NotImplementedError("crbm_b200 kernels are written for the DNA alphabet (input_dims == 4)")
         return _lib.load()
+
+    def _chain(self):
+        """The persistent chain (reference :168-173) as bit planes [2][local_batch][words]; the word layout follows the kernels
+        that train this model shape (include/crbm_b200.h: crbm_chain_layout)."""
+        if self._t_fantasy is None:
+            lib = self._require_cuda()
+            words = int(lib.crbm_chain_words(self.num_motifs, self.motif_length, self.pooling))
+            self._t_fantasy = _torch().zeros((2, self._local_batch, words), dtype=torch_int32(), device=self._device)
+        return self._t_fantasy
 
     def _as_packed(self, data):
         self._require_cuda()
@@ -444,7 +457,7 @@ class CRBM(object):
         a.learning_rate, a.momentum, a.rho, a.lambda_rate = self.learning_rate, self.momentum, self.rho, self.lambda_rate
         a.data, a.data_row_words, a.n_data, a.L = words_ptr, row_words, n_data, L
         a.batchsize = self._local_batch
-        a.fantasy_bits, a.v_model, a.v_row_words = self._t_fantasy.data_ptr(), st['v_model'].data_ptr(), st['v_row_words']
+        a.fantasy_bits, a.v_model, a.v_row_words = self._chain().data_ptr(), st['v_model'].data_ptr(), st['v_row_words']
         a.seed, a.step = self._seed + 7919 * self._rank, self._step
         a.u_v = None if u_v is None else u_v.data_ptr()
         a.u_h = None if u_h is None else u_h.data_ptr()
@@ -621,7 +634,7 @@ class CRBM(object):
         if g is None:
             # warm-up outside capture (first-use cudaFuncSetAttribute), state restored after
             tensors = (self._t_W, self._t_bias, self._t_c, self._t_vW, self._t_vb, self._t_vc,
-                       self._t_fantasy, eng['step_dev'], eng['batch_dev'])
+                       self._chain(), eng['step_dev'], eng['batch_dev'])
             saved = [t.clone() for t in tensors]
             side = torch.cuda.Stream(device=self._device)
             side.wait_stream(torch.cuda.current_stream())

@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "v2h.cuh"
+#include "tc_common.cuh"
 
 namespace crbm {
 
@@ -44,65 +45,6 @@ struct TcParams {
     int VP;            // real positions per warp of a tile: 32, or (32 / P) * P so that pool groups never straddle warps. Virtual
                        // position v of a sequence <-> real position (v / 32) * VP + v % 32, valid iff v % 32 < VP
 };
-
-// ---- PTX wrappers -------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-template <int COLS_UNUSED = 0>
-__device__ __forceinline__ void tmem_alloc(uint32_t *slot_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, fp16 inputs, fp32 accumulate; issued by one thread for the CTA
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// arrive on an mbarrier when all tcgen05.mma issued so far by this thread have completed (implies fence::before_thread_sync)
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// after tmem_ld_wait(): pins the uses of v behind the wait (the compiler sees no data dependence on the wait itself)
-__device__ __forceinline__ void tmem_ld_fence8(uint32_t (&v)[8]) {
-    asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]) :: "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes, 8-row groups
-// 1024 bytes apart (stride byte offset), 16-byte chunks XOR-swizzled with the row index inside a group.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                              // leading byte offset (ignored for swizzled K-major), bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset, bits [32,46)
-    d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell), bits [46,48)
-    d |= (uint64_t)2 << 61;                              // layout type SWIZZLE_128B, bits [61,64)
-    return d;
-}
-// byte offset of 16-byte chunk `chunk` (0..7) of row `r` inside one swizzle atom column (rows x 128 bytes)
-__device__ __forceinline__ uint32_t sw128_off(int r, int chunk) {
-    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + (((chunk ^ r) & 7) << 4));
-}
 
 constexpr int TC_TILE = 128;
 constexpr int A_ATOM_BYTES = TC_TILE * 128;
@@ -191,9 +133,6 @@ __device__ __forceinline__ void tc_issue_mma(const TcParams &p, uint32_t a_addr,
         umma_f16(tmem_d, ad, umma_desc_sw128(bhi_addr + atom * b_atom + koff), idesc, s > 0 ? 1u : 0u);
         umma_f16(tmem_d, ad, umma_desc_sw128(blo_addr + atom * b_atom + koff), idesc, 1u);
     }
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_PRODUCER_WARPS) : "memory"); }
 

@@ -712,7 +712,22 @@ static void fill_layout(int K, int M, crbm_stats_layout *l) {
     l->total = o;
 }
 
+static void fill_apply_params(const crbm_train_args *a, ApplyParams *p) {
+    p->W = a->W; p->b = a->b; p->c = a->c; p->vW = a->vW; p->vb = a->vb; p->vc = a->vc; p->stats = a->stats;
+    fill_layout(a->K, a->M, &p->lay);
+    p->K = a->K; p->M = a->M; p->ds = a->doublestranded ? 1 : 0;
+    p->lr = a->learning_rate; p->mu = a->momentum; p->rho = a->rho; p->lam = a->lambda_rate;
+    p->step_dev = a->step_dev; p->batch_index_dev = a->batch_index_dev; p->n_batches = a->n_batches;
+}
+static bool fused_update_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CRBM_FUSED_UPDATE"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 }  // namespace crbm
+
+extern "C" int crbm_train_apply(const crbm_train_args *a, void *stream);
+#include "train_tc_impl.cuh"
 
 using namespace crbm;
 
@@ -729,7 +744,8 @@ size_t crbm_train_stats_floats(int K, int M) {
     return (size_t)l.total;
 }
 size_t crbm_train_workspace_bytes(int K, int M) {
-    return 3 * partial_floats(K, M) * sizeof(float) + 256;
+    const size_t mma = 3 * partial_floats(K, M), tc = tt_workspace_floats(K, M);
+    return (mma > tc ? mma : tc) * sizeof(float) + 256;
 }
 
 int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L, const float *W, const float *b, int K, int M,
@@ -814,19 +830,6 @@ int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const 
     return CRBM_OK;
 }
 
-extern "C" int crbm_train_apply(const crbm_train_args *a, void *stream);
-static void fill_apply_params(const crbm_train_args *a, ApplyParams *p) {
-    p->W = a->W; p->b = a->b; p->c = a->c; p->vW = a->vW; p->vb = a->vb; p->vc = a->vc; p->stats = a->stats;
-    fill_layout(a->K, a->M, &p->lay);
-    p->K = a->K; p->M = a->M; p->ds = a->doublestranded ? 1 : 0;
-    p->lr = a->learning_rate; p->mu = a->momentum; p->rho = a->rho; p->lam = a->lambda_rate;
-    p->step_dev = a->step_dev; p->batch_index_dev = a->batch_index_dev; p->n_batches = a->n_batches;
-}
-static bool fused_update_enabled() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("CRBM_FUSED_UPDATE"); v = (e && e[0] == '0') ? 0 : 1; }
-    return v == 1;
-}
 // One training step as a chain of launches on ONE stream, in the order
 //     h2v -> v2h(chain, sample) [x cd_k]  ->  v2h(minibatch: P, Q statistics)  ->  reduce  ->  update
 // every kernel launched as a programmatic dependent of the one before it (common.cuh: launch_chain): the next grid's CTAs move in
@@ -852,6 +855,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     CRBM_CHECK_ARG(a->v_row_words >= packed_row_words(Lv), "crbm_train_accumulate: v_row_words too small");
     CRBM_CHECK_ARG(((uintptr_t)a->W & 15) == 0, "crbm_train_accumulate: W must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
+    if (train_uses_tc(K, M, P)) return train_phases_tc(a, phases, s, p2p != nullptr);     // tcgen05 / TMEM path (train_tc.cuh)
     crbm_stats_layout lay;
     fill_layout(K, M, &lay);
     float *st = a->stats;
@@ -1069,6 +1073,33 @@ int crbm_train_apply_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, voi
     p.ticket = p2p->ticket;
     const int n = a->K * 4 * a->M + a->K + 4;
     CRBM_CHECK_CUDA(launch_chain(apply_update_p2p_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, p));
+    CRBM_CHECK_LAUNCH();
+    return CRBM_OK;
+}
+
+// ---- the persistent chain as the host sees it ------------------------------------------------------------------------------
+int crbm_chain_layout(int K, int M, int pooling) { return (K > 0 && M > 0 && pooling > 0 && train_uses_tc(K, M, pooling)) ? 1 : 0; }
+size_t crbm_chain_words(int K, int M, int pooling) {
+    if (K <= 0 || M <= 0 || pooling <= 0) return 0;
+    return train_uses_tc(K, M, pooling) ? tt_chain_words(K, pooling) : (size_t)ceil_div(K, 32) * FANTASY_WORDS;
+}
+extern "C" int crbm_hidden_bits_to_dense(const uint32_t *bits, int B, int K, float *dense, void *stream);
+extern "C" int crbm_hidden_dense_to_bits(const float *dense, int B, int K, uint32_t *bits, void *stream);
+int crbm_chain_to_dense(const uint32_t *bits, int B, int K, int M, int pooling, float *dense, void *stream) {
+    CRBM_CHECK_ARG(bits && dense && B > 0 && K > 0 && M > 0 && pooling > 0, "crbm_chain_to_dense: bad arguments");
+    if (!train_uses_tc(K, M, pooling)) return crbm_hidden_bits_to_dense(bits, B, K, dense, stream);
+    const TtGeom g = tt_geom(K, M, pooling);
+    const long long n = (long long)B * K * FANTASY_LEN;
+    chain_lin_to_dense_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(bits, B, K, g.Kpad, g.hw, g.VP, dense);
+    CRBM_CHECK_LAUNCH();
+    return CRBM_OK;
+}
+int crbm_chain_from_dense(const float *dense, int B, int K, int M, int pooling, uint32_t *bits, void *stream) {
+    CRBM_CHECK_ARG(bits && dense && B > 0 && K > 0 && M > 0 && pooling > 0, "crbm_chain_from_dense: bad arguments");
+    if (!train_uses_tc(K, M, pooling)) return crbm_hidden_dense_to_bits(dense, B, K, bits, stream);
+    const TtGeom g = tt_geom(K, M, pooling);
+    const long long n = (long long)B * g.hw * g.Kpad;
+    chain_dense_to_lin_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dense, B, K, g.Kpad, g.hw, g.VP, bits);
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }

@@ -1,0 +1,452 @@
+// Host side and small kernels of the tcgen05 training path (included by train.cu after the shared update arithmetic):
+//   h2v_lin_kernel        A5 + A6 on the LINEAR chain planes the tcgen05 kernels write (bit = position, word-major, motif contiguous)
+//   reduce_tc_kernel      per-CTA statistics partials -> statistics vector, or -> sparsity factor + momentum update in the same launch
+//   chain <-> dense       conversions for tests / inspection
+//   train_phases_tc       the launch chain of one step
+#pragma once
+#include "train_tc.cuh"
+
+namespace crbm {
+
+#define CRBM_FOR_EACH_TT_P(X) X(1) X(2) X(4) X(5) X(10)
+#define CRBM_DECLARE_TT(PV) template <> int launch_v2h_train_tc<PV>(int, const TrainTcParams &, dim3, cudaStream_t);
+CRBM_FOR_EACH_TT_P(CRBM_DECLARE_TT)
+#undef CRBM_DECLARE_TT
+
+static bool tt_pool_built(int P) { return P == 1 || P == 2 || P == 4 || P == 5 || P == 10; }
+// The tcgen05 path covers motif_length <= 32 (4 M <= 128 contraction columns, one MMA N) and the pooling factors it is instantiated
+// for; everything else (and CRBM_TRAIN_KERNEL=mma) trains on the mma.sync kernels of v2h_mma.cuh.
+static bool train_uses_tc(int K, int M, int P) {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CRBM_TRAIN_KERNEL"); v = (e && e[0] == 'm') ? 0 : 1; }
+    (void)K;
+    return v == 1 && M <= 32 && tt_pool_built(P);
+}
+
+struct TtGeom { int VP, Kdim, ksteps, n_atoms, n_chunks, Kpad, G, hw, part_floats; };
+static TtGeom tt_geom(int K, int M, int P) {
+    TtGeom g;
+    g.VP = (32 / P) * P;
+    g.Kdim = 16 * ceil_div(4 * M, 16);
+    g.ksteps = g.Kdim / 16;
+    g.n_atoms = ceil_div(g.Kdim, 64);
+    g.n_chunks = ceil_div(K, TT_KC);
+    g.Kpad = g.n_chunks * TT_KC;
+    g.G = num_sms() / g.n_chunks > 0 ? num_sms() / g.n_chunks : 1;
+    g.hw = ceil_div(FANTASY_LEN, g.VP);
+    g.part_floats = tt_part_floats(g.Kdim);
+    return g;
+}
+static size_t tt_workspace_floats(int K, int M) {
+    if (M > 32) return 0;
+    const TtGeom g = tt_geom(K, M, 1);
+    return 2 * (size_t)g.n_chunks * g.G * g.part_floats;
+}
+static size_t tt_chain_words(int K, int P) {           // per (strand, particle)
+    const int VP = (32 / P) * P;
+    return (size_t)ceil_div(FANTASY_LEN, VP) * ceil_div(K, TT_KC) * TT_KC;
+}
+
+static int dispatch_train_tc(int P, int flags, const TrainTcParams &p, dim3 grid, cudaStream_t s) {
+    switch (P) {
+#define CRBM_CASE(PV) case PV: return launch_v2h_train_tc<PV>(flags, p, grid, s);
+        CRBM_FOR_EACH_TT_P(CRBM_CASE)
+#undef CRBM_CASE
+    }
+    set_error("tcgen05 training kernel: pooling %d not built", P);
+    return CRBM_ERR_UNSUPPORTED;
+}
+
+// ---- A5 + A6 on linear chain planes ---------------------------------------------------------------------------------------
+// Same hit-parallel scheme as h2v_bits_kernel (a work item = 16 visible positions of one particle, shared by `split` warps that deal
+// out the 32-motif tiles; set bits compacted into a warp-private list, consumed four at a time). The planes are
+// uint32 H[strand][n][w][Kpad]: bit b of word w of motif k is hidden position w * VP + b, so a lane reads the word of its motif
+// (32 consecutive motifs = one 128-byte line) and masks it to the positions that reach the item.
+struct H2VLinParams {
+    const uint32_t *bits;
+    int Bn, K, Kpad, hw, VP, kw, M, ds, words_per_row, split, split_log2;
+    const float *W, *c;
+    uint32_t *v_packed;
+    int v_row_words;
+    const float *u_v;
+    uint64_t seed;
+    uint32_t ctr_hi, iter;
+    const unsigned long long *step_dev;
+};
+
+__global__ void __launch_bounds__(512) h2v_lin_kernel(const H2VLinParams p) {
+    extern __shared__ __align__(128) unsigned char h2v_smem[];
+    const int M = p.M, Lv = FANTASY_LEN + M - 1;
+    pdl_wait();
+    pdl_launch_dependents();
+    const int wslot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int part = wslot & (p.split - 1);
+    const int item_raw = wslot >> p.split_log2;
+    const bool live = item_raw < p.Bn * p.words_per_row;
+    const int item = live ? item_raw : 0;
+    const int n = item / p.words_per_row, w = item - n * p.words_per_row, lane = threadIdx.x & 31;
+    const int pidx = lane & 15, ah = lane >> 4;
+    const int i = 16 * w + pidx;
+    const int strands = p.ds ? 2 : 1;
+    const int jlo = max(0, 16 * w - (M - 1)), jhi = min(FANTASY_LEN - 1, 16 * w + 15);
+    const int wlo = jlo / p.VP, whi = jhi / p.VP;
+    float acc0 = 0.f, acc1 = 0.f;
+    uint32_t *list = reinterpret_cast<uint32_t *>(h2v_smem + 16) + (threadIdx.x >> 5) * H2V_LIST;
+    for (int s = 0; s < strands; ++s) {
+        const float *Wbase = s == 0 ? p.W + (size_t)(2 * ah) * M : p.W + (size_t)(3 - 2 * ah) * M;
+        const int dir = s == 0 ? M : -M;
+        for (int t = live ? part : p.kw; t < p.kw; t += p.split) {
+            const int k = 32 * t + lane;
+            const uint32_t *plane = p.bits + ((size_t)s * p.Bn + n) * p.hw * p.Kpad + k;
+            for (int wq = wlo; wq <= whi; ++wq) {
+                uint32_t word = __ldg(plane + (size_t)wq * p.Kpad);
+                const int b0 = max(0, jlo - wq * p.VP), b1 = min(31, jhi - wq * p.VP);      // bits of this word that reach the item
+                const uint32_t mask = (b1 >= 31 ? 0xffffffffu : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
+                word = (k < p.K) ? (word & mask) : 0u;
+                if (__ballot_sync(0xffffffffu, word != 0u) == 0u) continue;
+                const int cnt = __popc(word);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                int pos = incl - cnt;
+                const int jbase = wq * p.VP;
+                const int krow = k * 4 * M;
+                while (word) {
+                    const int b = __ffs(word) - 1;
+                    word &= word - 1;
+                    list[pos++] = ((uint32_t)krow << 8) | (uint32_t)(jbase + b);
+                }
+                if (lane < 4) list[total + lane] = 0xFFu;            // padding entries: position 255 never matches
+                __syncwarp();
+                for (int h0 = 0; h0 < total; h0 += 4) {
+                    const uint4 d = *reinterpret_cast<const uint4 *>(list + h0);
+                    const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+                    float x0[4], x1[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int m = i - (int)(dd[u] & 0xFFu);
+                        const bool ok = m >= 0 && m < M;
+                        const float *wk = Wbase + (dd[u] >> 8) + (s == 0 ? m : M - 1 - m);
+                        x0[u] = ok ? wk[0] : 0.f;
+                        x1[u] = ok ? wk[dir] : 0.f;
+                    }
+                    acc0 += (x0[0] + x0[1]) + (x0[2] + x0[3]);
+                    acc1 += (x1[0] + x1[1]) + (x1[2] + x1[3]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (p.split > 1) {
+        float2 *mine = reinterpret_cast<float2 *>(list);
+        mine[lane] = make_float2(acc0, acc1);
+        __syncthreads();
+        if (part == 0) {
+            for (int o = 1; o < p.split; ++o) {
+                const float2 v = reinterpret_cast<const float2 *>(list + (size_t)o * H2V_LIST)[lane];
+                acc0 += v.x;
+                acc1 += v.y;
+            }
+        }
+    }
+    if (part != 0 || !live) return;
+    const float o0 = __shfl_xor_sync(0xffffffffu, acc0, 16), o1 = __shfl_xor_sync(0xffffffffu, acc1, 16);
+    const bool active = ah == 0 && i < Lv;
+    int pick = 0;
+    if (active) {
+        const float v0 = acc0 + __ldg(p.c), v1 = acc1 + __ldg(p.c + 1), v2 = o0 + __ldg(p.c + 2), v3 = o1 + __ldg(p.c + 3);
+        const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+        const float e0 = __expf(v0 - mx), e1 = __expf(v1 - mx), e2 = __expf(v2 - mx), e3 = __expf(v3 - mx);
+        const float tot = e0 + e1 + e2 + e3;
+        float u;
+        if (p.u_v) u = p.u_v[(size_t)n * Lv + i];
+        else {
+            const uint32_t hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) : 0u);
+            u = u01(philox4x32(make_uint4((uint32_t)(n * Lv + i), 0u, hi, RNG_VISIBLE | (p.iter << 8)),
+                               make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32))).x);
+        }
+        const float ut = u * tot;
+        pick = (e0 > ut) ? 0 : (e0 + e1 > ut) ? 1 : (e0 + e1 + e2 > ut) ? 2 : 3;
+    }
+    uint32_t v = active ? ((uint32_t)pick << (2 * pidx)) : 0u;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) p.v_packed[(size_t)n * p.v_row_words + FRONT_PAD_WORDS + w] = v;
+}
+
+// ---- statistics partials -> statistics vector / update -----------------------------------------------------------------------
+// partial of CTA x of chunk ch (train_tc.cuh): P[c][r] (Kdim x 128), Q[c][kl] (Kdim x 64), sum_p[4][128], sum_q[4][64].
+struct TcReduceParams {
+    const float *pos, *neg;        // [n_chunks][G][part_floats]; pos == null: empty minibatch shard (contributes zeros)
+    int G_pos, G_neg, part_floats, Kdim, n_chunks, K, M, ds;
+    float *stats;                  // destination when !fused
+    crbm_stats_layout lay;
+    float c0, c1, c2, c3;          // N*Lh, B*200, N*L, B*(199+M)
+    const uint32_t *cnt_rows[2];
+    int cnt_row_words[2], cnt_n[2], cnt_L[2];
+    const int *batch_index;
+    ApplyParams ap;
+    int fused;
+};
+// this warp's share (CTAs sub, sub + 4, ...) of one entry; the order is part of the contract between the fused and the two-launch path
+__device__ __forceinline__ float tc_sum(const float *src, int G, size_t stride, int sub) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int x = sub; x < G; x += 16) {
+        const float t0 = src[x * stride];
+        const float t1 = x + 4 < G ? src[(x + 4) * stride] : 0.f;
+        const float t2 = x + 8 < G ? src[(x + 8) * stride] : 0.f;
+        const float t3 = x + 12 < G ? src[(x + 12) * stride] : 0.f;
+        a0 += t0; a1 += t1; a2 += t2; a3 += t3;
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ float tc_sum4(const float *src, int G, size_t stride, int sub, int slot_stride) {
+    const float s0 = tc_sum(src, G, stride, sub), s1 = tc_sum(src + slot_stride, G, stride, sub);
+    const float s2 = tc_sum(src + 2 * slot_stride, G, stride, sub), s3 = tc_sum(src + 3 * slot_stride, G, stride, sub);
+    return (s0 + s1) + (s2 + s3);
+}
+
+__global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ float sh[5][4][32];
+    __shared__ float counts[8];
+    const ApplyParams &ap = p.ap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = warp >> 2, sub = warp & 3;
+    const int fourM = 4 * p.M;
+    const int n_w = p.n_chunks * fourM * 2;
+    const size_t pf = (size_t)p.part_floats;
+    const size_t q_off = (size_t)p.Kdim * TT_ROWS, s_off = (size_t)p.Kdim * 192;
+    const float nhd = p.c0, nhm = p.c1;
+    const float strands = p.ds ? 2.f : 1.f;
+    const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
+    auto total = [&](int r) { return (sh[r][0][lane] + sh[r][1][lane]) + (sh[r][2][lane] + sh[r][3][lane]); };
+    if ((int)blockIdx.x < n_w) {
+        const int half = blockIdx.x & 1, rest = blockIdx.x >> 1;
+        const int ch = rest / fourM, c = rest - ch * fourM, cr = fourM - 1 - c;
+        const int kl = 32 * half + lane, k = ch * TT_KC + kl;
+        const float *pos = p.pos ? p.pos + (size_t)ch * p.G_pos * pf : nullptr;
+        const float *neg = p.neg + (size_t)ch * p.G_neg * pf;
+        float v = 0.f;
+        if (row == 0) {
+            if (pos) {
+                v = tc_sum(pos + (size_t)c * TT_ROWS + kl, p.G_pos, pf, sub);
+                if (p.ds) v += tc_sum(pos + (size_t)cr * TT_ROWS + TT_KC + kl, p.G_pos, pf, sub);
+            }
+        } else if (row == 1) {
+            if (pos) v = tc_sum(pos + q_off + (size_t)c * TT_KC + kl, p.G_pos, pf, sub);
+        } else if (row == 2) {
+            v = tc_sum(neg + (size_t)c * TT_ROWS + kl, p.G_neg, pf, sub);
+            if (p.ds) v += tc_sum(neg + (size_t)cr * TT_ROWS + TT_KC + kl, p.G_neg, pf, sub);
+        } else {
+            if (pos) v = tc_sum4(pos + s_off + kl, p.G_pos, pf, sub, TT_ROWS);
+        }
+        sh[row][sub][lane] = v;
+        __syncthreads();
+        if (warp != 0 || k >= p.K) return;
+        const float vd = total(0), vq = total(1), vm = total(2), hf = total(3);
+        const int m = c >> 2, a = c & 3;
+        const int gid = (k * 4 + a) * p.M + m;
+        if (p.fused) {
+            const float gk = sparsity_factor(hf, nhd, ap.rho, ap.K);
+            const float vel = next_velocity(ap.vW[gid], vd, nd, vm, nm, __fmul_rn(gk, vq), ap.mu, ap.lr, ap.lam);
+            ap.vW[gid] = vel;
+            ap.W[gid] = __fadd_rn(ap.W[gid], vel);
+        } else {
+            p.stats[p.lay.vh_data + gid] = vd;
+            p.stats[p.lay.vh_q + gid] = vq;
+            p.stats[p.lay.vh_model + gid] = vm;
+        }
+    } else if ((int)blockIdx.x < n_w + 2 * p.n_chunks) {
+        const int bb = blockIdx.x - n_w, ch = bb >> 1, half = bb & 1;
+        const int kl = 32 * half + lane, k = ch * TT_KC + kl;
+        const float *pos = p.pos ? p.pos + (size_t)ch * p.G_pos * pf + s_off : nullptr;
+        const float *neg = p.neg + (size_t)ch * p.G_neg * pf + s_off;
+        float v = 0.f;
+        if (row == 0) v = pos ? tc_sum4(pos + kl, p.G_pos, pf, sub, TT_ROWS) : 0.f;
+        else if (row == 1) v = pos ? tc_sum4(pos + TT_KC + kl, p.G_pos, pf, sub, TT_ROWS) : 0.f;
+        else if (row == 2) v = tc_sum4(neg + kl, p.G_neg, pf, sub, TT_ROWS);
+        else v = tc_sum4(neg + TT_KC + kl, p.G_neg, pf, sub, TT_ROWS);
+        sh[row][sub][lane] = v;
+        if (row == 0) sh[4][sub][lane] = pos ? tc_sum4(pos + 4 * TT_ROWS + kl, p.G_pos, pf, sub, TT_KC) : 0.f;
+        __syncthreads();
+        if (warp != 0 || k >= p.K) return;
+        const float hf = total(0);
+        const float hdata = hf + total(1), hmodel = total(2) + total(3), hq = total(4);
+        if (p.fused) {
+            const float gk = sparsity_factor(hf, nhd, ap.rho, ap.K);
+            const float vel = next_velocity(ap.vb[k], hdata, nd, hmodel, nm, __fmul_rn(gk, hq), ap.mu, ap.lr, ap.lam);
+            ap.vb[k] = vel;
+            ap.b[k] = __fadd_rn(ap.b[k], vel);
+        } else {
+            p.stats[p.lay.h_fwd + k] = hf;
+            p.stats[p.lay.h_data + k] = hdata;
+            p.stats[p.lay.h_model + k] = hmodel;
+            p.stats[p.lay.h_q + k] = hq;
+        }
+    } else {
+        // base counts of the minibatch and of the sampled visible layer (A9); fused: the update of c and the cursors of the next step
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const uint32_t *rows = p.cnt_rows[w];
+            if (w == 0 && p.batch_index) rows += (size_t)(*p.batch_index) * p.cnt_n[0] * p.cnt_row_words[0];
+            if (p.cnt_n[w] > 0) count_bases_block(rows, p.cnt_row_words[w], p.cnt_n[w], p.cnt_L[w], counts + 4 * w);
+            else if (threadIdx.x < 4) counts[4 * w + threadIdx.x] = 0.f;
+            __syncthreads();
+        }
+        if (p.fused) {
+            if (threadIdx.x < 4) {
+                const int a = threadIdx.x;
+                const float v = next_velocity(ap.vc[a], __fadd_rn(counts[a], counts[3 - a]), p.c2, __fadd_rn(counts[4 + a], counts[7 - a]), p.c3,
+                                              0.f, ap.mu, ap.lr, 0.f);
+                ap.vc[a] = v;
+                ap.c[a] = __fadd_rn(ap.c[a], v);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (ap.step_dev) *ap.step_dev += 1ull;
+                if (ap.batch_index_dev) { const int nb = *ap.batch_index_dev + 1; *ap.batch_index_dev = nb >= ap.n_batches ? 0 : nb; }
+            }
+        } else {
+            if (threadIdx.x < 4) { p.stats[p.lay.v_data + threadIdx.x] = counts[threadIdx.x]; p.stats[p.lay.v_model + threadIdx.x] = counts[4 + threadIdx.x]; }
+            if (threadIdx.x == 0) {
+                p.stats[p.lay.n_hidden_data] = p.c0; p.stats[p.lay.n_hidden_model] = p.c1;
+                p.stats[p.lay.n_vis_data] = p.c2; p.stats[p.lay.n_vis_model] = p.c3;
+            }
+        }
+    }
+}
+
+// ---- linear chain planes <-> the reference's dense (B,K,1,200) tensors ------------------------------------------------------
+__global__ void chain_lin_to_dense_kernel(const uint32_t *__restrict__ bits, int Bn, int K, int Kpad, int hw, int VP, float *__restrict__ dense) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)Bn * K * FANTASY_LEN) return;
+    const int j = (int)(gid % FANTASY_LEN);
+    const int k = (int)((gid / FANTASY_LEN) % K);
+    const int n = (int)(gid / ((long long)FANTASY_LEN * K));
+    const uint32_t w = bits[((size_t)n * hw + j / VP) * Kpad + k];
+    dense[gid] = (float)((w >> (j % VP)) & 1u);
+}
+__global__ void chain_dense_to_lin_kernel(const float *__restrict__ dense, int Bn, int K, int Kpad, int hw, int VP, uint32_t *__restrict__ bits) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)Bn * hw * Kpad) return;
+    const int k = (int)(gid % Kpad);
+    const int wq = (int)((gid / Kpad) % hw);
+    const int n = (int)(gid / ((long long)Kpad * hw));
+    uint32_t w = 0u;
+    if (k < K)
+        for (int b = 0; b < VP; ++b) {
+            const int j = wq * VP + b;
+            if (j < FANTASY_LEN && dense[((size_t)n * K + k) * FANTASY_LEN + j] != 0.f) w |= 1u << b;
+        }
+    bits[gid] = w;
+}
+
+// ---- one training step on the tcgen05 kernels -----------------------------------------------------------------------------------
+//     h2v_lin -> v2h_train_tc<SAMPLE> [x cd_k, the last one with the model statistics] -> v2h_train_tc<P|Q> (minibatch) -> reduce_tc
+// the same chain of programmatic dependents as the mma.sync path (train.cu), two partial buffers in the workspace.
+static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s, bool p2p) {
+    const int K = a->K, M = a->M, P = a->pooling, Lh = a->L - M + 1;
+    const TtGeom g = tt_geom(K, M, P);
+    const int ds = a->doublestranded ? 1 : 0;
+    const int Lv = FANTASY_LEN + M - 1;
+    float *part_pos = reinterpret_cast<float *>(a->workspace);
+    float *part_neg = part_pos + (size_t)g.n_chunks * g.G * g.part_floats;
+    int rc;
+    auto base_params = [&](TrainTcParams &t) {
+        t.W = a->W; t.b = a->b; t.K = K; t.M = M; t.ds = ds;
+        t.ksteps = g.ksteps; t.n_atoms = g.n_atoms; t.Kdim = g.Kdim; t.part_floats = g.part_floats;
+        t.seed = a->seed; t.step_dev = a->step_dev;
+    };
+    // ---- negative phase ----------------------------------------------------------------------------------------------------
+    const int nb_neg = ceil_div(FANTASY_LEN, g.VP);
+    const int units_neg = ceil_div(a->batchsize * nb_neg, 2);
+    const int gx_neg = units_neg < g.G ? units_neg : g.G;
+    if (phases & CRBM_PHASE_NEGATIVE) {
+        const size_t n_u_v = (size_t)a->batchsize * Lv, n_u_h = (size_t)a->batchsize * K * (FANTASY_LEN / P);
+        const int kw = ceil_div(K, 32);
+        const int h2v_items = a->batchsize * ceil_div(Lv, 16);
+        int split_log2 = 0;
+        while (split_log2 < 2 && (4 << split_log2) <= kw && (long long)h2v_items * (2 << split_log2) <= 64ll * num_sms()) ++split_log2;
+        if (const char *e = getenv("CRBM_H2V_SPLIT")) split_log2 = atoi(e) <= 1 ? 0 : atoi(e) == 2 ? 1 : 2;
+        while ((1 << split_log2) > kw) --split_log2;
+        const int h2v_split = 1 << split_log2;
+        const int h2v_slots = h2v_items * h2v_split;
+        int h2v_nw = ceil_div(h2v_slots, num_sms());
+        h2v_nw = h2v_nw < 4 ? 4 : h2v_nw > 16 ? 16 : h2v_nw;
+        h2v_nw = ceil_div(h2v_nw, h2v_split) * h2v_split;
+        const size_t h2v_smem = 16 + (size_t)h2v_nw * H2V_LIST * sizeof(uint32_t);
+        static size_t lin_smem_configured[64];
+        int dev_id = 0;
+        CRBM_CHECK_CUDA(cudaGetDevice(&dev_id));
+        size_t &configured = lin_smem_configured[dev_id & 63];
+        if (configured < 48 * 1024) configured = 48 * 1024;
+        if (h2v_smem > configured) {
+            CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h2v_smem));
+            configured = h2v_smem;
+        }
+        for (int it = 0; it < a->cd_k; ++it) {
+            const bool last = it == a->cd_k - 1;
+            H2VLinParams h{};
+            h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.Kpad = g.Kpad; h.hw = g.hw; h.VP = g.VP; h.kw = kw; h.M = M; h.ds = ds;
+            h.words_per_row = ceil_div(Lv, 16); h.split = h2v_split; h.split_log2 = split_log2;
+            h.W = a->W; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words;
+            h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
+            h.seed = a->seed; h.step_dev = a->step_dev;
+            h.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; h.iter = (uint32_t)it;
+            CRBM_CHECK_CUDA(launch_chain(h2v_lin_kernel, dim3(ceil_div(h2v_slots, h2v_nw)), dim3(32 * h2v_nw), h2v_smem, s, h));
+            CRBM_CHECK_LAUNCH();
+
+            TrainTcParams q{};
+            base_params(q);
+            q.packed = a->v_model; q.row_words = a->v_row_words; q.n_rows = a->batchsize; q.L = Lv; q.Lh = FANTASY_LEN;
+            q.nblk32 = nb_neg; q.n_units = units_neg;
+            q.partial = part_neg; q.bits = a->fantasy_bits; q.hw = g.hw; q.Kpad = g.Kpad;
+            q.u_fwd = a->u_h ? a->u_h + it * n_u_h : nullptr;
+            q.u_rc = a->u_hp ? a->u_hp + it * n_u_h : nullptr;
+            q.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; q.iter = (uint32_t)it;
+            if ((rc = dispatch_train_tc(P, last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, dim3(gx_neg, g.n_chunks), s))) return rc;
+        }
+    }
+    // ---- positive phase + sparsity statistic ---------------------------------------------------------------------------------------
+    const int nb_pos = ceil_div(Lh, g.VP);
+    const int units_pos = ceil_div(a->n_data * nb_pos, 2);
+    const int gx_pos = units_pos < g.G ? (units_pos > 0 ? units_pos : 1) : g.G;
+    if ((phases & CRBM_PHASE_POSITIVE) && a->n_data > 0) {
+        TrainTcParams t{};
+        base_params(t);
+        t.packed = a->data; t.row_words = a->data_row_words; t.n_rows = a->n_data; t.L = a->L; t.Lh = Lh;
+        t.batch_index = a->batch_index_dev;
+        t.nblk32 = nb_pos; t.n_units = units_pos;
+        t.partial = part_pos;
+        t.pdl_late = 1;
+        if ((rc = dispatch_train_tc(P, F_STAT_P | F_STAT_Q, t, dim3(gx_pos, g.n_chunks), s))) return rc;
+    }
+    // ---- reduction (+ update) -----------------------------------------------------------------------------------------------------
+    if (phases & CRBM_PHASE_REDUCE) {
+        TcReduceParams r{};
+        r.pos = a->n_data > 0 ? part_pos : nullptr; r.neg = part_neg;
+        r.G_pos = gx_pos; r.G_neg = gx_neg; r.part_floats = g.part_floats; r.Kdim = g.Kdim; r.n_chunks = g.n_chunks;
+        r.K = K; r.M = M; r.ds = ds;
+        r.stats = a->stats;
+        fill_layout(K, M, &r.lay);
+        r.c0 = (float)a->n_data * Lh; r.c1 = (float)a->batchsize * FANTASY_LEN;
+        r.c2 = (float)a->n_data * a->L; r.c3 = (float)a->batchsize * Lv;
+        r.cnt_rows[0] = a->data; r.cnt_row_words[0] = a->data_row_words; r.cnt_n[0] = a->n_data; r.cnt_L[0] = a->L;
+        r.cnt_rows[1] = a->v_model; r.cnt_row_words[1] = a->v_row_words; r.cnt_n[1] = a->batchsize; r.cnt_L[1] = Lv;
+        r.batch_index = a->batch_index_dev;
+        r.fused = ((phases & CRBM_PHASE_APPLY) && !p2p && a->n_data > 0 && fused_update_enabled()) ? 1 : 0;
+        if (r.fused) fill_apply_params(a, &r.ap);
+        CRBM_CHECK_CUDA(launch_chain(reduce_tc_kernel, dim3(g.n_chunks * 4 * M * 2 + 2 * g.n_chunks + 1), dim3(512), 0, s, r));
+        CRBM_CHECK_LAUNCH();
+        if (r.fused) return CRBM_OK;
+    }
+    if (phases & CRBM_PHASE_APPLY) return crbm_train_apply(a, (void *)s);
+    return CRBM_OK;
+}
+
+}  // namespace crbm

@@ -132,7 +132,7 @@ typedef struct crbm_train_args {
     int data_row_words, n_data, L;
     /* persistent chain of this rank: `batchsize` particles */
     int batchsize;
-    uint32_t *fantasy_bits;        /* [2][batchsize][kw][crbm_fantasy_words()]; strand 1 unused when !doublestranded */
+    uint32_t *fantasy_bits;        /* [2][batchsize][crbm_chain_words(K, M, pooling)]; strand 1 unused when !doublestranded */
     uint32_t *v_model;             /* packed scratch, batchsize rows of 199+M bases (holds the last sampled V) */
     int v_row_words;
     /* randomness: Philox(seed, step) unless the matching pointer is non-NULL (tests replay reference uniforms) */
@@ -217,9 +217,20 @@ typedef struct crbm_stats_layout {
 } crbm_stats_layout;
 int crbm_train_stats_layout(int K, int M, crbm_stats_layout *out_host);
 
-/* fantasy particles <-> the reference's dense (B,K,1,200) fp32 tensors (tests, inspection) */
+/* fantasy particles <-> the reference's dense (B,K,1,200) fp32 tensors (tests, inspection): fragment-ordered bit planes */
 int crbm_hidden_bits_to_dense(const uint32_t *bits, int B, int K, float *dense, void *stream);
 int crbm_hidden_dense_to_bits(const float *dense, int B, int K, uint32_t *bits, void *stream);
+
+/* THE PERSISTENT CHAIN OF A MODEL (convRBM.py:168-173). Its device layout follows the kernels that train the model shape:
+ *   layout 0  fragment-ordered bit planes (above; the mma.sync kernels: motif_length > 32 or pooling not in {1,2,4,5,10})
+ *   layout 1  linear planes of the tcgen05 kernels: uint32 H[strand][n][w][Kpad], Kpad = 64 ceil(K/64), VP = (32/P) P;
+ *             bit b (< VP) of word w of motif k is hidden position w * VP + b
+ * args->fantasy_bits of the training entry points is uint32 [2][batchsize][crbm_chain_words(K, M, pooling)]; one strand plane
+ * (batchsize * crbm_chain_words words) converts to / from the reference's dense tensor with the two functions below. */
+int    crbm_chain_layout(int K, int M, int pooling);
+size_t crbm_chain_words(int K, int M, int pooling);
+int    crbm_chain_to_dense(const uint32_t *bits, int B, int K, int M, int pooling, float *dense, void *stream);
+int    crbm_chain_from_dense(const float *dense, int B, int K, int M, int pooling, uint32_t *bits, void *stream);
 
 /* launch counter: number of kernels this library has launched since load (bench.py's `gpu_launches`) */
 unsigned long long crbm_launch_count(void);

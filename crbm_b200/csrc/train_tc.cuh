@@ -32,7 +32,7 @@ namespace crbm {
 constexpr int TT_UNIT = 64;                   // hidden positions per unit
 constexpr int TT_KC = 64;                     // motifs per CTA
 constexpr int TT_ROWS = 128;                  // MMA rows: 2 strands x 64 motifs
-constexpr int TT_XSTAGES = 3;
+constexpr int TT_MAX_XSTAGES = 8;
 constexpr int TT_THREADS = 640;
 constexpr int TT_D2P_COL = 0, TT_D2Q_COL = 128, TT_D1_COL = 256;      // TMEM columns
 constexpr int TT_XATOM = TT_UNIT * 128;       // bytes of one 64-column swizzle atom of a one-hot tile (64 rows)
@@ -53,6 +53,7 @@ struct TrainTcParams {
     int part_floats;
     uint32_t *bits;                // linear chain planes [2][n_rows][hw][Kpad] (F_SAMPLE)
     int hw, Kpad;
+    int xstages, npsets;           // one-hot tiles in the ring (<= 8); P/Q operand sets (2, or 1 when shared memory is short)
     const float *u_fwd, *u_rc;     // injected uniforms [(n*K+k)*(Lh/P) + group] or null
     uint64_t seed;
     uint32_t ctr_hi, iter;
@@ -61,8 +62,8 @@ struct TrainTcParams {
 };
 
 __host__ __device__ inline int tt_part_floats(int Kdim) { return Kdim * 192 + 4 * 128 + 4 * 64; }
-__host__ __device__ inline size_t tt_smem_bytes(int n_atoms, bool stat) {
-    return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)TT_XSTAGES * n_atoms * TT_XATOM + (stat ? 2 * TT_PSET : 0) + 512 + 256;
+__host__ __device__ inline size_t tt_smem_bytes(int n_atoms, int xstages, int npsets) {
+    return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)xstages * n_atoms * TT_XATOM + (size_t)npsets * TT_PSET + 512 + 512;
 }
 
 // one-hot row of a 64-row tile (same chunk layout as scan_tc.cu: chunk ch = bases 2ch, 2ch+1 as eight fp16)
@@ -92,20 +93,32 @@ __device__ __forceinline__ void tmem_ld_fence16(uint32_t (&v)[16]) {
 
 static __device__ __noinline__ uint4 tt_philox(uint4 ctr, uint2 key) { return philox4x32(ctr, key); }
 
-// eight values scaled by 2^14 -> fp16 hi chunk and fp16 lo (residual) chunk, 16 bytes each
+// eight values (already scaled by 2^14) -> fp16 hi chunk (the top 11 significand bits, by truncation: exact in fp16) and fp16 lo
+// chunk (the exact remainder, rounded to 11 bits): 3 instructions per value
+__device__ __forceinline__ uint32_t tt_pack_half2(float a, float b) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+    return d;
+}
 __device__ __forceinline__ void tt_split8(const float *v, uint4 &hi, uint4 &lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float a = v[2 * i] * TT_PSCALE, b = v[2 * i + 1] * TT_PSCALE;
-        const __half2 hh = __floats2half2_rn(a, b);
-        const float2 back = __half22float2(hh);
-        const __half2 ll = __floats2half2_rn(a - back.x, b - back.y);
-        h[i] = *reinterpret_cast<const uint32_t *>(&hh);
-        l[i] = *reinterpret_cast<const uint32_t *>(&ll);
+        const float a = v[2 * i], b = v[2 * i + 1];
+        const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u), bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+        h[i] = tt_pack_half2(ah, bh);
+        l[i] = tt_pack_half2(a - ah, b - bh);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+    return ok != 0;
 }
 
 template <int FLAGS, int P>
@@ -119,16 +132,19 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
     const size_t w_bytes = (size_t)p.n_atoms * TT_WATOM, x_bytes = (size_t)p.n_atoms * TT_XATOM;
     unsigned char *Whi = smem, *Wlo = Whi + w_bytes;
     unsigned char *X = Wlo + w_bytes;
-    unsigned char *PQ = X + TT_XSTAGES * x_bytes;
-    float *bias_s = reinterpret_cast<float *>(PQ + (STAT ? 2 * TT_PSET : 0));
+    unsigned char *PQ = X + (size_t)p.xstages * x_bytes;
+    float *bias_s = reinterpret_cast<float *>(PQ + (STAT ? (size_t)p.npsets * TT_PSET : 0));
     uint64_t *x_full = reinterpret_cast<uint64_t *>(bias_s + TT_ROWS);
-    uint64_t *x_free = x_full + TT_XSTAGES;
-    uint64_t *d1_full = x_free + TT_XSTAGES;
+    uint64_t *x_free = x_full + TT_MAX_XSTAGES;
+    uint64_t *d1_full = x_free + TT_MAX_XSTAGES;
     uint64_t *d1_free = d1_full + 4;
     uint64_t *p_full = d1_free + 4;
     uint64_t *p_free = p_full + 2;
     uint64_t *d2_done = p_free + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d2_done + 1);
+    const int XS = p.xstages;
+    // scale of the accumulators: P == 1 evaluates 1 / (1 + 2^x) with x = -log2(e) a; the pooled softmax needs 2^x with x = +log2(e) a
+    constexpr float WSCALE = P == 1 ? -1.4426950408889634f : 1.4426950408889634f;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -137,28 +153,41 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
 
     if (warp == 3) tmem_alloc(tmem_slot, 512u);
     if (tid == 64) {
-        for (int i = 0; i < TT_XSTAGES; ++i) { mbar_init(x_full + i, 64); mbar_init(x_free + i, 1); }
+        for (int i = 0; i < TT_MAX_XSTAGES; ++i) { mbar_init(x_full + i, 64); mbar_init(x_free + i, 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(d1_full + i, 1); mbar_init(d1_free + i, 8); }
         for (int i = 0; i < 2; ++i) { mbar_init(p_full + i, 8); mbar_init(p_free + i, 1); }
         mbar_init(d2_done, 1);
     }
-    // ---- A of GEMM 1: both strands of the chunk's motifs, scaled by -log2(e), fp16 hi / lo, K-major SWIZZLE_128B ------------
-    for (int idx = tid; idx < TT_ROWS * Kdim; idx += TT_THREADS) {
-        const int r = idx / Kdim, c = idx - r * Kdim;
-        const int s = r >> 6, k = chunk * TT_KC + (r & 63), m = c >> 2, a = c & 3;
-        float w = 0.f;
-        if (k < p.K && m < p.M && (s == 0 || p.ds))
-            w = s == 0 ? __ldg(p.W + ((size_t)k * 4 + a) * p.M + m) : __ldg(p.W + ((size_t)k * 4 + (3 - a)) * p.M + (p.M - 1 - m));
-        w *= -1.4426950408889634f;
-        const __half hi = __float2half_rn(w);
-        const __half lo = __float2half_rn(w - __half2float(hi));
-        const uint32_t off = (uint32_t)(c >> 6) * TT_WATOM + sw128_off(r, (c >> 3) & 7) + (c & 7) * 2;
-        *reinterpret_cast<__half *>(Whi + off) = hi;
-        *reinterpret_cast<__half *>(Wlo + off) = lo;
+    // ---- A of GEMM 1: both strands of the chunk's motifs, scaled, fp16 hi / lo, K-major SWIZZLE_128B; one 16-byte chunk
+    // (motif positions 2 ch, 2 ch + 1, four bases each) per work item
+    for (int idx = tid; idx < TT_ROWS * (Kdim >> 3); idx += TT_THREADS) {
+        const int r = idx & (TT_ROWS - 1), ch = idx >> 7;
+        const int s = r >> 6, k = chunk * TT_KC + (r & 63);
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int m = 2 * ch + (e >> 2), a = e & 3;
+            float v = 0.f;
+            if (k < p.K && m < p.M && (s == 0 || p.ds))
+                v = s == 0 ? __ldg(p.W + ((size_t)k * 4 + a) * p.M + m) : __ldg(p.W + ((size_t)k * 4 + (3 - a)) * p.M + (p.M - 1 - m));
+            w[e] = v * WSCALE;
+        }
+        uint32_t hh[4], ll[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __half2 h2 = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(w[2 * e] - back.x, w[2 * e + 1] - back.y);
+            hh[e] = *reinterpret_cast<const uint32_t *>(&h2);
+            ll[e] = *reinterpret_cast<const uint32_t *>(&l2);
+        }
+        const uint32_t off = (uint32_t)(ch >> 3) * TT_WATOM + sw128_off(r, ch & 7);
+        *reinterpret_cast<uint4 *>(Whi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        *reinterpret_cast<uint4 *>(Wlo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
     }
     for (int r = tid; r < TT_ROWS; r += TT_THREADS) {
         const int k = chunk * TT_KC + (r & 63);
-        bias_s[r] = k < p.K ? -1.4426950408889634f * __ldg(p.b + k) : 0.f;
+        bias_s[r] = k < p.K ? WSCALE * __ldg(p.b + k) : 0.f;
     }
     fence_async_smem();
     tc_fence_before();
@@ -194,7 +223,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
         int csh = 0, cml = 0, nsh = 0, nml = 0;
         if (my_units > 0) load_row(0, cw, csh, cml);
         for (int t = 0; t < my_units; ++t) {
-            const int stage = t % TT_XSTAGES, use = t / TT_XSTAGES;
+            const int stage = t % XS, use = t / XS;
             if (t + 1 < my_units) load_row(t + 1, nw, nsh, nml);
             if (use > 0) mbar_wait(x_free + stage, (uint32_t)((use - 1) & 1));
             tt_build_row(X + (size_t)stage * x_bytes, tid, nch, cw, csh, cml);
@@ -210,51 +239,68 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
             const uint32_t whi = smem_u32(Whi), wlo = smem_u32(Wlo), xa = smem_u32(X), pq = smem_u32(PQ);
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TT_UNIT >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (1u << 16) | ((uint32_t)(Kdim >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
-            auto gemm1 = [&](int t) {
-                const int stage = t % TT_XSTAGES, buf = t & 3;
-                mbar_wait(x_full + stage, (uint32_t)((t / TT_XSTAGES) & 1));
-                if (t >= 4) mbar_wait(d1_free + buf, (uint32_t)(((t >> 2) - 1) & 1));
-                tc_fence_after();
-                const uint32_t d1 = tmem_base + TT_D1_COL + 64 * buf;
-                const uint32_t xs = xa + (uint32_t)(stage * x_bytes);
-                for (int s = 0; s < p.ksteps; ++s) {
-                    const uint32_t atom = s >> 2, koff = (s & 3) * 32;
-                    const uint64_t bd = umma_desc_sw128(xs + atom * TT_XATOM + koff);
-                    umma_f16(d1, umma_desc_sw128(whi + atom * TT_WATOM + koff), bd, idesc1, s > 0 ? 1u : 0u);
-                    umma_f16(d1, umma_desc_sw128(wlo + atom * TT_WATOM + koff), bd, idesc1, 1u);
-                }
-                umma_commit(d1_full + buf);
-                if (!STAT) umma_commit(x_free + stage);
-            };
-            int issued = 0;
-            for (int t = 0; t < my_units; ++t) {
-                while (issued < my_units && issued <= t + 2) gemm1(issued++);
-                if (STAT) {
-                    const int pr = t & 1, stage = t % TT_XSTAGES;
-                    mbar_wait(p_full + pr, (uint32_t)((t >> 1) & 1));
-                    tc_fence_after();
-                    const uint32_t set = pq + pr * TT_PSET, xs = xa + (uint32_t)(stage * x_bytes);
+            // Polling issue loop: GEMM 2 of the oldest finished unit first (it frees a one-hot stage and an operand set), else the
+            // next GEMM 1 whose tile is built and whose accumulator buffer has been drained. Nothing blocks behind a wait.
+            const int npm = p.npsets - 1;                         // 0 or 1
+            int g1 = 0, g2 = 0;
+            const int g2_total = STAT ? my_units : 0;
+            while (g1 < my_units || g2 < g2_total) {
+                bool progressed = false;
+                if (STAT && g2 < g1) {
+                    const int set_i = g2 & npm, use = p.npsets == 2 ? (g2 >> 1) : g2;
+                    if (mbar_test(p_full + set_i, (uint32_t)(use & 1))) {
+                        const int t = g2, stage = t % XS;
+                        tc_fence_after();
+                        const uint32_t set = pq + set_i * TT_PSET, xs = xa + (uint32_t)(stage * x_bytes);
 #pragma unroll
-                    for (int k2 = 0; k2 < TT_UNIT / 16; ++k2) {
-                        // B = the one-hot tile read MN-major: 16 positions = two 8-row groups (1024 bytes apart), c atoms TT_XATOM apart
-                        const uint64_t bd = umma_desc_sw128_mn(xs + k2 * 2048, TT_XATOM, 1024);
-                        const uint32_t acc = (t > 0 || k2 > 0) ? 1u : 0u;
-                        umma_f16(tmem_base + TT_D2P_COL, umma_desc_sw128(set + TT_PHI + k2 * 32), bd, idesc2, acc);
-                        umma_f16(tmem_base + TT_D2P_COL, umma_desc_sw128(set + TT_PLO + k2 * 32), bd, idesc2, 1u);
-                        if (STAT_Q) {
-                            // rows 64-127 of the Q operands alias the buffers that follow them (finite values; those D2 lanes are unused)
-                            umma_f16(tmem_base + TT_D2Q_COL, umma_desc_sw128(set + TT_QHI + k2 * 32), bd, idesc2, acc);
-                            umma_f16(tmem_base + TT_D2Q_COL, umma_desc_sw128(set + TT_QLO + k2 * 32), bd, idesc2, 1u);
+                        for (int k2 = 0; k2 < TT_UNIT / 16; ++k2) {
+                            // B = the one-hot tile read MN-major: 16 positions = two 8-row groups (1024 bytes apart), c atoms TT_XATOM apart
+                            const uint64_t bd = umma_desc_sw128_mn(xs + k2 * 2048, TT_XATOM, 1024);
+                            const uint32_t acc = (t > 0 || k2 > 0) ? 1u : 0u;
+                            umma_f16(tmem_base + TT_D2P_COL, umma_desc_sw128(set + TT_PHI + k2 * 32), bd, idesc2, acc);
+                            umma_f16(tmem_base + TT_D2P_COL, umma_desc_sw128(set + TT_PLO + k2 * 32), bd, idesc2, 1u);
+                            if (STAT_Q) {
+                                // rows 64-127 of the Q operands alias the buffers that follow them (finite values; those D2 lanes are unused)
+                                umma_f16(tmem_base + TT_D2Q_COL, umma_desc_sw128(set + TT_QHI + k2 * 32), bd, idesc2, acc);
+                                umma_f16(tmem_base + TT_D2Q_COL, umma_desc_sw128(set + TT_QLO + k2 * 32), bd, idesc2, 1u);
+                            }
                         }
+                        umma_commit(x_free + stage);
+                        // "the set may be overwritten": with two sets the waiter is the same group's next unit; with one shared set it is
+                        // the OTHER group's next unit, so each group has its own barrier and sees one phase at a time (a parity wait
+                        // cannot tell phases two apart: scratch/tt_sim.py)
+                        umma_commit(p_free + (p.npsets == 2 ? set_i : ((t + 1) & 1)));
+                        ++g2;
+                        progressed = true;
                     }
-                    umma_commit(x_free + stage);
-                    umma_commit(p_free + pr);
                 }
+                if (g1 < my_units) {
+                    const int t = g1, stage = t % XS, buf = t & 3;
+                    if (mbar_test(x_full + stage, (uint32_t)((t / XS) & 1)) &&
+                        (t < 4 || mbar_test(d1_free + buf, (uint32_t)(((t >> 2) - 1) & 1)))) {
+                        tc_fence_after();
+                        const uint32_t d1 = tmem_base + TT_D1_COL + 64 * buf;
+                        const uint32_t xs = xa + (uint32_t)(stage * x_bytes);
+                        for (int s = 0; s < p.ksteps; ++s) {
+                            const uint32_t atom = s >> 2, koff = (s & 3) * 32;
+                            const uint64_t bd = umma_desc_sw128(xs + atom * TT_XATOM + koff);
+                            umma_f16(d1, umma_desc_sw128(whi + atom * TT_WATOM + koff), bd, idesc1, s > 0 ? 1u : 0u);
+                            umma_f16(d1, umma_desc_sw128(wlo + atom * TT_WATOM + koff), bd, idesc1, 1u);
+                        }
+                        umma_commit(d1_full + buf);
+                        if (!STAT) umma_commit(x_free + stage);
+                        ++g1;
+                        progressed = true;
+                    }
+                }
+                if (!progressed) __nanosleep(20);
             }
             umma_commit(d2_done);
         }
     } else if (warp >= 4) {
         // ================================================= epilogue ========================================================
+        // All probabilities are carried SCALED by 2^14 (pv = 2^14 p, qv = 2^14 Q): the scale is folded into the reciprocal, the
+        // fp16 operands of GEMM 2 need it, and powers of two commute with every comparison and sum below.
         const int ew = warp - 4, q = warp & 3, wg = ew >> 2, pr = wg >> 1, h = wg & 1;
         const int r = 32 * q + lane, s = q >> 1, kl = r & 63, k = chunk * TT_KC + kl;
         const bool row_ok = k < p.K && (s == 0 || p.ds);
@@ -264,8 +310,9 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
         const uint32_t ctr_hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) : 0u);
         const uint32_t tag = (s == 0 ? RNG_HIDDEN : RNG_HIDDEN_RC) | (p.iter << 8);
         const float *inj = s == 0 ? p.u_fwd : p.u_rc;
+        const int npm = p.npsets - 1;
+        constexpr float INV_S = 1.0f / TT_PSCALE;
         float sum_p = 0.f, sum_q = 0.f;
-        unsigned char *set = PQ + pr * TT_PSET;
         for (int t = pr; t < my_units; t += 2) {
             const int ug = (int)blockIdx.x + t * G;
             const int b32 = 2 * ug + h;
@@ -288,35 +335,35 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
             float pv[32];
 #pragma unroll
             for (int i = 0; i < 16; ++i) { pv[i] = __uint_as_float(va[i]) + bias; pv[16 + i] = __uint_as_float(vb[i]) + bias; }
-            const bool full = row_ok && nv == 32;                // (warp-uniform only for nv; row_ok is per lane)
             float qv[STAT_Q ? 32 : 1];
             if (P == 1) {
-                // p = 1 / (1 + 2^x), x = -log2(e) (activity + b): two outputs share one reciprocal (MUFU is the busiest pipe)
+                // 2^14 p = 2^14 / (1 + 2^x), x = -log2(e) (activity + b). Two outputs share one reciprocal (MUFU is a busy pipe):
+                // a_i = 2^-14 (1 + e_i) (one FFMA), r = 1 / (a_0 a_1), 2^14 p_0 = r a_1, 2^14 p_1 = r a_0.
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float e0, e1, rr;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(pv[i], 60.f)));
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(pv[i + 1], 60.f)));
-                    const float a0 = 1.0f + e0, a1 = 1.0f + e1;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(pv[i], 40.f)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(pv[i + 1], 40.f)));
+                    const float a0 = fmaf(e0, INV_S, INV_S), a1 = fmaf(e1, INV_S, INV_S);
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(a0 * a1));
                     pv[i] = rr * a1;
                     pv[i + 1] = rr * a0;
                 }
-                if (!full) {
+                if (!(row_ok && nv == 32)) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) pv[i] = (row_ok && i < nv) ? pv[i] : 0.f;
                 }
                 if constexpr (STAT_Q) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) qv[i] = pv[i] - pv[i] * pv[i];
+                    for (int i = 0; i < 32; ++i) qv[i] = fmaf(-(pv[i] * INV_S), pv[i], pv[i]);      // 2^14 p (1 - p)
                 }
             } else {
                 // p = exp(a) / (P + sum_group exp(a)) (convRBM.py:252), a clamped at 40; groups are P consecutive registers
-                const float fpool = (float)P;
+                constexpr float fpool = (float)P;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(-pv[i], 57.7f)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(pv[i], 57.7f)));
                     pv[i] = (row_ok && i < nv && i < VP) ? e : 0.f;
                 }
 #pragma unroll
@@ -324,12 +371,13 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                     float tot = 0.f;
 #pragma unroll
                     for (int i = 0; i < P; ++i) tot += pv[g * P + i];
-                    float inv;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fpool + tot));
+                    float inv;                                   // 2^14 / (P + tot)
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fmaf(tot, INV_S, fpool * INV_S)));
+                    const float gq = inv * (fpool * INV_S);      // P / (P + tot) = 1 - sum_group p
 #pragma unroll
                     for (int i = 0; i < P; ++i) {
                         pv[g * P + i] *= inv;
-                        if constexpr (STAT_Q) qv[g * P + i] = pv[g * P + i] * (fpool * inv);
+                        if constexpr (STAT_Q) qv[g * P + i] = pv[g * P + i] * gq;
                     }
                 }
                 if constexpr (STAT_Q) {
@@ -339,15 +387,15 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
             }
             // ---- hidden sums (A9), per unit first so that the running sums grow by a few dozen terms at a time
             {
-                float us = 0.f;
+                float us0 = 0.f, us1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) us += pv[i];
-                sum_p += us;
+                for (int i = 0; i < 32; i += 2) { us0 += pv[i]; us1 += pv[i + 1]; }
+                sum_p += us0 + us1;
                 if constexpr (STAT_Q) {
-                    float uq = 0.f;
+                    float uq0 = 0.f, uq1 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) uq += qv[i];
-                    sum_q += uq;
+                    for (int i = 0; i < 32; i += 2) { uq0 += qv[i]; uq1 += qv[i + 1]; }
+                    sum_q += uq0 + uq1;
                 }
             }
             // ---- sampling (A3): the 32 positions of this (strand, motif, block) are one word of the chain planes
@@ -360,11 +408,11 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             const float u = (row_ok && i < nv) ? up[i] : 1.f;
-                            word |= (pv[i] > u ? 1u : 0u) << i;
+                            word |= (pv[i] > u * TT_PSCALE ? 1u : 0u) << i;
                         }
                     } else {
                         // 16-bit uniforms, eight per Philox draw; exact Bernoulli(p) through a second draw on the rare ties
-                        // (same scheme as v2h_mma.cuh)
+                        // (same scheme as v2h_mma.cuh); 65536 p = 4 pv
                         uint32_t ambw = 0u;
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
@@ -372,8 +420,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                             const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float tt = pv[8 * c4 + i] * 65536.f;
-                                const int ti = (int)tt, u16 = (int)((rw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                                const int ti = (int)(pv[8 * c4 + i] * 4.f), u16 = (int)((rw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
                                 word |= (ti > u16 ? 1u : 0u) << (8 * c4 + i);
                                 ambw |= (ti == u16 ? 1u : 0u) << (8 * c4 + i);
                             }
@@ -385,7 +432,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                                 const uint32_t r2w[4] = {r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) {
-                                    const float tt = pv[8 * c4 + i] * 65536.f;
+                                    const float tt = pv[8 * c4 + i] * 4.f;
                                     const float fr = tt - (float)(int)tt;
                                     const bool hit2 = fr * 65536.f > (float)((r2w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
                                     if ((ambw >> (8 * c4 + i)) & 1u) word |= (hit2 ? 1u : 0u) << (8 * c4 + i);
@@ -408,12 +455,13 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                             }
                             u = ug4[g & 3];
                         }
+                        const float us = u * TT_PSCALE;
                         float run = 0.f;
                         bool done = false;
 #pragma unroll
                         for (int i = 0; i < P; ++i) {
                             run += pv[g * P + i];
-                            const bool hit = !done && run > u;
+                            const bool hit = !done && run > us;
                             done = done || hit;
                             word |= (hit ? 1u : 0u) << (g * P + i);
                         }
@@ -421,9 +469,13 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                 }
                 if (n < p.n_rows) p.bits[(((size_t)s * p.n_rows + n) * p.hw + wb) * p.Kpad + chunk * TT_KC + kl] = word;
             }
-            // ---- A operands of GEMM 2: p (and Q) x 2^14 as fp16 hi / lo, K-major SWIZZLE_128B rows of 64 positions
+            // ---- A operands of GEMM 2: 2^14 p (and 2^14 Q) as fp16 hi / lo, K-major SWIZZLE_128B rows of 64 positions
             if (STAT) {
-                if (t >= 2) mbar_wait(p_free + pr, (uint32_t)(((t >> 1) - 1) & 1));     // GEMM 2 of unit t-2 has read this set
+                const int set_i = t & npm, use = p.npsets == 2 ? (t >> 1) : t;
+                unsigned char *set = PQ + set_i * TT_PSET;
+                // the GEMM 2 that read this set last has completed: unit t-2 (own set) or unit t-1 (shared set, own barrier)
+                if (p.npsets == 2) { if (use >= 1) mbar_wait(p_free + set_i, (uint32_t)((use - 1) & 1)); }
+                else if (t >= 1) mbar_wait(p_free + pr, (uint32_t)(((t - 1) >> 1) & 1));
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     uint4 hi, lo;
@@ -444,7 +496,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(p_full + pr);
+                if (lane == 0) mbar_arrive(p_full + set_i);
             }
         }
         // ---- statistics accumulators -> this CTA's partial: P[c][r], Q[c][kl], hidden sums per warpgroup ----------------------
@@ -471,8 +523,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                 }
             }
             float *sums = part + (size_t)Kdim * 192;
-            sums[wg * TT_ROWS + r] = sum_p;
-            if (s == 0) sums[4 * TT_ROWS + wg * TT_KC + kl] = STAT_Q ? sum_q : 0.f;
+            sums[wg * TT_ROWS + r] = sum_p * unscale;
+            if (s == 0) sums[4 * TT_ROWS + wg * TT_KC + kl] = STAT_Q ? sum_q * unscale : 0.f;
         }
     }
     tc_fence_before();

@@ -361,6 +361,14 @@ static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s,
         t.W = a->W; t.b = a->b; t.K = K; t.M = M; t.ds = ds;
         t.ksteps = g.ksteps; t.n_atoms = g.n_atoms; t.Kdim = g.Kdim; t.part_floats = g.part_floats;
         t.seed = a->seed; t.step_dev = a->step_dev;
+        // shared memory: W (hi, lo) + ring of one-hot tiles + P/Q operand sets. Two sets when they fit beside a ring of at least
+        // 6 tiles (a tile lives from its GEMM 1 until the GEMM 2 of the same unit, i.e. across the whole epilogue of the unit).
+        const size_t cap = 222 * 1024;
+        t.npsets = tt_smem_bytes(g.n_atoms, 6, 2) <= cap ? 2 : 1;
+        t.xstages = TT_MAX_XSTAGES;
+        while (t.xstages > 3 && tt_smem_bytes(g.n_atoms, t.xstages, t.npsets) > cap) --t.xstages;
+        if (const char *e = getenv("CRBM_TT_NPSETS")) t.npsets = atoi(e) == 2 ? 2 : 1;          // experiments
+        if (const char *e = getenv("CRBM_TT_XSTAGES")) t.xstages = atoi(e) < 2 ? 2 : atoi(e) > TT_MAX_XSTAGES ? TT_MAX_XSTAGES : atoi(e);
     };
     // ---- negative phase ----------------------------------------------------------------------------------------------------
     const int nb_neg = ceil_div(FANTASY_LEN, g.VP);

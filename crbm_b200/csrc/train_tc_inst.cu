@@ -13,7 +13,7 @@ static int launch_tt_variant(const TrainTcParams &p, dim3 grid, cudaStream_t str
     int dev = 0;
     CRBM_CHECK_CUDA(cudaGetDevice(&dev));
     // the CTA allocates all 512 TMEM columns: ask for more than half of the shared memory so that two CTAs never share an SM
-    size_t smem = tt_smem_bytes(p.n_atoms, (FLAGS & (F_STAT_P | F_STAT_Q)) != 0);
+    size_t smem = tt_smem_bytes(p.n_atoms, p.xstages, (FLAGS & (F_STAT_P | F_STAT_Q)) ? p.npsets : 0);
     if (smem < 120 * 1024) smem = 120 * 1024;
     if (smem > configured[dev & 63]) {
         CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_train_tc_kernel<FLAGS, CRBM_TT_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -61,7 +61,7 @@ struct TrainTcParams {
     int pdl_late;
 };
 
-__host__ __device__ inline int tt_part_floats(int Kdim) { return Kdim * 192 + 4 * 128 + 4 * 64; }
+__host__ __device__ inline int tt_part_floats(int Kdim) { return Kdim * 192 + 128 + 64; }
 __host__ __device__ inline size_t tt_smem_bytes(int n_atoms, int xstages, int npsets) {
     return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)xstages * n_atoms * TT_XATOM + (size_t)npsets * TT_PSET + 512 + 512;
 }
@@ -111,6 +111,18 @@ __device__ __forceinline__ void tt_split8(const float *v, uint4 &hi, uint4 &lo) 
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// wait with back-off: a spinning warp competes for issue slots with the warps that do the work
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(phase) : "memory");
+        if (ok) break;
+        __nanosleep(40);
+    }
 }
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t phase) {
     uint32_t ok;
@@ -320,7 +332,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
             int nv = n < p.n_rows ? min(VP, p.Lh - wb * VP) : 0;
             nv = nv < 0 ? 0 : nv;
             const int buf = t & 3;
-            mbar_wait(d1_full + buf, (uint32_t)((t >> 2) & 1));
+            mbar_wait_backoff(d1_full + buf, (uint32_t)((t >> 2) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + TT_D1_COL + 64 * buf + 32 * h;
             uint32_t va[16], vb[16];
@@ -474,8 +486,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                 const int set_i = t & npm, use = p.npsets == 2 ? (t >> 1) : t;
                 unsigned char *set = PQ + set_i * TT_PSET;
                 // the GEMM 2 that read this set last has completed: unit t-2 (own set) or unit t-1 (shared set, own barrier)
-                if (p.npsets == 2) { if (use >= 1) mbar_wait(p_free + set_i, (uint32_t)((use - 1) & 1)); }
-                else if (t >= 1) mbar_wait(p_free + pr, (uint32_t)(((t - 1) >> 1) & 1));
+                if (p.npsets == 2) { if (use >= 1) mbar_wait_backoff(p_free + set_i, (uint32_t)((use - 1) & 1)); }
+                else if (t >= 1) mbar_wait_backoff(p_free + pr, (uint32_t)(((t - 1) >> 1) & 1));
 #pragma unroll
                 for (int c8 = 0; c8 < 4; ++c8) {
                     uint4 hi, lo;
@@ -502,7 +514,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
         // ---- statistics accumulators -> this CTA's partial: P[c][r], Q[c][kl], hidden sums per warpgroup ----------------------
         if (STAT) {
             float *part = p.partial + ((size_t)chunk * G + blockIdx.x) * p.part_floats;
-            mbar_wait(d2_done, 0u);
+            mbar_wait_backoff(d2_done, 0u);
             tc_fence_after();
             const float unscale = 1.0f / TT_PSCALE;
             const uint32_t trow = tmem_base + ((uint32_t)(32 * q) << 16);
@@ -522,9 +534,20 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                         part[(size_t)Kdim * TT_ROWS + (size_t)(8 * cc + j) * TT_KC + kl] = my_units > 0 ? __uint_as_float(v[j]) * unscale : 0.f;
                 }
             }
-            float *sums = part + (size_t)Kdim * 192;
-            sums[wg * TT_ROWS + r] = sum_p * unscale;
-            if (s == 0) sums[4 * TT_ROWS + wg * TT_KC + kl] = STAT_Q ? sum_q * unscale : 0.f;
+            // hidden sums: the four warpgroups hold partial sums of the same rows; combined through shared memory (the operand sets
+            // are free: every GEMM 2 has completed) in a fixed order
+            float *comb = reinterpret_cast<float *>(PQ);
+            comb[wg * TT_ROWS + r] = sum_p;
+            if (s == 0) comb[4 * TT_ROWS + wg * TT_KC + kl] = sum_q;
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (wg == 0) {
+                float *sums = part + (size_t)Kdim * 192;
+                sums[r] = ((comb[r] + comb[TT_ROWS + r]) + (comb[2 * TT_ROWS + r] + comb[3 * TT_ROWS + r])) * unscale;
+                if (s == 0) {
+                    const float *cq = comb + 4 * TT_ROWS;
+                    sums[TT_ROWS + kl] = STAT_Q ? ((cq[kl] + cq[TT_KC + kl]) + (cq[2 * TT_KC + kl] + cq[3 * TT_KC + kl])) * unscale : 0.f;
+                }
+            }
         }
     }
     tc_fence_before();

@@ -15,12 +15,16 @@ CRBM_FOR_EACH_TT_P(CRBM_DECLARE_TT)
 
 static bool tt_pool_built(int P) { return P == 1 || P == 2 || P == 4 || P == 5 || P == 10; }
 // The tcgen05 path covers motif_length <= 32 (4 M <= 128 contraction columns, one MMA N) and the pooling factors it is instantiated
-// for; everything else (and CRBM_TRAIN_KERNEL=mma) trains on the mma.sync kernels of v2h_mma.cuh.
+// for; everything else trains on the mma.sync kernels of v2h_mma.cuh. Small un-pooled banks (K * M < 2048, e.g. 100 x 15) also stay
+// there: at that size a step is a chain of four 5-20 us launches, and the mma.sync kernels (two CTAs per SM, prologues overlapping
+// the predecessor's tail) are the faster ones (measured at C2: 42.0 us per step against 48.7 us on the tcgen05 kernels, whose CTAs own
+// the whole SM). The choice depends on the model shape only, because the layout of the persistent chain follows it.
+// CRBM_TRAIN_KERNEL = mma | tc overrides.
 static bool train_uses_tc(int K, int M, int P) {
     static int v = -1;
-    if (v < 0) { const char *e = getenv("CRBM_TRAIN_KERNEL"); v = (e && e[0] == 'm') ? 0 : 1; }
-    (void)K;
-    return v == 1 && M <= 32 && tt_pool_built(P);
+    if (v < 0) { const char *e = getenv("CRBM_TRAIN_KERNEL"); v = !e ? 2 : e[0] == 'm' ? 0 : e[0] == 't' ? 1 : 2; }
+    if (M > 32 || !tt_pool_built(P) || v == 0) return false;
+    return v == 1 || P > 1 || (long long)K * M >= 2048;
 }
 
 struct TtGeom { int VP, Kdim, ksteps, n_atoms, n_chunks, Kpad, G, hw, part_floats; };
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(512) h2v_lin_kernel(const H2VLinParams p) {
 }
 
 // ---- statistics partials -> statistics vector / update -----------------------------------------------------------------------
-// partial of CTA x of chunk ch (train_tc.cuh): P[c][r] (Kdim x 128), Q[c][kl] (Kdim x 64), sum_p[4][128], sum_q[4][64].
+// partial of CTA x of chunk ch (train_tc.cuh): P[c][r] (Kdim x 128), Q[c][kl] (Kdim x 64), sum_p[128], sum_q[64].
 struct TcReduceParams {
     const float *pos, *neg;        // [n_chunks][G][part_floats]; pos == null: empty minibatch shard (contributes zeros)
     int G_pos, G_neg, part_floats, Kdim, n_chunks, K, M, ds;
@@ -192,67 +196,61 @@ struct TcReduceParams {
     ApplyParams ap;
     int fused;
 };
-// this warp's share (CTAs sub, sub + 4, ...) of one entry; the order is part of the contract between the fused and the two-launch path
-__device__ __forceinline__ float tc_sum(const float *src, int G, size_t stride, int sub) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int x = sub; x < G; x += 16) {
-        const float t0 = src[x * stride];
-        const float t1 = x + 4 < G ? src[(x + 4) * stride] : 0.f;
-        const float t2 = x + 8 < G ? src[(x + 8) * stride] : 0.f;
-        const float t3 = x + 12 < G ? src[(x + 12) * stride] : 0.f;
-        a0 += t0; a1 += t1; a2 += t2; a3 += t3;
-    }
-    return (a0 + a1) + (a2 + a3);
-}
-__device__ __forceinline__ float tc_sum4(const float *src, int G, size_t stride, int sub, int slot_stride) {
-    const float s0 = tc_sum(src, G, stride, sub), s1 = tc_sum(src + slot_stride, G, stride, sub);
-    const float s2 = tc_sum(src + 2 * slot_stride, G, stride, sub), s3 = tc_sum(src + 3 * slot_stride, G, stride, sub);
-    return (s0 + s1) + (s2 + s3);
+// One CTA of 512 threads per (chunk, contraction column c): thread (kl, slice) adds the partials of the CTAs x = slice, slice + 8, ...
+// of its motif for the five sums the update of W[k, c] needs (six independent load streams, L2 resident), the eight slices are
+// combined through shared memory in a fixed order — the summation order is part of the contract between the fused and the two-launch
+// path (bit-identical parameters) — and the threads of slice 0 apply the update or write the statistics.
+constexpr int TCR_SLICES = 8;
+__device__ __forceinline__ float tcr_combine(const float (*sh)[TT_KC], int kl) {
+    return ((sh[0][kl] + sh[1][kl]) + (sh[2][kl] + sh[3][kl])) + ((sh[4][kl] + sh[5][kl]) + (sh[6][kl] + sh[7][kl]));
 }
 
 __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) {
     pdl_wait();
     pdl_launch_dependents();
-    __shared__ float sh[5][4][32];
+    __shared__ float sh[6][TCR_SLICES][TT_KC];
     __shared__ float counts[8];
     const ApplyParams &ap = p.ap;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = warp >> 2, sub = warp & 3;
+    const int kl = threadIdx.x & (TT_KC - 1), slice = threadIdx.x >> 6;
     const int fourM = 4 * p.M;
-    const int n_w = p.n_chunks * fourM * 2;
+    const int n_w = p.n_chunks * fourM;
     const size_t pf = (size_t)p.part_floats;
     const size_t q_off = (size_t)p.Kdim * TT_ROWS, s_off = (size_t)p.Kdim * 192;
     const float nhd = p.c0, nhm = p.c1;
     const float strands = p.ds ? 2.f : 1.f;
     const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
-    auto total = [&](int r) { return (sh[r][0][lane] + sh[r][1][lane]) + (sh[r][2][lane] + sh[r][3][lane]); };
     if ((int)blockIdx.x < n_w) {
-        const int half = blockIdx.x & 1, rest = blockIdx.x >> 1;
-        const int ch = rest / fourM, c = rest - ch * fourM, cr = fourM - 1 - c;
-        const int kl = 32 * half + lane, k = ch * TT_KC + kl;
-        const float *pos = p.pos ? p.pos + (size_t)ch * p.G_pos * pf : nullptr;
-        const float *neg = p.neg + (size_t)ch * p.G_neg * pf;
-        float v = 0.f;
-        if (row == 0) {
-            if (pos) {
-                v = tc_sum(pos + (size_t)c * TT_ROWS + kl, p.G_pos, pf, sub);
-                if (p.ds) v += tc_sum(pos + (size_t)cr * TT_ROWS + TT_KC + kl, p.G_pos, pf, sub);
+        const int ch = blockIdx.x / fourM, c = blockIdx.x - ch * fourM, cr = fourM - 1 - c;
+        const int k = ch * TT_KC + kl;
+        float df = 0.f, dr = 0.f, qq = 0.f, mf = 0.f, mr = 0.f, hf = 0.f;
+        if (p.pos) {
+            const float *pos = p.pos + (size_t)ch * p.G_pos * pf;
+            for (int x = slice; x < p.G_pos; x += TCR_SLICES) {
+                const float *b = pos + (size_t)x * pf;
+                df += b[(size_t)c * TT_ROWS + kl];
+                if (p.ds) dr += b[(size_t)cr * TT_ROWS + TT_KC + kl];
+                qq += b[q_off + (size_t)c * TT_KC + kl];
+                hf += b[s_off + kl];
             }
-        } else if (row == 1) {
-            if (pos) v = tc_sum(pos + q_off + (size_t)c * TT_KC + kl, p.G_pos, pf, sub);
-        } else if (row == 2) {
-            v = tc_sum(neg + (size_t)c * TT_ROWS + kl, p.G_neg, pf, sub);
-            if (p.ds) v += tc_sum(neg + (size_t)cr * TT_ROWS + TT_KC + kl, p.G_neg, pf, sub);
-        } else {
-            if (pos) v = tc_sum4(pos + s_off + kl, p.G_pos, pf, sub, TT_ROWS);
         }
-        sh[row][sub][lane] = v;
+        {
+            const float *neg = p.neg + (size_t)ch * p.G_neg * pf;
+            for (int x = slice; x < p.G_neg; x += TCR_SLICES) {
+                const float *b = neg + (size_t)x * pf;
+                mf += b[(size_t)c * TT_ROWS + kl];
+                if (p.ds) mr += b[(size_t)cr * TT_ROWS + TT_KC + kl];
+            }
+        }
+        sh[0][slice][kl] = df; sh[1][slice][kl] = dr; sh[2][slice][kl] = qq;
+        sh[3][slice][kl] = mf; sh[4][slice][kl] = mr; sh[5][slice][kl] = hf;
         __syncthreads();
-        if (warp != 0 || k >= p.K) return;
-        const float vd = total(0), vq = total(1), vm = total(2), hf = total(3);
+        if (slice != 0 || k >= p.K) return;
+        const float vd = tcr_combine(sh[0], kl) + tcr_combine(sh[1], kl), vq = tcr_combine(sh[2], kl);
+        const float vm = tcr_combine(sh[3], kl) + tcr_combine(sh[4], kl), hfs = tcr_combine(sh[5], kl);
         const int m = c >> 2, a = c & 3;
         const int gid = (k * 4 + a) * p.M + m;
         if (p.fused) {
-            const float gk = sparsity_factor(hf, nhd, ap.rho, ap.K);
+            const float gk = sparsity_factor(hfs, nhd, ap.rho, ap.K);
             const float vel = next_velocity(ap.vW[gid], vd, nd, vm, nm, __fmul_rn(gk, vq), ap.mu, ap.lr, ap.lam);
             ap.vW[gid] = vel;
             ap.W[gid] = __fadd_rn(ap.W[gid], vel);
@@ -261,32 +259,40 @@ __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) 
             p.stats[p.lay.vh_q + gid] = vq;
             p.stats[p.lay.vh_model + gid] = vm;
         }
-    } else if ((int)blockIdx.x < n_w + 2 * p.n_chunks) {
-        const int bb = blockIdx.x - n_w, ch = bb >> 1, half = bb & 1;
-        const int kl = 32 * half + lane, k = ch * TT_KC + kl;
-        const float *pos = p.pos ? p.pos + (size_t)ch * p.G_pos * pf + s_off : nullptr;
-        const float *neg = p.neg + (size_t)ch * p.G_neg * pf + s_off;
-        float v = 0.f;
-        if (row == 0) v = pos ? tc_sum4(pos + kl, p.G_pos, pf, sub, TT_ROWS) : 0.f;
-        else if (row == 1) v = pos ? tc_sum4(pos + TT_KC + kl, p.G_pos, pf, sub, TT_ROWS) : 0.f;
-        else if (row == 2) v = tc_sum4(neg + kl, p.G_neg, pf, sub, TT_ROWS);
-        else v = tc_sum4(neg + TT_KC + kl, p.G_neg, pf, sub, TT_ROWS);
-        sh[row][sub][lane] = v;
-        if (row == 0) sh[4][sub][lane] = pos ? tc_sum4(pos + 4 * TT_ROWS + kl, p.G_pos, pf, sub, TT_KC) : 0.f;
+    } else if ((int)blockIdx.x < n_w + p.n_chunks) {
+        const int ch = blockIdx.x - n_w;
+        const int k = ch * TT_KC + kl;
+        float hf = 0.f, hr = 0.f, hq = 0.f, mf = 0.f, mr = 0.f;
+        if (p.pos) {
+            const float *pos = p.pos + (size_t)ch * p.G_pos * pf + s_off;
+            for (int x = slice; x < p.G_pos; x += TCR_SLICES) {
+                const float *b = pos + (size_t)x * pf;
+                hf += b[kl]; hr += b[TT_KC + kl]; hq += b[TT_ROWS + kl];
+            }
+        }
+        {
+            const float *neg = p.neg + (size_t)ch * p.G_neg * pf + s_off;
+            for (int x = slice; x < p.G_neg; x += TCR_SLICES) {
+                const float *b = neg + (size_t)x * pf;
+                mf += b[kl]; mr += b[TT_KC + kl];
+            }
+        }
+        sh[0][slice][kl] = hf; sh[1][slice][kl] = hr; sh[2][slice][kl] = hq; sh[3][slice][kl] = mf; sh[4][slice][kl] = mr;
         __syncthreads();
-        if (warp != 0 || k >= p.K) return;
-        const float hf = total(0);
-        const float hdata = hf + total(1), hmodel = total(2) + total(3), hq = total(4);
+        if (slice != 0 || k >= p.K) return;
+        const float hfs = tcr_combine(sh[0], kl);
+        const float hdata = hfs + tcr_combine(sh[1], kl), hqs = tcr_combine(sh[2], kl);
+        const float hmodel = tcr_combine(sh[3], kl) + tcr_combine(sh[4], kl);
         if (p.fused) {
-            const float gk = sparsity_factor(hf, nhd, ap.rho, ap.K);
-            const float vel = next_velocity(ap.vb[k], hdata, nd, hmodel, nm, __fmul_rn(gk, hq), ap.mu, ap.lr, ap.lam);
+            const float gk = sparsity_factor(hfs, nhd, ap.rho, ap.K);
+            const float vel = next_velocity(ap.vb[k], hdata, nd, hmodel, nm, __fmul_rn(gk, hqs), ap.mu, ap.lr, ap.lam);
             ap.vb[k] = vel;
             ap.b[k] = __fadd_rn(ap.b[k], vel);
         } else {
-            p.stats[p.lay.h_fwd + k] = hf;
+            p.stats[p.lay.h_fwd + k] = hfs;
             p.stats[p.lay.h_data + k] = hdata;
             p.stats[p.lay.h_model + k] = hmodel;
-            p.stats[p.lay.h_q + k] = hq;
+            p.stats[p.lay.h_q + k] = hqs;
         }
     } else {
         // base counts of the minibatch and of the sampled visible layer (A9); fused: the update of c and the cursors of the next step
@@ -363,8 +369,8 @@ static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s,
         t.seed = a->seed; t.step_dev = a->step_dev;
         // shared memory: W (hi, lo) + ring of one-hot tiles + P/Q operand sets. Two sets when they fit beside a ring of at least
         // 6 tiles (a tile lives from its GEMM 1 until the GEMM 2 of the same unit, i.e. across the whole epilogue of the unit).
-        const size_t cap = 222 * 1024;
-        t.npsets = tt_smem_bytes(g.n_atoms, 6, 2) <= cap ? 2 : 1;
+        const size_t cap = 227 * 1024;                              // opt-in maximum of dynamic shared memory per CTA on sm_100
+        t.npsets = tt_smem_bytes(g.n_atoms, 4, 2) <= cap ? 2 : 1;
         t.xstages = TT_MAX_XSTAGES;
         while (t.xstages > 3 && tt_smem_bytes(g.n_atoms, t.xstages, t.npsets) > cap) --t.xstages;
         if (const char *e = getenv("CRBM_TT_NPSETS")) t.npsets = atoi(e) == 2 ? 2 : 1;          // experiments
@@ -449,7 +455,7 @@ static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s,
         r.batch_index = a->batch_index_dev;
         r.fused = ((phases & CRBM_PHASE_APPLY) && !p2p && a->n_data > 0 && fused_update_enabled()) ? 1 : 0;
         if (r.fused) fill_apply_params(a, &r.ap);
-        CRBM_CHECK_CUDA(launch_chain(reduce_tc_kernel, dim3(g.n_chunks * 4 * M * 2 + 2 * g.n_chunks + 1), dim3(512), 0, s, r));
+        CRBM_CHECK_CUDA(launch_chain(reduce_tc_kernel, dim3(g.n_chunks * 4 * M + g.n_chunks + 1), dim3(512), 0, s, r));
         CRBM_CHECK_LAUNCH();
         if (r.fused) return CRBM_OK;
     }

@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """Headline benchmark: CD-1 training throughput (nucleotides/s) of the cRBM on BASELINE.json's configs[1]
-("synthetic 1M x 200 bp one-hot, 100 motifs x 15 bp, pooling=1, CD-1, batch 100 on 1 B200"), plus motif-scan nt/s.
+("synthetic 1M x 200 bp one-hot, 100 motifs x 15 bp, pooling=1, CD-1, batch 100 on 1 B200"), with the other BASELINE
+configurations as sub-records of the same JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4] [--only-headline]
 
 One "step" = one minibatch update (`theano_trainingFct`, reference secomo/convRBM.py:373-438) on `batch` sequences per
-GPU. Weak scaling: every rank trains `batch` sequences per step, one all-reduce of the statistics vector per step.
-  value  : whole-job data nucleotides/s with the packed dataset resident in HBM (CUDA-graph replay of steps)
-  e2e    : same metric through the reference-facing call `CRBM._trainingFct(one-hot NumPy batch)`: pinned-host ->
-           device copy of the fp32 one-hot minibatch, packing, the step, and a device -> host read of the updated
-           visible bias every step
-  scan   : `motifHitProbs` kernel (getHitProbs) nt/s with fp32 probabilities written to HBM
-  roofline / cpu_baseline: see DESIGN.md "Measurement".
-`--impl reference` times the CPU restatement of the reference's Theano graph (oracle/crbm_torch_cpu.py; Theano itself is
-not installable offline) on the host cores with the same metric/config.
+GPU. Weak scaling: every rank trains `batch` sequences per step, one exchange of the statistics vector per step.
+  value        whole-job data nucleotides/s of the headline workload, packed dataset resident in HBM (CUDA-graph replay)
+  e2e          same metric through the reference-facing call `CRBM._trainingFct(one-hot batch in host memory)`
+  roofline     the dominant launch of the step timed alone (tensor pipe) + whole-step fractions; see DESIGN.md "Measurement"
+  c3, c4       BASELINE configs 3 and 4 (training; K=128/M=20/pooling 5/1 kb and K=512/M=25/CD-5/500 bp), same fields
+  c5           BASELINE config 5: the 512 x 25 motif scan, both getHitProbs strand branches, dense (HBM roofline) and with the
+               callers' reductions fused over the whole 3e9-nt job (sharded over the ranks)
+  scan         getHitProbs at the headline shape (dense, fused reductions, and end to end with host buffers)
+  eval         the per-epoch evaluation pass (free energy + sampled hidden mean, convRBM.py:466-472,616-624)
+  cpu_baseline the reference's train step restated with torch-CPU ops, on the host cores (N = 1 only)
+`--impl reference` times that CPU restatement (oracle/crbm_torch_cpu.py; Theano itself is not installable offline) with
+the same metric/config.
 """
 import argparse
 import json
@@ -30,32 +34,44 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # BASELINE.json configs[1..3]; n_seq is the per-rank synthetic dataset (each minibatch is read once per epoch)
     'c2': dict(name='C2: synthetic 1M x 200 bp, K=100, M=15, pooling=1, CD-1, batch 100/GPU', K=100, M=15, P=1, cd_k=1,
-               batch=100, L=200, n_seq=1000000, default_steps=10000),
+               batch=100, L=200, n_seq=1000000, default_steps=10000, sub_steps=2048),
     'c3': dict(name='C3: synthetic x 1 kb, K=128, M=20, pooling=5, CD-1, batch 128/GPU', K=128, M=20, P=5, cd_k=1,
-               batch=128, L=1000, n_seq=262144, default_steps=2048),
+               batch=128, L=1000, n_seq=262144, default_steps=2048, sub_steps=1024),
     'c4': dict(name='C4: synthetic x 500 bp, K=512, M=25, pooling=1, CD-5, batch 128/GPU', K=512, M=25, P=1, cd_k=5,
-               batch=128, L=500, n_seq=65536, default_steps=512),
+               batch=128, L=500, n_seq=65536, default_steps=512, sub_steps=256),
 }
+C5 = dict(name='C5: getHitProbs scan of a 3e9-nt synthetic genome (3M x 1 kb), K=512, M=25, both strand branches', K=512, M=25, P=1,
+          L=1000, total_nt=3.0e9)
 METRIC = 'CD-1 train nt/s'
-SCAN_TRAFFIC = 8209066664   # dram__bytes_read.sum + dram__bytes_write.sum of the scan launch (profiles/r01_ncu_metrics_h.md), padded rows, 107 526 x 200 bp, K=100
+
+
+def load_json(name):
+    try:
+        with open(os.path.join(ROOT, name)) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def peaks():
-    try:
-        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-            p = json.load(f)
+    p = load_json('MEASURED_PEAKS.json')
+    if p:
         return float(p['hbm_gbs']), 'MEASURED_PEAKS.json', float(p.get('sm_max_mhz', 1965.0))
-    except Exception:
-        return 6650.0, 'fallback (B200_PROFILING.md)', 1965.0
+    return 6650.0, 'fallback (B200_PROFILING.md)', 1965.0
 
 
 def tensor_peak():
-    try:
-        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
-            p = json.load(f)
+    p = load_json('MEASURED_PEAKS.json')
+    if p:
         return float(p['bf16_tflops']), 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)'
-    except Exception:
-        return 1590.0, 'fallback (B200_PROFILING.md)'
+    return 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (profiles/r02_traffic.json)."""
+    t = load_json(os.path.join('profiles', 'r02_traffic.json')) or {}
+    e = t.get(key)
+    return (e['dram_bytes_read'] + e['dram_bytes_write']) if e else None
 
 
 class ClockSampler(threading.Thread):
@@ -88,6 +104,9 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# CPU arm
+# ---------------------------------------------------------------------------------------------------------------------------
 def run_reference(args, wl, rank, world):
     """CPU arm: the reference's train step restated with torch-CPU ops, all host threads, bounded sample."""
     if rank != 0:
@@ -150,165 +169,94 @@ def cpu_baseline_sample(wl, budget_s=12.0):
             'sample': '%d train steps of %d x %d bp in %.1f s (torch-CPU restatement of the Theano graph)' % (n, wl['batch'], Lt, dt)}
 
 
-def main():
-    # exactly one line on stdout: libraries that print there (NCCL's version banner) are sent to stderr
-    real_stdout = os.fdopen(os.dup(1), 'w')
-    os.dup2(2, 1)
-    sys.stdout = real_stdout
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=None)
-    ap.add_argument('--warmup', type=int, default=None)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-scan', action='store_true')
-    ap.add_argument('--no-e2e', action='store_true')
-    ap.add_argument('--steps-per-graph', type=int, default=8)
-    args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+# ---------------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------------
+class Ctx(object):
+    def __init__(self, rank, world, local_rank, dev, dist):
+        self.rank, self.world, self.local_rank, self.dev, self.dist = rank, world, local_rank, dev, dist
 
-    if args.impl == 'reference':
-        args.steps = args.steps if args.steps is not None else 40
-        args.warmup = args.warmup if args.warmup is not None else 3
-        run_reference(args, wl, rank, world)
-        return
-    args.steps = args.steps if args.steps is not None else wl['default_steps']
-    args.warmup = args.warmup if args.warmup is not None else 64
-    args.warmup = max(args.warmup, 3)
+    def barrier(self):
+        import torch
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
 
+    def max_over_ranks(self, ms):
+        import torch
+        if self.dist is None:
+            return ms
+        t = torch.tensor([ms], device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def train_workload(ctx, wl, steps, warmup, spg, sampler=None):
+    """Time `steps` training steps of workload `wl` (graph replay, dataset resident in HBM). Returns (record, model, data)."""
     import numpy as np
     import torch
     import crbm_b200
-    from crbm_b200 import _lib
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=dev)
-    lib = _lib.load()
-
     K, M, P, B, L = wl['K'], wl['M'], wl['P'], wl['batch'], wl['L']
     np.random.seed(0)
-    model = crbm_b200.CRBM(K, M, epochs=1, batchsize=B * world, pooling=P, cd_k=wl['cd_k'], seed=1234 + rank, device=dev)
+    model = crbm_b200.CRBM(K, M, epochs=1, batchsize=B * ctx.world, pooling=P, cd_k=wl['cd_k'], seed=1234 + ctx.rank, device=ctx.dev)
     Lt = model._truncated_length(L)
     n_seq = wl['n_seq']
-    data = crbm_b200.PackedSequences.random(n_seq, Lt, seed=1234 + rank, device=dev)
+    data = crbm_b200.PackedSequences.random(n_seq, Lt, seed=1234 + ctx.rank, device=ctx.dev)
     data.is_local_shard = True      # weak scaling: every rank owns its own synthetic dataset
+    nb = n_seq // B
 
     def run_steps(count, first):
-        model._train_full_batches(data, first % (n_seq // B), count, steps_per_graph=args.steps_per_graph)
+        model._train_full_batches(data, first % nb, count, steps_per_graph=spg)
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    # priming (untimed, before the W warm-up steps): enough steps for every CUDA graph the timed region replays to exist
-    # (the 8-step graph, the single-step graph for the remainder, the data-parallel alignment steps)
-    prime = 2 * args.steps_per_graph + 3
+    # priming (untimed, before the W warm-up steps): every CUDA graph the timed region replays is captured here — the spg-step
+    # graph, the graph of the remainder steps % spg, and the data-parallel alignment steps
+    prime = 2 * spg + 2
     run_steps(prime, 0)
-    run_steps(args.warmup, prime)
-    barrier()
+    if steps % spg:
+        run_steps(spg + steps % spg, prime)
+        prime += spg + steps % spg
+    run_steps(warmup, prime)
+    ctx.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    ctx.barrier()
     e0.record()
-    run_steps(args.steps, prime + args.warmup)
+    run_steps(steps, prime + warmup)
     e1.record()
-    barrier()
+    ctx.barrier()
     ms = e0.elapsed_time(e1)
-    if rank == 0 and world == 1:
+    if sampler is not None and ctx.world == 1:
         # short runs end before nvidia-smi's first 100 ms sample: keep the load on until a few samples exist
         t_end = time.time() + 1.5
         while len(sampler.rows) < 4 and time.time() < t_end:
-            run_steps(args.steps_per_graph, 0)
+            run_steps(spg, 0)
             torch.cuda.synchronize()
-    clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    nt_per_step = B * Lt * world
-    value = args.steps * nt_per_step / (ms * 1e-3)
-    launches_per_step = model._engine.get('launches_per_step', 0)   # counted while capturing the step graph
-
-    line = {'metric': METRIC, 'value': value, 'unit': 'nt/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': wl['name'], 'batch_per_gpu': B, 'seq_len': Lt, 'global_batch': B * world,
-                       'parallelism': 'dp%d' % world, 'steps_per_graph': args.steps_per_graph,
-                       'l2': 'every step reads a new minibatch from a %d-sequence packed dataset (%.0f MB); model state '
-                             '(W, tables, persistent chain) is on-chip/L2 resident by design' % (n_seq, n_seq * data.row_words * 4 / 1e6)},
-            'gpu_launches': launches_per_step * args.steps}
-
-    if rank == 0:
-        hbm_peak, peak_src, sm_max = peaks()
-        # --- per-kernel device time of one step (CUDA events around eager launches on the launching stream) ------------
-        state = (model._t_W, model._t_bias, model._t_c, model._t_vW, model._t_vb, model._t_vc, model._chain())
-        saved = [t.clone() for t in state]
-        kern = time_step_kernels(model, data, B, dev)
-        for t, v in zip(state, saved):              # the per-phase timing trains this rank alone: keep the replicas identical
-            t.copy_(v)
-        line['step_kernels_us'] = kern
-        pos_us = kern['positive_phase_kernel']
-        Lh = Lt - M + 1
-        # Algorithmic work of the positive-phase launch (DESIGN.md "Measurement"): per hidden position and motif the
-        # one-hot contraction over 4*M inputs, 2 flops each, for x and x' (up-pass) and for the P, P', Q statistics.
-        alg_flops = 2.0 * B * Lh * K * 4 * M * 5
-        alg_bytes = B * data.row_words * 4 + K * 4 * M * 4 + K * 4          # packed minibatch + W + b, read once
-        adds = B * Lh * K * M * 5                                           # SURVEY 8d gather-add count of the same work
-        tf = alg_flops / (pos_us * 1e-6) / 1e12 if pos_us else None
-        tpeak = tensor_peak()
-        pooled = P != 1
-        line['roofline'] = {
-            'bound': 'tensor', 'kernel': ('v2h_mma_kernel<KS=%d, %s%s> (positive-phase launch%s)' % ((M + 3) // 4, 'STAT_P|STAT_Q' if M <= 16 else 'STAT_P> + <STAT_Q', ', POOL' if pooled else '', '' if M <= 16 else 'es')),
-            'achieved': tf, 'peak': tpeak[0], 'unit': 'TFLOP/s', 'frac': (tf / tpeak[0]) if tf else None,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this launch, ncu --set full (profiles/r01_ncu_metrics_h.md)
-            'traffic': 62720 if (args.workload == 'c2' and not pooled) else None,
-            'peak_source': tpeak[1], 'launch_us': pos_us, 'algorithmic_flops_per_launch': alg_flops,
-            'note': 'dense-equivalent flops of the one-hot contractions (x, x\', and the P, P\', Q statistics); the fp16 hi/lo / '
-                    'bf16x2 operand splits and tile padding are overhead, not counted. At 100 x 200 bp per step the launch is '
-                    'latency/issue bound (ncu: profiles/), not throughput bound.',
-            'hbm_frac': (alg_bytes / (pos_us * 1e-6) / 1e9 / hbm_peak) if pos_us else None,
-            'gather_adds_per_launch': adds,
-            'fp32_add_frac': (adds / (pos_us * 1e-6) / (148 * 128 * sm_max * 1e6)) if pos_us else None}
-        if not args.no_scan:
-            line['scan'] = bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src, world, rank)
-        if not args.no_e2e:
-            line['e2e'] = bench_e2e(model, B, Lt, world, dev, min(args.steps, 2000))
-        if not args.no_cpu_baseline:
-            line['cpu_baseline'] = cpu_baseline_sample(wl)
-        line['clocks'] = clocks
-        print(json.dumps(line), flush=True)
-    else:
-        # the other ranks scan their own shard (no communication on the data path) and feed their own minibatches
-        if not args.no_scan:
-            bench_scan(model, K, M, Lt, dev, 1.0, '', world, rank)
-        if not args.no_e2e:
-            bench_e2e(model, B, Lt, world, dev, min(args.steps, 2000))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    ms = ctx.max_over_ranks(ms)
+    rec = {'workload': wl['name'], 'value': steps * B * Lt * ctx.world / (ms * 1e-3), 'unit': 'nt/s', 'steps': steps,
+           'ms_per_step': ms / steps, 'batch_per_gpu': B, 'seq_len': Lt,
+           'gpu_launches': model._engine.get('launches_per_step', 0) * steps}
+    return rec, model, data
 
 
-def time_step_kernels(model, data, B, dev):
-    """Device time of the phases of one training step. Each phase is captured 20x back to back in a CUDA graph and the
-    graph is timed with CUDA events on the launching stream, so host launch latency is excluded. The positive-phase
-    kernel is obtained as (accumulate) - (accumulate with an empty minibatch): the latter launches everything but it."""
+def work_per_step(wl, Lt):
+    """gather-adds of one step (one add per (position, motif, motif base) of every contraction) and the dense-equivalent
+    flops of the same contractions (2 flops per one-hot input, 4 inputs per motif base)."""
+    K, M, B, cd_k = wl['K'], wl['M'], wl['batch'], wl['cd_k']
+    Lh = Lt - M + 1
+    pos_data = B * Lh                     # x, x', P(x)V, P'(x)V, Q(x)V
+    pos_chain = B * 200                   # per sweep x, x'; last sweep also P(x)V, P'(x)V
+    adds = K * M * (5 * pos_data + (2 * cd_k + 2) * pos_chain)
+    return adds, 8.0 * adds
+
+
+def phase_times(model, data, B, dev):
+    """Device time of the phases of one training step, each captured 20x back to back in a CUDA graph (no host launch latency) and
+    timed ALONE with CUDA events on the launching stream: chain sweeps (h2v + v2h, x cd_k), positive phase (one launch; two for
+    motif_length > 16 on the mma.sync path), reduction + update, and the whole step."""
     import torch
     from crbm_b200 import _lib
     lib = _lib.load()
     reps, rounds = 20, 5
     full = model._fill_args(data.words.data_ptr(), data.row_words, B, data.L)
-    empty = model._fill_args(data.words.data_ptr(), data.row_words, 0, data.L)
 
     def timed(fn):
         side = torch.cuda.Stream(device=dev)
@@ -331,16 +279,66 @@ def time_step_kernels(model, data, B, dev):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e3 / (reps * rounds)
 
+    s = _lib.stream_handle
+    ph = lambda mask: (lambda: _lib.check(lib.crbm_train_phases(full, mask, s()), 'train_phases'))
+    state = (model._t_W, model._t_bias, model._t_c, model._t_vW, model._t_vb, model._t_vc, model._chain())
+    saved = [t.clone() for t in state]
     out = {}
-    out['accumulate'] = timed(lambda: _lib.check(lib.crbm_train_accumulate(full, _lib.stream_handle())))
-    out['accumulate_without_positive_phase'] = timed(lambda: _lib.check(lib.crbm_train_accumulate(empty, _lib.stream_handle())))
-    out['apply'] = timed(lambda: _lib.check(lib.crbm_train_apply(full, _lib.stream_handle())))
-    out['fused_step'] = timed(lambda: _lib.check(lib.crbm_train_step(full, _lib.stream_handle())))
-    out['positive_phase_kernel'] = max(0.0, out['accumulate'] - out['accumulate_without_positive_phase'])
+    out['whole_step'] = timed(lambda: _lib.check(lib.crbm_train_step(full, s()), 'train_step'))
+    for t, v in zip(state, saved):
+        t.copy_(v)
+    out['chain_sweeps'] = timed(ph(_lib.PHASE_NEGATIVE))
+    out['positive_phase'] = timed(ph(_lib.PHASE_POSITIVE))
+    out['reduce_update'] = timed(ph(_lib.PHASE_REDUCE | _lib.PHASE_APPLY))
+    for t, v in zip(state, saved):              # the per-phase timing trains this rank alone: keep the replicas identical
+        t.copy_(v)
     return out
 
 
-def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src, world=1, rank=0):
+def train_roofline(wl, Lt, rec, kern, key):
+    K, M, P, B = wl['K'], wl['M'], wl['P'], wl['batch']
+    Lh = Lt - M + 1
+    from crbm_b200 import _lib
+    tc = bool(_lib.load().crbm_chain_layout(K, M, P))
+    pos_us = kern['positive_phase']
+    # positive-phase launch: per hidden position and motif the one-hot contraction over 4 M inputs, 2 flops each, for x and x'
+    # (up-pass) and for the P, P', Q statistics
+    alg_flops = 2.0 * B * Lh * K * 4 * M * 5
+    tpeak, tsrc = tensor_peak()
+    hbm_peak, _, sm_max = peaks()
+    tf = alg_flops / (pos_us * 1e-6) / 1e12 if pos_us else None
+    adds, dense = work_per_step(wl, Lt)
+    step_s = rec['ms_per_step'] * 1e-3
+    name = ('v2h_train_tc_kernel<STAT_P|STAT_Q, P=%d> (tcgen05.mma, statistics accumulated in TMEM; positive-phase launch)' % P) if tc else \
+        ('v2h_mma_kernel<KS=%d, %s%s> (mma.sync; positive-phase launch%s)' % ((M + 3) // 4, 'STAT_P|STAT_Q' if M <= 16 else 'STAT_P> + <STAT_Q',
+                                                                             ', POOL' if P != 1 else '', '' if M <= 16 else 'es'))
+    return {'bound': 'tensor', 'kernel': name, 'achieved': tf, 'peak': tpeak, 'unit': 'TFLOP/s', 'frac': (tf / tpeak) if tf else None,
+            'traffic': ncu_traffic(key), 'peak_source': tsrc, 'launch_us': pos_us, 'algorithmic_flops_per_launch': alg_flops,
+            'share_of_step': pos_us / kern['whole_step'] if kern.get('whole_step') else None,
+            'note': 'dense-equivalent flops of the one-hot contractions (x, x\', and the P, P\', Q statistics); the fp16 hi/lo operand '
+                    'splits and tile padding are overhead, not counted',
+            'whole_step': {'gather_adds_per_step': adds, 'fp32_add_frac': adds / step_s / (148 * 128 * sm_max * 1e6),
+                           'dense_equivalent_tflops': dense / step_s / 1e12, 'tensor_frac': dense / step_s / 1e12 / tpeak,
+                           'us_per_step': rec['ms_per_step'] * 1e3,
+                           'note': 'SURVEY 8d work of the whole step (positive phase, cd_k chain sweeps, sparsity statistic) over the '
+                                   'measured step time; fp32_add_frac is against 148 SM x 128 lanes x %d MHz' % int(sm_max)}}
+
+
+def timed_calls(ctx, fn, reps=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return ctx.max_over_ranks(e0.elapsed_time(e1) / reps)
+
+
+def bench_scan(ctx, model, K, M, Lt, traffic_key):
     """getHitProbs kernel (tcgen05 / TMEM, csrc/scan_tc.cu) with fp32 output materialised in HBM; input and output larger
     than L2. Timed in the layout CRBM.motifHitProbs uses on the device (rows padded to a multiple of 8 floats, so every store
     covers whole 32-byte sectors) and in the reference's contiguous (N,K,1,Lh) layout. Algorithmic bytes count Lh floats
@@ -349,72 +347,95 @@ def bench_scan(model, K, M, Lt, dev, hbm_peak, peak_src, world=1, rank=0):
     import crbm_b200
     from crbm_b200 import _lib
     lib = _lib.load()
+    hbm_peak, peak_src, _ = peaks()
+    dev, world, rank = ctx.dev, ctx.world, ctx.rank
     Lh = Lt - M + 1
     n = max(1024, min(200000, int(8e9 // (4 * K * Lh))))
     seqs = crbm_b200.PackedSequences.random(n, Lt, seed=99 + rank, device=dev)      # this rank's shard of the sequences
     s = _lib.stream_handle()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-
-    def timed(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            torch.cuda.synchronize()
-        e0.record()
-        for _ in range(reps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
-        if world > 1:                               # whole job = all shards; time = slowest rank
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
-
-    ms_by_pitch = {}
-    pitch_fast = (Lh + 7) // 8 * 8
-    for pitch in sorted({pitch_fast, Lh}, reverse=True):
-        out = torch.empty((n, K, 1, pitch), dtype=torch.float32, device=dev)
-        ms_by_pitch[pitch] = timed(lambda: _lib.check(lib.crbm_v2h_dense_strided(
-            _lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias), K, M, model.pooling,
-            _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(out), pitch, s), 'scan'))
-        del out
-    pitch = pitch_fast
-    ms = ms_by_pitch[pitch]
-    nt = n * Lt * world                          # whole job
-    alg = n * (Lt / 4.0) + 4.0 * n * K * Lh      # per GPU (the roofline is per device)
+    out_rec = {}
+    for mode_name, mode in (('forward', _lib.STRAND_FWD), ('both_strands_summed', _lib.STRAND_SUM)):
+        ms_by_pitch = {}
+        pitch_fast = (Lh + 7) // 8 * 8
+        for pitch in sorted({pitch_fast, Lh}, reverse=True):
+            if mode != _lib.STRAND_FWD and pitch != pitch_fast:
+                continue
+            out = torch.empty((n, K, 1, pitch), dtype=torch.float32, device=dev)
+            ms_by_pitch[pitch] = timed_calls(ctx, lambda: _lib.check(lib.crbm_v2h_dense_strided(
+                _lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias), K, M, model.pooling,
+                mode, _lib.OUT_PROBABILITY, _lib.ptr(out), pitch, s), 'scan'))
+            del out
+        ms = ms_by_pitch[pitch_fast]
+        nt = n * Lt * world                          # whole job
+        alg = n * (Lt / 4.0) + 4.0 * n * K * Lh      # per GPU (the roofline is per device)
+        rec = {'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
+               'sequences_per_gpu': n, 'n_gpus': world, 'ms': ms, 'output_GB_per_gpu': 4.0 * n * K * Lh / 1e9,
+               'roofline': {'bound': 'hbm', 'kernel': ('v2h_dense_tc_kernel<PROB> (tcgen05.mma, TMEM accumulators)' if model.pooling == 1 else
+                                                    'v2h_dense_tc_kernel<PROB, POOL> (tcgen05.mma, TMEM accumulators, pool groups summed by warp shuffles)'),
+                            'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak,
+                            'traffic': ncu_traffic(traffic_key) if (mode == _lib.STRAND_FWD and traffic_key) else None,
+                            'algorithmic_bytes': alg, 'peak_source': peak_src, 'bytes_per_nt': alg / (n * Lt)}}
+        if Lh in ms_by_pitch and Lh != pitch_fast:
+            rec['layout'] = ('output rows padded from %d to %d floats (32-byte sectors); contiguous (N,K,1,Lh) layout: %.3f ms = %.3e nt/s'
+                             % (Lh, pitch_fast, ms_by_pitch[Lh], nt / (ms_by_pitch[Lh] * 1e-3)))
+        out_rec[mode_name] = rec
     # fused reductions (max / argmax / mean over positions per sequence and motif): nothing but (N,K) results is written
     mx = torch.empty((n, K), dtype=torch.float32, device=dev)
     am = torch.empty((n, K), dtype=torch.int32, device=dev)
     mean = torch.empty((n, K), dtype=torch.float32, device=dev)
-    fused = None
-    if model.pooling == 1:                      # (the fused reductions of pooled probabilities are not built)
-        ms_red = timed(lambda: _lib.check(lib.crbm_scan_reduce(
+    for mode_name, mode in (('forward', _lib.STRAND_FWD), ('both_strands_summed', _lib.STRAND_SUM)):
+        ms_red = timed_calls(ctx, lambda: _lib.check(lib.crbm_scan_reduce(
             _lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias), K, M, model.pooling,
-            _lib.STRAND_FWD, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am), _lib.ptr(mean), s), 'scan_reduce'))
-        fused = {'metric': 'motif-scan nt/s, max/argmax/mean over positions fused (no dense output)',
-                 'value': nt / (ms_red * 1e-3), 'unit': 'nt/s', 'ms': ms_red}
-    return {'fused_reductions': fused,
-            'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
-            'sequences_per_gpu': n, 'n_gpus': world, 'ms': ms, 'output_GB_per_gpu': 4.0 * n * K * Lh / 1e9,
-            'layout': 'output rows padded from %d to %d floats (32-byte sectors); contiguous (N,K,1,Lh) layout: %.3f ms = %.3e nt/s'
-                      % (Lh, pitch, ms_by_pitch[Lh], nt / (ms_by_pitch[Lh] * 1e-3)),
-            'sharding': 'sequences sharded across ranks, weights replicated, no collective on the data path',
-            'roofline': {'bound': 'hbm', 'kernel': ('v2h_dense_tc_kernel<PROB> (tcgen05.mma, TMEM accumulators)' if model.pooling == 1 else
-                                                 'v2h_dense_tc_kernel<PROB, POOL> (tcgen05.mma, TMEM accumulators, pool groups summed by warp shuffles)'),
-                         'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak,
-                         'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak,
-                         # ncu --set full on this launch (107 526 x 200 bp, K=100, padded rows): dram written + read
-                         'traffic': SCAN_TRAFFIC if (n == 107526 and K == 100) else None, 'algorithmic_bytes': alg,
-                         'peak_source': peak_src, 'bytes_per_nt': alg / (n * Lt)}}
+            mode, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am), _lib.ptr(mean), s), 'scan_reduce'), reps=3, warm=1)
+        out_rec[mode_name]['fused_reductions'] = {
+            'metric': 'motif-scan nt/s, max/argmax/mean over positions fused (no dense output)',
+            'value': n * Lt * world / (ms_red * 1e-3), 'unit': 'nt/s', 'ms': ms_red}
+    out_rec['sharding'] = 'sequences sharded across ranks, weights replicated, no collective on the data path'
+    return out_rec
 
 
-def bench_e2e(model, B, Lt, world, dev, steps):
+def bench_scan_job(ctx, model, K, M, Lt, total_nt):
+    """The whole C5 job through the API: `CRBM.motifHitSummary(packed sequences resident in HBM)` over total_nt / world
+    nucleotides per rank, both strand branches (the branch is the model's `doublestranded` flag, convRBM.py:507-514)."""
+    import torch
+    import crbm_b200
+    # every rank scans the shard it would own on 8 GPUs (SURVEY 8d: 375 000 sequences per GPU): the whole 3e9-nt job at N = 8,
+    # N/8 of it at smaller N (weak scaling; `total_nt` states what was scanned)
+    n = int(total_nt / 8 / Lt)
+    seqs = crbm_b200.PackedSequences.random(n, Lt, seed=7 + ctx.rank, device=ctx.dev)
+    warm = seqs.rows(0, min(n, 4096))
+    rec = {'metric': 'motif-scan nt/s, CRBM.motifHitSummary over the whole job (max/argmax/mean per sequence and motif)',
+           'total_nt': float(n) * Lt * ctx.world, 'sequences_per_gpu': n, 'unit': 'nt/s'}
+    for name, ds in (('forward', True), ('both_strands_summed', False)):
+        model.doublestranded = ds
+        model.motifHitSummary(warm)
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = model.motifHitSummary(seqs)          # includes the device->host copy of the three (N,K) results
+        e1.record()
+        torch.cuda.synchronize()
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+        rec[name] = {'value': float(n) * Lt * ctx.world / (ms * 1e-3), 'seconds': ms * 1e-3,
+                     'd2h_bytes_per_gpu': int(sum(v.nbytes for v in res.values()))}
+        del res
+    model.doublestranded = True
+    return rec
+
+
+def bench_eval(ctx, model, K, M, Lt):
+    """The per-epoch evaluation pass of fit() (convRBM.py:616-624 -> theano_evaluateData :466-472): mean free energy and the mean of
+    a sampled forward-strand hidden layer over a test set, through CRBM._epoch_metrics (batches dealt out over the ranks)."""
+    import crbm_b200
+    n = 100000 // max(1, (Lt * K) // 20000) * ctx.world
+    n = max(model.batchsize * ctx.world, n // model.batchsize * model.batchsize)
+    test = crbm_b200.PackedSequences.random(n, Lt, seed=11, device=ctx.dev)       # the same test set on every rank
+    ms = timed_calls(ctx, lambda: model._epoch_metrics(test), reps=3, warm=1)
+    return {'metric': 'evaluation pass nt/s (mean free energy + sampled hidden mean over the test set)', 'value': n * Lt / (ms * 1e-3),
+            'unit': 'nt/s', 'sequences': n, 'ms': ms, 'n_gpus': ctx.world}
+
+
+def bench_e2e_train(ctx, model, B, Lt, steps):
     """Through the reference-facing call with HOST buffers, every step: a pinned one-hot fp32 minibatch is copied host -> device
     inside `CRBM._trainingFct`, the step runs, and the updated visible bias c (16 bytes) is read device -> host.
     `value`: the read-back is an asynchronous copy into a ring of pinned slots (consumed after a stream synchronisation every
@@ -441,23 +462,15 @@ def bench_e2e(model, B, Lt, world, dev, steps):
     def run(blocking, n):
         for i in range(5):
             one(i, True)
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
+        ctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n):
             one(i, blocking)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return n * B * Lt * world / (ms * 1e-3)
+        ms = ctx.max_over_ranks(e0.elapsed_time(e1))
+        return n * B * Lt * ctx.world / (ms * 1e-3)
 
     steps = max(ring, steps // ring * ring)
     blocking = run(True, min(steps, 1024))
@@ -466,6 +479,149 @@ def bench_e2e(model, B, Lt, world, dev, steps):
             'blocking_read_value': blocking,
             'call': 'CRBM._trainingFct(one-hot fp32 batch in pinned host memory) + read back c every step (asynchronous copy into a '
                     'pinned ring, stream synchronised every %d steps; blocking_read_value: host blocks on every read-back)' % ring}
+
+
+def bench_e2e_scan(ctx, model, K, M, Lt):
+    """The scan through the reference-facing calls with HOST buffers: `motifHitProbs(one-hot NumPy array)` returns the (N,K,1,Lh)
+    NumPy array (host->device copy of the one-hot input, packing, scan, device->host copy of the probabilities inside the timed
+    region); `motifHitSummary` the three (N,K) reductions."""
+    import numpy as np
+    import torch
+    Lh = Lt - M + 1
+    n = max(256, min(20000, int(1.5e9 // (4 * K * Lh))))
+    rs = np.random.RandomState(3 + ctx.rank)
+    codes = rs.randint(0, 4, size=(n, Lt))
+    D = np.zeros((n, 1, 4, Lt), dtype=np.float32)
+    for a in range(4):
+        D[:, 0, a, :] = codes == a
+    rec = {}
+    for name, fn in (('motifHitProbs', model.motifHitProbs), ('motifHitSummary', model.motifHitSummary)):
+        fn(D[:64])
+        best, out_bytes = None, 0
+        for _ in range(3):
+            ctx.barrier()
+            t0 = time.perf_counter()
+            res = fn(D)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            out_bytes = res.nbytes if hasattr(res, 'nbytes') else sum(v.nbytes for v in res.values())
+            del res
+        ms = ctx.max_over_ranks(best * 1e3)
+        rec[name] = {'value': n * Lt * ctx.world / (ms * 1e-3), 'unit': 'nt/s', 'ms': ms, 'sequences_per_gpu': n,
+                     'h2d_bytes': int(D.nbytes), 'd2h_bytes': int(out_bytes)}
+    rec['call'] = 'host one-hot fp32 (N,1,4,L) in, NumPy result out; wall clock around the call (it returns host data), best of 3'
+    return rec
+
+
+def main():
+    # exactly one line on stdout: libraries that print there (NCCL's version banner) are sent to stderr
+    real_stdout = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=None)
+    ap.add_argument('--warmup', type=int, default=None)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-scan', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--only-headline', action='store_true', help='skip the c3 / c4 / c5 / eval sub-records')
+    ap.add_argument('--steps-per-graph', type=int, default=8)
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        args.steps = args.steps if args.steps is not None else 40
+        args.warmup = args.warmup if args.warmup is not None else 3
+        run_reference(args, wl, rank, world)
+        return
+    args.steps = args.steps if args.steps is not None else wl['default_steps']
+    args.warmup = args.warmup if args.warmup is not None else 64
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import crbm_b200  # noqa: F401
+    from crbm_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    _lib.load()
+    ctx = Ctx(rank, world, local_rank, dev, dist)
+    spg = args.steps_per_graph
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    rec, model, data = train_workload(ctx, wl, args.steps, args.warmup, spg, sampler if rank == 0 else None)
+    clocks = sampler.stop() if rank == 0 else None
+    K, M, B, Lt = wl['K'], wl['M'], wl['batch'], rec['seq_len']
+
+    line = {'metric': METRIC, 'value': rec['value'], 'unit': 'nt/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': rec['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': wl['name'], 'batch_per_gpu': B, 'seq_len': Lt, 'global_batch': B * world,
+                       'parallelism': 'dp%d' % world, 'steps_per_graph': spg,
+                       'l2': 'every step reads a new minibatch from a %d-sequence packed dataset (%.0f MB); model state '
+                             '(W, persistent chain) is on-chip/L2 resident by design' % (wl['n_seq'], wl['n_seq'] * data.row_words * 4 / 1e6)},
+            'gpu_launches': rec['gpu_launches']}
+
+    # every rank runs every section (the sections synchronise the ranks); rank 0 keeps the records
+    if rank == 0:
+        kern = phase_times(model, data, B, dev)
+        line['step_kernels_us'] = kern
+        line['roofline'] = train_roofline(wl, Lt, rec, kern, args.workload + '_positive')
+    if not args.no_scan:
+        sc = bench_scan(ctx, model, K, M, Lt, args.workload + '_scan')
+        if not args.no_e2e:
+            sc['e2e'] = bench_e2e_scan(ctx, model, K, M, Lt)
+        line['scan'] = sc
+    if not args.no_e2e:
+        line['e2e'] = bench_e2e_train(ctx, model, B, Lt, min(args.steps, 2000))
+    if not args.only_headline:
+        line['eval'] = bench_eval(ctx, model, K, M, Lt)
+    del model, data
+    torch.cuda.empty_cache()
+
+    if not args.only_headline:
+        for key in ('c2', 'c3', 'c4'):
+            if key == args.workload:
+                continue
+            w2 = WORKLOADS[key]
+            r2, m2, d2 = train_workload(ctx, w2, w2['sub_steps'], 16, spg)
+            if rank == 0:
+                k2 = phase_times(m2, d2, w2['batch'], dev)
+                r2['step_kernels_us'] = k2
+                r2['roofline'] = train_roofline(w2, r2['seq_len'], r2, k2, key + '_positive')
+            r2['n_gpus'], r2['scaling'] = world, 'weak'
+            if key == 'c4':
+                # config 5 shares config 4's motif bank: the 512 x 25 scan
+                Lt5 = C5['L']
+                c5 = {'workload': C5['name']}
+                c5['dense'] = bench_scan(ctx, m2, C5['K'], C5['M'], Lt5, 'c5_scan')
+                c5['job'] = bench_scan_job(ctx, m2, C5['K'], C5['M'], Lt5, C5['total_nt'])
+                line['c5'] = c5
+            line[key] = r2
+            del m2, d2
+            torch.cuda.empty_cache()
+
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            line['cpu_baseline'] = cpu_baseline_sample(wl)
+        line['clocks'] = clocks
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

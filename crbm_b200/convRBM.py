@@ -265,7 +265,7 @@ class CRBM(object):
         return obj
 
     # ---- bottom-up builders (reference :238-275), eager ------------------------------------------------------------
-    def _v2h_device(self, seqs, strand_mode, out_kind, start=0, end=None):
+    def _v2h_device(self, seqs, strand_mode, out_kind, start=0, end=None, buf=None):
         """(end-start, K, 1, Lh) device tensor of activities / probabilities of rows [start, end) of `seqs`.
         It is a view of a buffer whose rows are padded to a multiple of 8 floats: the tcgen05 scan kernel then writes
         whole 32-byte sectors only; the values are those of the contiguous layout."""
@@ -277,15 +277,36 @@ class CRBM(object):
             raise ValueError("sequences of length %d are shorter than the motif (%d)" % (seqs.L, M))
         end = seqs.N if end is None else end
         n = end - start
-        pooled = self.pooling != 1 and out_kind == _lib.OUT_PROBABILITY
-        pitch = Lh if (pooled and os.environ.get('CRBM_POOL_KERNEL', '')[:1] == 'c') else (Lh + 7) // 8 * 8
-        buf = torch.empty((n, K, 1, pitch), dtype=torch.float32, device=self._device)
+        pitch = self._scan_pitch(Lh, out_kind)
+        if buf is None:
+            buf = torch.empty((n, K, 1, pitch), dtype=torch.float32, device=self._device)
+        else:
+            buf = buf[:n]
         _lib.check(lib.crbm_v2h_dense_strided(_lib.ptr(seqs.words[start:]), seqs.row_words, n, seqs.L, _lib.ptr(self._t_W),
                                               _lib.ptr(self._t_bias), K, M, self.pooling, strand_mode, out_kind,
                                               _lib.ptr(buf), pitch, _lib.stream_handle()), 'v2h_dense')
         return buf[:, :, :, :Lh]
 
-    def _v2h(self, data, strand_mode, out_kind, max_chunk_bytes=1 << 30):
+    def _scan_pitch(self, Lh, out_kind):
+        pooled = self.pooling != 1 and out_kind == _lib.OUT_PROBABILITY
+        return Lh if (pooled and os.environ.get('CRBM_POOL_KERNEL', '')[:1] == 'c') else (Lh + 7) // 8 * 8
+
+    def _staging(self, name, shape, dtype):
+        """Pinned host staging buffers, kept on the model and reused across calls (allocating pinned memory costs about as much as
+        copying through it once; a result array in pageable memory is filled from them with a host memcpy)."""
+        torch = _torch()
+        cache = self.__dict__.setdefault('_pinned', {})
+        key = (name, tuple(shape), dtype)
+        if key not in cache:
+            for k in [k for k in cache if k[0] == name]:
+                del cache[k]
+            cache[key] = torch.empty(shape, dtype=dtype, pin_memory=True)
+        return cache[key]
+
+    def _v2h(self, data, strand_mode, out_kind, max_chunk_bytes=128 << 20):
+        """Scan `data` and return the (N,K,1,Lh) float32 array on the host. The sequences are scanned in chunks into two device
+        buffers; a chunk is copied device -> pinned staging buffer on a second stream while the next chunk is scanned, and from
+        there into the result array by the host."""
         seqs = self._as_packed(data)
         K, M = self.num_motifs, self.motif_length
         Lh = seqs.L - M + 1
@@ -293,11 +314,36 @@ class CRBM(object):
             raise ValueError("sequences of length %d are shorter than the motif (%d)" % (seqs.L, M))
         torch = _torch()
         out = np.empty((seqs.N, K, 1, Lh), dtype=np.float32)
-        host = torch.from_numpy(out)
-        rows = max(1, int(max_chunk_bytes // (4 * K * Lh)))
-        for s in range(0, seqs.N, rows):
+        rows = max(1, min(seqs.N, int(max_chunk_bytes // (4 * K * Lh))))
+        nbuf = min(2, -(-seqs.N // rows))
+        pitch = self._scan_pitch(Lh, out_kind)
+        main = torch.cuda.current_stream(self._device)
+        side = torch.cuda.Stream(device=self._device)
+        bufs = [torch.empty((rows, K, 1, pitch), dtype=torch.float32, device=self._device) for _ in range(nbuf)]
+        stage = [self._staging('scan%d' % i, (rows, K, 1, Lh), torch.float32) for i in range(nbuf)]
+        copied = [None, None]
+        pending = []                                            # (chunk start, end, staging index) whose copies are in flight
+
+        def drain(upto):
+            while len(pending) > upto:
+                s0, e0, j = pending.pop(0)
+                copied[j].synchronize()
+                np.copyto(out[s0:e0], stage[j].numpy()[:e0 - s0])
+
+        for i, s in enumerate(range(0, seqs.N, rows)):
             e = min(seqs.N, s + rows)
-            host[s:e].copy_(self._v2h_device(seqs, strand_mode, out_kind, s, e))
+            drain(nbuf - 1)                                     # the staging buffer this chunk will use has been emptied
+            view = self._v2h_device(seqs, strand_mode, out_kind, s, e, buf=bufs[i % nbuf])
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                stage[i % nbuf][:e - s].copy_(view, non_blocking=True)
+                copied[i % nbuf] = torch.cuda.Event()
+                copied[i % nbuf].record(side)
+            main.wait_event(copied[i % nbuf])                   # (orders the next scan into this device buffer after the copy)
+            pending.append((s, e, i % nbuf))
+        drain(0)
         return out
 
     def _bottomUpActivity(self, data, flip_motif=False):
@@ -390,22 +436,57 @@ class CRBM(object):
         mode = _lib.STRAND_FWD if self.doublestranded else _lib.STRAND_SUM
         return self._v2h(data, mode, _lib.OUT_PROBABILITY)
 
-    def motifHitSummary(self, data):
+    def motifHitSummary(self, data, chunk_rows=None):
         """Per sequence and motif: max over positions of motifHitProbs, its position and the mean over positions —
         the reductions secomo.utils applies to motifHitProbs (utils.py:155,245-247,306) — computed inside the scan kernel,
-        so the (N,K,1,Lh) tensor is never materialised. Returns dict(max=(N,K) float32, argmax=(N,K) int32, mean=(N,K))."""
+        so the (N,K,1,Lh) tensor is never materialised. Returns dict(max=(N,K) float32, argmax=(N,K) int32, mean=(N,K)).
+        Long inputs are scanned in chunks of `chunk_rows` sequences (two sets of device buffers; the device->host copy of a
+        chunk into pinned staging memory overlaps the scan of the next one)."""
         lib = self._require_cuda()
         torch = _torch()
         seqs = self._as_packed(data)
         K, M = self.num_motifs, self.motif_length
-        mx = torch.empty((seqs.N, K), dtype=torch.float32, device=self._device)
-        am = torch.empty((seqs.N, K), dtype=torch.int32, device=self._device)
-        mean = torch.empty((seqs.N, K), dtype=torch.float32, device=self._device)
+        N = seqs.N
+        rows = max(1, min(N, int(chunk_rows or max(1024, (64 << 20) // (4 * K)))))
+        nbuf = min(2, -(-N // rows))
+        names = (('max', torch.float32, np.float32), ('argmax', torch.int32, np.int32), ('mean', torch.float32, np.float32))
+        out = {nm: np.empty((N, K), dtype=npd) for nm, _, npd in names}
+        bufs = [{nm: torch.empty((rows, K), dtype=td, device=self._device) for nm, td, _ in names} for _ in range(nbuf)]
+        stage = [{nm: self._staging('sum_%s%d' % (nm, i), (rows, K), td) for nm, td, _ in names} for i in range(nbuf)]
         mode = _lib.STRAND_FWD if self.doublestranded else _lib.STRAND_SUM
-        _lib.check(lib.crbm_scan_reduce(_lib.ptr(seqs.words), seqs.row_words, seqs.N, seqs.L, _lib.ptr(self._t_W),
-                                        _lib.ptr(self._t_bias), K, M, self.pooling, mode, _lib.OUT_PROBABILITY,
-                                        _lib.ptr(mx), _lib.ptr(am), _lib.ptr(mean), _lib.stream_handle()), 'scan_reduce')
-        return dict(max=mx.cpu().numpy(), argmax=am.cpu().numpy(), mean=mean.cpu().numpy())
+        main = torch.cuda.current_stream(self._device)
+        side = torch.cuda.Stream(device=self._device)
+        copied = [None, None]
+        pending = []
+
+        def drain(upto):
+            while len(pending) > upto:
+                s0, e0, j = pending.pop(0)
+                copied[j].synchronize()
+                for nm, _, _ in names:
+                    np.copyto(out[nm][s0:e0], stage[j][nm].numpy()[:e0 - s0])
+
+        for i, s in enumerate(range(0, N, rows)):
+            e = min(N, s + rows)
+            j = i % nbuf
+            drain(nbuf - 1)
+            b = bufs[j]
+            _lib.check(lib.crbm_scan_reduce(_lib.ptr(seqs.words[s:]), seqs.row_words, e - s, seqs.L, _lib.ptr(self._t_W),
+                                            _lib.ptr(self._t_bias), K, M, self.pooling, mode, _lib.OUT_PROBABILITY,
+                                            _lib.ptr(b['max']), _lib.ptr(b['argmax']), _lib.ptr(b['mean']), _lib.stream_handle()),
+                       'scan_reduce')
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                for nm, _, _ in names:
+                    stage[j][nm][:e - s].copy_(b[nm][:e - s], non_blocking=True)
+                copied[j] = torch.cuda.Event()
+                copied[j].record(side)
+            main.wait_event(copied[j])
+            pending.append((s, e, j))
+        drain(0)
+        return out
 
     def _free_energy_device(self, seqs, want_seq, want_motif, want_count, uniforms=None):
         lib = self._require_cuda()
@@ -709,9 +790,7 @@ class CRBM(object):
                 for _ in range(big):
                     g.replay()
             if rest:
-                g1 = self._graph_for(eng, 1)
-                for _ in range(rest):
-                    g1.replay()
+                self._graph_for(eng, rest).replay()      # the remainder as ONE graph of `rest` steps (cached per length)
         self._step += count
 
     def _train_epoch(self, seqs):
@@ -847,18 +926,29 @@ class CRBM(object):
         return self._as_packed(data[:, :, :, :nseq])
 
     def _epoch_metrics(self, test):
-        """Unweighted mean over test batches of [mean FE, mean H sample] (reference :616-627), one launch."""
+        """Unweighted mean over test batches of [mean FE, mean H sample] (reference :616-627). Under data parallelism the
+        batches are dealt out in contiguous runs, every rank evaluates its run in one launch, and the two sums of batch means
+        are all-reduced (eval metrics sharded + one small all-reduce per epoch)."""
         torch = _torch()
-        fe, _, cnt = self._free_energy_device(test, True, False, True)
-        lh = test.L - self.motif_length + 1
         idx = self._iterateBatchIndices(test.N, self.batchsize)
-        meanfe = meannmh = 0.0
-        starts = torch.tensor([s for s, _ in idx] + [test.N], device=self._device)
-        cfe = torch.cat([torch.zeros(1, device=self._device, dtype=torch.float64), fe.double().cumsum(0)])
-        ccn = torch.cat([torch.zeros(1, device=self._device, dtype=torch.float64), cnt.double().cumsum(0)])
-        sizes = (starts[1:] - starts[:-1]).double()
-        meanfe = float(((cfe[starts[1:]] - cfe[starts[:-1]]) / sizes).mean().item())
-        meannmh = float(((ccn[starts[1:]] - ccn[starts[:-1]]) / (sizes * self.num_motifs * lh)).mean().item())
+        nb = len(idx)
+        lo, hi = (self._rank * nb) // self._world, ((self._rank + 1) * nb) // self._world
+        sums = torch.zeros(2, dtype=torch.float64, device=self._device)
+        if hi > lo:
+            s0, e0 = idx[lo][0], idx[hi - 1][1]
+            part = test.rows(s0, e0)
+            fe, _, cnt = self._free_energy_device(part, True, False, True)
+            lh = test.L - self.motif_length + 1
+            starts = torch.tensor([s - s0 for s, _ in idx[lo:hi]] + [e0 - s0], device=self._device)
+            cfe = torch.cat([torch.zeros(1, device=self._device, dtype=torch.float64), fe.double().cumsum(0)])
+            ccn = torch.cat([torch.zeros(1, device=self._device, dtype=torch.float64), cnt.double().cumsum(0)])
+            sizes = (starts[1:] - starts[:-1]).double()
+            sums[0] = ((cfe[starts[1:]] - cfe[starts[:-1]]) / sizes).sum()
+            sums[1] = ((ccn[starts[1:]] - ccn[starts[:-1]]) / (sizes * self.num_motifs * lh)).sum()
+        if self._world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(sums)
+        meanfe, meannmh = (sums / nb).tolist()
         return meanfe, meannmh
 
     def fit(self, training_data, test_data=None):

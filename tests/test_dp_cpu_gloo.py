@@ -158,3 +158,47 @@ def test_local_shard_row_selection():
     with pytest.raises(Exception):
         os.environ.pop('RANK', None)
         crbm_b200.CRBM(3, 4, batchsize=0)
+
+
+# ---- replicas start identical: rank 0's unseeded draw of W is broadcast (reference :127 draws from the global NumPy generator) ----
+def _replica_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import crbm_b200
+    np.random.seed(1000 + rank)                        # the ranks' generators differ, as they do for an unseeded caller
+    m = crbm_b200.CRBM(5, 7, batchsize=4, device='cpu')
+    first = m.motifs.get_value().copy()
+    # a caller that sets different values per rank is brought back in line at the start of fit(): _sync_replicas
+    m.motifs.set_value(np.full((5, 1, 4, 7), float(rank), dtype=np.float32))
+    m._sync_replicas()
+    q.put((rank, first, m.motifs.get_value(), m._local_batch))
+    dist.destroy_process_group()
+
+
+def test_replicas_share_rank0_parameters():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29850 + os.getpid() % 100
+    procs = [ctx.Process(target=_replica_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r: (a, b, lb) for r, a, b, lb in (q.get(timeout=180) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_array_equal(res[0][0], res[1][0])            # same W although the generators were seeded differently
+    assert np.abs(res[0][0]).max() > 0
+    np.testing.assert_array_equal(res[1][1], 0.0)                  # rank 1 took rank 0's values again
+    assert res[0][2] == 2 and res[1][2] == 2
+
+
+def test_epoch_metric_batches_are_dealt_out_once():
+    """CRBM._epoch_metrics: rank r evaluates batches [r*nb//W, (r+1)*nb//W) — every batch exactly once, contiguous rows."""
+    for nb in (1, 2, 5, 8, 13):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = (r * nb) // world, ((r + 1) * nb) // world
+                seen += list(range(lo, hi))
+            assert seen == list(range(nb))

@@ -45,6 +45,7 @@ def _jobs():
         jobs.append((os.path.join(CSRC, 'v2h_mma_inst.cu'), os.path.join(OBJ, 'v2h_mma_inst_%d.o' % ks), ['-DCRBM_KS=%d' % ks]))
     for pp in TT_POOLS:
         jobs.append((os.path.join(CSRC, 'train_tc_inst.cu'), os.path.join(OBJ, 'train_tc_inst_%d.o' % pp), ['-DCRBM_TT_P=%d' % pp]))
+        jobs.append((os.path.join(CSRC, 'scan_rt_inst.cu'), os.path.join(OBJ, 'scan_rt_inst_%d.o' % pp), ['-DCRBM_TT_P=%d' % pp]))
     return jobs
 
 

@@ -796,6 +796,14 @@ int crbm_scan_reduce(const uint32_t *packed, int row_words, int N, int L, const 
         CRBM_CHECK_ARG(Lh % pooling == 0, "crbm_scan_reduce: hidden length %d not divisible by pooling %d", Lh, pooling);
         pool = pooling;
     }
+    if (rows_uses_tc(M, pool)) {
+        // tcgen05 / TMEM kernel with the motif on the TMEM lane: the reductions over positions are register operations (scan_rt.cuh)
+        RowsTcParams r{};
+        r.packed = packed; r.row_words = row_words; r.n_rows = N; r.L = L; r.Lh = Lh;
+        r.W = W; r.b = b; r.K = K; r.M = M; r.strand_mode = strand_mode; r.out_kind = out_kind;
+        r.out_max = out_max; r.out_argmax = out_argmax; r.out_mean = out_mean;
+        return launch_rows_tc(RT_REDUCE, pool, r, (cudaStream_t)stream);
+    }
     Tiling t = make_tiling(K, M, pool, Lh, N);
     ScanReduceParams sp{};
     sp.d = DenseParams{packed, row_words, N, L, Lh, W, b, K, M, pool, strand_mode, out_kind, t.bv, t.nblk, t.n_items, nullptr};
@@ -816,6 +824,18 @@ int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const 
     if (fe_seq) CRBM_CHECK_CUDA(cudaMemsetAsync(fe_seq, 0, sizeof(float) * N, s));
     if (fe_motif) CRBM_CHECK_CUDA(cudaMemsetAsync(fe_motif, 0, sizeof(float) * (size_t)N * K, s));
     if (hsample_count) CRBM_CHECK_CUDA(cudaMemsetAsync(hsample_count, 0, sizeof(float) * N, s));
+    if (rows_uses_tc(M, pooling)) {
+        RowsTcParams r{};
+        r.packed = packed; r.row_words = row_words; r.n_rows = N; r.L = L; r.Lh = Lh;
+        r.W = W; r.b = b; r.K = K; r.M = M; r.ds = doublestranded ? 1 : 0; r.out_kind = CRBM_OUT_PROBABILITY;
+        r.fe_motif = fe_motif; r.fe_seq = fe_seq; r.count = hsample_count; r.uniforms = uniforms;
+        r.seed = seed; r.ctr_hi = (uint32_t)offset;
+        rc = launch_rows_tc(RT_FE, pooling, r, s);
+        if (rc) return rc;
+        fe_finish_kernel<<<N, 128, 0, s>>>(packed, row_words, N, L, K, c, fe_seq, fe_motif);
+        CRBM_CHECK_LAUNCH();
+        return CRBM_OK;
+    }
     Tiling t = make_tiling(K, M, pooling, Lh, N);
     V2HParams p{};
     p.packed = packed; p.row_words = row_words; p.n_rows = N; p.L = L; p.Lh = Lh;

@@ -361,9 +361,9 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                     pv[i] = rr * a1;
                     pv[i + 1] = rr * a0;
                 }
-                if (!(row_ok && nv == 32)) {
+                if (nv != 32) {                               // warp-uniform: the last block of a sequence, the tail of the input
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) pv[i] = (row_ok && i < nv) ? pv[i] : 0.f;
+                    for (int i = 0; i < 32; ++i) pv[i] = i < nv ? pv[i] : 0.f;
                 }
                 if constexpr (STAT_Q) {
 #pragma unroll
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                 for (int i = 0; i < 32; ++i) {
                     float e;
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(pv[i], 57.7f)));
-                    pv[i] = (row_ok && i < nv && i < VP) ? e : 0.f;
+                    pv[i] = i < VP ? e : 0.f;
                 }
 #pragma unroll
                 for (int g = 0; g < NG; ++g) {
@@ -395,6 +395,13 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                 if constexpr (STAT_Q) {
 #pragma unroll
                     for (int i = VP; i < 32; ++i) qv[i] = 0.f;
+                }
+                if (nv != VP) {                               // warp-uniform; nv is a multiple of P: whole groups drop out
+#pragma unroll
+                    for (int i = 0; i < VP; ++i) {
+                        pv[i] = i < nv ? pv[i] : 0.f;
+                        if constexpr (STAT_Q) qv[i] = i < nv ? qv[i] : 0.f;
+                    }
                 }
             }
             // ---- hidden sums (A9), per unit first so that the running sums grow by a few dozen terms at a time
@@ -479,7 +486,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                         }
                     }
                 }
-                if (n < p.n_rows) p.bits[(((size_t)s * p.n_rows + n) * p.hw + wb) * p.Kpad + chunk * TT_KC + kl] = word;
+                if (n < p.n_rows) p.bits[(((size_t)s * p.n_rows + n) * p.hw + wb) * p.Kpad + chunk * TT_KC + kl] = row_ok ? word : 0u;
             }
             // ---- A operands of GEMM 2: 2^14 p (and 2^14 Q) as fp16 hi / lo, K-major SWIZZLE_128B rows of 64 positions
             if (STAT) {
@@ -537,8 +544,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
             // hidden sums: the four warpgroups hold partial sums of the same rows; combined through shared memory (the operand sets
             // are free: every GEMM 2 has completed) in a fixed order
             float *comb = reinterpret_cast<float *>(PQ);
-            comb[wg * TT_ROWS + r] = sum_p;
-            if (s == 0) comb[4 * TT_ROWS + wg * TT_KC + kl] = sum_q;
+            comb[wg * TT_ROWS + r] = row_ok ? sum_p : 0.f;       // rows beyond K / of the unused strand hold values of no meaning
+            if (s == 0) comb[4 * TT_ROWS + wg * TT_KC + kl] = row_ok ? sum_q : 0.f;
             asm volatile("bar.sync 2, 512;" ::: "memory");
             if (wg == 0) {
                 float *sums = part + (size_t)Kdim * 192;

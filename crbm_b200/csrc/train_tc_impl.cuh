@@ -5,6 +5,7 @@
 //   train_phases_tc       the launch chain of one step
 #pragma once
 #include "train_tc.cuh"
+#include "scan_rt.cuh"
 
 namespace crbm {
 
@@ -13,7 +14,37 @@ namespace crbm {
 CRBM_FOR_EACH_TT_P(CRBM_DECLARE_TT)
 #undef CRBM_DECLARE_TT
 
+#define CRBM_DECLARE_RT(PV) template <> int launch_v2h_rows_tc<PV>(int, const RowsTcParams &, dim3, cudaStream_t);
+CRBM_FOR_EACH_TT_P(CRBM_DECLARE_RT)
+#undef CRBM_DECLARE_RT
+
 static bool tt_pool_built(int P) { return P == 1 || P == 2 || P == 4 || P == 5 || P == 10; }
+// scan reductions / free energy on the tcgen05 rows kernel (scan_rt.cuh): motif_length <= 32, pooling one of the built factors;
+// CRBM_ROWS_KERNEL=mma keeps the mma.sync / CUDA-core kernels
+static bool rows_uses_tc(int M, int P) {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CRBM_ROWS_KERNEL"); v = (e && e[0] == 'm') ? 0 : 1; }
+    return v == 1 && M <= 32 && tt_pool_built(P);
+}
+static int launch_rows_tc(int mode, int P, RowsTcParams &p, cudaStream_t s) {
+    p.Kdim = 16 * ceil_div(4 * p.M, 16);
+    p.ksteps = p.Kdim / 16;
+    p.n_atoms = ceil_div(p.Kdim, 64);
+    const int VP = (32 / P) * P;
+    p.nblk32 = ceil_div(p.Lh, VP);
+    p.n_quads = ceil_div(p.n_rows, 4);
+    p.xstages = TT_MAX_XSTAGES;
+    const int n_chunks = ceil_div(p.K, mode == RT_REDUCE ? TT_ROWS : TT_KC);
+    int gx = num_sms() / n_chunks > 0 ? num_sms() / n_chunks : 1;
+    if (gx > p.n_quads) gx = p.n_quads;
+    switch (P) {
+#define CRBM_CASE(PV) case PV: return launch_v2h_rows_tc<PV>(mode, p, dim3(gx, n_chunks), s);
+        CRBM_FOR_EACH_TT_P(CRBM_CASE)
+#undef CRBM_CASE
+    }
+    set_error("tcgen05 rows kernel: pooling %d not built", P);
+    return CRBM_ERR_UNSUPPORTED;
+}
 // The tcgen05 path covers motif_length <= 32 (4 M <= 128 contraction columns, one MMA N) and the pooling factors it is instantiated
 // for; everything else trains on the mma.sync kernels of v2h_mma.cuh. Small un-pooled banks (K * M < 2048, e.g. 100 x 15) also stay
 // there: at that size a step is a chain of four 5-20 us launches, and the mma.sync kernels (two CTAs per SM, prologues overlapping

@@ -435,6 +435,38 @@ def bench_eval(ctx, model, K, M, Lt):
             'unit': 'nt/s', 'sequences': n, 'ms': ms, 'n_gpus': ctx.world}
 
 
+def bench_ingest(ctx, Lt):
+    """Streaming ingest: a synthetic FASTA file -> PackedSequences on the device (blocks parsed on the host with NumPy,
+    one pinned-memory copy of 1 byte per base per block, packed to 2 bits on the device while the next block is parsed)."""
+    import tempfile
+    import numpy as np
+    import torch
+    import crbm_b200
+    n = 200000
+    rs = np.random.RandomState(5 + ctx.rank)
+    letters = np.frombuffer(b'ACGT', dtype=np.uint8)[rs.randint(0, 4, size=(n, Lt))]
+    path = os.path.join(tempfile.gettempdir(), 'crbm_b200_bench_%d_%d.fa' % (os.getpid(), ctx.rank))
+    rows = np.empty((n, Lt + 10), dtype=np.uint8)
+    rows[:, :9] = np.frombuffer(b'>s0000000', dtype=np.uint8)
+    rows[:, 9] = 10
+    rows[:, 10:10 + Lt - 1 + 1] = letters
+    with open(path, 'wb') as f:
+        f.write(np.concatenate([rows, np.full((n, 1), 10, dtype=np.uint8)], axis=1).tobytes())
+    try:
+        crbm_b200.PackedSequences.from_fasta(path)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        seqs = crbm_b200.PackedSequences.from_fasta(path)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        assert seqs.N == n and seqs.L == Lt
+    finally:
+        os.remove(path)
+    ms = ctx.max_over_ranks(dt * 1e3)
+    return {'metric': 'FASTA -> packed sequences resident in HBM, nt/s (host parsing included)', 'value': n * Lt * ctx.world / (ms * 1e-3),
+            'unit': 'nt/s', 'records_per_gpu': n, 'file_MB': (n * (Lt + 11)) / 1e6, 'ms': ms}
+
+
 def bench_e2e_train(ctx, model, B, Lt, steps):
     """Through the reference-facing call with HOST buffers, every step: a pinned one-hot fp32 minibatch is copied host -> device
     inside `CRBM._trainingFct`, the step runs, and the updated visible bias c (16 bytes) is read device -> host.
@@ -589,6 +621,7 @@ def main():
         line['e2e'] = bench_e2e_train(ctx, model, B, Lt, min(args.steps, 2000))
     if not args.only_headline:
         line['eval'] = bench_eval(ctx, model, K, M, Lt)
+        line['ingest'] = bench_ingest(ctx, Lt)
     del model, data
     torch.cuda.empty_cache()
 

@@ -75,6 +75,7 @@ SIGNATURES = {
                                        c_void_p, ctypes.c_longlong, c_void_p]),
     'crbm_scan_reduce': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    'crbm_position_sum': (c_int, [c_void_p, c_int, c_int, c_int, ctypes.c_longlong, c_void_p, c_void_p]),
     'crbm_pool_probability': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'crbm_sample_hidden': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_u64, c_u64, c_void_p, c_void_p]),
     'crbm_h2v_dense': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),

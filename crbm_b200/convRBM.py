@@ -488,6 +488,29 @@ class CRBM(object):
         drain(0)
         return out
 
+    def motifHitPositionMean(self, data, max_chunk_bytes=256 << 20):
+        """Mean hit probability per (motif, position) over the sequences, (K, L-M+1) float32: what
+        `secomo.utils.positionalDensityPlot` draws (utils.py:113-116, `motifHitProbs(seqs).mean(axis=(0, 2))`). The sequences are
+        scanned in chunks into one reused device buffer and summed over the sequence axis on the device (crbm_position_sum), so
+        neither the host nor the device ever holds the (N,K,1,Lh) tensor."""
+        lib = self._require_cuda()
+        torch = _torch()
+        seqs = self._as_packed(data)
+        K, M = self.num_motifs, self.motif_length
+        Lh = seqs.L - M + 1
+        if Lh <= 0:
+            raise ValueError("sequences of length %d are shorter than the motif (%d)" % (seqs.L, M))
+        mode = _lib.STRAND_FWD if self.doublestranded else _lib.STRAND_SUM
+        pitch = self._scan_pitch(Lh, _lib.OUT_PROBABILITY)
+        rows = max(1, min(seqs.N, int(max_chunk_bytes // (4 * K * pitch))))
+        buf = torch.empty((rows, K, 1, pitch), dtype=torch.float32, device=self._device)
+        acc = torch.zeros((K, Lh), dtype=torch.float32, device=self._device)
+        for s in range(0, seqs.N, rows):
+            e = min(seqs.N, s + rows)
+            self._v2h_device(seqs, mode, _lib.OUT_PROBABILITY, s, e, buf=buf)
+            _lib.check(lib.crbm_position_sum(_lib.ptr(buf), e - s, K, Lh, pitch, _lib.ptr(acc), _lib.stream_handle()), 'position_sum')
+        return (acc / float(seqs.N)).cpu().numpy()
+
     def _free_energy_device(self, seqs, want_seq, want_motif, want_count, uniforms=None):
         lib = self._require_cuda()
         torch = _torch()

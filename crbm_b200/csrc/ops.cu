@@ -214,6 +214,27 @@ __global__ void dense_to_bits_kernel(const float *__restrict__ dense, int Bn, in
     bits[gid] = w;
 }
 
+// ---- sum over sequences of a dense (n,K,1,Lh) chunk (rows `row_stride` floats apart), accumulated into acc[K][Lh] ------------
+// One thread per (motif, position): consecutive threads read consecutive positions of one row (coalesced), a thread walks the
+// sequences of the chunk in order, so the sum is deterministic. Four independent partial sums hide the load latency.
+__global__ void position_sum_kernel(const float *__restrict__ dense, int n, int K, int Lh, long long row_stride, float *__restrict__ acc) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)K * Lh) return;
+    const int k = (int)(gid / Lh), j = (int)(gid - (long long)k * Lh);
+    const float *src = dense + (size_t)k * row_stride + j;
+    const size_t seq_stride = (size_t)K * row_stride;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int i = 0;
+    for (; i + 4 <= n; i += 4) {
+        a0 += src[(size_t)i * seq_stride];
+        a1 += src[(size_t)(i + 1) * seq_stride];
+        a2 += src[(size_t)(i + 2) * seq_stride];
+        a3 += src[(size_t)(i + 3) * seq_stride];
+    }
+    for (; i < n; ++i) a0 += src[(size_t)i * seq_stride];
+    acc[gid] += (a0 + a1) + (a2 + a3);
+}
+
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace crbm
@@ -260,6 +281,13 @@ int crbm_random_bases(uint32_t *packed, int row_words, int N, int L, uint64_t se
     CRBM_CHECK_ARG(packed && N > 0 && L > 0, "crbm_random_bases: bad arguments");
     CRBM_CHECK_ARG(row_words >= packed_row_words(L) && row_words % 4 == 0, "crbm_random_bases: bad row_words %d", row_words);
     random_bases_kernel<<<blocks_for((long long)N * (row_words / 4), 256), 256, 0, (cudaStream_t)stream>>>(packed, row_words, N, L, seed);
+    CRBM_CHECK_LAUNCH();
+    return CRBM_OK;
+}
+
+int crbm_position_sum(const float *dense, int n, int K, int Lh, long long row_stride, float *acc, void *stream) {
+    CRBM_CHECK_ARG(dense && acc && n > 0 && K > 0 && Lh > 0 && row_stride >= Lh, "crbm_position_sum: bad arguments");
+    position_sum_kernel<<<blocks_for((long long)K * Lh, 128), 128, 0, (cudaStream_t)stream>>>(dense, n, K, Lh, row_stride, acc);
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }

@@ -91,6 +91,85 @@ def seqToCodes(seqs):
     return np.stack(rows)
 
 
+# ---- streaming ingest ---------------------------------------------------------------------------------------------
+_N_CODE = 4                                             # 'N' / 'n': the record is skipped (reference sequences.py:47-50)
+_STREAM_LUT = _CODE_LUT.copy()
+_STREAM_LUT[ord('N')] = _STREAM_LUT[ord('n')] = _N_CODE
+
+
+def iterFastaCodes(filename, chunk_bytes=32 << 20, quiet=False):
+    """Streams a multi-FASTA file as (n, L) uint8 base-code arrays (A0 C1 G2 T3, case-insensitive), one per `chunk_bytes` of file,
+    without ever holding the file or a per-record Python object: a block of bytes is split into records with NumPy (header lines
+    and line ends removed by masks, record lengths by a segmented count), so multi-line records and CRLF files are handled.
+    Semantics of the reference reader (secomo/sequences.py:33-52, 20-31): records containing N/n are skipped ("skip sequence
+    containing N" is printed once per skipped record unless `quiet`), any other non-ACGT letter raises KeyError, and all records
+    must have the same length (the reference's one-hot array cannot be built otherwise)."""
+    carry = b''
+    L0 = None
+    with open(filename, 'rb') as f:
+        while True:
+            block = f.read(chunk_bytes)
+            last = not block
+            buf = carry + block
+            if not buf:
+                return
+            if not last:
+                cut = buf.rfind(b'>')                       # the last record of the block may be incomplete: keep it for the next one
+                if cut <= 0:
+                    carry = buf
+                    continue
+                buf, carry = buf[:cut], buf[cut:]
+            else:
+                carry = b''
+            a = np.frombuffer(buf, dtype=np.uint8)
+            nl = a == 10
+            start = np.concatenate(([True], nl[:-1]))        # first byte of every line
+            hdr_start = np.flatnonzero(start & (a == ord('>')))
+            if hdr_start.size == 0:
+                if last:
+                    return
+                continue
+            nl_pos = np.flatnonzero(nl)
+            # end of every header line (its newline, or the end of the buffer)
+            idx = np.searchsorted(nl_pos, hdr_start)
+            if nl_pos.size:
+                hdr_end = np.where(idx < nl_pos.size, nl_pos[np.minimum(idx, nl_pos.size - 1)], a.size - 1)
+            else:
+                hdr_end = np.full(hdr_start.shape, a.size - 1)
+            is_hdr = np.zeros(a.size + 1, dtype=np.int8)
+            np.add.at(is_hdr, hdr_start, 1)
+            np.add.at(is_hdr, hdr_end + 1, -1)
+            in_hdr = np.cumsum(is_hdr[:-1]) > 0
+            keep = ~(in_hdr | nl | (a == 13) | (a == 32) | (a == 9))
+            keep[:hdr_start[0]] = False                      # anything before the first header is not a record
+            rec_of_byte = np.cumsum(start & (a == ord('>'))) - 1
+            lengths = np.bincount(rec_of_byte[keep], minlength=hdr_start.size)
+            seq = _STREAM_LUT[a[keep]]
+            nz = lengths > 0
+            if not np.all(nz):                               # header without sequence lines: an empty record, dropped like an N record
+                lengths = lengths[nz]
+            if lengths.size:
+                if L0 is None:
+                    L0 = int(lengths[0])
+                if np.any(lengths != L0):
+                    raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
+                codes = seq.reshape(-1, L0)
+                bad = codes == 255
+                if bad.any():
+                    r, c = np.argwhere(bad)[0]
+                    raise KeyError(chr(int(a[keep].reshape(-1, L0)[r, c])))
+                has_n = (codes == _N_CODE).any(axis=1)
+                if has_n.any():
+                    if not quiet:
+                        for _ in range(int(has_n.sum())):
+                            print("skip sequence containing N")
+                    codes = codes[~has_n]
+                if codes.shape[0]:
+                    yield np.ascontiguousarray(codes)
+            if last:
+                return
+
+
 def codesToOneHot(codes):
     codes = np.asarray(codes)
     N, Ln = codes.shape
@@ -192,6 +271,11 @@ def unpackCodesHost(words, L):
     return codes.reshape(words.shape[0], nw * 16)[:, :int(L)].astype(np.uint8)
 
 
+def ctypes_stream(stream):
+    import ctypes
+    return ctypes.c_void_p(stream.cuda_stream)
+
+
 class PackedSequences(object):
     """N sequences of L bases, 2 bits per base, resident in GPU memory in the row layout of include/crbm_b200.h."""
 
@@ -270,10 +354,57 @@ class PackedSequences(object):
         return cls(torch.from_numpy(words.view(np.int32)).to(device), words.shape[0], L)
 
     @classmethod
-    def from_fasta(cls, filename, device='cuda'):
-        """FASTA file -> packed sequences on the device (records containing N are skipped as readSeqsFromFasta does)."""
-        codes = seqToCodes(readSeqsFromFasta(filename))
-        return cls.from_packed_host(packCodesHost(codes), codes.shape[1], device)
+    def from_fasta(cls, filename, device='cuda', chunk_bytes=32 << 20, quiet=True):
+        """FASTA file -> packed sequences on the device, streamed (semantics of readSeqsFromFasta + seqToOneHot,
+        reference sequences.py:33-52,101-117: N records skipped, case folded, KeyError on other letters).
+
+        The file is read in blocks of `chunk_bytes` (iterFastaCodes); the base codes of a block (1 byte per base) go through one of
+        two pinned staging buffers, one asynchronous host->device copy per block on a side stream, and are packed to 2 bits per base
+        on the device (crbm_pack_codes) while the host parses the next block. Neither the file nor a one-hot array is ever held in
+        host memory; the device tensor is sized from the file size (an upper bound: header bytes count as bases)."""
+        import torch
+        from . import _lib
+        lib = _lib.load()
+        dev = torch.device(device)
+        size = os.path.getsize(filename)
+        words, rw, Ln, n_done = None, 0, None, 0
+        main = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(main)
+        stage, dbuf, done = [None, None], [None, None], [None, None]
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        for i, codes in enumerate(iterFastaCodes(filename, chunk_bytes, quiet)):
+            n, j = codes.shape[0], i & 1
+            if words is None:
+                Ln = codes.shape[1]
+                cap = size // (Ln + 2) + 1
+                words, rw = cls._alloc(cap, Ln, dev)
+                side.wait_stream(main)
+            if n_done + n > words.shape[0]:                  # (cannot happen for a well-formed file; keep the bound honest)
+                grown = torch.zeros((max(2 * words.shape[0], n_done + n), rw), dtype=torch.int32, device=dev)
+                side.synchronize()
+                grown[:n_done] = words[:n_done]
+                words = grown
+                side.wait_stream(main)
+            if stage[j] is None or stage[j].shape[0] < n:
+                if done[j] is not None:
+                    done[j].synchronize()
+                stage[j] = torch.empty((max(n, 1), Ln), dtype=torch.uint8, pin_memory=True)
+                dbuf[j] = torch.empty((max(n, 1), Ln), dtype=torch.uint8, device=dev)
+            if done[j] is not None:
+                done[j].synchronize()                           # the copy that read this staging buffer two blocks ago has finished
+            np.copyto(stage[j].numpy()[:n], codes)
+            with torch.cuda.stream(side):
+                dbuf[j][:n].copy_(stage[j][:n], non_blocking=True)
+                _lib.check(lib.crbm_pack_codes(_lib.ptr(dbuf[j]), n, Ln, _lib.ptr(words[n_done:]), rw, _lib.ptr(bad),
+                                               ctypes_stream(side)), 'pack_codes')
+                done[j] = torch.cuda.Event()
+                done[j].record(side)
+            n_done += n
+        if words is None:
+            raise ValueError("no usable record in %s" % filename)
+        main.wait_stream(side)
+        return cls(words[:n_done], n_done, Ln)
 
     @classmethod
     def random(cls, N, L, seed=1234, device='cuda'):

@@ -7,7 +7,8 @@ Sequence logos, positional density, t-SNE and violin plots need matplotlib / sea
 scope). What they visualise is written to `motif_hit_summary.npz` instead:
   * max / argmax / mean of the hit probabilities over positions per (sequence, motif) — computed inside the scan kernel
     (`CRBM.motifHitSummary`; the reductions of utils.py:155,245-247,306),
-  * the mean hit probability per (motif, position) over the first 100 sequences (utils.py:116).
+  * the mean hit probability per (motif, position) over the sequences (utils.py:116), reduced on the device
+    (`CRBM.motifHitPositionMean`).
 """
 import os
 
@@ -34,7 +35,7 @@ def tutorial(path, num_motifs=10, motif_length=15, epochs=1):
     head = data[:100]
     matches = model.motifHitProbs(head)                          # (100, K, 1, 186) per-position match probabilities
     summary = model.motifHitSummary(data)                        # fused reductions over all 3997 sequences
-    density = matches.mean(axis=(0, 2))                          # (K, positions)
+    density = model.motifHitPositionMean(data)                   # (K, positions), reduced on the device over all sequences
     np.savez(os.path.join(path, 'motif_hit_summary.npz'), max=summary['max'], argmax=summary['argmax'], mean=summary['mean'],
              positional_density=density)
     return {'model': model, 'pfms': pfms, 'matches': matches, 'summary': summary, 'positional_density': density}

@@ -91,6 +91,12 @@ int crbm_scan_reduce(const uint32_t *packed, int row_words, int N, int L,
                      const float *W, const float *b, int K, int M, int pooling,
                      int strand_mode, int out_kind, float *out_max, int *out_argmax, float *out_mean, void *stream);
 
+/* Per-position sum over sequences of a dense chunk (reference secomo/utils.py:113-116: `motifHitProbs(seqs).mean(axis=(0,2))`, the
+ * positional density): acc[k*Lh + j] += sum_{i<n} dense[(i*K + k) * row_stride + j]. `dense` is a chunk written by
+ * crbm_v2h_dense_strided (row_stride = its out_row_stride); acc (K*Lh floats, zeroed by the caller before the first chunk) is
+ * accumulated in sequence order, so the result does not depend on timing. */
+int crbm_position_sum(const float *dense, int n, int K, int Lh, long long row_stride, float *acc, void *stream);
+
 /* ---- A2 on a given activity tensor (eager `_bottomUpProbability(activities)`) --------------------------- */
 int crbm_pool_probability(const float *act, int N, int K, int Lh, int pooling, float *prob, void *stream);
 

@@ -27,7 +27,9 @@ def main():
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', device_id=dev)
     import crbm_b200
-    K, M, B, L, NB = 100, 15, 32, 200, 40
+    # DP_CHECK_SHAPE=tc: a bank that trains on the tcgen05 kernels (K * M >= 2048), pooled; default: the mma.sync path (C2's bank)
+    tc = os.environ.get('DP_CHECK_SHAPE', '') == 'tc'
+    K, M, B, L, NB, P = (128, 20, 32, 209, 40, 5) if tc else (100, 15, 32, 200, 40, 1)
     rs = np.random.RandomState(3)
     W = (0.5 * rs.randn(K, 1, 4, M)).astype(np.float32)
     data = crbm_b200.PackedSequences.random(NB * B, L, seed=50 + rank, device=dev)
@@ -35,7 +37,7 @@ def main():
 
     def run(mode, steps_eager, steps_graph):
         os.environ['CRBM_DP'] = mode
-        m = crbm_b200.CRBM(K, M, epochs=1, batchsize=B * world, cd_k=1, seed=11, device=dev)
+        m = crbm_b200.CRBM(K, M, epochs=1, batchsize=B * world, cd_k=1, pooling=P, seed=11, device=dev)
         m.motifs.set_value(W)
         snaps = []
         for i in range(steps_eager):
@@ -74,7 +76,7 @@ def main():
     # timing of the two modes, graph replay, a few hundred steps (informational)
     for mode in ('nccl', 'p2p'):
         os.environ['CRBM_DP'] = mode
-        m = crbm_b200.CRBM(K, M, epochs=1, batchsize=B * world, cd_k=1, seed=11, device=dev)
+        m = crbm_b200.CRBM(K, M, epochs=1, batchsize=B * world, cd_k=1, pooling=P, seed=11, device=dev)
         m._train_full_batches(data, 0, 16)
         dist.barrier(); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -85,8 +87,24 @@ def main():
         dist.barrier(); torch.cuda.synchronize()
         if rank == 0:
             print("dp%d %s: %.1f us/step" % (world, mode, e0.elapsed_time(e1) * 1e3 / 320))
+    # fit() under data parallelism without any seeding by the caller: every rank draws its own W (reference :127 uses the global
+    # NumPy generator), rank 0's is broadcast, the ranks train on their shards of the same global minibatches, the epoch metrics
+    # are all-reduced, and the replicas must end bit-identical
+    os.environ['CRBM_DP'] = 'p2p'
+    np.random.seed(1000 + rank)
+    m = crbm_b200.CRBM(K, M, epochs=2, batchsize=8 * world, cd_k=1, pooling=P, device=dev)
+    rs2 = np.random.RandomState(77)                       # the same global training set on every rank
+    codes = rs2.randint(0, 4, size=(8 * world * 3 + 3, L))
+    D = np.zeros((codes.shape[0], 1, 4, L), dtype=np.float32)
+    for a in range(4):
+        D[:, 0, a, :] = codes == a
+    m.fit(D)
+    for name in ('motifs', 'bias', 'c'):
+        v = getattr(m, name).get_value()
+        assert np.isfinite(v).all()
+        same_on_all_ranks(v, 'fit() replica %s' % name)
     if rank == 0:
-        print("DP_P2P_CHECK_OK world=%d" % world)
+        print("DP_P2P_CHECK_OK world=%d shape=%s" % (world, 'tc' if tc else 'mma'))
     dist.barrier()
     dist.destroy_process_group()
 

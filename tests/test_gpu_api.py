@@ -290,3 +290,17 @@ def test_streamlined_onehot_step_equals_packed_step_and_validates(data):
     m._trainingFct(bad)
     with pytest.raises(ValueError):
         m.motifs.get_value()
+
+
+def test_streamed_fasta_ingest_matches_host_packing(tmp_path):
+    """PackedSequences.from_fasta streams blocks through pinned staging buffers and packs on the device: same rows as packing the
+    record reader's codes, for block sizes that split the file many times."""
+    import crbm_b200
+    from crbm_b200.sequences import readSeqsFromFasta, seqToCodes, sample_fasta_path
+    p = sample_fasta_path()
+    codes = seqToCodes(readSeqsFromFasta(p))
+    want = crbm_b200.PackedSequences.from_codes(codes).words.cpu().numpy()
+    for cb in (32 << 20, 40000, 3000):
+        got = crbm_b200.PackedSequences.from_fasta(p, chunk_bytes=cb)
+        assert (got.N, got.L) == codes.shape
+        np.testing.assert_array_equal(got.words.cpu().numpy(), want)

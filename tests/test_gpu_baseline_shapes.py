@@ -198,3 +198,32 @@ def test_scan_c5_both_strand_modes(crbm, O, K, M, P, L, ds):
     # wherever the maximum is not clear-cut the reported position must still hold a value within tolerance of the maximum
     pos = s['argmax'].astype(np.int64)
     np.testing.assert_allclose(np.take_along_axis(w, pos[:, :, None], axis=2)[:, :, 0], w.max(axis=2), **TOL)
+
+
+@pytest.mark.parametrize('K,M,P,L,ds,N', [(100, 15, 1, 200, True, 37), (16, 9, 4, 105, False, 11), (130, 25, 1, 330, True, 5)])
+def test_position_mean_matches_oracle(crbm, O, K, M, P, L, ds, N):
+    """Per-(motif, position) mean over sequences (secomo/utils.py:113-116), reduced on the device in chunks, against the oracle."""
+    rs = np.random.RandomState(K + M + N)
+    m, W, b, c = make_model(crbm, rs, K, M, P, ds, N, 1, wscale=0.3, bias=-2.5)
+    Lt = m._truncated_length(L)
+    D = onehot(rs.randint(0, 4, size=(N, Lt)))
+    want = O.hit_probs(D.astype(np.float64), W.astype(np.float64), b.astype(np.float64), P, ds).mean(axis=(0, 2))
+    got = m.motifHitPositionMean(D, max_chunk_bytes=4 * K * (Lt - M + 8) * 7)      # several chunks, a ragged last one
+    assert got.shape == want.shape and got.dtype == np.float32
+    np.testing.assert_allclose(got, want, **TOL)
+    np.testing.assert_allclose(m.motifHitPositionMean(D), want, **TOL)
+
+
+def test_small_shapes_on_the_tcgen05_training_path():
+    """Small un-pooled banks train on the mma.sync kernels by default (train_tc_impl.cuh: train_uses_tc); CRBM_TRAIN_KERNEL=tc
+    forces the tcgen05 kernels, and the whole-step parity tests must pass on them too (read once per process: subprocess)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CRBM_TRAIN_KERNEL='tc')
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', os.path.join(root, 'tests', 'test_gpu_parity.py'),
+                        os.path.join(root, 'tests', 'test_gpu_api.py'), '-k', 'train or step or graph or phase or chain or fantasy'],
+                       capture_output=True, text=True, timeout=900, cwd=root, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert ' passed' in r.stdout

@@ -84,6 +84,7 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_u64, c_u64, c_void_p]),
     'crbm_train_stats_floats': (c_size_t, [c_int, c_int]),
     'crbm_train_workspace_bytes': (c_size_t, [c_int, c_int]),
+    'crbm_train_workspace_bytes_for': (c_size_t, [c_int, c_int, c_int]),
     'crbm_train_accumulate': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_apply': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_step': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
@@ -98,6 +99,8 @@ SIGNATURES = {
     'crbm_chain_words': (c_size_t, [c_int, c_int, c_int]),
     'crbm_chain_to_dense': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'crbm_chain_from_dense': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'crbm_fasta_parse_block_host': (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_longlong),
+                                            ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_int)]),
     'crbm_launch_count': (ctypes.c_ulonglong, []),
 }
 

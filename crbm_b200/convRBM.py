@@ -543,7 +543,7 @@ class CRBM(object):
             st['v_row_words'] = lib.crbm_packed_row_words(lv)
             st['v_model'] = torch.zeros((self._local_batch, st['v_row_words']), dtype=torch.int32, device=self._device)
             st['stats'] = torch.zeros(int(lib.crbm_train_stats_floats(K, M)), dtype=torch.float32, device=self._device)
-            st['ws_bytes'] = int(lib.crbm_train_workspace_bytes(K, M))
+            st['ws_bytes'] = int(lib.crbm_train_workspace_bytes_for(K, M, self._local_batch))
             st['workspace'] = torch.empty(st['ws_bytes'], dtype=torch.uint8, device=self._device)
             lay = _lib.StatsLayout()
             _lib.check(lib.crbm_train_stats_layout(K, M, lay), 'stats_layout')

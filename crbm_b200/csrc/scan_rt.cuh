@@ -227,21 +227,34 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
             if (MODE == RT_REDUCE) {
                 if (!prob || P == 1) {
                     // key = the activity (up to the positive factor log2 e): its maximum is the maximum of the sigmoid too
-                    const float sgn = prob ? -1.f : 1.f;
+                    // (for probabilities the accumulator is -log2(e) a: the minimum; for activities the maximum)
                     const bool fullblk = nv == 32;                 // warp-uniform; the masked path runs once per sequence
-                    float bm = -INFINITY;
-                    if (fullblk) {
+                    float bm;
+                    if (prob) {
+                        bm = INFINITY;
+                        if (fullblk) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) bm = fmaxf(bm, sgn * pv[i]);
+                            for (int i = 0; i < 32; ++i) bm = fminf(bm, pv[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) bm = fminf(bm, i < nv ? pv[i] : INFINITY);
+                        }
                     } else {
+                        bm = -INFINITY;
+                        if (fullblk) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) bm = fmaxf(bm, i < nv ? sgn * pv[i] : -INFINITY);
+                            for (int i = 0; i < 32; ++i) bm = fmaxf(bm, pv[i]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) bm = fmaxf(bm, i < nv ? pv[i] : -INFINITY);
+                        }
                     }
-                    if (bm > best) {                            // strict: an earlier block keeps a tie (numpy.argmax)
+                    const float key = prob ? -bm : bm;
+                    if (key > best) {                           // strict: an earlier block keeps a tie (numpy.argmax)
                         int at = 0;
 #pragma unroll
-                        for (int i = 31; i >= 0; --i) at = (i < nv && sgn * pv[i] == bm) ? i : at;
-                        best = bm;
+                        for (int i = 31; i >= 0; --i) at = (i < nv && pv[i] == bm) ? i : at;
+                        best = key;
                         bpos = wb * VP + at;
                     }
                     if (prob) {
@@ -326,7 +339,19 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
                     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lt) : "f"(tot));
                     const float sp = rt_softplus(tot, P == 1 ? ymax : lt);
                     if (fullblk || g * P < nv) fe += sp;
-                    if (counting) {
+                    if (counting && P == 1 && !p.uniforms) {
+                        // one Bernoulli(e / (1 + e)) per position from 16-bit uniforms, eight per Philox draw; a tie of the 16 bits
+                        // (2^-16 per position) is resolved towards "off": the count is a monitoring statistic (NumH, convRBM.py:469)
+                        if ((g & 7) == 0) {
+                            const uint4 rnd = tt_philox(make_uint4(rowid, (uint32_t)(wb * 8 + (g >> 3)), p.ctr_hi, RNG_EVAL), key);
+                            ug4[0] = __uint_as_float(rnd.x); ug4[1] = __uint_as_float(rnd.y); ug4[2] = __uint_as_float(rnd.z); ug4[3] = __uint_as_float(rnd.w);
+                        }
+                        const uint32_t u16 = (__float_as_uint(ug4[(g & 7) >> 1]) >> (16 * (g & 1))) & 0xffffu;
+                        float inv;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fpool + tot));
+                        const bool hit = (int)(e[0] * inv * 65536.f) > (int)u16 && (fullblk || g < nv);
+                        cnt += hit ? 1.f : 0.f;
+                    } else if (counting) {
                         float u;
                         if (p.uniforms) u = (row_ok && g * P < nv) ? p.uniforms[(size_t)rowid * groups_per_seq + wb * NG + g] : 1.f;
                         else {

@@ -743,10 +743,11 @@ size_t crbm_train_stats_floats(int K, int M) {
     fill_layout(K, M, &l);
     return (size_t)l.total;
 }
-size_t crbm_train_workspace_bytes(int K, int M) {
-    const size_t mma = 3 * partial_floats(K, M), tc = tt_workspace_floats(K, M);
+size_t crbm_train_workspace_bytes_for(int K, int M, int batchsize) {
+    const size_t mma = 3 * partial_floats(K, M), tc = tt_workspace_floats(K, M, batchsize > 0 ? batchsize : 1);
     return (mma > tc ? mma : tc) * sizeof(float) + 256;
 }
+size_t crbm_train_workspace_bytes(int K, int M) { return crbm_train_workspace_bytes_for(K, M, 512); }
 
 int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L, const float *W, const float *b, int K, int M,
                            int pooling, int strand_mode, int out_kind, float *out, long long out_row_stride, void *stream) {
@@ -869,7 +870,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     CRBM_CHECK_ARG(Lh % P == 0, "crbm_train_accumulate: hidden length %d not divisible by pooling %d (truncate as fit() does)", Lh, P);
     CRBM_CHECK_ARG(FANTASY_LEN % P == 0, "crbm_train_accumulate: pooling %d does not divide the fantasy length 200 "
                    "(the reference fails on this reshape too)", P);
-    CRBM_CHECK_ARG(a->workspace_bytes >= crbm_train_workspace_bytes(K, M), "crbm_train_accumulate: workspace too small");
+    CRBM_CHECK_ARG(a->workspace_bytes >= crbm_train_workspace_bytes_for(K, M, a->batchsize), "crbm_train_accumulate: workspace too small (crbm_train_workspace_bytes_for)");
     CRBM_CHECK_ARG(a->data_row_words >= packed_row_words(a->L), "crbm_train_accumulate: data_row_words too small");
     const int Lv = FANTASY_LEN + M - 1;
     CRBM_CHECK_ARG(a->v_row_words >= packed_row_words(Lv), "crbm_train_accumulate: v_row_words too small");

@@ -1,5 +1,6 @@
 // Host side and small kernels of the tcgen05 training path (included by train.cu after the shared update arithmetic):
-//   h2v_lin_kernel        A5 + A6 on the LINEAR chain planes the tcgen05 kernels write (bit = position, word-major, motif contiguous)
+//   h2v_chunk_kernel      A5 on the LINEAR chain planes the tcgen05 kernels write (bit = position, word-major, motif contiguous),
+//   h2v_finish_kernel     per motif chunk with its weights in shared memory; A6 (softmax, sampling) after the chunks are added
 //   reduce_tc_kernel      per-CTA statistics partials -> statistics vector, or -> sparsity factor + momentum update in the same launch
 //   chain <-> dense       conversions for tests / inspection
 //   train_phases_tc       the launch chain of one step
@@ -72,10 +73,11 @@ static TtGeom tt_geom(int K, int M, int P) {
     g.part_floats = tt_part_floats(g.Kdim);
     return g;
 }
-static size_t tt_workspace_floats(int K, int M) {
+static size_t tt_workspace_floats(int K, int M, int batchsize) {
     if (M > 32) return 0;
     const TtGeom g = tt_geom(K, M, 1);
-    return 2 * (size_t)g.n_chunks * g.G * g.part_floats;
+    // two sets of per-CTA statistics partials + the per-chunk visible activities of the chain (h2v_chunk_kernel)
+    return 2 * (size_t)g.n_chunks * g.G * g.part_floats + (size_t)g.n_chunks * batchsize * (32 * ceil_div(FANTASY_LEN + M - 1, 32)) * 4;
 }
 static size_t tt_chain_words(int K, int P) {           // per (strand, particle)
     const int VP = (32 / P) * P;
@@ -92,15 +94,126 @@ static int dispatch_train_tc(int P, int flags, const TrainTcParams &p, dim3 grid
     return CRBM_ERR_UNSUPPORTED;
 }
 
-// ---- A5 + A6 on linear chain planes ---------------------------------------------------------------------------------------
-// Same hit-parallel scheme as h2v_bits_kernel (a work item = 16 visible positions of one particle, shared by `split` warps that deal
-// out the 32-motif tiles; set bits compacted into a warp-private list, consumed four at a time). The planes are
-// uint32 H[strand][n][w][Kpad]: bit b of word w of motif k is hidden position w * VP + b, so a lane reads the word of its motif
-// (32 consecutive motifs = one 128-byte line) and masks it to the positions that reach the item.
-struct H2VLinParams {
+// ---- A5 + A6 on the linear chain planes: motif chunks with the weight slice in shared memory -----------------------------------
+// The planes are uint32 H[strand][n][w][Kpad]: bit b of word w of motif k is hidden position w * VP + b (32 consecutive motifs of one
+// word index = one 128-byte line). The first version walked 16-position items over ALL motifs with the weights in L1/L2 (the scheme
+// of h2v_bits_kernel, train.cu): ncu at K = 512 (profiles/r02_train_tc.md) showed 40.7 M warp instructions for 0.39 M hits, issue
+// slots 68 % busy — bound by the instructions of its per-round bookkeeping (80 rounds per item) and by four scalar weight loads per
+// hit, not by memory. Here a CTA owns a chunk of 64 motifs whose weights sit in shared memory transposed to
+// W4[kl][m] = (W[k,A,m], W[k,C,m], W[k,G,m], W[k,T,m]): a hit costs ONE 16-byte shared-memory load per lane. A work item is 32
+// visible positions of one particle (lane = position, four base accumulators); the lane first acts as "motif lane" and gathers the
+// set bits of all words of both strands and both 32-motif tiles that reach the item in ONE compaction round. The chunk's partial
+// activities go to act_part[chunk][n][i] (float4); h2v_finish_kernel adds the chunks in a fixed order, takes the 4-way softmax and
+// draws the base. Per hit and item: ~12 instructions instead of ~100.
+struct H2VChunkParams {
     const uint32_t *bits;
-    int Bn, K, Kpad, hw, VP, kw, M, ds, words_per_row, split, split_log2;
-    const float *W, *c;
+    int Bn, K, Kpad, hw, VP, M, ds, items_per_row, lv_pad;
+    const float *W;
+    float4 *act_part;          // [n_chunks][Bn][lv_pad]
+};
+constexpr int H2C_WARPS = 8;
+constexpr int H2C_LIST = 1024 + 4;
+
+__global__ void __launch_bounds__(32 * H2C_WARPS) h2v_chunk_kernel(const H2VChunkParams p) {
+    extern __shared__ __align__(128) unsigned char h2c_smem[];
+    float4 *W4 = reinterpret_cast<float4 *>(h2c_smem);                                   // [64][M]
+    uint32_t *lists = reinterpret_cast<uint32_t *>(h2c_smem + (size_t)TT_KC * p.M * 16);
+    const int M = p.M, chunk = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_wait();
+    pdl_launch_dependents();
+    for (int e = threadIdx.x; e < TT_KC * M; e += blockDim.x) {
+        const int kl = e / M, m = e - kl * M, k = chunk * TT_KC + kl;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < p.K) {
+            const float *src = p.W + (size_t)k * 4 * M + m;
+            w = make_float4(__ldg(src), __ldg(src + M), __ldg(src + 2 * M), __ldg(src + 3 * M));
+        }
+        W4[e] = w;
+    }
+    __syncthreads();
+    uint32_t *list = lists + warp * H2C_LIST;
+    const int strands = p.ds ? 2 : 1;
+    const int n_items = p.Bn * p.items_per_row;
+    for (int item = blockIdx.x * H2C_WARPS + warp; item < n_items; item += gridDim.x * H2C_WARPS) {
+        const int n = item / p.items_per_row, w32 = item - n * p.items_per_row;
+        const int i = 32 * w32 + lane;
+        const int jlo = max(0, 32 * w32 - (M - 1)), jhi = min(FANTASY_LEN - 1, 32 * w32 + 31);
+        const int wlo = jlo / p.VP, whi = jhi / p.VP;
+        // this lane as motif lane: its words (strand, tile, word) masked to the hidden positions that reach the item
+        uint32_t wd[12];
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int k = chunk * TT_KC + 32 * t + lane;
+                const uint32_t *plane = p.bits + ((size_t)s * p.Bn + n) * p.hw * p.Kpad + k;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const int wq = wlo + q;
+                    uint32_t word = 0u;
+                    if (s < strands && wq <= whi && k < p.K) {
+                        const int b0 = max(0, jlo - wq * p.VP), b1 = min(31, jhi - wq * p.VP);
+                        const uint32_t mask = (b1 >= 31 ? 0xffffffffu : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
+                        word = __ldg(plane + (size_t)wq * p.Kpad) & mask;
+                    }
+                    wd[(s * 2 + t) * 3 + q] = word;
+                }
+            }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (;;) {
+            // up to 32 hits per lane and pass, so that a pass never exceeds the list (dense chains take several passes)
+            int mine = 0;
+#pragma unroll
+            for (int u = 0; u < 12; ++u) mine += __popc(wd[u]);
+            if (__ballot_sync(0xffffffffu, mine != 0) == 0u) break;
+            const int take = min(mine, 32);
+            int incl = take;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int pos = incl - take, left = take;
+#pragma unroll
+            for (int u = 0; u < 12; ++u) {
+                const int s = u / 6, t = (u / 3) & 1, q = u % 3;
+                const uint32_t tagk = ((uint32_t)s << 15) | ((uint32_t)(32 * t + lane) << 8);
+                const int jbase = (wlo + q) * p.VP;
+                while (wd[u] && left > 0) {
+                    const int b = __ffs(wd[u]) - 1;
+                    wd[u] &= wd[u] - 1;
+                    list[pos++] = tagk | (uint32_t)(jbase + b);
+                    --left;
+                }
+            }
+            if (lane < 4) list[total + lane] = 0xFFu;          // padding entries: position 255 never matches
+            __syncwarp();
+            for (int h0 = 0; h0 < total; h0 += 4) {
+                const uint4 d = *reinterpret_cast<const uint4 *>(list + h0);
+                const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int m = i - (int)(dd[u] & 0xFFu);
+                    const int kl = (dd[u] >> 8) & 63;
+                    const bool rc = (dd[u] >> 15) & 1u;        // warp-uniform
+                    if (m >= 0 && m < M) {
+                        const float4 w = W4[kl * M + (rc ? M - 1 - m : m)];
+                        if (rc) { acc.x += w.w; acc.y += w.z; acc.z += w.y; acc.w += w.x; }      // W[k, 3-a, M-1-m] (convRBM.py:285)
+                        else { acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w; }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        p.act_part[((size_t)chunk * p.Bn + n) * p.lv_pad + i] = acc;
+    }
+}
+
+struct H2VFinishParams {
+    const float4 *act_part;
+    int Bn, n_chunks, lv_pad, Lv;
+    const float *c;
     uint32_t *v_packed;
     int v_row_words;
     const float *u_v;
@@ -108,109 +221,36 @@ struct H2VLinParams {
     uint32_t ctr_hi, iter;
     const unsigned long long *step_dev;
 };
-
-__global__ void __launch_bounds__(512) h2v_lin_kernel(const H2VLinParams p) {
-    extern __shared__ __align__(128) unsigned char h2v_smem[];
-    const int M = p.M, Lv = FANTASY_LEN + M - 1;
+__global__ void __launch_bounds__(256) h2v_finish_kernel(const H2VFinishParams p) {
     pdl_wait();
     pdl_launch_dependents();
-    const int wslot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int part = wslot & (p.split - 1);
-    const int item_raw = wslot >> p.split_log2;
-    const bool live = item_raw < p.Bn * p.words_per_row;
-    const int item = live ? item_raw : 0;
-    const int n = item / p.words_per_row, w = item - n * p.words_per_row, lane = threadIdx.x & 31;
-    const int pidx = lane & 15, ah = lane >> 4;
-    const int i = 16 * w + pidx;
-    const int strands = p.ds ? 2 : 1;
-    const int jlo = max(0, 16 * w - (M - 1)), jhi = min(FANTASY_LEN - 1, 16 * w + 15);
-    const int wlo = jlo / p.VP, whi = jhi / p.VP;
-    float acc0 = 0.f, acc1 = 0.f;
-    uint32_t *list = reinterpret_cast<uint32_t *>(h2v_smem + 16) + (threadIdx.x >> 5) * H2V_LIST;
-    for (int s = 0; s < strands; ++s) {
-        const float *Wbase = s == 0 ? p.W + (size_t)(2 * ah) * M : p.W + (size_t)(3 - 2 * ah) * M;
-        const int dir = s == 0 ? M : -M;
-        for (int t = live ? part : p.kw; t < p.kw; t += p.split) {
-            const int k = 32 * t + lane;
-            const uint32_t *plane = p.bits + ((size_t)s * p.Bn + n) * p.hw * p.Kpad + k;
-            for (int wq = wlo; wq <= whi; ++wq) {
-                uint32_t word = __ldg(plane + (size_t)wq * p.Kpad);
-                const int b0 = max(0, jlo - wq * p.VP), b1 = min(31, jhi - wq * p.VP);      // bits of this word that reach the item
-                const uint32_t mask = (b1 >= 31 ? 0xffffffffu : ((1u << (b1 + 1)) - 1u)) & ~((1u << b0) - 1u);
-                word = (k < p.K) ? (word & mask) : 0u;
-                if (__ballot_sync(0xffffffffu, word != 0u) == 0u) continue;
-                const int cnt = __popc(word);
-                int incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += up;
-                }
-                const int total = __shfl_sync(0xffffffffu, incl, 31);
-                int pos = incl - cnt;
-                const int jbase = wq * p.VP;
-                const int krow = k * 4 * M;
-                while (word) {
-                    const int b = __ffs(word) - 1;
-                    word &= word - 1;
-                    list[pos++] = ((uint32_t)krow << 8) | (uint32_t)(jbase + b);
-                }
-                if (lane < 4) list[total + lane] = 0xFFu;            // padding entries: position 255 never matches
-                __syncwarp();
-                for (int h0 = 0; h0 < total; h0 += 4) {
-                    const uint4 d = *reinterpret_cast<const uint4 *>(list + h0);
-                    const uint32_t dd[4] = {d.x, d.y, d.z, d.w};
-                    float x0[4], x1[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int m = i - (int)(dd[u] & 0xFFu);
-                        const bool ok = m >= 0 && m < M;
-                        const float *wk = Wbase + (dd[u] >> 8) + (s == 0 ? m : M - 1 - m);
-                        x0[u] = ok ? wk[0] : 0.f;
-                        x1[u] = ok ? wk[dir] : 0.f;
-                    }
-                    acc0 += (x0[0] + x0[1]) + (x0[2] + x0[3]);
-                    acc1 += (x1[0] + x1[1]) + (x1[2] + x1[3]);
-                }
-                __syncwarp();
-            }
-        }
-    }
-    if (p.split > 1) {
-        float2 *mine = reinterpret_cast<float2 *>(list);
-        mine[lane] = make_float2(acc0, acc1);
-        __syncthreads();
-        if (part == 0) {
-            for (int o = 1; o < p.split; ++o) {
-                const float2 v = reinterpret_cast<const float2 *>(list + (size_t)o * H2V_LIST)[lane];
-                acc0 += v.x;
-                acc1 += v.y;
-            }
-        }
-    }
-    if (part != 0 || !live) return;
-    const float o0 = __shfl_xor_sync(0xffffffffu, acc0, 16), o1 = __shfl_xor_sync(0xffffffffu, acc1, 16);
-    const bool active = ah == 0 && i < Lv;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = gid / p.lv_pad, i = gid - n * p.lv_pad, lane = threadIdx.x & 31;
     int pick = 0;
-    if (active) {
-        const float v0 = acc0 + __ldg(p.c), v1 = acc1 + __ldg(p.c + 1), v2 = o0 + __ldg(p.c + 2), v3 = o1 + __ldg(p.c + 3);
-        const float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-        const float e0 = __expf(v0 - mx), e1 = __expf(v1 - mx), e2 = __expf(v2 - mx), e3 = __expf(v3 - mx);
+    const bool live = n < p.Bn;
+    if (live && i < p.Lv) {
+        float4 a = make_float4(__ldg(p.c), __ldg(p.c + 1), __ldg(p.c + 2), __ldg(p.c + 3));
+        for (int ch = 0; ch < p.n_chunks; ++ch) {              // fixed order: the sample does not depend on timing
+            const float4 v = p.act_part[((size_t)ch * p.Bn + n) * p.lv_pad + i];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        const float mx = fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w));
+        const float e0 = __expf(a.x - mx), e1 = __expf(a.y - mx), e2 = __expf(a.z - mx), e3 = __expf(a.w - mx);
         const float tot = e0 + e1 + e2 + e3;
         float u;
-        if (p.u_v) u = p.u_v[(size_t)n * Lv + i];
+        if (p.u_v) u = p.u_v[(size_t)n * p.Lv + i];
         else {
             const uint32_t hi = p.ctr_hi + (p.step_dev ? (uint32_t)(*p.step_dev) : 0u);
-            u = u01(philox4x32(make_uint4((uint32_t)(n * Lv + i), 0u, hi, RNG_VISIBLE | (p.iter << 8)),
+            u = u01(philox4x32(make_uint4((uint32_t)(n * p.Lv + i), 0u, hi, RNG_VISIBLE | (p.iter << 8)),
                                make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32))).x);
         }
         const float ut = u * tot;
         pick = (e0 > ut) ? 0 : (e0 + e1 > ut) ? 1 : (e0 + e1 + e2 > ut) ? 2 : 3;
     }
-    uint32_t v = active ? ((uint32_t)pick << (2 * pidx)) : 0u;
+    uint32_t v = (uint32_t)pick << (2 * (lane & 15));
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) p.v_packed[(size_t)n * p.v_row_words + FRONT_PAD_WORDS + w] = v;
+    if (live && (lane & 15) == 0) p.v_packed[(size_t)n * p.v_row_words + FRONT_PAD_WORDS + (i >> 4)] = v;
 }
 
 // ---- statistics partials -> statistics vector / update -----------------------------------------------------------------------
@@ -413,37 +453,36 @@ static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s,
     const int gx_neg = units_neg < g.G ? units_neg : g.G;
     if (phases & CRBM_PHASE_NEGATIVE) {
         const size_t n_u_v = (size_t)a->batchsize * Lv, n_u_h = (size_t)a->batchsize * K * (FANTASY_LEN / P);
-        const int kw = ceil_div(K, 32);
-        const int h2v_items = a->batchsize * ceil_div(Lv, 16);
-        int split_log2 = 0;
-        while (split_log2 < 2 && (4 << split_log2) <= kw && (long long)h2v_items * (2 << split_log2) <= 64ll * num_sms()) ++split_log2;
-        if (const char *e = getenv("CRBM_H2V_SPLIT")) split_log2 = atoi(e) <= 1 ? 0 : atoi(e) == 2 ? 1 : 2;
-        while ((1 << split_log2) > kw) --split_log2;
-        const int h2v_split = 1 << split_log2;
-        const int h2v_slots = h2v_items * h2v_split;
-        int h2v_nw = ceil_div(h2v_slots, num_sms());
-        h2v_nw = h2v_nw < 4 ? 4 : h2v_nw > 16 ? 16 : h2v_nw;
-        h2v_nw = ceil_div(h2v_nw, h2v_split) * h2v_split;
-        const size_t h2v_smem = 16 + (size_t)h2v_nw * H2V_LIST * sizeof(uint32_t);
-        static size_t lin_smem_configured[64];
+        const int items_per_row = ceil_div(Lv, 32), lv_pad = 32 * items_per_row;
+        float4 *act_part = reinterpret_cast<float4 *>(part_neg + (size_t)g.n_chunks * g.G * g.part_floats);
+        CRBM_CHECK_ARG(a->workspace_bytes >= tt_workspace_floats(K, M, a->batchsize) * sizeof(float),
+                       "crbm_train_accumulate: workspace too small for batchsize %d (crbm_train_workspace_bytes_for)", a->batchsize);
+        const size_t h2c_smem = (size_t)TT_KC * M * 16 + (size_t)H2C_WARPS * H2C_LIST * sizeof(uint32_t);
+        static size_t h2c_configured[64];
         int dev_id = 0;
         CRBM_CHECK_CUDA(cudaGetDevice(&dev_id));
-        size_t &configured = lin_smem_configured[dev_id & 63];
-        if (configured < 48 * 1024) configured = 48 * 1024;
-        if (h2v_smem > configured) {
-            CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_lin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h2v_smem));
-            configured = h2v_smem;
+        if (h2c_smem > h2c_configured[dev_id & 63]) {
+            CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h2c_smem));
+            h2c_configured[dev_id & 63] = h2c_smem;
         }
+        const int h2c_items = a->batchsize * items_per_row;
+        int h2c_gx = ceil_div(h2c_items, H2C_WARPS);
+        const int h2c_cap = (3 * num_sms()) / g.n_chunks > 0 ? (3 * num_sms()) / g.n_chunks : 1;
+        if (h2c_gx > h2c_cap) h2c_gx = h2c_cap;
         for (int it = 0; it < a->cd_k; ++it) {
             const bool last = it == a->cd_k - 1;
-            H2VLinParams h{};
-            h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.Kpad = g.Kpad; h.hw = g.hw; h.VP = g.VP; h.kw = kw; h.M = M; h.ds = ds;
-            h.words_per_row = ceil_div(Lv, 16); h.split = h2v_split; h.split_log2 = split_log2;
-            h.W = a->W; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words;
-            h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
-            h.seed = a->seed; h.step_dev = a->step_dev;
-            h.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; h.iter = (uint32_t)it;
-            CRBM_CHECK_CUDA(launch_chain(h2v_lin_kernel, dim3(ceil_div(h2v_slots, h2v_nw)), dim3(32 * h2v_nw), h2v_smem, s, h));
+            H2VChunkParams h{};
+            h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.Kpad = g.Kpad; h.hw = g.hw; h.VP = g.VP; h.M = M; h.ds = ds;
+            h.items_per_row = items_per_row; h.lv_pad = lv_pad; h.W = a->W; h.act_part = act_part;
+            CRBM_CHECK_CUDA(launch_chain(h2v_chunk_kernel, dim3(h2c_gx, g.n_chunks), dim3(32 * H2C_WARPS), h2c_smem, s, h));
+            CRBM_CHECK_LAUNCH();
+            H2VFinishParams f{};
+            f.act_part = act_part; f.Bn = a->batchsize; f.n_chunks = g.n_chunks; f.lv_pad = lv_pad; f.Lv = Lv;
+            f.c = a->c; f.v_packed = a->v_model; f.v_row_words = a->v_row_words;
+            f.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
+            f.seed = a->seed; f.step_dev = a->step_dev;
+            f.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; f.iter = (uint32_t)it;
+            CRBM_CHECK_CUDA(launch_chain(h2v_finish_kernel, dim3(ceil_div(a->batchsize * lv_pad, 256)), dim3(256), 0, s, f));
             CRBM_CHECK_LAUNCH();
 
             TrainTcParams q{};

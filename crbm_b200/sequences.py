@@ -97,6 +97,50 @@ _STREAM_LUT = _CODE_LUT.copy()
 _STREAM_LUT[ord('N')] = _STREAM_LUT[ord('n')] = _N_CODE
 
 
+def _iter_fasta_codes_native(lib, filename, chunk_bytes, quiet):
+    """iterFastaCodes on the one-pass C parser of the library (crbm_fasta_parse_block_host, csrc/api.cu)."""
+    import ctypes
+    carry = b''
+    L0 = ctypes.c_int(0)
+    nrec, nskip, bad = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_int(0)
+    with open(filename, 'rb') as f:
+        while True:
+            block = f.read(chunk_bytes)
+            last = not block
+            buf = carry + block
+            if not buf:
+                return
+            if not last:
+                cut = buf.rfind(b'\n>')                      # the last record of the block may be incomplete: keep it for the next one
+                if cut < 0:
+                    carry = buf
+                    continue
+                buf, carry = buf[:cut + 1], buf[cut + 1:]
+            else:
+                carry = b''
+            # every record needs at least 3 bytes ('>', newline, one base): an upper bound on the records of the block
+            cap = len(buf) // 3 + 1
+            width = L0.value if L0.value > 0 else len(buf)
+            if L0.value > 0:
+                cap = min(cap, len(buf) // (L0.value + 2) + 1)
+            out = np.empty(cap * width if L0.value > 0 else len(buf), dtype=np.uint8)
+            rc = lib.crbm_fasta_parse_block_host(buf, len(buf), out.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(L0),
+                                                 ctypes.byref(nrec), ctypes.byref(nskip), ctypes.byref(bad))
+            if rc == -11:
+                raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
+            if rc == -12:
+                raise KeyError(chr(bad.value))
+            if rc != 0:
+                raise RuntimeError("crbm_fasta_parse_block_host failed (%d)" % rc)
+            if not quiet:
+                for _ in range(int(nskip.value)):
+                    print("skip sequence containing N")
+            if nrec.value:
+                yield out[:nrec.value * L0.value].reshape(int(nrec.value), L0.value)
+            if last:
+                return
+
+
 def iterFastaCodes(filename, chunk_bytes=32 << 20, quiet=False):
     """Streams a multi-FASTA file as (n, L) uint8 base-code arrays (A0 C1 G2 T3, case-insensitive), one per `chunk_bytes` of file,
     without ever holding the file or a per-record Python object: a block of bytes is split into records with NumPy (header lines
@@ -104,6 +148,15 @@ def iterFastaCodes(filename, chunk_bytes=32 << 20, quiet=False):
     Semantics of the reference reader (secomo/sequences.py:33-52, 20-31): records containing N/n are skipped ("skip sequence
     containing N" is printed once per skipped record unless `quiet`), any other non-ACGT letter raises KeyError, and all records
     must have the same length (the reference's one-hot array cannot be built otherwise)."""
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except Exception:                                        # library not built: the NumPy parser below does the same job
+        lib = None
+    if lib is not None:
+        for codes in _iter_fasta_codes_native(lib, filename, chunk_bytes, quiet):
+            yield codes
+        return
     carry = b''
     L0 = None
     with open(filename, 'rb') as f:

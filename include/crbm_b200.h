@@ -159,7 +159,8 @@ typedef struct crbm_train_args {
 } crbm_train_args;
 
 size_t crbm_train_stats_floats(int K, int M);
-size_t crbm_train_workspace_bytes(int K, int M);
+size_t crbm_train_workspace_bytes(int K, int M);                          /* for persistent chains of up to 512 particles */
+size_t crbm_train_workspace_bytes_for(int K, int M, int batchsize);       /* any chain size (args->batchsize) */
 /* positive phase on `data`, cd_k Gibbs sweeps of the persistent chain, statistics -> args->stats (overwritten). */
 int crbm_train_accumulate(const crbm_train_args *args, void *stream);
 /* sparsity factor, momentum update of W,b,c from (all-reduced) args->stats. */
@@ -237,6 +238,15 @@ int    crbm_chain_layout(int K, int M, int pooling);
 size_t crbm_chain_words(int K, int M, int pooling);
 int    crbm_chain_to_dense(const uint32_t *bits, int B, int K, int M, int pooling, float *dense, void *stream);
 int    crbm_chain_from_dense(const float *dense, int B, int K, int M, int pooling, uint32_t *bits, void *stream);
+
+/* ---- A0, host side of the streaming ingest (secomo/sequences.py:33-52 readSeqsFromFasta + :20-31 the base table) ------------
+ * One pass over `n` bytes of COMPLETE multi-FASTA records (HOST pointers): header lines dropped, line ends / blanks inside a
+ * record dropped, letters mapped A0 C1 G2 T3 case-insensitively into codes[record][L]; records containing N/n are skipped and
+ * counted in *n_skipped (the reference prints "skip sequence containing N" for each). *L_io is the record length (0 = not yet
+ * known: taken from the first record). Returns CRBM_OK, -11 if a record's length differs (the reference's one-hot array cannot be
+ * built), -12 for any other letter (*bad_char = the letter; the reference raises KeyError). */
+int crbm_fasta_parse_block_host(const unsigned char *buf_host, size_t n, unsigned char *codes_host, size_t capacity_records,
+                                int *L_io, long long *n_records, long long *n_skipped, int *bad_char);
 
 /* launch counter: number of kernels this library has launched since load (bench.py's `gpu_launches`) */
 unsigned long long crbm_launch_count(void);

@@ -37,6 +37,7 @@ class TrainArgs(ctypes.Structure):
         ('u_v', c_void_p), ('u_h', c_void_p), ('u_hp', c_void_p),
         ('step_dev', c_void_p), ('batch_index_dev', c_void_p), ('n_batches', c_int),
         ('stats', c_void_p), ('workspace', c_void_p), ('workspace_bytes', c_size_t),
+        ('c_trace', c_void_p), ('c_trace_slots', c_int),
     ]
 
 
@@ -89,6 +90,7 @@ SIGNATURES = {
     'crbm_train_apply': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_step': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_phases': (c_int, [ctypes.POINTER(TrainArgs), c_int, c_void_p]),
+    'crbm_train_step_hostfed': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p, c_void_p, c_void_p]),
     'crbm_train_step_onehot': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'crbm_train_accumulate_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
     'crbm_train_apply_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),

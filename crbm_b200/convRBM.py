@@ -568,6 +568,7 @@ class CRBM(object):
         a.u_hp = None if u_hp is None else u_hp.data_ptr()
         a.step_dev, a.batch_index_dev, a.n_batches = None, None, 0
         a.stats, a.workspace, a.workspace_bytes = st['stats'].data_ptr(), st['workspace'].data_ptr(), st['ws_bytes']
+        a.c_trace, a.c_trace_slots = self._trace_args()
         return a
 
     # ---- data parallel: one-shot all-reduce over NVLink peer memory, fused into the update --------------------------------
@@ -867,17 +868,6 @@ class CRBM(object):
         if eng is None or eng['key'] != (n, L):
             eng = self._onehot_engine_for(data, n, L)
         torch = eng['torch']
-        src = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)) if isinstance(data, np.ndarray) else data
-        if src.dtype != torch.float32 or not src.is_contiguous():
-            src = src.to(torch.float32).contiguous()
-        if src.is_cuda:
-            # the library copies `src` on the side stream: order that copy after whatever produced the tensor on the current
-            # stream, and keep its memory from being reused before the copy has run
-            eng['side'].wait_stream(torch.cuda.current_stream(self._device))
-            src.record_stream(eng['side'])
-        # (a pinned HOST tensor is read asynchronously: it must stay unmodified until the step has executed on the device —
-        # after a stream synchronisation, or once a device->host read issued after this call has completed; pageable NumPy
-        # input is copied synchronously by the driver and may be reused at once.)
         a, pa = eng['args'], None
         if self._dp:
             # data parallel: statistics into buffer `parity` of the peer-mapped double buffer, sequence number per step
@@ -888,37 +878,99 @@ class CRBM(object):
             self._dp_seq += 1
         else:
             a.step = self._step
-        # One C call issues the whole step (crbm_train_step_onehot): chain sweeps on the current stream; copy of the batch into
-        # the staging buffer + packing + validation on the side stream, overlapping them; then positive phase, reduction, update.
-        rc = eng['fn'](a, pa, src.data_ptr(), eng['c_staging'], eng['c_bad'], eng['c_side'], eng['c_done'], eng['c_ready'],
-                       torch.cuda.current_stream(self._device).cuda_stream)
-        if rc != _lib.OK:
-            _lib.check(rc, 'train_step_onehot')
+        a.c_trace, a.c_trace_slots = self._trace_args()
+        stream = torch.cuda.current_stream(self._device).cuda_stream
+        if eng['hostfed']:
+            # One C call, one stream, no copy node (crbm_train_step_hostfed): the packing kernel reads the one-hot array where it
+            # lies — device memory, or page-locked host memory over PCIe — while the chain sweeps run.
+            if isinstance(data, np.ndarray) or not (data.is_cuda or data.is_pinned()) or data.dtype != torch.float32 or not data.is_contiguous():
+                # pageable / strided / non-fp32 input: one host-side copy into a ring of page-locked buffers (a slot is reused only
+                # after the step that read it has executed)
+                slot = eng['ring'][eng['ring_pos'] % len(eng['ring'])]
+                eng['ring_pos'] += 1
+                slot['event'].synchronize()
+                src = slot['buf']
+                if isinstance(data, np.ndarray):
+                    np.copyto(slot['np'], data, casting='unsafe')
+                else:
+                    src.copy_(data)
+                rc = eng['fn_hostfed'](a, pa, src.data_ptr(), eng['c_bad'], stream)
+                slot['event'].record()
+            else:
+                # (a pinned HOST tensor or a device tensor is read by the kernels of this step: it must stay unmodified until the
+                # step has executed on the device — after a stream synchronisation, or once a later trace slot has been written)
+                rc = eng['fn_hostfed'](a, pa, data.data_ptr(), eng['c_bad'], stream)
+            if rc != _lib.OK:
+                _lib.check(rc, 'train_step_hostfed')
+        else:
+            src = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)) if isinstance(data, np.ndarray) else data
+            if src.dtype != torch.float32 or not src.is_contiguous():
+                src = src.to(torch.float32).contiguous()
+            if src.is_cuda:
+                # the library copies `src` on the side stream: order that copy after whatever produced the tensor on the current
+                # stream, and keep its memory from being reused before the copy has run
+                eng['side'].wait_stream(torch.cuda.current_stream(self._device))
+                src.record_stream(eng['side'])
+            # CRBM_HOSTFED=copy: the first version of this call (crbm_train_step_onehot): chain sweeps on the current stream; copy of
+            # the batch into a staging buffer + packing + validation on a side stream; then positive phase, reduction, update.
+            rc = eng['fn'](a, pa, src.data_ptr(), eng['c_staging'], eng['c_bad'], eng['c_side'], eng['c_done'], eng['c_ready'], stream)
+            if rc != _lib.OK:
+                _lib.check(rc, 'train_step_onehot')
         eng['pending'] = True
         self._step += 1
 
     def _onehot_engine_for(self, data, n, L):
-        """Persistent buffers, side stream and events of the streamlined one-hot training call for batches of (n, L)."""
+        """Persistent buffers of the streamlined one-hot training call for batches of (n, L)."""
         lib = self._require_cuda()
         torch = _torch()
         if tuple(data.shape[1:3]) != (1, 4):
             raise ValueError("expected one-hot data of shape (N,1,4,L), got %r" % (tuple(data.shape),))
         self._check_deferred()
         rw = lib.crbm_packed_row_words(L)
-        eng = dict(key=(n, L), pending=False, torch=torch, fn=lib.crbm_train_step_onehot, rw=rw)
-        eng['staging'] = torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device)
+        eng = dict(key=(n, L), pending=False, torch=torch, fn=lib.crbm_train_step_onehot, fn_hostfed=lib.crbm_train_step_hostfed, rw=rw)
+        eng['hostfed'] = os.environ.get('CRBM_HOSTFED', 'zerocopy') != 'copy'
         eng['words'] = torch.zeros((n, rw), dtype=torch.int32, device=self._device)
         eng['bad'] = torch.zeros(1, dtype=torch.int32, device=self._device)
         eng['args'] = self._fill_args(eng['words'].data_ptr(), rw, n, L)
-        main = torch.cuda.current_stream(self._device)
-        eng['side'] = torch.cuda.Stream(device=self._device)
-        eng['ready'], eng['done'] = torch.cuda.Event(), torch.cuda.Event()
-        eng['ready'].record(eng['side'])
-        eng['done'].record(main)
-        eng['c_staging'], eng['c_bad'] = eng['staging'].data_ptr(), eng['bad'].data_ptr()
-        eng['c_side'], eng['c_done'], eng['c_ready'] = eng['side'].cuda_stream, eng['done'].cuda_event, eng['ready'].cuda_event
+        eng['c_bad'] = eng['bad'].data_ptr()
+        if eng['hostfed']:
+            eng['ring'], eng['ring_pos'] = [], 0
+            for _ in range(4):
+                buf = torch.empty((n, 1, 4, L), dtype=torch.float32).pin_memory()
+                ev = torch.cuda.Event()
+                ev.record()
+                eng['ring'].append(dict(buf=buf, np=buf.numpy(), event=ev))
+        else:
+            eng['staging'] = torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device)
+            main = torch.cuda.current_stream(self._device)
+            eng['side'] = torch.cuda.Stream(device=self._device)
+            eng['ready'], eng['done'] = torch.cuda.Event(), torch.cuda.Event()
+            eng['ready'].record(eng['side'])
+            eng['done'].record(main)
+            eng['c_staging'] = eng['staging'].data_ptr()
+            eng['c_side'], eng['c_done'], eng['c_ready'] = eng['side'].cuda_stream, eng['done'].cuda_event, eng['ready'].cuda_event
         self._onehot_engine = eng
         return eng
+
+    # ---- per-step trace of the visible bias in page-locked host memory ------------------------------------------------------
+    def traceVisibleBias(self, slots=64):
+        """Have every training step also store the updated visible bias c into slot (step % slots) of a page-locked host
+        array, written by the update kernel itself over PCIe (crbm_train_args.c_trace): a training loop can log c per step
+        without a device->host copy in the stream. Returns the (slots, 4) float32 NumPy view; entries are valid after the next
+        device synchronisation. slots=0 switches the trace off."""
+        torch = _torch()
+        self._require_cuda()
+        if slots <= 0:
+            self._c_trace = None
+            return None
+        t = torch.zeros((int(slots), 4), dtype=torch.float32).pin_memory()
+        self._c_trace = t
+        self._engine = None          # captured graphs hold the old argument block
+        return t.numpy()
+
+    def _trace_args(self):
+        t = getattr(self, '_c_trace', None)
+        return (t.data_ptr(), int(t.shape[0])) if t is not None else (None, 0)
 
     def _evaluateData(self, data, uniforms=None):
         """[mean free energy, mean of a sampled forward-strand H] (reference :466-472, 517-522)."""

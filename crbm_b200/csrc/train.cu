@@ -40,6 +40,7 @@ static int dispatch_fused(int MW, int flags, const V2HParams &p, dim3 grid, cuda
 }
 #define CRBM_FOR_EACH_KS(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9)
 #define CRBM_DECLARE_KS(KSV) template <> int launch_v2h_mma<KSV>(int, const V2HParams &, dim3, cudaStream_t); \
+    template <> int launch_v2h_mma_dual<KSV>(const V2HDualParams &, dim3, cudaStream_t); \
     template <> int launch_v2h_dense_mma<KSV>(const DenseParams &, dim3, cudaStream_t); \
     template <> int launch_v2h_scan_reduce<KSV>(const ScanReduceParams &, cudaStream_t);
 CRBM_FOR_EACH_KS(CRBM_DECLARE_KS)
@@ -52,6 +53,20 @@ static int dispatch_mma(int KS, int flags, const V2HParams &p, dim3 grid, cudaSt
     }
     set_error("MMA k-step bucket %d not built", KS);
     return CRBM_ERR_UNSUPPORTED;
+}
+static int dispatch_mma_dual(int KS, const V2HDualParams &d, dim3 grid, cudaStream_t s) {
+    switch (KS) {
+#define CRBM_CASE(KSV) case KSV: return launch_v2h_mma_dual<KSV>(d, grid, s);
+        CRBM_FOR_EACH_KS(CRBM_CASE)
+#undef CRBM_CASE
+    }
+    set_error("MMA k-step bucket %d not built", KS);
+    return CRBM_ERR_UNSUPPORTED;
+}
+static bool dual_enabled() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CRBM_DUAL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
 }
 static int dispatch_dense_mma(int KS, const DenseParams &p, dim3 grid, cudaStream_t s) {
     switch (KS) {
@@ -260,6 +275,75 @@ __global__ void __launch_bounds__(512) h2v_bits_kernel(const H2VParams p) {
     if (lane == 0) p.v_packed[(size_t)n * p.v_row_words + FRONT_PAD_WORDS + w] = v;
 }
 
+// ---- A0 inside the step: one-hot fp32 minibatch -> packed rows, read where it lies (device memory or mapped host memory) ----------
+// The host-fed training call (crbm_train_step_hostfed) has no staging copy: this kernel reads the caller's (n,1,4,L) fp32 array
+// itself. A warp owns 128 consecutive bases of one sequence: lane l loads the float4 of bases 4l..4l+3 of each of the four channel
+// rows, i.e. every warp-wide load is 512 contiguous bytes (over PCIe: full-size read requests, all of a minibatch in flight at
+// once), turns them into four 2-bit codes, and four lanes assemble one packed word by shuffles. Rows whose length or address is not
+// a multiple of 4 floats take scalar loads. Pad words of the rows are never written (the caller zeroes the buffer once).
+// Programmatic dependent launch: the kernel depends on nothing its predecessors in the step write (the packed rows were last read by
+// the previous step, which had completed before the predecessor could trigger), so it starts while the chain sweeps run and only
+// waits before it exits.
+struct PackRowsParams {
+    const float *src;
+    int n, L, vec;
+    uint32_t *dst;
+    int row_words;
+    int *bad;
+};
+__global__ void __launch_bounds__(256) pack_rows_kernel(const PackRowsParams p) {
+    pdl_launch_dependents();
+    const int segs = ceil_div(p.L, 128);
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (wid < p.n * segs) {
+        const int n = wid / segs, seg = wid - n * segs;
+        const int i0 = 128 * seg + 4 * lane;
+        const float *row = p.src + (size_t)n * 4 * p.L;
+        float v[4][4];
+        if (p.vec && i0 + 4 <= p.L) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const float4 f = __ldcv(reinterpret_cast<const float4 *>(row + (size_t)a * p.L + i0));
+                v[a][0] = f.x; v[a][1] = f.y; v[a][2] = f.z; v[a][3] = f.w;
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) v[a][e] = (i0 + e < p.L) ? __ldcv(row + (size_t)a * p.L + i0 + e) : (a == 0 ? 1.f : 0.f);
+        }
+        uint32_t byte = 0u;
+        int nbad = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = v[0][e], c = v[1][e], g = v[2][e], t = v[3][e];
+            const int ones = (a == 1.f) + (c == 1.f) + (g == 1.f) + (t == 1.f);
+            const int zeros = (a == 0.f) + (c == 0.f) + (g == 0.f) + (t == 0.f);
+            if (ones != 1 || zeros != 3) ++nbad;
+            const uint32_t code = (c == 1.f) ? 1u : (g == 1.f) ? 2u : (t == 1.f) ? 3u : 0u;
+            byte |= ((i0 + e < p.L) ? code : 0u) << (2 * e);
+        }
+        uint32_t word = byte << (8 * (lane & 3));
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        if ((lane & 3) == 0 && i0 < p.L) p.dst[(size_t)n * p.row_words + FRONT_PAD_WORDS + 8 * seg + (lane >> 2)] = word;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nbad += __shfl_xor_sync(0xffffffffu, nbad, o);
+        if (lane == 0 && nbad) atomicAdd(p.bad, nbad);
+    }
+    pdl_wait();
+}
+struct PackJob { const float *src; int *bad; };
+static int launch_pack_job(const PackJob &job, const crbm_train_args *a, cudaStream_t s) {
+    PackRowsParams p{};
+    p.src = job.src; p.n = a->n_data; p.L = a->L; p.dst = const_cast<uint32_t *>(a->data); p.row_words = a->data_row_words; p.bad = job.bad;
+    p.vec = (a->L % 4 == 0 && ((uintptr_t)job.src & 15) == 0) ? 1 : 0;
+    const int warps = a->n_data * ceil_div(a->L, 128);
+    CRBM_CHECK_CUDA(launch_chain(pack_rows_kernel, dim3(ceil_div(warps, 8)), dim3(256), 0, s, p));
+    CRBM_CHECK_LAUNCH();
+    return CRBM_OK;
+}
+
 // ---- per-CTA partial accumulators -> stats ------------------------------------------------------------------------------
 // One launch reduces every partial buffer of the step (positive phase P|Q, optional separate Q, negative phase).
 // One CTA of 128 threads per (set, k-tile, accumulator slot): its four warps each add a quarter of the CTA partials
@@ -410,7 +494,14 @@ struct ApplyParams {
     unsigned long long *step_dev;
     int *batch_index_dev;
     int n_batches;
+    float *c_trace;                // optional per-step trace of c (crbm_train_args::c_trace; may be mapped host memory)
+    int c_trace_slots;
+    unsigned long long step;       // host-side step when step_dev is null
 };
+// Store the updated c[a] into the trace slot of this step (called by the thread that owns c[a], BEFORE the step cursor advances).
+__device__ __forceinline__ void trace_c(const ApplyParams &p, int a, float v, unsigned long long step) {
+    if (p.c_trace) p.c_trace[(size_t)(step % (unsigned long long)p.c_trace_slots) * 4 + a] = v;
+}
 // The update arithmetic, shared by the single-rank and the peer-memory kernel with explicit roundings (no FMA contraction that
 // could differ between the two), so that a one-rank exchange reproduces the plain step bit for bit.
 __device__ __forceinline__ float sparsity_factor(float h_fwd, float nhd, float rho, int K) {
@@ -447,14 +538,18 @@ __global__ void apply_update_kernel(const ApplyParams p) {
             p.vb[k] = v;
             p.b[k] = __fadd_rn(p.b[k], v);
         }
-    } else if (gid < nW + p.K + 4) {
-        const int a = gid - nW - p.K;
-        // f_a + f_{3-a}, convRBM.py:345
-        const float v = next_velocity(p.vc[a], __fadd_rn(st[p.lay.v_data + a], st[p.lay.v_data + 3 - a]), st[p.lay.n_vis_data],
-                                      __fadd_rn(st[p.lay.v_model + a], st[p.lay.v_model + 3 - a]), st[p.lay.n_vis_model], 0.f, p.mu, p.lr, 0.f);
-        p.vc[a] = v;
-        p.c[a] = __fadd_rn(p.c[a], v);
-    } else if (gid == nW + p.K + 4) {
+    } else if (gid == nW + p.K) {
+        // c (4 entries), its trace slot and the cursors of the next step: one thread, so that the trace sees the step before it advances
+        const unsigned long long step = p.step_dev ? *p.step_dev : p.step;
+        for (int a = 0; a < 4; ++a) {
+            // f_a + f_{3-a}, convRBM.py:345
+            const float v = next_velocity(p.vc[a], __fadd_rn(st[p.lay.v_data + a], st[p.lay.v_data + 3 - a]), st[p.lay.n_vis_data],
+                                          __fadd_rn(st[p.lay.v_model + a], st[p.lay.v_model + 3 - a]), st[p.lay.n_vis_model], 0.f, p.mu, p.lr, 0.f);
+            p.vc[a] = v;
+            const float cn = __fadd_rn(p.c[a], v);
+            p.c[a] = cn;
+            trace_c(p, a, cn, step);
+        }
         if (p.step_dev) *p.step_dev += 1ull;
         if (p.batch_index_dev) { const int nb = *p.batch_index_dev + 1; *p.batch_index_dev = nb >= p.n_batches ? 0 : nb; }
     }
@@ -541,7 +636,9 @@ __global__ void __launch_bounds__(512) reduce_update_kernel(const FusedUpdatePar
             const float v = next_velocity(ap.vc[a], __fadd_rn(counts[a], counts[3 - a]), R.c2, __fadd_rn(counts[4 + a], counts[7 - a]), R.c3,
                                           0.f, ap.mu, ap.lr, 0.f);
             ap.vc[a] = v;
-            ap.c[a] = __fadd_rn(ap.c[a], v);
+            const float cn = __fadd_rn(ap.c[a], v);
+            ap.c[a] = cn;
+            trace_c(ap, a, cn, ap.step_dev ? *ap.step_dev : ap.step);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -652,7 +749,9 @@ __global__ void __launch_bounds__(256) apply_update_p2p_kernel(const ApplyP2PPar
         p2p_sums<6>(p, idx, s);
         const float v = next_velocity(ap.vc[a], __fadd_rn(s[2], s[3]), s[0], __fadd_rn(s[4], s[5]), s[1], 0.f, ap.mu, ap.lr, 0.f);
         ap.vc[a] = v;
-        ap.c[a] = __fadd_rn(ap.c[a], v);
+        const float cn = __fadd_rn(ap.c[a], v);
+        ap.c[a] = cn;
+        trace_c(ap, a, cn, ap.step_dev ? *ap.step_dev : ap.step);      // (the cursor advances after every block has finished)
     }
     // the step / minibatch counters are advanced by the last block to finish: every block has read *sequence_dev by then
     __syncthreads();
@@ -718,6 +817,7 @@ static void fill_apply_params(const crbm_train_args *a, ApplyParams *p) {
     p->K = a->K; p->M = a->M; p->ds = a->doublestranded ? 1 : 0;
     p->lr = a->learning_rate; p->mu = a->momentum; p->rho = a->rho; p->lam = a->lambda_rate;
     p->step_dev = a->step_dev; p->batch_index_dev = a->batch_index_dev; p->n_batches = a->n_batches;
+    p->c_trace = a->c_trace_slots > 0 ? a->c_trace : nullptr; p->c_trace_slots = a->c_trace_slots; p->step = a->step;
 }
 static bool fused_update_enabled() {
     static int v = -1;
@@ -860,7 +960,7 @@ int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const 
 // `accumulate` - `accumulate without positive phase` = the positive kernel's stand-alone time.)
 // `phases` selects which part is launched; the partial-sum buffers in the workspace are fixed, so the parts may be issued by
 // separate calls (e.g. the chain sweeps while the next minibatch is still being copied in).
-static int train_phases_impl(const crbm_train_args *a, int phases, void *stream, const crbm_p2p_args *p2p = nullptr) {
+static int train_phases_impl(const crbm_train_args *a, int phases, void *stream, const crbm_p2p_args *p2p = nullptr, const PackJob *pack = nullptr) {
     CRBM_CHECK_ARG(a && a->W && a->b && a->c && a->data && a->fantasy_bits && a->v_model && a->stats && a->workspace,
                    "crbm_train_accumulate: null pointer in args");
     const int K = a->K, M = a->M, P = a->pooling, Lh = a->L - M + 1;
@@ -876,7 +976,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     CRBM_CHECK_ARG(a->v_row_words >= packed_row_words(Lv), "crbm_train_accumulate: v_row_words too small");
     CRBM_CHECK_ARG(((uintptr_t)a->W & 15) == 0, "crbm_train_accumulate: W must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    if (train_uses_tc(K, M, P)) return train_phases_tc(a, phases, s, p2p != nullptr);     // tcgen05 / TMEM path (train_tc.cuh)
+    if (train_uses_tc(K, M, P)) return train_phases_tc(a, phases, s, p2p != nullptr, pack);     // tcgen05 / TMEM path (train_tc.cuh)
     crbm_stats_layout lay;
     fill_layout(K, M, &lay);
     float *st = a->stats;
@@ -895,10 +995,32 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     ReduceParams red{};
     red.ktiles = mma ? ceil_div(K, 16) : ceil_div(K, KTILE);        // tiles of the partial buffers: m-tiles / k-tiles
     red.MW = 3 * ceil_div(M, 3); red.KS = KS; red.mma = mma ? 1 : 0; red.M = M; red.K = K;
-    auto add_set = [&](const float *partial, const Tiling &t, bool has_p, bool has_q) -> ReduceSet & {
+    // two-role launch (v2h_mma_dual_kernel): positive phase and the last chain sweep in one grid
+    Tiling tn = make_tiling(K, M, P, FANTASY_LEN, a->batchsize);
+    Tiling t = make_tiling(K, M, P, Lh, a->n_data);
+    const bool combined = mma ? KS <= 4 : t.MW <= 15;
+    const bool dual = mma && P == 1 && combined && a->n_data > 0 && dual_enabled() &&
+                      (phases & CRBM_PHASE_NEGATIVE) && (phases & CRBM_PHASE_POSITIVE);
+    int gy_pos = mma_gy(K, t.n_items), gy_neg = mma_gy(K, tn.n_items);
+    if (dual) {
+        // ONE wave of CTAs shared by the two roles (two per SM in total). The chain role starts later (it waits for h2v) and both
+        // roles are bound by the latency of a warp's item chain, so the split follows the item counts with the chain role weighted
+        // up. Measured at C2 (42 CTAs per m-tile; us per step): two full waves 42+42: 42.6 (= two launches), 21+21: 46.1,
+        // 28+14: 61.6, 18+24: 42.2, 15+27: 38.9, 14+28: 39.7.
+        const int G = (2 * num_sms()) / ceil_div(K, 16) > 2 ? (2 * num_sms()) / ceil_div(K, 16) : 2;
+        const double wp = (double)t.n_items, wn = 1.6 * (double)tn.n_items;
+        int x = (int)(G * wp / (wp + wn) + 0.5);
+        x = x < G / 4 ? G / 4 : x > (3 * G) / 4 ? (3 * G) / 4 : x;
+        x = x < 1 ? 1 : x;
+        if (x < gy_pos) gy_pos = x;
+        if (G - x < gy_neg) gy_neg = G - x > 0 ? G - x : 1;
+        if (const char *e = getenv("CRBM_DUAL_GY_POS")) { const int v = atoi(e); if (v > 0 && v <= mma_gy(K, t.n_items)) gy_pos = v; }
+        if (const char *e = getenv("CRBM_DUAL_GY_NEG")) { const int v = atoi(e); if (v > 0 && v <= mma_gy(K, tn.n_items)) gy_neg = v; }
+    }
+    auto add_set = [&](const float *partial, const Tiling &t, bool has_p, bool has_q, int gy_mma) -> ReduceSet & {
         ReduceSet &S = red.set[red.nsets];
         const int per = mma ? 8 * KS : 4 * t.MW;
-        S.partial = partial; S.gy = mma ? mma_gy(K, t.n_items) : t.gy;
+        S.partial = partial; S.gy = mma ? gy_mma : t.gy;
         S.np = has_p ? per : 0; S.nq = has_q ? per : 0; S.nacc = S.np + S.nq + (mma ? 6 : 4);
         red.block_start[red.nsets + 1] = red.block_start[red.nsets] + red.ktiles * S.nacc;
         ++red.nsets;
@@ -906,7 +1028,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     };
 
     // ---- negative phase: cd_k Gibbs sweeps of the persistent chain (convRBM.py:391-413) -----------------------------
-    Tiling tn = make_tiling(K, M, P, FANTASY_LEN, a->batchsize);
+    V2HParams q_last{};                  // the last chain sweep's v2h launch, deferred into the two-role launch
     if (phases & CRBM_PHASE_NEGATIVE) {
         const size_t n_u_v = (size_t)a->batchsize * Lv, n_u_h = (size_t)a->batchsize * K * (FANTASY_LEN / P);
         const size_t bits_bytes = (size_t)2 * a->batchsize * kw * FANTASY_WORDS * sizeof(uint32_t);
@@ -961,44 +1083,53 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
             q.seed = a->seed; q.step_dev = a->step_dev;
             q.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; q.iter = (uint32_t)it;
             if (P != 1) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));  // the pooled samplers OR their hits in
-            if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
+            if (last && dual) q_last = q;
+            else if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
         }
     }
 
     // ---- positive phase on the minibatch (convRBM.py:377-388) and the sparsity statistic (:440-451) ----------
-    Tiling t = make_tiling(K, M, P, Lh, a->n_data);
     V2HParams p{};
     p.packed = a->data; p.row_words = a->data_row_words; p.n_rows = a->n_data; p.L = a->L; p.Lh = Lh;
     p.W = a->W; p.b = a->b; p.K = K; p.M = M; p.pooling = P; p.ds = ds;
     p.bv = t.bv; p.nblk = t.nblk; p.n_items = t.n_items;
     p.batch_index = a->batch_index_dev;
     p.pdl_late = 1;
-    const bool combined = mma ? KS <= 4 : t.MW <= 15;
     const bool pos = (phases & CRBM_PHASE_POSITIVE) != 0;
+    if (pack && pos && a->n_data > 0) {
+        // host-fed step: the minibatch is packed here, concurrently with the chain sweeps; the positive phase then reads what its
+        // predecessor wrote and waits for it like every other kernel of the chain
+        if ((rc = launch_pack_job(*pack, a, s))) return rc;
+        p.pdl_late = 0;
+    }
     if (a->n_data == 0) {
         // a data-parallel rank whose shard of a short batch is empty contributes zeros (its statistics are not written below)
         if (phases & CRBM_PHASE_REDUCE) CRBM_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(float) * lay.total, s));
     } else if (combined) {
         p.partial = part0;
-        if (pos && (rc = run_fused(F_STAT_P | F_STAT_Q, p, t))) return rc;
-        ReduceSet &S = add_set(part0, t, true, true);
+        if (dual) {
+            V2HDualParams d{};
+            d.pos = p; d.neg = q_last; d.gy_pos = gy_pos;
+            if ((rc = dispatch_mma_dual(KS, d, dim3(ceil_div(K, 16), gy_pos + gy_neg), s))) return rc;
+        } else if (pos && (rc = run_fused(F_STAT_P | F_STAT_Q, p, t))) return rc;
+        ReduceSet &S = add_set(part0, t, true, true, gy_pos);
         S.vh_p = st + lay.vh_data; S.vh_q = st + lay.vh_q;
         S.h_sum = st + lay.h_data; S.h_fwd = st + lay.h_fwd; S.h_q = st + lay.h_q;
     } else {
         p.partial = part0;
         if (pos && (rc = run_fused(F_STAT_P, p, t))) return rc;
-        ReduceSet &S = add_set(part0, t, true, false);
+        ReduceSet &S = add_set(part0, t, true, false, gy_pos);
         S.vh_p = st + lay.vh_data; S.h_sum = st + lay.h_data; S.h_fwd = st + lay.h_fwd;
         p.partial = part2;
         p.ds = 0;                                   // the sparsity statistic uses the forward strand only (convRBM.py:443)
         if (pos && (rc = run_fused(F_STAT_Q, p, t))) return rc;
-        ReduceSet &Sq = add_set(part2, t, false, true);
+        ReduceSet &Sq = add_set(part2, t, false, true, gy_pos);
         Sq.vh_q = st + lay.vh_q; Sq.h_q = st + lay.h_q;
     }
 
     // ---- per-CTA partial sums of both phases -> statistics vector ---------------------------------------------------------
     if (phases & CRBM_PHASE_REDUCE) {
-        ReduceSet &Sn = add_set(part1, tn, true, false);
+        ReduceSet &Sn = add_set(part1, tn, true, false, gy_neg);
         Sn.vh_p = st + lay.vh_model; Sn.h_sum = st + lay.h_model;
         red.counts = st + lay.n_hidden_data;
         red.c0 = (float)a->n_data * Lh; red.c1 = (float)a->batchsize * FANTASY_LEN;
@@ -1062,6 +1193,21 @@ int crbm_train_step_onehot(const crbm_train_args *a, const crbm_p2p_args *p2p, c
     return CRBM_OK;
 }
 
+int crbm_train_step_hostfed(const crbm_train_args *a, const crbm_p2p_args *p2p, const float *onehot, int *bad_count, void *stream) {
+    CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc && onehot && bad_count, "crbm_train_step_hostfed: null argument");
+    CRBM_CHECK_ARG(a->n_data > 0 && !a->batch_index_dev, "crbm_train_step_hostfed: needs a non-empty minibatch addressed directly");
+    PackJob job{onehot, bad_count};
+    const int all = CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE;
+    if (p2p) {
+        CRBM_CHECK_ARG(p2p->n_ranks > 0 && p2p->n_ranks <= CRBM_MAX_PEERS && p2p->rank >= 0 && p2p->rank < p2p->n_ranks && p2p->ticket &&
+                       (p2p->parity == 0 || p2p->parity == 1), "crbm_train_step_hostfed: bad p2p arguments");
+        int rc = train_phases_impl(a, all, stream, p2p, &job);
+        if (!rc) rc = crbm_train_apply_p2p(a, p2p, stream);
+        return rc;
+    }
+    return train_phases_impl(a, all | CRBM_PHASE_APPLY, stream, nullptr, &job);
+}
+
 int crbm_train_accumulate(const crbm_train_args *a, void *stream) {
     return train_phases_impl(a, CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE, stream);
 }
@@ -1085,6 +1231,7 @@ int crbm_train_apply_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, voi
     ap.K = a->K; ap.M = a->M; ap.ds = a->doublestranded ? 1 : 0;
     ap.lr = a->learning_rate; ap.mu = a->momentum; ap.rho = a->rho; ap.lam = a->lambda_rate;
     ap.step_dev = a->step_dev; ap.batch_index_dev = a->batch_index_dev; ap.n_batches = a->n_batches;
+    ap.c_trace = a->c_trace_slots > 0 ? a->c_trace : nullptr; ap.c_trace_slots = a->c_trace_slots; ap.step = a->step;
     p.n_ranks = p2p->n_ranks; p.parity = p2p->parity;
     for (int r = 0; r < p2p->n_ranks; ++r) p.peer_stats[r] = p2p->peer_stats[r];
     p.local_flags = p2p->peer_flags[p2p->rank];
@@ -1134,7 +1281,7 @@ int crbm_train_apply(const crbm_train_args *a, void *stream) {
     CRBM_CHECK_ARG(a && a->W && a->b && a->c && a->vW && a->vb && a->vc && a->stats, "crbm_train_apply: null pointer in args");
     ApplyParams p{};
     fill_apply_params(a, &p);
-    const int n = a->K * 4 * a->M + a->K + 5;
+    const int n = a->K * 4 * a->M + a->K + 1;
     CRBM_CHECK_CUDA(launch_chain(apply_update_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, (cudaStream_t)stream, p));
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;

@@ -381,7 +381,9 @@ __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) 
                 const float v = next_velocity(ap.vc[a], __fadd_rn(counts[a], counts[3 - a]), p.c2, __fadd_rn(counts[4 + a], counts[7 - a]), p.c3,
                                               0.f, ap.mu, ap.lr, 0.f);
                 ap.vc[a] = v;
-                ap.c[a] = __fadd_rn(ap.c[a], v);
+                const float cn = __fadd_rn(ap.c[a], v);
+                ap.c[a] = cn;
+                trace_c(ap, a, cn, ap.step_dev ? *ap.step_dev : ap.step);
             }
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -426,7 +428,7 @@ __global__ void chain_dense_to_lin_kernel(const float *__restrict__ dense, int B
 // ---- one training step on the tcgen05 kernels -----------------------------------------------------------------------------------
 //     h2v_lin -> v2h_train_tc<SAMPLE> [x cd_k, the last one with the model statistics] -> v2h_train_tc<P|Q> (minibatch) -> reduce_tc
 // the same chain of programmatic dependents as the mma.sync path (train.cu), two partial buffers in the workspace.
-static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s, bool p2p) {
+static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s, bool p2p, const PackJob *pack = nullptr) {
     const int K = a->K, M = a->M, P = a->pooling, Lh = a->L - M + 1;
     const TtGeom g = tt_geom(K, M, P);
     const int ds = a->doublestranded ? 1 : 0;
@@ -508,6 +510,10 @@ static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s,
         t.nblk32 = nb_pos; t.n_units = units_pos;
         t.partial = part_pos;
         t.pdl_late = 1;
+        if (pack) {             // host-fed step: see train_phases_impl
+            if ((rc = launch_pack_job(*pack, a, s))) return rc;
+            t.pdl_late = 0;
+        }
         if ((rc = dispatch_train_tc(P, F_STAT_P | F_STAT_Q, t, dim3(gx_pos, g.n_chunks), s))) return rc;
     }
     // ---- reduction (+ update) -----------------------------------------------------------------------------------------------------

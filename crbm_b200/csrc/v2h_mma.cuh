@@ -185,18 +185,19 @@ __device__ __forceinline__ float fast_sigmoid(float x) {
 // grid (m-tiles of 16 motifs, CTAs), 256 threads, two CTAs per SM: every warp owns the CTA's m-tile for a stream of
 // 16-position blocks. (ncu on the first version with 32-motif warps: 254 registers, 8 warps/SM, one wave of 4.05 blocks
 // per warp on average but 5 at most; 16-motif warps need <= 128 registers, and m-tiles beyond K are not launched.)
+// The body is shared by the single-role kernel and by the two-role kernel below: `mtile` is the CTA's m-tile, `by` / `gy` its index
+// and the number of CTAs among those that walk the same item stream (blockIdx.y / gridDim.y in the single-role kernel).
 template <int KS, int FLAGS, bool POOL>
-__global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
+__device__ __forceinline__ void v2h_mma_body(const V2HParams &p, unsigned char *smem, const int mtile, const int by, const int gy) {
     using Sh = MmaShape<KS>;
     using Ac = MmaAcc<KS, FLAGS>;
     constexpr int NT2 = Sh::NT2;
     constexpr bool STAT_P = FLAGS & F_STAT_P, STAT_Q = FLAGS & F_STAT_Q, SAMPLE = FLAGS & F_SAMPLE;
-    extern __shared__ __align__(128) unsigned char smem[];
     uint32_t *wimg = reinterpret_cast<uint32_t *>(smem);
     float *wtile = reinterpret_cast<float *>(smem + Sh::wimg_bytes);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + Sh::wimg_bytes + Sh::wtile_bytes);
 
-    const int mtile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int g = lane >> 2, q = lane & 3;
     build_w_fragments<KS>(wimg, wtile, bar, p.W, p.K, p.M, mtile);
     const uint4 *wfrag = reinterpret_cast<const uint4 *>(wimg) + lane;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
     // waits before it exits, so that "this grid has completed" still implies "everything before it has".
     if (!p.pdl_late) pdl_wait();
     pdl_launch_dependents();
-    for (int item = blockIdx.y * nwarps + warp; item < p.n_items; item += gridDim.y * nwarps) {
+    for (int item = by * nwarps + warp; item < p.n_items; item += gy * nwarps) {
         const int n = item / p.nblk, jb = item - n * p.nblk, j0 = POOL ? jb * p.bv : jb * 16;
         const uint32_t *row = packed + (size_t)n * p.row_words + (j0 >> 4);     // word holding bases j0-16 .. j0-1 (j0 % 16 == 0)
         uint32_t wd[5];                                                        // wd[i]: bases j0-16+16i .. j0-1+16i
@@ -597,11 +598,34 @@ __global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
             __syncthreads();
         }
         if (warp == 0) {
-            float *dst = p.partial + ((size_t)(mtile * gridDim.y + blockIdx.y) * NACC) * 32 + lane;
+            float *dst = p.partial + ((size_t)(mtile * gy + by) * NACC) * 32 + lane;
             visit([&](int o, float &v) { dst[o * 32] = v; });
         }
     }
     if (p.pdl_late) pdl_wait();
+}
+
+template <int KS, int FLAGS, bool POOL>
+__global__ void __launch_bounds__(256, 2) v2h_mma_kernel(const V2HParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    v2h_mma_body<KS, FLAGS, POOL>(p, smem, blockIdx.x, blockIdx.y, gridDim.y);
+}
+
+// Two roles in ONE grid (un-pooled, motif_length <= 16, the last chain sweep of a step): the CTAs with blockIdx.y < gy_pos run the
+// positive phase on the minibatch (P and Q statistics), the others the chain sweep (sampling + model statistics). The positive
+// phase depends on nothing in flight, so its CTAs — dispatched first — start while the predecessor (h2v of the chain) is still
+// running and share the SMs with it; the chain CTAs block in griddepcontrol.wait until h2v has completed. One launch boundary,
+// one prologue / ramp / tail per step less than two back-to-back single-role launches (C2: 42 -> ~35 us per step), and the h2v
+// kernel (latency bound, few registers) no longer has the GPU to itself.
+struct V2HDualParams {
+    V2HParams pos, neg;
+    int gy_pos;
+};
+template <int KS>
+__global__ void __launch_bounds__(256, 2) v2h_mma_dual_kernel(const V2HDualParams d) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    if ((int)blockIdx.y < d.gy_pos) v2h_mma_body<KS, F_STAT_P | F_STAT_Q, false>(d.pos, smem, blockIdx.x, blockIdx.y, d.gy_pos);
+    else v2h_mma_body<KS, F_STAT_P | F_SAMPLE, false>(d.neg, smem, blockIdx.x, blockIdx.y - d.gy_pos, gridDim.y - d.gy_pos);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -864,6 +888,7 @@ __global__ void __launch_bounds__(256, 3) v2h_scan_reduce_kernel(const ScanReduc
 }
 
 template <int KS> int launch_v2h_mma(int flags, const V2HParams &p, dim3 grid, cudaStream_t stream);
+template <int KS> int launch_v2h_mma_dual(const V2HDualParams &d, dim3 grid, cudaStream_t stream);
 template <int KS> int launch_v2h_scan_reduce(const ScanReduceParams &p, cudaStream_t stream);
 template <int KS> int launch_v2h_dense_mma(const DenseParams &p, dim3 grid, cudaStream_t stream);
 

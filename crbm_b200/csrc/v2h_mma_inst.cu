@@ -41,6 +41,26 @@ int launch_v2h_mma<CRBM_KS>(int flags, const V2HParams &p, dim3 grid, cudaStream
 }
 
 template <>
+int launch_v2h_mma_dual<CRBM_KS>(const V2HDualParams &d, dim3 grid, cudaStream_t stream) {
+#if CRBM_KS <= 4
+    static bool configured = false;
+    constexpr size_t sa = mma_smem_bytes<CRBM_KS, F_STAT_P | F_STAT_Q>(), sb = mma_smem_bytes<CRBM_KS, F_STAT_P | F_SAMPLE>();
+    constexpr size_t smem = sa > sb ? sa : sb;
+    if (!configured) {
+        CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_mma_dual_kernel<CRBM_KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    CRBM_CHECK_CUDA(launch_chain(v2h_mma_dual_kernel<CRBM_KS>, grid, dim3(256), smem, stream, d));
+    CRBM_CHECK_LAUNCH();
+    return CRBM_OK;
+#else
+    (void)d; (void)grid; (void)stream;
+    set_error("v2h_mma_dual<KS=%d>: the two-role kernel is built for motif_length <= 16", CRBM_KS);
+    return CRBM_ERR_UNSUPPORTED;
+#endif
+}
+
+template <>
 int launch_v2h_dense_mma<CRBM_KS>(const DenseParams &p, dim3 grid, cudaStream_t stream) {
     static bool configured = false;
     constexpr size_t smem = MmaShape<CRBM_KS>::smem_bytes + 8 * MTILE * 34 * sizeof(float);

@@ -156,6 +156,13 @@ typedef struct crbm_train_args {
     float *stats;                  /* crbm_train_stats_floats(K,M) un-normalised sums; all-reduced (sum) across ranks */
     void  *workspace;              /* crbm_train_workspace_bytes(...) bytes of scratch */
     size_t workspace_bytes;
+    /* optional per-step trace of the visible bias (what a training loop that logs a metric reads back after theano_trainingFct,
+     * convRBM.py:524-526): if c_trace != NULL the update kernel also stores the updated c (4 floats) into slot (step % c_trace_slots)
+     * of c_trace, `step` being the Philox step of the update (args->step or *step_dev). c_trace may be page-locked host memory
+     * mapped into the device's address space: the result then crosses PCIe as part of the update kernel and the host reads it
+     * after its next synchronisation without a copy node in the stream. */
+    float *c_trace;
+    int c_trace_slots;
 } crbm_train_args;
 
 size_t crbm_train_stats_floats(int K, int M);
@@ -186,6 +193,15 @@ int crbm_train_phases(const crbm_train_args *args, int phases, void *stream);
  * (data parallel, see below) the minibatch is this rank's shard, args->stats points at buffer `parity`, and the last two phases
  * are crbm_train_accumulate_p2p's publishing reduction and crbm_train_apply_p2p. Returns without synchronising. */
 struct crbm_p2p_args;
+/* The same call without a staging copy, side stream or events: `onehot` ((n_data,1,4,L) fp32) is read by the packing kernel itself,
+ * so it must be DEVICE-ACCESSIBLE — device memory, or page-locked host memory mapped into the device's address space (cudaHostAlloc /
+ * cudaHostRegister under unified addressing; pass the device-side alias cudaHostGetDevicePointer returns). Every kernel of the step is
+ * a programmatic dependent of its predecessor on ONE stream:
+ *     h2v, v2h (chain sweeps)  ->  pack (reads `onehot` over PCIe while the sweeps run; 512-byte coalesced reads)  ->  positive phase
+ *     ->  reduction  ->  update
+ * The buffer behind `onehot` must stay unmodified until the step has executed. *bad_count accumulates the number of positions that
+ * are not one-hot. With c_trace set (above) a whole host-fed step needs no stream operation besides its kernels. */
+int crbm_train_step_hostfed(const crbm_train_args *args, const struct crbm_p2p_args *p2p, const float *onehot, int *bad_count, void *stream);
 int crbm_train_step_onehot(const crbm_train_args *args, const struct crbm_p2p_args *p2p, const float *host_onehot, float *staging,
                            int *bad_count, void *copy_stream, void *consumed_event, void *ready_event, void *stream);
 

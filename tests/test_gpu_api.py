@@ -292,6 +292,71 @@ def test_streamlined_onehot_step_equals_packed_step_and_validates(data):
         m.motifs.get_value()
 
 
+@pytest.mark.parametrize('kind', ['numpy', 'pinned', 'cuda', 'strided', 'copy'])
+@pytest.mark.parametrize('L', [200, 197])
+def test_hostfed_step_reads_the_batch_where_it_lies(data, kind, L, monkeypatch):
+    """crbm_train_step_hostfed: the packing kernel inside the step reads the one-hot minibatch from page-locked host memory
+    (zero copy), from device memory, or from the ring of pinned buffers pageable / strided input is copied into; lengths that are
+    not a multiple of four floats take the scalar loads. Same parameters as the explicit packed path, bit for bit. `copy` is
+    the older staging-copy call (CRBM_HOSTFED=copy)."""
+    import torch
+    import crbm_b200
+    from crbm_b200 import CRBM
+    if kind == 'copy':
+        monkeypatch.setenv('CRBM_HOSTFED', 'copy')
+    d = np.ascontiguousarray(data[:120, :, :, :L])
+    out = []
+    for fast in (True, False):
+        np.random.seed(3)
+        m = CRBM(num_motifs=12, motif_length=9, cd_k=1, seed=5, batchsize=20)
+        keep = []
+        for i in range(6):
+            batch = d[20 * i:20 * (i + 1)]
+            if not fast:
+                m._train_packed(crbm_b200.PackedSequences.from_onehot(batch), 0, 20)
+                continue
+            if kind == 'pinned':
+                src = torch.from_numpy(batch.copy()).pin_memory()
+            elif kind == 'cuda':
+                src = torch.from_numpy(batch.copy()).cuda()
+            elif kind == 'strided':
+                src = torch.from_numpy(np.repeat(batch, 2, axis=3))[:, :, :, ::2]
+                assert not src.is_contiguous()
+            else:
+                src = batch
+            keep.append(src)                  # pinned / device input must stay alive and unmodified until the step has run
+            m._trainingFct(src)
+        out.append((m.motifs.get_value(), m.bias.get_value(), m.c.get_value(), m.fantasy_h.get_value()))
+    for a, b in zip(*out):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_visible_bias_trace_in_pinned_host_memory(data):
+    """crbm_train_args.c_trace: every update kernel (host-fed eager step, packed eager step, graph replay) stores the step's c into
+    slot step % slots of a page-locked host array."""
+    import torch
+    import crbm_b200
+    from crbm_b200 import CRBM
+    np.random.seed(3)
+    m = CRBM(num_motifs=12, motif_length=9, cd_k=1, seed=5, batchsize=20)
+    trace = m.traceVisibleBias(8)
+    seen = []
+    for i in range(3):
+        m._trainingFct(data[20 * i:20 * (i + 1)])
+        seen.append(m.c.get_value().ravel().copy())
+    seqs = crbm_b200.PackedSequences.from_onehot(data[:200])
+    m._train_packed(seqs, 60, 80)
+    seen.append(m.c.get_value().ravel().copy())
+    torch.cuda.synchronize()
+    for i in range(4):
+        np.testing.assert_array_equal(trace[i], seen[i])
+    m._train_full_batches(seqs, 0, 10)                  # steps 4..13 by graph replay: slots 6, 7, 0..5 are rewritten
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(trace[13 % 8], m.c.get_value().ravel())
+    assert len({tuple(r) for r in trace}) == 8
+    assert m.traceVisibleBias(0) is None
+
+
 def test_streamed_fasta_ingest_matches_host_packing(tmp_path):
     """PackedSequences.from_fasta streams blocks through pinned staging buffers and packs on the device: same rows as packing the
     record reader's codes, for block sizes that split the file many times."""

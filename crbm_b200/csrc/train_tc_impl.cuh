@@ -7,6 +7,7 @@
 #pragma once
 #include "train_tc.cuh"
 #include "scan_rt.cuh"
+#include "h2v_tc.cuh"
 
 namespace crbm {
 
@@ -76,8 +77,16 @@ static TtGeom tt_geom(int K, int M, int P) {
 static size_t tt_workspace_floats(int K, int M, int batchsize) {
     if (M > 32) return 0;
     const TtGeom g = tt_geom(K, M, 1);
-    // two sets of per-CTA statistics partials + the per-chunk visible activities of the chain (h2v_chunk_kernel)
-    return 2 * (size_t)g.n_chunks * g.G * g.part_floats + (size_t)g.n_chunks * batchsize * (32 * ceil_div(FANTASY_LEN + M - 1, 32)) * 4;
+    // two sets of per-CTA statistics partials + the per-chunk visible activities of the chain (h2v_chunk_kernel) + the weight image
+    // of the dense h2v GEMM (h2v_tc.cuh: 2 strands x Kpad / 64 k-chunks of 32 KB)
+    return 2 * (size_t)g.n_chunks * g.G * g.part_floats + (size_t)g.n_chunks * batchsize * (32 * ceil_div(FANTASY_LEN + M - 1, 32)) * 4 +
+           (size_t)2 * g.n_chunks * (2 * HT_A_BYTES / 4);
+}
+// h2v of the tcgen05 path: dense GEMM on the tensor cores (h2v_tc.cuh) or the sparse walk over the set bits (h2v_chunk_kernel)
+static bool h2v_uses_tc(int kk) {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CRBM_H2V_KERNEL"); v = !e ? 2 : e[0] == 'c' ? 0 : e[0] == 't' ? 1 : 2; }
+    return v == 1 || (v == 2 && kk >= 512);
 }
 static size_t tt_chain_words(int K, int P) {           // per (strand, particle)
     const int VP = (32 / P) * P;
@@ -471,8 +480,35 @@ static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s,
         int h2c_gx = ceil_div(h2c_items, H2C_WARPS);
         const int h2c_cap = (3 * num_sms()) / g.n_chunks > 0 ? (3 * num_sms()) / g.n_chunks : 1;
         if (h2c_gx > h2c_cap) h2c_gx = h2c_cap;
+        // dense above 512 contraction columns (strands x Kpad): measured C4 (1024 columns) 886 -> 551 us per step; below, a particle is
+        // a handful of MMAs and the sparse walk is faster (C3, 256 columns: 98 us per step against 107). CRBM_H2V_KERNEL=chunk|tc overrides.
+        const bool h2v_dense = h2v_uses_tc((ds ? 2 : 1) * g.Kpad);
+        unsigned char *a_img = reinterpret_cast<unsigned char *>(act_part + (size_t)g.n_chunks * a->batchsize * lv_pad);
+        const int nkc = (ds ? 2 : 1) * g.n_chunks;
+        if (h2v_dense) {
+            // the weight image of the step's h2v GEMMs (W does not change between the sweeps of a step)
+            static size_t ht_configured[64];
+            if (ht_smem_bytes() > ht_configured[dev_id & 63]) {
+                CRBM_CHECK_CUDA(cudaFuncSetAttribute(h2v_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ht_smem_bytes()));
+                ht_configured[dev_id & 63] = ht_smem_bytes();
+            }
+            H2VPrepParams pp{a->W, K, g.Kpad, M, nkc, a_img};
+            CRBM_CHECK_CUDA(launch_chain(h2v_prep_kernel, dim3(ceil_div(nkc * 1024, 256)), dim3(256), 0, s, pp));
+            CRBM_CHECK_LAUNCH();
+        }
         for (int it = 0; it < a->cd_k; ++it) {
             const bool last = it == a->cd_k - 1;
+            if (h2v_dense) {
+                H2VTcParams h{};
+                h.a_img = a_img; h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.Kpad = g.Kpad; h.hw = g.hw; h.VP = g.VP;
+                h.M = M; h.nkc = nkc; h.c = a->c; h.v_packed = a->v_model; h.v_row_words = a->v_row_words; h.Lv = Lv;
+                h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
+                h.seed = a->seed; h.step_dev = a->step_dev;
+                h.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; h.iter = (uint32_t)it;
+                const int gx = a->batchsize < num_sms() ? a->batchsize : num_sms();
+                CRBM_CHECK_CUDA(launch_chain(h2v_tc_kernel, dim3(gx), dim3(HT_THREADS), ht_smem_bytes(), s, h));
+                CRBM_CHECK_LAUNCH();
+            } else {
             H2VChunkParams h{};
             h.bits = a->fantasy_bits; h.Bn = a->batchsize; h.K = K; h.Kpad = g.Kpad; h.hw = g.hw; h.VP = g.VP; h.M = M; h.ds = ds;
             h.items_per_row = items_per_row; h.lv_pad = lv_pad; h.W = a->W; h.act_part = act_part;
@@ -486,6 +522,7 @@ static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s,
             f.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; f.iter = (uint32_t)it;
             CRBM_CHECK_CUDA(launch_chain(h2v_finish_kernel, dim3(ceil_div(a->batchsize * lv_pad, 256)), dim3(256), 0, s, f));
             CRBM_CHECK_LAUNCH();
+            }
 
             TrainTcParams q{};
             base_params(q);

@@ -1272,6 +1272,12 @@ int crbm_chain_from_dense(const float *dense, int B, int K, int M, int pooling, 
     return CRBM_OK;
 }
 
+// debugging aid (not part of the ABI in include/crbm_b200.h): clock64() marks of CTA 0 of the last h2v_tc_kernel launch (CRBM_H2V_DEBUG=1)
+int crbm_debug_h2v_timeline(long long *host16) {
+    CRBM_CHECK_CUDA(cudaMemcpyFromSymbol(host16, g_h2v_timeline, 16 * sizeof(long long)));
+    return CRBM_OK;
+}
+
 int crbm_train_step(const crbm_train_args *a, void *stream) {
     CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc, "crbm_train_step: null pointer in args");
     return train_phases_impl(a, CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE | CRBM_PHASE_APPLY, stream);

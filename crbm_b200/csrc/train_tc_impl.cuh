@@ -505,8 +505,13 @@ static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s,
                 h.u_v = a->u_v ? a->u_v + it * n_u_v : nullptr;
                 h.seed = a->seed; h.step_dev = a->step_dev;
                 h.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; h.iter = (uint32_t)it;
-                const int gx = a->batchsize < num_sms() ? a->batchsize : num_sms();
-                CRBM_CHECK_CUDA(launch_chain(h2v_tc_kernel, dim3(gx), dim3(HT_THREADS), ht_smem_bytes(), s, h));
+                static const int cl_env = [] { const char *e = getenv("CRBM_H2V_CLUSTER"); const int v = e ? atoi(e) : 4; return v == 1 || v == 2 || v == 4 ? v : 4; }();
+                h.cl = cl_env;
+                static const int dbg_env = [] { const char *e = getenv("CRBM_H2V_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
+                h.dbg = dbg_env;
+                const int groups = ceil_div(a->batchsize, h.cl), max_clusters = num_sms() / h.cl;
+                const int gx = (groups < max_clusters ? groups : max_clusters) * h.cl;
+                CRBM_CHECK_CUDA(launch_h2v_tc(h, gx, s));
                 CRBM_CHECK_LAUNCH();
             } else {
             H2VChunkParams h{};

@@ -8,7 +8,7 @@ There is no CPU fallback: anything that computes raises if no CUDA device / libr
 Differences a caller can observe (all documented in DESIGN.md):
   * random numbers come from Philox, not MRG31k3p (same distributions; `seed=` keyword added, default clock like :155);
   * exp() is evaluated with the group maximum subtracted, so results stay finite where the reference overflows;
-  * motif_length <= 33 and pooling <= 16 (NotImplementedError beyond), input_dims must be 4 to compute;
+  * any motif_length / pooling (beyond 33 / 16 on slower shape-generic kernels); input_dims must be 4 to compute;
   * `fit`/`motifHitProbs`/`freeEnergy` also accept a GPU-resident `PackedSequences` (2 bit/base);
   * under torch.distributed (one process per GPU) `fit` is data-parallel: every minibatch and the persistent chain
     are sharded across ranks and one all-reduce of the statistics vector per step keeps all replicas identical.

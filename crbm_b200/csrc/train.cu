@@ -6,6 +6,7 @@
 //   apply_update        A11 sparsity factor + A12 momentum update of W, b, c
 #include <stdlib.h>
 #include "v2h_mma.cuh"
+#include "generic.cuh"
 
 namespace crbm {
 
@@ -99,8 +100,33 @@ static int dispatch_dense(int MW, const DenseParams &p, dim3 grid, cudaStream_t 
 static int check_shape(const char *who, int K, int M, int pooling, int Lh) {
     CRBM_CHECK_ARG(K > 0 && M > 0 && pooling > 0, "%s: K, M, pooling must be positive", who);
     CRBM_CHECK_ARG(Lh > 0, "%s: sequences shorter than the motif", who);
-    if (M > CRBM_MAX_MOTIF_LEN) { set_error("%s: motif_length %d > %d is not covered by the sm_100a kernels", who, M, CRBM_MAX_MOTIF_LEN); return CRBM_ERR_UNSUPPORTED; }
-    if (pooling > CRBM_MAX_POOLING) { set_error("%s: pooling %d > %d is not covered by the sm_100a kernels", who, pooling, CRBM_MAX_POOLING); return CRBM_ERR_UNSUPPORTED; }
+    return CRBM_OK;
+}
+// motif_length > CRBM_MAX_MOTIF_LEN or pooling > CRBM_MAX_POOLING: the shape-generic kernels (generic.cuh). CRBM_GENERIC=1 sends
+// every shape there (tests compare them with the fixtures of the tuned kernels).
+static bool shape_is_generic(int M, int P) {
+    static int force = -1;
+    if (force < 0) { const char *e = getenv("CRBM_GENERIC"); force = (e && e[0] == '1') ? 1 : 0; }
+    return force == 1 || M > CRBM_MAX_MOTIF_LEN || P > CRBM_MAX_POOLING;
+}
+static int launch_gen_v2h(const GenParams &g, cudaStream_t s) {
+    const size_t smem = (size_t)8 * g.M * sizeof(float);
+    static size_t configured[64];
+    int dev_id = 0;
+    CRBM_CHECK_CUDA(cudaGetDevice(&dev_id));
+    if (smem > 48 * 1024 && smem > configured[dev_id & 63]) {
+        CRBM_CHECK_CUDA(cudaFuncSetAttribute(gen_v2h_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev_id & 63] = smem;
+    }
+    const bool per_row = g.mode == GEN_REDUCE || g.mode == GEN_FE;
+    const bool prob = g.mode != GEN_DENSE && g.mode != GEN_REDUCE ? true : g.out_kind == CRBM_OUT_PROBABILITY;
+    const long long items = per_row ? g.n_rows : (long long)g.n_rows * (g.Lh / (prob ? g.P : 1));
+    long long gy = (items + 255) / 256;
+    const long long cap = (8ll * num_sms()) / g.K + 1;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    gen_v2h_kernel<<<dim3(g.K, (unsigned)gy), 256, smem, s>>>(g);
+    CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }
 
@@ -109,7 +135,7 @@ static Tiling make_tiling(int K, int M, int pooling, int Lh, int n_rows) {
     Tiling t;
     t.MW = 3 * ceil_div(M, 3);
     t.ktiles = ceil_div(K, KTILE);
-    t.bv = (BLOCK_POS / pooling) * pooling;
+    t.bv = pooling <= BLOCK_POS ? (BLOCK_POS / pooling) * pooling : pooling;      // (pooling > 16 runs on the shape-generic kernels)
     t.nblk = ceil_div(Lh, t.bv);
     t.n_items = n_rows * t.nblk;
     const int per_tile = num_sms() / t.ktiles > 0 ? num_sms() / t.ktiles : 1;
@@ -845,7 +871,10 @@ size_t crbm_train_stats_floats(int K, int M) {
 }
 size_t crbm_train_workspace_bytes_for(int K, int M, int batchsize) {
     const size_t mma = 3 * partial_floats(K, M), tc = tt_workspace_floats(K, M, batchsize > 0 ? batchsize : 1);
-    return (mma > tc ? mma : tc) * sizeof(float) + 256;
+    // shape-generic path: three probability buffers for a chunk of rows (all particles of the chain; minibatch rows in chunks)
+    const size_t gen = M > CRBM_MAX_MOTIF_LEN ? (size_t)3 * K * (batchsize > 0 ? batchsize : 1) * 1024 : 0;
+    const size_t m2 = mma > tc ? mma : tc;
+    return (m2 > gen ? m2 : gen) * sizeof(float) + 256;
 }
 size_t crbm_train_workspace_bytes(int K, int M) { return crbm_train_workspace_bytes_for(K, M, 512); }
 
@@ -863,6 +892,12 @@ int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L, 
     if (out_kind == CRBM_OUT_PROBABILITY)
         CRBM_CHECK_ARG(Lh % pooling == 0, "crbm_v2h_dense: hidden length %d not divisible by pooling %d", Lh, pooling);
     else pool = 1;
+    if (shape_is_generic(M, pool)) {
+        GenParams g{};
+        g.packed = packed; g.row_words = row_words; g.n_rows = N; g.L = L; g.Lh = Lh; g.W = W; g.b = b; g.K = K; g.M = M; g.P = pool;
+        g.mode = GEN_DENSE; g.strand_mode = strand_mode; g.out_kind = out_kind; g.out = out; g.out_row_stride = out_row_stride;
+        return launch_gen_v2h(g, (cudaStream_t)stream);
+    }
     Tiling t = make_tiling(K, M, pool, Lh, N);
     DenseParams p{packed, row_words, N, L, Lh, W, b, K, M, pool, strand_mode, out_kind, t.bv, t.nblk, t.n_items, out};
     if ((pool == 1 || pool_uses_mma()) && scan_uses_tcgen05()) return launch_v2h_dense_tc(p, out_row_stride, (cudaStream_t)stream);
@@ -897,6 +932,13 @@ int crbm_scan_reduce(const uint32_t *packed, int row_words, int N, int L, const 
         CRBM_CHECK_ARG(Lh % pooling == 0, "crbm_scan_reduce: hidden length %d not divisible by pooling %d", Lh, pooling);
         pool = pooling;
     }
+    if (shape_is_generic(M, pool)) {
+        GenParams g{};
+        g.packed = packed; g.row_words = row_words; g.n_rows = N; g.L = L; g.Lh = Lh; g.W = W; g.b = b; g.K = K; g.M = M; g.P = pool;
+        g.mode = GEN_REDUCE; g.strand_mode = strand_mode; g.out_kind = out_kind;
+        g.out_max = out_max; g.out_argmax = out_argmax; g.out_mean = out_mean;
+        return launch_gen_v2h(g, (cudaStream_t)stream);
+    }
     if (rows_uses_tc(M, pool)) {
         // tcgen05 / TMEM kernel with the motif on the TMEM lane: the reductions over positions are register operations (scan_rt.cuh)
         RowsTcParams r{};
@@ -925,6 +967,17 @@ int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const 
     if (fe_seq) CRBM_CHECK_CUDA(cudaMemsetAsync(fe_seq, 0, sizeof(float) * N, s));
     if (fe_motif) CRBM_CHECK_CUDA(cudaMemsetAsync(fe_motif, 0, sizeof(float) * (size_t)N * K, s));
     if (hsample_count) CRBM_CHECK_CUDA(cudaMemsetAsync(hsample_count, 0, sizeof(float) * N, s));
+    if (shape_is_generic(M, pooling)) {
+        GenParams g{};
+        g.packed = packed; g.row_words = row_words; g.n_rows = N; g.L = L; g.Lh = Lh; g.W = W; g.b = b; g.K = K; g.M = M; g.P = pooling;
+        g.mode = GEN_FE; g.ds = doublestranded ? 1 : 0; g.fe_motif = fe_motif; g.fe_seq = fe_seq; g.count = hsample_count;
+        g.u_fwd = uniforms; g.seed = seed; g.ctr_hi = (uint32_t)offset;
+        rc = launch_gen_v2h(g, s);
+        if (rc) return rc;
+        fe_finish_kernel<<<N, 128, 0, s>>>(packed, row_words, N, L, K, c, fe_seq, fe_motif);
+        CRBM_CHECK_LAUNCH();
+        return CRBM_OK;
+    }
     if (rows_uses_tc(M, pooling)) {
         RowsTcParams r{};
         r.packed = packed; r.row_words = row_words; r.n_rows = N; r.L = L; r.Lh = Lh;
@@ -960,6 +1013,60 @@ int crbm_free_energy(const uint32_t *packed, int row_words, int N, int L, const 
 // `accumulate` - `accumulate without positive phase` = the positive kernel's stand-alone time.)
 // `phases` selects which part is launched; the partial-sum buffers in the workspace are fixed, so the parts may be issued by
 // separate calls (e.g. the chain sweeps while the next minibatch is still being copied in).
+// ---- shape-generic training (generic.cuh): probabilities of a chunk of rows -> statistics, chunk by chunk -------------------------
+struct GenCountParams {
+    const uint32_t *rows[2];
+    int row_words[2], n[2], L[2];
+    const int *batch_index;
+    float *out[2], *scalars;
+    float c0, c1, c2, c3;
+};
+__global__ void __launch_bounds__(256) gen_counts_kernel(const GenCountParams p) {
+    const int w = blockIdx.x;
+    const uint32_t *rows = p.rows[w];
+    if (w == 0 && p.batch_index) rows += (size_t)(*p.batch_index) * p.n[0] * p.row_words[0];
+    if (p.n[w] > 0) count_bases_block(rows, p.row_words[w], p.n[w], p.L[w], p.out[w]);
+    else if (threadIdx.x < 4) p.out[w][threadIdx.x] = 0.f;
+    if (w == 0 && threadIdx.x == 0) { p.scalars[0] = p.c0; p.scalars[1] = p.c1; p.scalars[2] = p.c2; p.scalars[3] = p.c3; }
+}
+// v2h over `n_rows` rows (the chain: sampling into the bit planes; the minibatch: P and Q), in chunks that fit the workspace, and —
+// when `want_stats` — the statistics of every chunk added into vh_p / vh_q / h_* in chunk order.
+static int gen_train_rows(const crbm_train_args *a, const uint32_t *rows, int row_words, int n_rows, int L, int Lh, const int *batch_index,
+                          int batch_rows, int sample, int iter, bool want_stats, bool want_q, float *vh_p, float *vh_q, float *h_sum,
+                          float *h_fwd, float *h_q, cudaStream_t s) {
+    const int K = a->K, M = a->M;
+    const size_t ws_floats = (a->workspace_bytes - 256) / sizeof(float);
+    const size_t per_row = (size_t)K * Lh;
+    const size_t max_rows = ws_floats / (3 * per_row);
+    if (max_rows < 1) { set_error("shape-generic training: workspace too small for one row of %d x %d probabilities", K, Lh); return CRBM_ERR_ARG; }
+    float *pf = reinterpret_cast<float *>(a->workspace);
+    float *pr = pf + max_rows * per_row, *q = pr + max_rows * per_row;
+    const size_t n_u = (size_t)n_rows * K * (Lh / a->pooling);
+    int rc;
+    for (int r0 = 0, chunk = 0; r0 < n_rows; r0 += (int)max_rows, ++chunk) {
+        const int nr = (int)(n_rows - r0 < (long long)max_rows ? n_rows - r0 : max_rows);
+        GenParams g{};
+        g.packed = rows; g.row_words = row_words; g.n_rows = nr; g.L = L; g.Lh = Lh; g.row0 = r0;
+        g.batch_index = batch_index; g.batch_rows = batch_rows;
+        g.W = a->W; g.b = a->b; g.K = K; g.M = M; g.P = a->pooling; g.ds = a->doublestranded ? 1 : 0; g.mode = GEN_TRAIN;
+        g.pf = pf; g.pr = g.ds ? pr : nullptr; g.q = want_q ? q : nullptr;
+        g.sample = sample; g.bits = a->fantasy_bits; g.chain_rows = a->batchsize; g.ktiles = ceil_div(K, 32);
+        g.u_fwd = (sample && a->u_h) ? a->u_h + iter * n_u : nullptr;
+        g.u_rc = (sample && a->u_hp) ? a->u_hp + iter * n_u : nullptr;
+        g.seed = a->seed; g.step_dev = a->step_dev; g.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; g.iter = (uint32_t)iter;
+        if ((rc = launch_gen_v2h(g, s))) return rc;
+        if (!want_stats) continue;
+        GenStatsParams t{};
+        t.packed = rows; t.row_words = row_words; t.n_rows = nr; t.Lh = Lh; t.row0 = r0; t.batch_index = batch_index; t.batch_rows = batch_rows;
+        t.K = K; t.M = M; t.accumulate = chunk > 0 ? 1 : 0;
+        t.pf = pf; t.pr = g.pr; t.q = g.q; t.vh_p = vh_p; t.vh_q = vh_q; t.h_sum = h_sum; t.h_fwd = h_fwd; t.h_q = h_q;
+        const int warps = K * 4 * M + K;
+        gen_stats_kernel<<<ceil_div(warps, 8), 256, 0, s>>>(t);
+        CRBM_CHECK_LAUNCH();
+    }
+    return CRBM_OK;
+}
+
 static int train_phases_impl(const crbm_train_args *a, int phases, void *stream, const crbm_p2p_args *p2p = nullptr, const PackJob *pack = nullptr) {
     CRBM_CHECK_ARG(a && a->W && a->b && a->c && a->data && a->fantasy_bits && a->v_model && a->stats && a->workspace,
                    "crbm_train_accumulate: null pointer in args");
@@ -976,7 +1083,8 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     CRBM_CHECK_ARG(a->v_row_words >= packed_row_words(Lv), "crbm_train_accumulate: v_row_words too small");
     CRBM_CHECK_ARG(((uintptr_t)a->W & 15) == 0, "crbm_train_accumulate: W must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
-    if (train_uses_tc(K, M, P)) return train_phases_tc(a, phases, s, p2p != nullptr, pack);     // tcgen05 / TMEM path (train_tc.cuh)
+    const bool gen = shape_is_generic(M, P);                                                    // generic.cuh
+    if (!gen && train_uses_tc(K, M, P)) return train_phases_tc(a, phases, s, p2p != nullptr, pack);     // tcgen05 / TMEM path (train_tc.cuh)
     crbm_stats_layout lay;
     fill_layout(K, M, &lay);
     float *st = a->stats;
@@ -999,7 +1107,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     Tiling tn = make_tiling(K, M, P, FANTASY_LEN, a->batchsize);
     Tiling t = make_tiling(K, M, P, Lh, a->n_data);
     const bool combined = mma ? KS <= 4 : t.MW <= 15;
-    const bool dual = mma && P == 1 && combined && a->n_data > 0 && dual_enabled() &&
+    const bool dual = !gen && mma && P == 1 && combined && a->n_data > 0 && dual_enabled() &&
                       (phases & CRBM_PHASE_NEGATIVE) && (phases & CRBM_PHASE_POSITIVE);
     int gy_pos = mma_gy(K, t.n_items), gy_neg = mma_gy(K, tn.n_items);
     if (dual) {
@@ -1082,7 +1190,12 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
             q.u_rc = a->u_hp ? a->u_hp + it * n_u_h : nullptr;
             q.seed = a->seed; q.step_dev = a->step_dev;
             q.ctr_hi = a->step_dev ? 0u : (uint32_t)a->step; q.iter = (uint32_t)it;
-            if (P != 1) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));  // the pooled samplers OR their hits in
+            if (P != 1 || gen) CRBM_CHECK_CUDA(cudaMemsetAsync(a->fantasy_bits, 0, bits_bytes, s));  // the pooled / generic samplers OR their hits in
+            if (gen) {
+                if ((rc = gen_train_rows(a, a->v_model, a->v_row_words, a->batchsize, Lv, FANTASY_LEN, nullptr, 0, /*sample*/ 1, it,
+                                         last, false, st + lay.vh_model, nullptr, st + lay.h_model, nullptr, nullptr, s))) return rc;
+                continue;
+            }
             if (last && dual) q_last = q;
             else if ((rc = run_fused(last ? (F_STAT_P | F_SAMPLE) : F_SAMPLE, q, tn))) return rc;
         }
@@ -1104,7 +1217,20 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     }
     if (a->n_data == 0) {
         // a data-parallel rank whose shard of a short batch is empty contributes zeros (its statistics are not written below)
-        if (phases & CRBM_PHASE_REDUCE) CRBM_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(float) * lay.total, s));
+        if (gen) {
+            // (the generic path writes its statistics directly: only the minibatch's share is zeroed, the model's was written above)
+            if (phases & CRBM_PHASE_POSITIVE) {
+                const size_t nW = (size_t)K * 4 * M;
+                CRBM_CHECK_CUDA(cudaMemsetAsync(st + lay.vh_data, 0, sizeof(float) * nW, s));
+                CRBM_CHECK_CUDA(cudaMemsetAsync(st + lay.vh_q, 0, sizeof(float) * nW, s));
+                CRBM_CHECK_CUDA(cudaMemsetAsync(st + lay.h_data, 0, sizeof(float) * K, s));
+                CRBM_CHECK_CUDA(cudaMemsetAsync(st + lay.h_q, 0, sizeof(float) * K, s));
+                CRBM_CHECK_CUDA(cudaMemsetAsync(st + lay.h_fwd, 0, sizeof(float) * K, s));
+            }
+        } else if (phases & CRBM_PHASE_REDUCE) CRBM_CHECK_CUDA(cudaMemsetAsync(st, 0, sizeof(float) * lay.total, s));
+    } else if (gen) {
+        if (pos && (rc = gen_train_rows(a, a->data, a->data_row_words, a->n_data, a->L, Lh, a->batch_index_dev, a->n_data, 0, 0, true, true,
+                                        st + lay.vh_data, st + lay.vh_q, st + lay.h_data, st + lay.h_fwd, st + lay.h_q, s))) return rc;
     } else if (combined) {
         p.partial = part0;
         if (dual) {
@@ -1128,6 +1254,20 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     }
 
     // ---- per-CTA partial sums of both phases -> statistics vector ---------------------------------------------------------
+    if (gen) {
+        if (phases & CRBM_PHASE_REDUCE) {
+            GenCountParams c{};
+            c.rows[0] = a->data; c.row_words[0] = a->data_row_words; c.n[0] = a->n_data; c.L[0] = a->L;
+            c.rows[1] = a->v_model; c.row_words[1] = a->v_row_words; c.n[1] = a->batchsize; c.L[1] = Lv;
+            c.batch_index = a->batch_index_dev;
+            c.out[0] = st + lay.v_data; c.out[1] = st + lay.v_model; c.scalars = st + lay.n_hidden_data;
+            c.c0 = (float)a->n_data * Lh; c.c1 = (float)a->batchsize * FANTASY_LEN; c.c2 = (float)a->n_data * a->L; c.c3 = (float)a->batchsize * Lv;
+            gen_counts_kernel<<<2, 256, 0, s>>>(c);
+            CRBM_CHECK_LAUNCH();
+        }
+        if (phases & CRBM_PHASE_APPLY) return crbm_train_apply(a, stream);
+        return CRBM_OK;
+    }
     if (phases & CRBM_PHASE_REDUCE) {
         ReduceSet &Sn = add_set(part1, tn, true, false, gy_neg);
         Sn.vh_p = st + lay.vh_model; Sn.h_sum = st + lay.h_model;

@@ -56,7 +56,7 @@ static int launch_rows_tc(int mode, int P, RowsTcParams &p, cudaStream_t s) {
 static bool train_uses_tc(int K, int M, int P) {
     static int v = -1;
     if (v < 0) { const char *e = getenv("CRBM_TRAIN_KERNEL"); v = !e ? 2 : e[0] == 'm' ? 0 : e[0] == 't' ? 1 : 2; }
-    if (M > 32 || !tt_pool_built(P) || v == 0) return false;
+    if (M > 32 || !tt_pool_built(P) || v == 0 || shape_is_generic(M, P)) return false;
     return v == 1 || P > 1 || (long long)K * M >= 2048;
 }
 

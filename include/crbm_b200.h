@@ -34,10 +34,13 @@ extern "C" {
 
 #define CRBM_OK                0
 #define CRBM_ERR_ARG          -1   /* invalid argument (shape, null pointer, ...) */
-#define CRBM_ERR_UNSUPPORTED  -2   /* valid for the reference but outside what the kernels cover (M>33, P>16) */
+#define CRBM_ERR_UNSUPPORTED  -2   /* valid for the reference but not built (a variant that was compiled out) */
 #define CRBM_ERR_CUDA         -3   /* a CUDA runtime call failed */
 
 #define CRBM_FANTASY_LEN     200   /* convRBM.py:168: hidden length of the persistent chain */
+/* Largest shapes of the TUNED kernels (tensor-core and register-blocked paths). They are not limits of the library: longer motifs
+ * and larger pooling factors run on the shape-generic kernels (csrc/generic.cuh), like the reference, which has no limit
+ * (convRBM.py:68-108). */
 #define CRBM_MAX_MOTIF_LEN    33
 #define CRBM_MAX_POOLING      16
 

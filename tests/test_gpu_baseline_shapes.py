@@ -94,6 +94,8 @@ SHAPES = [
     (512, 25, 1, 500, True, 2, 3, 12),       # C4 bank, short minibatch against a larger persistent chain
     (128, 20, 5, 999, False, 2, 3, 3),       # C3 bank, single stranded, CD-2
     (100, 15, 1, 200, True, 1, 20, 20),      # C2
+    (24, 50, 1, 300, True, 2, 5, 5),         # motif_length 50: beyond the tuned kernels -> shape-generic kernels (csrc/generic.cuh)
+    (12, 40, 20, 259, False, 1, 4, 6),       # pooling 20 (and motif_length 40), single stranded
 ]
 
 
@@ -134,7 +136,7 @@ def test_gradient_terms_match_oracle(crbm, O, K, M, P, L, ds, cd_k, N, bs):
         assert np.mean(v != want['v_model']) < 1e-3
 
 
-@pytest.mark.parametrize('K,M,P,L,ds,cd_k,N,bs', SHAPES[:4])
+@pytest.mark.parametrize('K,M,P,L,ds,cd_k,N,bs', SHAPES[:4] + SHAPES[5:])
 def test_train_steps_match_oracle_baseline_shapes(crbm, O, K, M, P, L, ds, cd_k, N, bs):
     """Two whole steps (parameters, velocities, persistent chain) at the C3 / C4 shapes."""
     rs = np.random.RandomState(7 * K + M + P + cd_k)
@@ -173,7 +175,8 @@ def test_train_steps_match_oracle_baseline_shapes(crbm, O, K, M, P, L, ds, cd_k,
 
 # ---- C5: the 512 x 25 scan, both getHitProbs branches, dense and fused ------------------------------------------------------
 @pytest.mark.parametrize('K,M,P,L,ds', [(512, 25, 1, 500, True), (512, 25, 1, 500, False), (512, 25, 4, 500, False),
-                                        (128, 20, 5, 999, True), (100, 15, 1, 200, False)])
+                                        (128, 20, 5, 999, True), (100, 15, 1, 200, False),
+                                        (24, 50, 1, 300, True), (12, 40, 20, 259, False), (10, 64, 8, 327, True)])
 def test_scan_c5_both_strand_modes(crbm, O, K, M, P, L, ds):
     rs = np.random.RandomState(K + M + P + int(ds))
     N = 3
@@ -225,5 +228,20 @@ def test_small_shapes_on_the_tcgen05_training_path():
     r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', os.path.join(root, 'tests', 'test_gpu_parity.py'),
                         os.path.join(root, 'tests', 'test_gpu_api.py'), '-k', 'train or step or graph or phase or chain or fantasy'],
                        capture_output=True, text=True, timeout=900, cwd=root, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert ' passed' in r.stdout
+
+
+def test_shape_generic_kernels_pass_the_parity_suite():
+    """The shape-generic kernels (csrc/generic.cuh: any motif_length, any pooling factor) forced onto the small shapes of the
+    parity suite (CRBM_GENERIC=1, read once per process: subprocess): fixtures, oracle, graph replay == eager, phases, loop-back."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CRBM_GENERIC='1')
+    r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', os.path.join(root, 'tests', 'test_gpu_parity.py'),
+                        os.path.join(root, 'tests', 'test_gpu_api.py')],
+                       capture_output=True, text=True, timeout=1200, cwd=root, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert ' passed' in r.stdout

@@ -472,9 +472,10 @@ def bench_ingest(ctx, Lt):
 
 def bench_e2e_train(ctx, model, B, Lt, steps):
     """Through the reference-facing call with HOST buffers, every step: `CRBM._trainingFct(one-hot fp32 minibatch in page-locked host
-    memory)` — the step's packing kernel reads the batch over PCIe (crbm_train_step_hostfed: zero copy, 16 B per nucleotide cross the
-    bus inside the timed region) — and the updated visible bias c (16 bytes) comes back device -> host every step, written by the
-    update kernel into a ring of page-locked slots (CRBM.traceVisibleBias).
+    memory)` — the call enqueues the host -> device copy of the batch (16 B per nucleotide) on the copy engine into a ring of staging
+    buffers and the step's kernels on the compute stream, whose packing kernel waits for the copy's flag (crbm_train_step_staged) — and
+    the updated visible bias c (16 bytes) comes back device -> host every step, written by the update kernel into a ring of page-locked
+    slots (CRBM.traceVisibleBias).
     `value`: the host consumes the ring after a stream synchronisation every `ring` steps, so it keeps issuing steps while the
     device works — the way a training loop that logs a metric runs.
     `blocking_read_value`: the host waits for every step's result before it issues the next step."""
@@ -521,9 +522,10 @@ def bench_e2e_train(ctx, model, B, Lt, steps):
     assert np.all(np.isfinite(sink))
     return {'value': value, 'unit': 'nt/s', 'h2d_bytes_per_step': B * 4 * Lt * 4, 'd2h_bytes_per_step': 16, 'steps': steps,
             'blocking_read_value': blocking,
-            'call': 'CRBM._trainingFct(one-hot fp32 batch in pinned host memory, read over PCIe by the packing kernel of the step) + c of '
-                    'every step written device -> host by the update kernel into a pinned ring (consumed after a stream synchronisation '
-                    'every %d steps; blocking_read_value: the host waits for every step before issuing the next)' % ring}
+            'call': 'CRBM._trainingFct(one-hot fp32 batch in pinned host memory; copied host -> device by the copy engine inside the call, '
+                    'the packing kernel of the step waits for its flag) + c of every step written device -> host by the update kernel into '
+                    'a pinned ring (consumed after a stream synchronisation every %d steps; blocking_read_value: the host waits for every '
+                    'step before issuing the next)' % ring}
 
 
 def bench_e2e_scan(ctx, model, K, M, Lt):

@@ -91,6 +91,7 @@ SIGNATURES = {
     'crbm_train_step': (c_int, [ctypes.POINTER(TrainArgs), c_void_p]),
     'crbm_train_phases': (c_int, [ctypes.POINTER(TrainArgs), c_int, c_void_p]),
     'crbm_train_step_hostfed': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p, c_void_p, c_void_p]),
+    'crbm_train_step_staged': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'crbm_train_step_onehot': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'crbm_train_accumulate_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
     'crbm_train_apply_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),

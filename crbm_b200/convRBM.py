@@ -881,9 +881,38 @@ class CRBM(object):
         a.c_trace, a.c_trace_slots = self._trace_args()
         stream = torch.cuda.current_stream(self._device).cuda_stream
         if eng['hostfed']:
+            on_device = (not isinstance(data, np.ndarray)) and data.is_cuda and data.dtype == torch.float32 and data.is_contiguous()
+            if eng['staged'] and not on_device:
+                # crbm_train_step_staged: the batch crosses PCIe on the copy engine AHEAD of the step (ring of device staging
+                # buffers, one per step in flight; the step's packing kernel waits for a flag the copy engine writes). Nothing
+                # but kernels on the compute stream; a host that runs ahead of the device hides the transfer.
+                i = eng['staged_pos']
+                eng['staged_pos'] = i + 1
+                R = len(eng['stage'])
+                slot = i % R
+                if i >= R and i % eng['gate_every'] == 0:
+                    # the event recorded after step i - R + 3: the slots of steps i .. i + 3 are free
+                    eng['gate_events'][((i - R + 4) // eng['gate_every']) % len(eng['gate_events'])].synchronize()
+                if isinstance(data, np.ndarray) or not data.is_pinned() or data.dtype != torch.float32 or not data.is_contiguous():
+                    hb = eng['ring'][slot]
+                    if isinstance(data, np.ndarray):
+                        np.copyto(hb['np'], data, casting='unsafe')
+                    else:
+                        hb['buf'].copy_(data)
+                    src_ptr = hb['buf'].data_ptr()
+                else:
+                    src_ptr = data.data_ptr()
+                eng['seq_np'][slot] = (i + 1) & 0x7fffffff
+                rc = eng['fn_staged'](a, pa, src_ptr, eng['stage'][slot].data_ptr(), eng['flags_ptr'] + 4 * slot, eng['seq_ptr'] + 4 * slot,
+                                      eng['c_bad'], eng['c_side'], stream)
+                if rc != _lib.OK:
+                    _lib.check(rc, 'train_step_staged')
+                if (i + 1) % eng['gate_every'] == 0:
+                    # recorded every few steps: the slot of step i is reused R steps later, after this event has been waited for
+                    eng['gate_events'][((i + 1) // eng['gate_every']) % len(eng['gate_events'])].record()
             # One C call, one stream, no copy node (crbm_train_step_hostfed): the packing kernel reads the one-hot array where it
             # lies — device memory, or page-locked host memory over PCIe — while the chain sweeps run.
-            if isinstance(data, np.ndarray) or not (data.is_cuda or data.is_pinned()) or data.dtype != torch.float32 or not data.is_contiguous():
+            elif isinstance(data, np.ndarray) or not (data.is_cuda or data.is_pinned()) or data.dtype != torch.float32 or not data.is_contiguous():
                 # pageable / strided / non-fp32 input: one host-side copy into a ring of page-locked buffers (a slot is reused only
                 # after the step that read it has executed)
                 slot = eng['ring'][eng['ring_pos'] % len(eng['ring'])]
@@ -928,18 +957,33 @@ class CRBM(object):
         self._check_deferred()
         rw = lib.crbm_packed_row_words(L)
         eng = dict(key=(n, L), pending=False, torch=torch, fn=lib.crbm_train_step_onehot, fn_hostfed=lib.crbm_train_step_hostfed, rw=rw)
-        eng['hostfed'] = os.environ.get('CRBM_HOSTFED', 'zerocopy') != 'copy'
+        mode = os.environ.get('CRBM_HOSTFED', 'staged')
+        eng['hostfed'] = mode != 'copy'
+        eng['staged'] = mode == 'staged'
+        eng['fn_staged'] = lib.crbm_train_step_staged
         eng['words'] = torch.zeros((n, rw), dtype=torch.int32, device=self._device)
         eng['bad'] = torch.zeros(1, dtype=torch.int32, device=self._device)
         eng['args'] = self._fill_args(eng['words'].data_ptr(), rw, n, L)
         eng['c_bad'] = eng['bad'].data_ptr()
         if eng['hostfed']:
+            R = 8 if eng['staged'] else 4
             eng['ring'], eng['ring_pos'] = [], 0
-            for _ in range(4):
+            for _ in range(R):
                 buf = torch.empty((n, 1, 4, L), dtype=torch.float32).pin_memory()
                 ev = torch.cuda.Event()
                 ev.record()
                 eng['ring'].append(dict(buf=buf, np=buf.numpy(), event=ev))
+            if eng['staged']:
+                eng['stage'] = [torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device) for _ in range(R)]
+                eng['flags'] = torch.zeros(R, dtype=torch.int32, device=self._device)
+                eng['seq'] = torch.zeros(R, dtype=torch.int32).pin_memory()
+                eng['seq_np'] = eng['seq'].numpy()
+                eng['flags_ptr'], eng['seq_ptr'] = eng['flags'].data_ptr(), eng['seq'].data_ptr()
+                eng['staged_pos'], eng['gate_every'] = 0, 4
+                eng['gate_events'] = [torch.cuda.Event() for _ in range(2 * R // 4 + 2)]
+                eng['side'] = torch.cuda.Stream(device=self._device)
+                eng['c_side'] = eng['side'].cuda_stream
+                torch.cuda.synchronize(self._device)
         else:
             eng['staging'] = torch.empty((n, 1, 4, L), dtype=torch.float32, device=self._device)
             main = torch.cuda.current_stream(self._device)

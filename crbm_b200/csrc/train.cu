@@ -316,9 +316,28 @@ struct PackRowsParams {
     uint32_t *dst;
     int row_words;
     int *bad;
+    const unsigned int *ready_flag;      // staged variant: src is a device buffer a DMA copy fills; wait until *ready_flag == ready_value
+    unsigned int ready_value;
 };
 __global__ void __launch_bounds__(256) pack_rows_kernel(const PackRowsParams p) {
     pdl_launch_dependents();
+    if (p.ready_flag) {
+        // the producer is the copy engine (crbm_train_step_staged): it makes progress independently of the SMs, so spinning here
+        // cannot dead-lock; bounded all the same (~2 s), a missing copy poisons the validation counter instead of hanging the GPU
+        __shared__ int arrived;
+        if (threadIdx.x == 0) {
+            unsigned int seen = 0u;
+            long long spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ready_flag) : "memory");
+                if (seen == p.ready_value) break;
+                if (++spins > (1ll << 25)) { *p.bad = (int)0x80000000; break; }
+                __nanosleep(64);
+            }
+            arrived = 1;
+        }
+        __syncthreads();
+    }
     const int segs = ceil_div(p.L, 128);
     const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (wid < p.n * segs) {
@@ -359,11 +378,12 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const PackRowsParams p) 
     }
     pdl_wait();
 }
-struct PackJob { const float *src; int *bad; };
+struct PackJob { const float *src; int *bad; const unsigned int *ready_flag; unsigned int ready_value; };
 static int launch_pack_job(const PackJob &job, const crbm_train_args *a, cudaStream_t s) {
     PackRowsParams p{};
     p.src = job.src; p.n = a->n_data; p.L = a->L; p.dst = const_cast<uint32_t *>(a->data); p.row_words = a->data_row_words; p.bad = job.bad;
     p.vec = (a->L % 4 == 0 && ((uintptr_t)job.src & 15) == 0) ? 1 : 0;
+    p.ready_flag = job.ready_flag; p.ready_value = job.ready_value;
     const int warps = a->n_data * ceil_div(a->L, 128);
     CRBM_CHECK_CUDA(launch_chain(pack_rows_kernel, dim3(ceil_div(warps, 8)), dim3(256), 0, s, p));
     CRBM_CHECK_LAUNCH();
@@ -1333,10 +1353,27 @@ int crbm_train_step_onehot(const crbm_train_args *a, const crbm_p2p_args *p2p, c
     return CRBM_OK;
 }
 
+static int train_step_packjob(const crbm_train_args *a, const crbm_p2p_args *p2p, const PackJob &job, void *stream);
 int crbm_train_step_hostfed(const crbm_train_args *a, const crbm_p2p_args *p2p, const float *onehot, int *bad_count, void *stream) {
     CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc && onehot && bad_count, "crbm_train_step_hostfed: null argument");
     CRBM_CHECK_ARG(a->n_data > 0 && !a->batch_index_dev, "crbm_train_step_hostfed: needs a non-empty minibatch addressed directly");
-    PackJob job{onehot, bad_count};
+    PackJob job{onehot, bad_count, nullptr, 0u};
+    return train_step_packjob(a, p2p, job, stream);
+}
+
+int crbm_train_step_staged(const crbm_train_args *a, const crbm_p2p_args *p2p, const float *host_onehot, float *staging_dev,
+                           unsigned int *ready_flag_dev, const unsigned int *seq_host, int *bad_count, void *copy_stream, void *stream) {
+    CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc && host_onehot && staging_dev && ready_flag_dev && seq_host && bad_count && copy_stream,
+                   "crbm_train_step_staged: null argument");
+    CRBM_CHECK_ARG(a->n_data > 0 && !a->batch_index_dev, "crbm_train_step_staged: needs a non-empty minibatch addressed directly");
+    cudaStream_t cs = (cudaStream_t)copy_stream;
+    CRBM_CHECK_CUDA(cudaMemcpyAsync(staging_dev, host_onehot, sizeof(float) * 4 * (size_t)a->n_data * a->L, cudaMemcpyHostToDevice, cs));
+    CRBM_CHECK_CUDA(cudaMemcpyAsync(ready_flag_dev, seq_host, sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
+    PackJob job{staging_dev, bad_count, ready_flag_dev, *seq_host};
+    return train_step_packjob(a, p2p, job, stream);
+}
+
+static int train_step_packjob(const crbm_train_args *a, const crbm_p2p_args *p2p, const PackJob &job, void *stream) {
     const int all = CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE;
     if (p2p) {
         CRBM_CHECK_ARG(p2p->n_ranks > 0 && p2p->n_ranks <= CRBM_MAX_PEERS && p2p->rank >= 0 && p2p->rank < p2p->n_ranks && p2p->ticket &&

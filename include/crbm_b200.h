@@ -205,6 +205,15 @@ struct crbm_p2p_args;
  * The buffer behind `onehot` must stay unmodified until the step has executed. *bad_count accumulates the number of positions that
  * are not one-hot. With c_trace set (above) a whole host-fed step needs no stream operation besides its kernels. */
 int crbm_train_step_hostfed(const crbm_train_args *args, const struct crbm_p2p_args *p2p, const float *onehot, int *bad_count, void *stream);
+/* The host-fed step with the minibatch crossing PCIe AHEAD of the step: on `copy_stream` the call enqueues two DMA copies — host_onehot
+ * ((n_data,1,4,L) fp32, page-locked) -> staging_dev (device, same size), then the 4-byte sequence value *seq_host (page-locked) ->
+ * *ready_flag_dev — and on `stream` the same chain of kernels as crbm_train_step_hostfed, whose packing kernel reads staging_dev after
+ * it has seen *ready_flag_dev == *seq_host (only the copy engine is waited for: it makes progress whatever the SMs do). There is no
+ * event or other stream operation between the kernels of `stream`; a host that runs ahead of the device (a ring of staging buffers
+ * and flags, one per step in flight) hides the transfer completely. The caller must not reuse staging_dev / ready_flag_dev / seq_host
+ * before the step has executed. If the flag does not arrive within ~2 s the step proceeds and *bad_count is set to INT_MIN. */
+int crbm_train_step_staged(const crbm_train_args *args, const struct crbm_p2p_args *p2p, const float *host_onehot, float *staging_dev,
+                           unsigned int *ready_flag_dev, const unsigned int *seq_host, int *bad_count, void *copy_stream, void *stream);
 int crbm_train_step_onehot(const crbm_train_args *args, const struct crbm_p2p_args *p2p, const float *host_onehot, float *staging,
                            int *bad_count, void *copy_stream, void *consumed_event, void *ready_event, void *stream);
 

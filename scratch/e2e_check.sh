@@ -11,12 +11,7 @@ except Exception as e:
 P
 }
 run zc_dual CRBM_DUAL=1
-run zc_nodual CRBM_DUAL=0
 run copy CRBM_HOSTFED=copy
-run g16_26 CRBM_DUAL_GY_POS=16 CRBM_DUAL_GY_NEG=26
-run g17_25 CRBM_DUAL_GY_POS=17 CRBM_DUAL_GY_NEG=25
-run g18_24 CRBM_DUAL_GY_POS=18 CRBM_DUAL_GY_NEG=24
-run g15_27 CRBM_DUAL_GY_POS=15 CRBM_DUAL_GY_NEG=27
-run g21_21 CRBM_DUAL_GY_POS=21 CRBM_DUAL_GY_NEG=21
+run zerocopy CRBM_HOSTFED=zerocopy
 python bench.py --gpus 1 --steps 20 --warmup 5 --only-headline --no-scan > gpurun_out/e2e_driver20.json 2> gpurun_out/e2e_driver20.err; python -c "
 import json; d=json.loads([l for l in open('gpurun_out/e2e_driver20.json') if l.startswith('{')][0]); print('driver-like 20 steps:', d['ms_per_step']*1e3, d['e2e']['value'])"

@@ -291,30 +291,33 @@ def test_streamlined_onehot_step_equals_packed_step_and_validates(data):
         m.motifs.get_value()
 
 
-@pytest.mark.parametrize('kind', ['numpy', 'pinned', 'cuda', 'strided', 'copy'])
+@pytest.mark.parametrize('kind', ['numpy', 'pinned', 'cuda', 'strided', 'copy', 'zerocopy', 'zerocopy-numpy'])
 @pytest.mark.parametrize('L', [200, 197])
 def test_hostfed_step_reads_the_batch_where_it_lies(data, kind, L, monkeypatch):
-    """crbm_train_step_hostfed: the packing kernel inside the step reads the one-hot minibatch from page-locked host memory
-    (zero copy), from device memory, or from the ring of pinned buffers pageable / strided input is copied into; lengths that are
-    not a multiple of four floats take the scalar loads. Same parameters as the explicit packed path, bit for bit. `copy` is
-    the older staging-copy call (CRBM_HOSTFED=copy)."""
+    """The host-fed step: by default (crbm_train_step_staged) the batch is copied by the copy engine into a ring of device staging
+    buffers ahead of the step, whose packing kernel waits for the copy's flag; device-resident input and CRBM_HOSTFED=zerocopy
+    (crbm_train_step_hostfed) are read by the packing kernel where they lie (device memory / page-locked host memory over PCIe);
+    pageable / strided input goes through a ring of pinned buffers; lengths that are not a multiple of four floats take the scalar
+    loads. Same parameters as the explicit packed path, bit for bit. `copy` is the first version (CRBM_HOSTFED=copy)."""
     import torch
     import crbm_b200
     from crbm_b200 import CRBM
     if kind == 'copy':
         monkeypatch.setenv('CRBM_HOSTFED', 'copy')
-    d = np.ascontiguousarray(data[:120, :, :, :L])
+    if kind.startswith('zerocopy'):
+        monkeypatch.setenv('CRBM_HOSTFED', 'zerocopy')
+    d = np.ascontiguousarray(data[:240, :, :, :L])
     out = []
     for fast in (True, False):
         np.random.seed(3)
         m = CRBM(num_motifs=12, motif_length=9, cd_k=1, seed=5, batchsize=20)
         keep = []
-        for i in range(6):
+        for i in range(12):                       # more steps than the ring of staging buffers has slots
             batch = d[20 * i:20 * (i + 1)]
             if not fast:
                 m._train_packed(crbm_b200.PackedSequences.from_onehot(batch), 0, 20)
                 continue
-            if kind == 'pinned':
+            if kind in ('pinned', 'zerocopy'):
                 src = torch.from_numpy(batch.copy()).pin_memory()
             elif kind == 'cuda':
                 src = torch.from_numpy(batch.copy()).cuda()

@@ -48,7 +48,7 @@ class P2PArgs(ctypes.Structure):
     """struct crbm_p2p_args."""
     _fields_ = [('n_ranks', c_int), ('rank', c_int), ('parity', c_int), ('sequence', ctypes.c_ulonglong),
                 ('peer_stats', c_void_p * MAX_PEERS), ('peer_flags', c_void_p * MAX_PEERS), ('stats_stride', c_size_t),
-                ('error_flag', c_void_p), ('ticket', c_void_p)]
+                ('error_flag', c_void_p), ('ticket', c_void_p), ('peer_ll', c_void_p * MAX_PEERS), ('ll_parity_stride', c_size_t)]
 
 
 class StatsLayout(ctypes.Structure):
@@ -93,6 +93,8 @@ SIGNATURES = {
     'crbm_train_step_hostfed': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p, c_void_p, c_void_p]),
     'crbm_train_step_staged': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'crbm_train_step_onehot': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'crbm_train_step_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
+    'crbm_p2p_ll_elems': (c_size_t, [c_int, c_int, c_int]),
     'crbm_train_accumulate_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
     'crbm_train_apply_p2p': (c_int, [ctypes.POINTER(TrainArgs), ctypes.POINTER(P2PArgs), c_void_p]),
     'crbm_train_stats_layout': (c_int, [c_int, c_int, ctypes.POINTER(StatsLayout)]),

@@ -590,6 +590,10 @@ class CRBM(object):
             self._p2p = dict(buf=buf, hdl=None, stride=stride, peer_stats=[buf.data_ptr()], peer_flags=[buf.data_ptr() + 2 * stride * 4],
                              ticket=torch.zeros(1, dtype=torch.int32, device=self._device),
                              error=torch.zeros(1, dtype=torch.int32, device=self._device), local_stats=buf.data_ptr())
+            ll = int(lib.crbm_p2p_ll_elems(self.num_motifs, self.motif_length, self.pooling))
+            if ll and os.environ.get('CRBM_DP_LL', '1') != '0':
+                self._p2p['ll_buf'] = torch.zeros(2 * ll, dtype=torch.int64, device=self._device)
+                self._p2p['ll_stride'], self._p2p['peer_ll'] = ll, [self._p2p['ll_buf'].data_ptr()]
             return self._p2p
         if self._world == 1 or self._world > _lib.MAX_PEERS or os.environ.get('CRBM_DP', 'p2p') != 'p2p':
             return None
@@ -609,6 +613,15 @@ class CRBM(object):
             p = dict(buf=buf, hdl=hdl, stride=stride, peer_stats=ptrs, peer_flags=[x + flag_off for x in ptrs],
                      ticket=torch.zeros(1, dtype=torch.int32, device=self._device),
                      error=torch.zeros(1, dtype=torch.int32, device=self._device), local_stats=buf.data_ptr())
+            # receive buffers of the fused exchange (reduce_update_ll_kernel): 2 parities x crbm_p2p_ll_elems 8-byte elements
+            ll = int(lib.crbm_p2p_ll_elems(self.num_motifs, self.motif_length, self.pooling))
+            if ll and os.environ.get('CRBM_DP_LL', '1') != '0':
+                llbuf = symm_mem.empty(2 * ll, dtype=torch.int64, device=self._device)
+                llbuf.zero_()
+                torch.cuda.synchronize(self._device)
+                llh = symm_mem.rendezvous(llbuf, dist.group.WORLD.group_name)
+                p['ll_buf'], p['ll_hdl'], p['ll_stride'] = llbuf, llh, ll
+                p['peer_ll'] = [int(x) for x in llh.buffer_ptrs]
             dist.barrier()
             self._p2p = p
             return p
@@ -616,22 +629,28 @@ class CRBM(object):
             warnings.warn("crbm_b200: peer-memory all-reduce unavailable (%s); falling back to NCCL all_reduce" % (e,))
             return None
 
-    def _p2p_args(self, p, parity, sequence):
+    def _p2p_args(self, p, parity, sequence, ll_ok=True):
         a = _lib.P2PArgs()
         a.n_ranks, a.rank, a.parity, a.sequence = self._world, self._rank, parity, sequence
         for r in range(self._world):
             a.peer_stats[r], a.peer_flags[r] = p['peer_stats'][r], p['peer_flags'][r]
         a.stats_stride, a.error_flag, a.ticket = p['stride'], p['error'].data_ptr(), p['ticket'].data_ptr()
+        if ll_ok and 'peer_ll' in p:
+            # fused exchange inside the reduction + update launch; only when every rank has rows in this step (all ranks must
+            # take the same branch)
+            for r in range(self._world):
+                a.peer_ll[r] = p['peer_ll'][r]
+            a.ll_parity_stride = p['ll_stride']
         return a
 
-    def _p2p_step(self, args, p, parity, sequence):
-        """accumulate into buffer `parity`, publish, then the fused all-reduce + update (both on the current stream)."""
+    def _p2p_step(self, args, p, parity, sequence, ll_ok=True):
+        """One data-parallel step on the current stream: statistics into buffer `parity`, exchange over peer memory, update
+        (one launch for reduction + exchange + update where crbm_train_step_p2p fuses them)."""
         lib = _lib.load()
         s = _lib.stream_handle()
         args.stats = p['local_stats'] + parity * p['stride'] * 4
-        pa = self._p2p_args(p, parity, sequence)
-        _lib.check(lib.crbm_train_accumulate_p2p(args, pa, s), 'train_accumulate_p2p')
-        _lib.check(lib.crbm_train_apply_p2p(args, pa, s), 'train_apply_p2p')
+        pa = self._p2p_args(p, parity, sequence, ll_ok)
+        _lib.check(lib.crbm_train_step_p2p(args, pa, s), 'train_step_p2p')
 
     def _p2p_check(self, collective=False):
         """Raise if the peer-memory exchange of an earlier step timed out on this rank (the kernel then poisons the
@@ -655,11 +674,13 @@ class CRBM(object):
         lib = self._require_cuda()
         torch = _torch()
         n = end - start
+        ll_ok = True
         if self._world > 1 and not local_shard:
             per = (n + self._world - 1) // self._world
             lo = min(n, self._rank * per)
             hi = min(n, lo + per)
             start, end = start + lo, start + hi
+            ll_ok = (self._world - 1) * per < n          # no rank's shard of this step is empty
         u_v = u_h = u_hp = None
         if uniforms is not None:
             conv = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self._device)
@@ -671,7 +692,7 @@ class CRBM(object):
             p = self._p2p_setup()
             if p is not None:
                 a.step = self._dp_seq
-                self._p2p_step(a, p, self._dp_seq & 1, self._dp_seq + 1)
+                self._p2p_step(a, p, self._dp_seq & 1, self._dp_seq + 1, ll_ok and end > start)
             else:
                 import torch.distributed as dist
                 _lib.check(lib.crbm_train_accumulate(a, s), 'train_accumulate')
@@ -785,15 +806,19 @@ class CRBM(object):
             spg = steps_per_graph - (steps_per_graph & 1)
             eager(min(count, (self._dp_seq & 1) + (0 if ('p2p_warm' in eng) else 2)))
             eng['p2p_warm'] = True
-            if spg >= 2 and count - done >= spg:
+            if spg >= 2 and count - done >= 2:
                 eng['step_dev'].fill_(self._dp_seq)
                 eng['batch_dev'].fill_(first_batch + done)
-                g = self._graph_for(eng, spg, 'p2p')
-                nrep = (count - done) // spg
-                for _ in range(nrep):
-                    g.replay()
-                self._dp_seq += nrep * spg
-                done += nrep * spg
+                while count - done >= 2:
+                    # graphs of spg steps, then ONE graph of the remaining even number of steps (cached per length); only a last
+                    # odd step runs eagerly
+                    n = spg if count - done >= spg else (count - done) & ~1
+                    g = self._graph_for(eng, n, 'p2p')
+                    nrep = (count - done) // n
+                    for _ in range(nrep):
+                        g.replay()
+                    self._dp_seq += nrep * n
+                    done += nrep * n
             eager(count - done)
             self._step += count
             return
@@ -839,13 +864,15 @@ class CRBM(object):
         result is checked at the next call / synchronisation point."""
         if (uniforms is None and self._use_graphs and not isinstance(data, PackedSequences) and getattr(data, 'ndim', 0) == 4
                 and (not self._dp or self._p2p_setup() is not None)):
+            ll_ok = True
             if self._world > 1 and not local_shard:         # this rank's rows of the global minibatch
                 n = int(data.shape[0])
                 per = (n + self._world - 1) // self._world
                 lo = min(n, self._rank * per)
                 data = data[lo:min(n, lo + per)]
+                ll_ok = (self._world - 1) * per < n
             if int(data.shape[0]) > 0:
-                return self._train_step_onehot(data)
+                return self._train_step_onehot(data, ll_ok)
         seqs = self._as_packed(data)
         self._train_packed(seqs, 0, seqs.N, uniforms, local_shard)
 
@@ -861,7 +888,7 @@ class CRBM(object):
                 eng['bad'].zero_()
                 raise ValueError("input is not one-hot at %d positions (expected exactly one 1 among A,C,G,T)" % nbad)
 
-    def _train_step_onehot(self, data):
+    def _train_step_onehot(self, data, ll_ok=True):
         shape = data.shape
         n, L = int(shape[0]), int(shape[3])
         eng = getattr(self, '_onehot_engine', None)
@@ -874,7 +901,7 @@ class CRBM(object):
             p = self._p2p
             a.step = self._dp_seq
             a.stats = p['local_stats'] + (self._dp_seq & 1) * p['stride'] * 4
-            pa = self._p2p_args(p, self._dp_seq & 1, self._dp_seq + 1)
+            pa = self._p2p_args(p, self._dp_seq & 1, self._dp_seq + 1, ll_ok)
             self._dp_seq += 1
         else:
             a.step = self._step

@@ -694,6 +694,178 @@ __global__ void __launch_bounds__(512) reduce_update_kernel(const FusedUpdatePar
     }
 }
 
+// ---- reduction + all-reduce + update in ONE launch (data parallel, tensor-pipe partial layout) ---------------------------------
+// reduce_update_kernel with the exchange between its two halves, at CTA granularity and without fences or separate flags: after a CTA
+// has reduced its rows of the per-CTA partials, warp w PUSHES row w (32 values) into the receive buffers of every rank as 8-byte
+// stores that carry the value and the step's sequence number together (the "LL" scheme of NCCL's low-latency protocol: an aligned
+// 8-byte store is a single transaction, so a matching sequence number proves the value next to it has arrived), then polls its own
+// receive buffer until the 32 x n_ranks pairs of its row carry the sequence number, adds them in rank order — bit-identical sums on
+// every rank — and hands the sums to warp 0, which applies the update with the arithmetic of the single-rank kernel. One NVLink
+// one-way latency per step instead of a flag round trip plus a pull round trip, no launch boundary between reduction and update, and the
+// CTAs of fast m-tiles exchange while slow ones still reduce. Receive buffers are double buffered by step parity (a rank can be at most
+// one exchange ahead of its slowest peer). CTA i of one rank only waits for CTA i of the others, which never waits for anything
+// before it sends, and CTAs are dispatched in index order on every rank: no dead-lock. With one rank the result is bit-identical to
+// reduce_update_kernel.
+constexpr int LL_ROWS = 8;                                      // rows of 32 (value, sequence) pairs per (CTA, source rank)
+struct FusedLLParams {
+    FusedUpdateParams f;
+    int n_ranks, rank;
+    unsigned long long *peer_ll[CRBM_MAX_PEERS];   // every rank's receive buffer of this step's parity: [n_cta][CRBM_MAX_PEERS][LL_ROWS][32]
+    unsigned long long sequence;
+    const unsigned long long *sequence_dev;
+    int *error_flag;
+    unsigned int *ticket;
+};
+__device__ __forceinline__ size_t ll_index(int cta, int src, int row, int lane) {
+    return (((size_t)cta * CRBM_MAX_PEERS + src) * LL_ROWS + row) * 32 + lane;
+}
+// push this lane's value of `row` to every rank, then gather the row from every rank and add in rank order
+__device__ __forceinline__ float ll_allreduce_row(const FusedLLParams &p, int cta, int row, int lane, float v, uint32_t seq, int &timed_out) {
+    const unsigned long long packet = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
+#pragma unroll
+    for (int r = 0; r < CRBM_MAX_PEERS; ++r)
+        if (r < p.n_ranks) asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p.peer_ll[r] + ll_index(cta, p.rank, row, lane)), "l"(packet) : "memory");
+    const unsigned long long *mine = p.peer_ll[p.rank];
+    unsigned long long x[CRBM_MAX_PEERS];
+    long long spins = 0;
+    for (;;) {
+        bool all = true;
+#pragma unroll
+        for (int r = 0; r < CRBM_MAX_PEERS; ++r)
+            if (r < p.n_ranks) {
+                asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(x[r]) : "l"(mine + ll_index(cta, r, row, lane)) : "memory");
+                all = all && ((uint32_t)(x[r] >> 32) == seq);
+            }
+        if (__all_sync(0xffffffffu, all)) break;
+        if (++spins > (1ll << 24)) { timed_out = 1; break; }          // a peer is gone (seconds): do not hang the GPU
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < CRBM_MAX_PEERS; ++r)
+        if (r < p.n_ranks) sum += __uint_as_float((uint32_t)x[r]);
+    return sum;
+}
+__global__ void __launch_bounds__(512) reduce_update_ll_kernel(const FusedLLParams P) {
+    pdl_wait();
+    pdl_launch_dependents();
+    __shared__ float sh[5][4][32];
+    __shared__ float gs[LL_ROWS][32];
+    __shared__ float counts[8];
+    __shared__ int timed_out_s;
+    const FusedUpdateParams &p = P.f;
+    const ReduceParams &R = p.red;
+    const ApplyParams &ap = p.ap;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = warp >> 2, sub = warp & 3;
+    const int g = lane >> 2, q = lane & 3;
+    const ReduceSet &D = R.set[p.sd], &Q = R.set[p.sq], &Mo = R.set[p.sm];
+    const float strands = ap.ds ? 2.f : 1.f;
+    const int n_w = R.ktiles * p.per, cta = blockIdx.x;
+    const uint32_t seq = (uint32_t)(P.sequence_dev ? *P.sequence_dev + 1ull : P.sequence);
+    if (threadIdx.x == 0) timed_out_s = 0;
+    auto total = [&](int r) { return (sh[r][0][lane] + sh[r][1][lane]) + (sh[r][2][lane] + sh[r][3][lane]); };
+    int timed_out = 0;
+    if (cta < n_w) {
+        const int kt = cta / p.per, o = cta - kt * p.per;
+        const int r = o & 3, t = o >> 2, h = r >> 1;
+        const ReduceSet &S = row == 0 ? D : row == 1 ? Q : row == 2 ? Mo : D;
+        const int slot = row == 0 ? o : row == 1 ? p.q_off + o : row == 2 ? o : D.np + D.nq + h;
+        sh[row][sub][lane] = warp_partial(S, kt, slot, lane, sub);
+        __syncthreads();
+        // rows 0-3: data P, data Q, model P, forward hidden sum; rows 4, 5: this rank's N*Lh and B*200
+        if (warp < 6) {
+            const float v = warp < 4 ? total(warp) : warp == 4 ? R.c0 : R.c1;
+            gs[warp][lane] = ll_allreduce_row(P, cta, warp, lane, v, seq, timed_out);
+            if (timed_out) timed_out_s = 1;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int k = kt * 16 + 8 * h + g;
+            const int col = 8 * t + 2 * q + (r & 1), m = col >> 2, a = col & 3;
+            if (k < ap.K && m < ap.M) {
+                const int gid = (k * 4 + a) * ap.M + m;
+                if (timed_out_s) { ap.W[gid] = __int_as_float(0x7fc00000); ap.vW[gid] = __int_as_float(0x7fc00000); }
+                else {
+                    const float vd = gs[0][lane], vq = gs[1][lane], vm = gs[2][lane], nhd = gs[4][lane], nhm = gs[5][lane];
+                    const float hf = gs[3][lane & 28];
+                    const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
+                    const float gk = sparsity_factor(hf, nhd, ap.rho, ap.K);
+                    const float v = next_velocity(ap.vW[gid], vd, nd, vm, nm, __fmul_rn(gk, vq), ap.mu, ap.lr, ap.lam);
+                    ap.vW[gid] = v;
+                    ap.W[gid] = __fadd_rn(ap.W[gid], v);
+                }
+            }
+        }
+    } else if (cta < n_w + 2 * R.ktiles) {
+        const int kt = (cta - n_w) >> 1, h = (cta - n_w) & 1;
+        const int bd = D.np + D.nq, bq = Q.np + Q.nq, bm = Mo.np + Mo.nq;
+        if (row == 0) sh[0][sub][lane] = warp_partial(D, kt, bd + h, lane, sub);
+        else if (row == 1) sh[1][sub][lane] = warp_partial(D, kt, bd + 2 + h, lane, sub);
+        else if (row == 2) sh[2][sub][lane] = warp_partial(Mo, kt, bm + h, lane, sub);
+        else sh[3][sub][lane] = warp_partial(Mo, kt, bm + 2 + h, lane, sub);
+        if (row == 0) sh[4][sub][lane] = warp_partial(Q, kt, bq + 4 + h, lane, sub);
+        __syncthreads();
+        // rows 0-4: sum_p, sum_pr (data), sum_p, sum_pr (model), sum_q; rows 5, 6: N*Lh, B*200
+        if (warp < 7) {
+            const float v = warp < 5 ? total(warp) : warp == 5 ? R.c0 : R.c1;
+            gs[warp][lane] = ll_allreduce_row(P, cta, warp, lane, v, seq, timed_out);
+            if (timed_out) timed_out_s = 1;
+        }
+        __syncthreads();
+        const int k = kt * 16 + 8 * h + g;
+        if (warp == 0 && q == 0 && k < ap.K) {
+            if (timed_out_s) { ap.b[k] = __int_as_float(0x7fc00000); ap.vb[k] = __int_as_float(0x7fc00000); }
+            else {
+                const float hf = gs[0][lane], nhd = gs[5][lane], nhm = gs[6][lane];
+                const float hdata = hf + gs[1][lane], hmodel = gs[2][lane] + gs[3][lane], hq = gs[4][lane];
+                const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
+                const float gk = sparsity_factor(hf, nhd, ap.rho, ap.K);
+                const float v = next_velocity(ap.vb[k], hdata, nd, hmodel, nm, __fmul_rn(gk, hq), ap.mu, ap.lr, ap.lam);
+                ap.vb[k] = v;
+                ap.b[k] = __fadd_rn(ap.b[k], v);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const uint32_t *rows = R.cnt_rows[w];
+            if (w == 0 && R.batch_index) rows += (size_t)(*R.batch_index) * R.cnt_n[0] * R.cnt_row_words[0];
+            count_bases_block(rows, R.cnt_row_words[w], R.cnt_n[w], R.cnt_L[w], counts + 4 * w);
+            __syncthreads();
+        }
+        // row 0: the eight base counts in lanes 0-7; row 1: N*L and B*(199+M) in lanes 0, 1
+        if (warp < 2) {
+            const float v = warp == 0 ? (lane < 8 ? counts[lane] : 0.f) : (lane == 0 ? R.c2 : lane == 1 ? R.c3 : 0.f);
+            gs[warp][lane] = ll_allreduce_row(P, cta, warp, lane, v, seq, timed_out);
+            if (timed_out) timed_out_s = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            const int a = threadIdx.x;
+            if (timed_out_s) { ap.c[a] = __int_as_float(0x7fc00000); ap.vc[a] = __int_as_float(0x7fc00000); }
+            else {
+                const float v = next_velocity(ap.vc[a], __fadd_rn(gs[0][a], gs[0][3 - a]), gs[1][0], __fadd_rn(gs[0][4 + a], gs[0][7 - a]), gs[1][1],
+                                              0.f, ap.mu, ap.lr, 0.f);
+                ap.vc[a] = v;
+                const float cn = __fadd_rn(ap.c[a], v);
+                ap.c[a] = cn;
+                trace_c(ap, a, cn, ap.step_dev ? *ap.step_dev : ap.step);
+            }
+        }
+    }
+    // the step / minibatch cursors are advanced by the last CTA to finish: every CTA has read *sequence_dev by then
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (timed_out_s) *P.error_flag = 1;
+        const unsigned int t = atomicAdd(P.ticket, 1u);
+        if (t == gridDim.x - 1) {
+            *P.ticket = 0u;
+            if (ap.step_dev) *ap.step_dev += 1ull;
+            if (ap.batch_index_dev) { const int nb = *ap.batch_index_dev + 1; *ap.batch_index_dev = nb >= ap.n_batches ? 0 : nb; }
+        }
+    }
+}
+
 // ---- A11 + A12 fused with a one-shot all-reduce over peer memory (data parallel) ------------------------------------------
 // Every rank's statistics buffer is mapped into every other rank's address space (NVLink). A thread block first waits
 // until all ranks have published this step's sequence number (their reduce kernels finished), then each thread adds its
@@ -1299,16 +1471,29 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
         red.batch_index = a->batch_index_dev;
         red.cnt_out[0] = st + lay.v_data; red.cnt_out[1] = st + lay.v_model;
         // single rank, tensor-pipe layout, update requested in the same call: reduction and update in one launch
-        if ((phases & CRBM_PHASE_APPLY) && mma && !p2p && a->n_data > 0 && fused_update_enabled()) {
+        if ((phases & CRBM_PHASE_APPLY) && mma && a->n_data > 0 && fused_update_enabled() && (!p2p || p2p->peer_ll[0])) {
             FusedUpdateParams f{};
             f.red = red;
             fill_apply_params(a, &f.ap);
             f.per = 8 * KS;
             f.sd = 0; f.sq = combined ? 0 : 1; f.sm = red.nsets - 1; f.q_off = combined ? f.per : 0;
-            CRBM_CHECK_CUDA(launch_chain(reduce_update_kernel, dim3(red.ktiles * (f.per + 2) + 1), dim3(512), 0, s, f));
+            const int n_cta = red.ktiles * (f.per + 2) + 1;
+            if (!p2p) {
+                CRBM_CHECK_CUDA(launch_chain(reduce_update_kernel, dim3(n_cta), dim3(512), 0, s, f));
+            } else {
+                // data parallel: reduction, all-reduce over NVLink peer memory and update in one launch (reduce_update_ll_kernel)
+                FusedLLParams L{};
+                L.f = f; L.n_ranks = p2p->n_ranks; L.rank = p2p->rank;
+                for (int r = 0; r < p2p->n_ranks; ++r) L.peer_ll[r] = p2p->peer_ll[r] + (size_t)p2p->parity * p2p->ll_parity_stride;
+                L.sequence = p2p->sequence; L.sequence_dev = a->step_dev; L.error_flag = p2p->error_flag; L.ticket = p2p->ticket;
+                CRBM_CHECK_ARG(p2p->ll_parity_stride >= (size_t)n_cta * CRBM_MAX_PEERS * LL_ROWS * 32 && p2p->error_flag,
+                               "crbm_train_step_p2p: receive buffer too small (crbm_p2p_ll_elems)");
+                CRBM_CHECK_CUDA(launch_chain(reduce_update_ll_kernel, dim3(n_cta), dim3(512), 0, s, L));
+            }
             CRBM_CHECK_LAUNCH();
             return CRBM_OK;
         }
+        if (p2p && (phases & CRBM_PHASE_APPLY)) { set_error("crbm_train_step_p2p: internal: the fused exchange is not available for this step"); return CRBM_ERR_UNSUPPORTED; }
         CRBM_CHECK_CUDA(launch_chain(reduce_partials_kernel, dim3(red.block_start[red.nsets] + 2), dim3(128), 0, s, red));
         CRBM_CHECK_LAUNCH();
     }
@@ -1353,12 +1538,12 @@ int crbm_train_step_onehot(const crbm_train_args *a, const crbm_p2p_args *p2p, c
     return CRBM_OK;
 }
 
-static int train_step_packjob(const crbm_train_args *a, const crbm_p2p_args *p2p, const PackJob &job, void *stream);
+static int train_step_packjob(const crbm_train_args *a, const crbm_p2p_args *p2p, const PackJob *job, void *stream);
 int crbm_train_step_hostfed(const crbm_train_args *a, const crbm_p2p_args *p2p, const float *onehot, int *bad_count, void *stream) {
     CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc && onehot && bad_count, "crbm_train_step_hostfed: null argument");
     CRBM_CHECK_ARG(a->n_data > 0 && !a->batch_index_dev, "crbm_train_step_hostfed: needs a non-empty minibatch addressed directly");
     PackJob job{onehot, bad_count, nullptr, 0u};
-    return train_step_packjob(a, p2p, job, stream);
+    return train_step_packjob(a, p2p, &job, stream);
 }
 
 int crbm_train_step_staged(const crbm_train_args *a, const crbm_p2p_args *p2p, const float *host_onehot, float *staging_dev,
@@ -1370,19 +1555,42 @@ int crbm_train_step_staged(const crbm_train_args *a, const crbm_p2p_args *p2p, c
     CRBM_CHECK_CUDA(cudaMemcpyAsync(staging_dev, host_onehot, sizeof(float) * 4 * (size_t)a->n_data * a->L, cudaMemcpyHostToDevice, cs));
     CRBM_CHECK_CUDA(cudaMemcpyAsync(ready_flag_dev, seq_host, sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
     PackJob job{staging_dev, bad_count, ready_flag_dev, *seq_host};
-    return train_step_packjob(a, p2p, job, stream);
+    return train_step_packjob(a, p2p, &job, stream);
 }
 
-static int train_step_packjob(const crbm_train_args *a, const crbm_p2p_args *p2p, const PackJob &job, void *stream) {
+// the fused exchange (reduce_update_ll_kernel) serves the mma.sync partial layout with a non-empty shard on every rank (the caller
+// passes the receive buffers only then); everything else exchanges the statistics vector (crbm_train_apply_p2p)
+static bool ll_exchange_possible(const crbm_train_args *a, const crbm_p2p_args *p2p) {
+    if (!p2p || !p2p->peer_ll[0] || a->n_data <= 0 || !fused_update_enabled()) return false;
+    if (shape_is_generic(a->M, a->pooling) || train_uses_tc(a->K, a->M, a->pooling)) return false;
+    return a->pooling == 1 || pool_uses_mma();
+}
+static int train_step_packjob(const crbm_train_args *a, const crbm_p2p_args *p2p, const PackJob *job, void *stream) {
     const int all = CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE;
     if (p2p) {
         CRBM_CHECK_ARG(p2p->n_ranks > 0 && p2p->n_ranks <= CRBM_MAX_PEERS && p2p->rank >= 0 && p2p->rank < p2p->n_ranks && p2p->ticket &&
-                       (p2p->parity == 0 || p2p->parity == 1), "crbm_train_step_hostfed: bad p2p arguments");
-        int rc = train_phases_impl(a, all, stream, p2p, &job);
-        if (!rc) rc = crbm_train_apply_p2p(a, p2p, stream);
+                       (p2p->parity == 0 || p2p->parity == 1), "crbm_train_step_p2p: bad p2p arguments");
+        if (ll_exchange_possible(a, p2p)) return train_phases_impl(a, all | CRBM_PHASE_APPLY, stream, p2p, job);
+        crbm_p2p_args plain = *p2p;
+        for (int r = 0; r < CRBM_MAX_PEERS; ++r) plain.peer_ll[r] = nullptr;
+        int rc = train_phases_impl(a, all, stream, &plain, job);
+        if (!rc) rc = crbm_train_apply_p2p(a, &plain, stream);
         return rc;
     }
-    return train_phases_impl(a, all | CRBM_PHASE_APPLY, stream, nullptr, &job);
+    return train_phases_impl(a, all | CRBM_PHASE_APPLY, stream, nullptr, job);
+}
+
+int crbm_train_step_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, void *stream) {
+    CRBM_CHECK_ARG(a && a->vW && a->vb && a->vc && p2p, "crbm_train_step_p2p: null argument");
+    for (int r = 0; r < p2p->n_ranks && r < CRBM_MAX_PEERS; ++r) CRBM_CHECK_ARG(p2p->peer_stats[r] && p2p->peer_flags[r], "crbm_train_step_p2p: null peer pointer");
+    return train_step_packjob(a, p2p, nullptr, stream);
+}
+
+size_t crbm_p2p_ll_elems(int K, int M, int pooling) {
+    if (K <= 0 || M <= 0 || pooling <= 0 || shape_is_generic(M, pooling) || train_uses_tc(K, M, pooling)) return 0;
+    const int KS = ceil_div(M, 4);
+    const size_t n_cta = (size_t)ceil_div(K, 16) * (8 * KS + 2) + 1;
+    return n_cta * CRBM_MAX_PEERS * LL_ROWS * 32;
 }
 
 int crbm_train_accumulate(const crbm_train_args *a, void *stream) {

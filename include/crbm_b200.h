@@ -238,8 +238,21 @@ typedef struct crbm_p2p_args {
     size_t stats_stride;                             /* floats between the two buffers (>= crbm_train_stats_floats) */
     int *error_flag;                                 /* device int, set to 1 if a peer never showed up */
     unsigned int *ticket;                            /* device counter (zero-initialised) electing the last CTA */
+    /* optional receive buffers of the FUSED exchange (crbm_train_step_p2p), peer-mapped, zero-initialised, per rank
+     * 2 * ll_parity_stride 8-byte elements with ll_parity_stride >= crbm_p2p_ll_elems(K, M, pooling); NULL: not used */
+    unsigned long long *peer_ll[CRBM_MAX_PEERS];
+    size_t ll_parity_stride;
 } crbm_p2p_args;
 int crbm_train_accumulate_p2p(const crbm_train_args *args, const crbm_p2p_args *p2p, void *stream);
+/* One whole data-parallel step. Where the model shape trains on the mma.sync kernels (small un-pooled banks such as C2), every rank
+ * has rows in the step and p2p->peer_ll is set, reduction, all-reduce and update are ONE launch (reduce_update_ll_kernel): a CTA
+ * that has reduced its rows of the per-CTA partials pushes them into every rank's receive buffer as 8-byte (value, sequence number)
+ * stores — an aligned 8-byte store is one transaction, so the sequence number proves its value has arrived: no fence, no flag —
+ * polls its own buffer, adds the ranks in rank order (bit-identical on every rank) and applies the update; one NVLink one-way latency
+ * per step. Otherwise crbm_train_accumulate_p2p + crbm_train_apply_p2p. All ranks must take the same branch: pass peer_ll only
+ * when no rank's shard of the step is empty. crbm_p2p_ll_elems returns 0 for shapes the fused exchange does not serve. */
+int crbm_train_step_p2p(const crbm_train_args *args, const crbm_p2p_args *p2p, void *stream);
+size_t crbm_p2p_ll_elems(int K, int M, int pooling);
 int crbm_train_apply_p2p(const crbm_train_args *args, const crbm_p2p_args *p2p, void *stream);
 
 /* layout of `stats` (offsets in floats), for hosts that want to inspect gradients */

@@ -706,9 +706,8 @@ __global__ void __launch_bounds__(512) reduce_update_kernel(const FusedUpdatePar
 // one exchange ahead of its slowest peer). CTA i of one rank only waits for CTA i of the others, which never waits for anything
 // before it sends, and CTAs are dispatched in index order on every rank: no dead-lock. With one rank the result is bit-identical to
 // reduce_update_kernel.
-constexpr int LL_ROWS = 8;                                      // rows of 32 (value, sequence) pairs per (CTA, source rank)
-struct FusedLLParams {
-    FusedUpdateParams f;
+constexpr int LL_ROWS = 12;                                     // rows of 32 (value, sequence) pairs per (CTA, source rank)
+struct LLView {
     int n_ranks, rank;
     unsigned long long *peer_ll[CRBM_MAX_PEERS];   // every rank's receive buffer of this step's parity: [n_cta][CRBM_MAX_PEERS][LL_ROWS][32]
     unsigned long long sequence;
@@ -716,11 +715,15 @@ struct FusedLLParams {
     int *error_flag;
     unsigned int *ticket;
 };
+struct FusedLLParams {
+    FusedUpdateParams f;
+    LLView ll;
+};
 __device__ __forceinline__ size_t ll_index(int cta, int src, int row, int lane) {
     return (((size_t)cta * CRBM_MAX_PEERS + src) * LL_ROWS + row) * 32 + lane;
 }
 // push this lane's value of `row` to every rank, then gather the row from every rank and add in rank order
-__device__ __forceinline__ float ll_allreduce_row(const FusedLLParams &p, int cta, int row, int lane, float v, uint32_t seq, int &timed_out) {
+__device__ __forceinline__ float ll_allreduce_row(const LLView &p, int cta, int row, int lane, float v, uint32_t seq, int &timed_out) {
     const unsigned long long packet = ((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v);
 #pragma unroll
     for (int r = 0; r < CRBM_MAX_PEERS; ++r)
@@ -761,7 +764,7 @@ __global__ void __launch_bounds__(512) reduce_update_ll_kernel(const FusedLLPara
     const ReduceSet &D = R.set[p.sd], &Q = R.set[p.sq], &Mo = R.set[p.sm];
     const float strands = ap.ds ? 2.f : 1.f;
     const int n_w = R.ktiles * p.per, cta = blockIdx.x;
-    const uint32_t seq = (uint32_t)(P.sequence_dev ? *P.sequence_dev + 1ull : P.sequence);
+    const uint32_t seq = (uint32_t)(P.ll.sequence_dev ? *P.ll.sequence_dev + 1ull : P.ll.sequence);
     if (threadIdx.x == 0) timed_out_s = 0;
     auto total = [&](int r) { return (sh[r][0][lane] + sh[r][1][lane]) + (sh[r][2][lane] + sh[r][3][lane]); };
     int timed_out = 0;
@@ -775,7 +778,7 @@ __global__ void __launch_bounds__(512) reduce_update_ll_kernel(const FusedLLPara
         // rows 0-3: data P, data Q, model P, forward hidden sum; rows 4, 5: this rank's N*Lh and B*200
         if (warp < 6) {
             const float v = warp < 4 ? total(warp) : warp == 4 ? R.c0 : R.c1;
-            gs[warp][lane] = ll_allreduce_row(P, cta, warp, lane, v, seq, timed_out);
+            gs[warp][lane] = ll_allreduce_row(P.ll, cta, warp, lane, v, seq, timed_out);
             if (timed_out) timed_out_s = 1;
         }
         __syncthreads();
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(512) reduce_update_ll_kernel(const FusedLLPara
         // rows 0-4: sum_p, sum_pr (data), sum_p, sum_pr (model), sum_q; rows 5, 6: N*Lh, B*200
         if (warp < 7) {
             const float v = warp < 5 ? total(warp) : warp == 5 ? R.c0 : R.c1;
-            gs[warp][lane] = ll_allreduce_row(P, cta, warp, lane, v, seq, timed_out);
+            gs[warp][lane] = ll_allreduce_row(P.ll, cta, warp, lane, v, seq, timed_out);
             if (timed_out) timed_out_s = 1;
         }
         __syncthreads();
@@ -836,7 +839,7 @@ __global__ void __launch_bounds__(512) reduce_update_ll_kernel(const FusedLLPara
         // row 0: the eight base counts in lanes 0-7; row 1: N*L and B*(199+M) in lanes 0, 1
         if (warp < 2) {
             const float v = warp == 0 ? (lane < 8 ? counts[lane] : 0.f) : (lane == 0 ? R.c2 : lane == 1 ? R.c3 : 0.f);
-            gs[warp][lane] = ll_allreduce_row(P, cta, warp, lane, v, seq, timed_out);
+            gs[warp][lane] = ll_allreduce_row(P.ll, cta, warp, lane, v, seq, timed_out);
             if (timed_out) timed_out_s = 1;
         }
         __syncthreads();
@@ -856,14 +859,20 @@ __global__ void __launch_bounds__(512) reduce_update_ll_kernel(const FusedLLPara
     // the step / minibatch cursors are advanced by the last CTA to finish: every CTA has read *sequence_dev by then
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (timed_out_s) *P.error_flag = 1;
-        const unsigned int t = atomicAdd(P.ticket, 1u);
+        if (timed_out_s) *P.ll.error_flag = 1;
+        const unsigned int t = atomicAdd(P.ll.ticket, 1u);
         if (t == gridDim.x - 1) {
-            *P.ticket = 0u;
+            *P.ll.ticket = 0u;
             if (ap.step_dev) *ap.step_dev += 1ull;
             if (ap.batch_index_dev) { const int nb = *ap.batch_index_dev + 1; *ap.batch_index_dev = nb >= ap.n_batches ? 0 : nb; }
         }
     }
+}
+
+static void fill_ll_view(const crbm_train_args *a, const crbm_p2p_args *p2p, LLView *v) {
+    v->n_ranks = p2p->n_ranks; v->rank = p2p->rank;
+    for (int r = 0; r < p2p->n_ranks; ++r) v->peer_ll[r] = p2p->peer_ll[r] + (size_t)p2p->parity * p2p->ll_parity_stride;
+    v->sequence = p2p->sequence; v->sequence_dev = a->step_dev; v->error_flag = p2p->error_flag; v->ticket = p2p->ticket;
 }
 
 // ---- A11 + A12 fused with a one-shot all-reduce over peer memory (data parallel) ------------------------------------------
@@ -1276,7 +1285,7 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
     CRBM_CHECK_ARG(((uintptr_t)a->W & 15) == 0, "crbm_train_accumulate: W must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const bool gen = shape_is_generic(M, P);                                                    // generic.cuh
-    if (!gen && train_uses_tc(K, M, P)) return train_phases_tc(a, phases, s, p2p != nullptr, pack);     // tcgen05 / TMEM path (train_tc.cuh)
+    if (!gen && train_uses_tc(K, M, P)) return train_phases_tc(a, phases, s, p2p, pack);     // tcgen05 / TMEM path (train_tc.cuh)
     crbm_stats_layout lay;
     fill_layout(K, M, &lay);
     float *st = a->stats;
@@ -1483,9 +1492,8 @@ static int train_phases_impl(const crbm_train_args *a, int phases, void *stream,
             } else {
                 // data parallel: reduction, all-reduce over NVLink peer memory and update in one launch (reduce_update_ll_kernel)
                 FusedLLParams L{};
-                L.f = f; L.n_ranks = p2p->n_ranks; L.rank = p2p->rank;
-                for (int r = 0; r < p2p->n_ranks; ++r) L.peer_ll[r] = p2p->peer_ll[r] + (size_t)p2p->parity * p2p->ll_parity_stride;
-                L.sequence = p2p->sequence; L.sequence_dev = a->step_dev; L.error_flag = p2p->error_flag; L.ticket = p2p->ticket;
+                L.f = f;
+                fill_ll_view(a, p2p, &L.ll);
                 CRBM_CHECK_ARG(p2p->ll_parity_stride >= (size_t)n_cta * CRBM_MAX_PEERS * LL_ROWS * 32 && p2p->error_flag,
                                "crbm_train_step_p2p: receive buffer too small (crbm_p2p_ll_elems)");
                 CRBM_CHECK_CUDA(launch_chain(reduce_update_ll_kernel, dim3(n_cta), dim3(512), 0, s, L));
@@ -1562,8 +1570,8 @@ int crbm_train_step_staged(const crbm_train_args *a, const crbm_p2p_args *p2p, c
 // passes the receive buffers only then); everything else exchanges the statistics vector (crbm_train_apply_p2p)
 static bool ll_exchange_possible(const crbm_train_args *a, const crbm_p2p_args *p2p) {
     if (!p2p || !p2p->peer_ll[0] || a->n_data <= 0 || !fused_update_enabled()) return false;
-    if (shape_is_generic(a->M, a->pooling) || train_uses_tc(a->K, a->M, a->pooling)) return false;
-    return a->pooling == 1 || pool_uses_mma();
+    if (shape_is_generic(a->M, a->pooling)) return false;
+    return train_uses_tc(a->K, a->M, a->pooling) || a->pooling == 1 || pool_uses_mma();
 }
 static int train_step_packjob(const crbm_train_args *a, const crbm_p2p_args *p2p, const PackJob *job, void *stream) {
     const int all = CRBM_PHASE_NEGATIVE | CRBM_PHASE_POSITIVE | CRBM_PHASE_REDUCE;
@@ -1587,9 +1595,11 @@ int crbm_train_step_p2p(const crbm_train_args *a, const crbm_p2p_args *p2p, void
 }
 
 size_t crbm_p2p_ll_elems(int K, int M, int pooling) {
-    if (K <= 0 || M <= 0 || pooling <= 0 || shape_is_generic(M, pooling) || train_uses_tc(K, M, pooling)) return 0;
-    const int KS = ceil_div(M, 4);
-    const size_t n_cta = (size_t)ceil_div(K, 16) * (8 * KS + 2) + 1;
+    if (K <= 0 || M <= 0 || pooling <= 0 || shape_is_generic(M, pooling)) return 0;
+    size_t n_cta;
+    if (train_uses_tc(K, M, pooling)) n_cta = (size_t)ceil_div(K, TT_KC) * (4 * M + 1) + 1;         // reduce_tc_kernel
+    else if (pooling == 1 || pool_uses_mma()) n_cta = (size_t)ceil_div(K, 16) * (8 * ceil_div(M, 4) + 2) + 1;   // reduce_update_ll_kernel
+    else return 0;
     return n_cta * CRBM_MAX_PEERS * LL_ROWS * 32;
 }
 

@@ -275,6 +275,7 @@ struct TcReduceParams {
     const int *batch_index;
     ApplyParams ap;
     int fused;
+    LLView ll;                     // ll.n_ranks > 0 (data parallel, fused): the sums are exchanged over peer memory inside this launch
 };
 // One CTA of 512 threads per (chunk, contraction column c): thread (kl, slice) adds the partials of the CTAs x = slice, slice + 8, ...
 // of its motif for the five sums the update of W[k, c] needs (six independent load streams, L2 resident), the eight slices are
@@ -289,18 +290,29 @@ __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) 
     pdl_wait();
     pdl_launch_dependents();
     __shared__ float sh[6][TCR_SLICES][TT_KC];
+    __shared__ float loc[5][TT_KC];
+    __shared__ float gs[LL_ROWS][32];
     __shared__ float counts[8];
+    __shared__ int timed_out_s;
     const ApplyParams &ap = p.ap;
     const int kl = threadIdx.x & (TT_KC - 1), slice = threadIdx.x >> 6;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int fourM = 4 * p.M;
     const int n_w = p.n_chunks * fourM;
     const size_t pf = (size_t)p.part_floats;
     const size_t q_off = (size_t)p.Kdim * TT_ROWS, s_off = (size_t)p.Kdim * 192;
-    const float nhd = p.c0, nhm = p.c1;
+    float nhd = p.c0, nhm = p.c1;
     const float strands = p.ds ? 2.f : 1.f;
-    const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
-    if ((int)blockIdx.x < n_w) {
-        const int ch = blockIdx.x / fourM, c = blockIdx.x - ch * fourM, cr = fourM - 1 - c;
+    // data parallel, fused (crbm_train_step_p2p): the CTA's sums go through the exchange of reduce_update_ll_kernel (train.cu) before the
+    // update: rows of 32 (value, sequence) pairs pushed to every rank, gathered and added in rank order
+    const bool ll = p.ll.n_ranks > 0;
+    const uint32_t seq = ll ? (uint32_t)(p.ll.sequence_dev ? *p.ll.sequence_dev + 1ull : p.ll.sequence) : 0u;
+    const int cta = blockIdx.x;
+    int timed_out = 0;
+    if (threadIdx.x == 0) timed_out_s = 0;
+    const float nan = __int_as_float(0x7fc00000);
+    if (cta < n_w) {
+        const int ch = cta / fourM, c = cta - ch * fourM, cr = fourM - 1 - c;
         const int k = ch * TT_KC + kl;
         float df = 0.f, dr = 0.f, qq = 0.f, mf = 0.f, mr = 0.f, hf = 0.f;
         if (p.pos) {
@@ -324,23 +336,45 @@ __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) 
         sh[0][slice][kl] = df; sh[1][slice][kl] = dr; sh[2][slice][kl] = qq;
         sh[3][slice][kl] = mf; sh[4][slice][kl] = mr; sh[5][slice][kl] = hf;
         __syncthreads();
-        if (slice != 0 || k >= p.K) return;
-        const float vd = tcr_combine(sh[0], kl) + tcr_combine(sh[1], kl), vq = tcr_combine(sh[2], kl);
-        const float vm = tcr_combine(sh[3], kl) + tcr_combine(sh[4], kl), hfs = tcr_combine(sh[5], kl);
-        const int m = c >> 2, a = c & 3;
-        const int gid = (k * 4 + a) * p.M + m;
-        if (p.fused) {
-            const float gk = sparsity_factor(hfs, nhd, ap.rho, ap.K);
-            const float vel = next_velocity(ap.vW[gid], vd, nd, vm, nm, __fmul_rn(gk, vq), ap.mu, ap.lr, ap.lam);
-            ap.vW[gid] = vel;
-            ap.W[gid] = __fadd_rn(ap.W[gid], vel);
-        } else {
-            p.stats[p.lay.vh_data + gid] = vd;
-            p.stats[p.lay.vh_q + gid] = vq;
-            p.stats[p.lay.vh_model + gid] = vm;
+        float vd = 0.f, vq = 0.f, vm = 0.f, hfs = 0.f;
+        if (slice == 0) {
+            vd = tcr_combine(sh[0], kl) + tcr_combine(sh[1], kl); vq = tcr_combine(sh[2], kl);
+            vm = tcr_combine(sh[3], kl) + tcr_combine(sh[4], kl); hfs = tcr_combine(sh[5], kl);
         }
-    } else if ((int)blockIdx.x < n_w + p.n_chunks) {
-        const int ch = blockIdx.x - n_w;
+        if (ll) {
+            // rows 0-7: data P, Q, model P, forward hidden sum (two rows of 32 motifs each); row 8: N*Lh, B*200 in lanes 0, 1
+            if (slice == 0) { loc[0][kl] = vd; loc[1][kl] = vq; loc[2][kl] = vm; loc[3][kl] = hfs; }
+            __syncthreads();
+            if (warp < 9) {
+                const float v = warp < 8 ? loc[warp >> 1][32 * (warp & 1) + lane] : (lane == 0 ? p.c0 : lane == 1 ? p.c1 : 0.f);
+                gs[warp][lane] = ll_allreduce_row(p.ll, cta, warp, lane, v, seq, timed_out);
+                if (timed_out) timed_out_s = 1;
+            }
+            __syncthreads();
+            const int hrow = kl >> 5, hl = kl & 31;
+            vd = gs[hrow][hl]; vq = gs[2 + hrow][hl]; vm = gs[4 + hrow][hl]; hfs = gs[6 + hrow][hl];
+            nhd = gs[8][0]; nhm = gs[8][1];
+        }
+        if (slice == 0 && k < p.K) {
+            const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
+            const int m = c >> 2, a = c & 3;
+            const int gid = (k * 4 + a) * p.M + m;
+            if (p.fused) {
+                if (timed_out_s) { ap.vW[gid] = nan; ap.W[gid] = nan; }
+                else {
+                    const float gk = sparsity_factor(hfs, nhd, ap.rho, ap.K);
+                    const float vel = next_velocity(ap.vW[gid], vd, nd, vm, nm, __fmul_rn(gk, vq), ap.mu, ap.lr, ap.lam);
+                    ap.vW[gid] = vel;
+                    ap.W[gid] = __fadd_rn(ap.W[gid], vel);
+                }
+            } else {
+                p.stats[p.lay.vh_data + gid] = vd;
+                p.stats[p.lay.vh_q + gid] = vq;
+                p.stats[p.lay.vh_model + gid] = vm;
+            }
+        }
+    } else if (cta < n_w + p.n_chunks) {
+        const int ch = cta - n_w;
         const int k = ch * TT_KC + kl;
         float hf = 0.f, hr = 0.f, hq = 0.f, mf = 0.f, mr = 0.f;
         if (p.pos) {
@@ -359,20 +393,42 @@ __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) 
         }
         sh[0][slice][kl] = hf; sh[1][slice][kl] = hr; sh[2][slice][kl] = hq; sh[3][slice][kl] = mf; sh[4][slice][kl] = mr;
         __syncthreads();
-        if (slice != 0 || k >= p.K) return;
-        const float hfs = tcr_combine(sh[0], kl);
-        const float hdata = hfs + tcr_combine(sh[1], kl), hqs = tcr_combine(sh[2], kl);
-        const float hmodel = tcr_combine(sh[3], kl) + tcr_combine(sh[4], kl);
-        if (p.fused) {
-            const float gk = sparsity_factor(hfs, nhd, ap.rho, ap.K);
-            const float vel = next_velocity(ap.vb[k], hdata, nd, hmodel, nm, __fmul_rn(gk, hqs), ap.mu, ap.lr, ap.lam);
-            ap.vb[k] = vel;
-            ap.b[k] = __fadd_rn(ap.b[k], vel);
-        } else {
-            p.stats[p.lay.h_fwd + k] = hfs;
-            p.stats[p.lay.h_data + k] = hdata;
-            p.stats[p.lay.h_model + k] = hmodel;
-            p.stats[p.lay.h_q + k] = hqs;
+        float hfs = 0.f, hrs = 0.f, hqs = 0.f, mfs = 0.f, mrs = 0.f;
+        if (slice == 0) {
+            hfs = tcr_combine(sh[0], kl); hrs = tcr_combine(sh[1], kl); hqs = tcr_combine(sh[2], kl);
+            mfs = tcr_combine(sh[3], kl); mrs = tcr_combine(sh[4], kl);
+        }
+        if (ll) {
+            // rows 0-9: sum_p, sum_pr (data), sum_q, sum_p, sum_pr (model), two rows each; row 10: N*Lh, B*200
+            if (slice == 0) { loc[0][kl] = hfs; loc[1][kl] = hrs; loc[2][kl] = hqs; loc[3][kl] = mfs; loc[4][kl] = mrs; }
+            __syncthreads();
+            if (warp < 11) {
+                const float v = warp < 10 ? loc[warp >> 1][32 * (warp & 1) + lane] : (lane == 0 ? p.c0 : lane == 1 ? p.c1 : 0.f);
+                gs[warp][lane] = ll_allreduce_row(p.ll, cta, warp, lane, v, seq, timed_out);
+                if (timed_out) timed_out_s = 1;
+            }
+            __syncthreads();
+            const int hrow = kl >> 5, hl = kl & 31;
+            hfs = gs[hrow][hl]; hrs = gs[2 + hrow][hl]; hqs = gs[4 + hrow][hl]; mfs = gs[6 + hrow][hl]; mrs = gs[8 + hrow][hl];
+            nhd = gs[10][0]; nhm = gs[10][1];
+        }
+        if (slice == 0 && k < p.K) {
+            const float nd = __fmul_rn(strands, nhd), nm = __fmul_rn(strands, nhm);
+            const float hdata = hfs + hrs, hmodel = mfs + mrs;
+            if (p.fused) {
+                if (timed_out_s) { ap.vb[k] = nan; ap.b[k] = nan; }
+                else {
+                    const float gk = sparsity_factor(hfs, nhd, ap.rho, ap.K);
+                    const float vel = next_velocity(ap.vb[k], hdata, nd, hmodel, nm, __fmul_rn(gk, hqs), ap.mu, ap.lr, ap.lam);
+                    ap.vb[k] = vel;
+                    ap.b[k] = __fadd_rn(ap.b[k], vel);
+                }
+            } else {
+                p.stats[p.lay.h_fwd + k] = hfs;
+                p.stats[p.lay.h_data + k] = hdata;
+                p.stats[p.lay.h_model + k] = hmodel;
+                p.stats[p.lay.h_q + k] = hqs;
+            }
         }
     } else {
         // base counts of the minibatch and of the sampled visible layer (A9); fused: the update of c and the cursors of the next step
@@ -384,18 +440,34 @@ __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) 
             else if (threadIdx.x < 4) counts[4 * w + threadIdx.x] = 0.f;
             __syncthreads();
         }
+        float nvd = p.c2, nvm = p.c3;
+        if (ll) {
+            // row 0: the eight base counts in lanes 0-7; row 1: N*L and B*(199+M) in lanes 0, 1
+            if (warp < 2) {
+                const float v = warp == 0 ? (lane < 8 ? counts[lane] : 0.f) : (lane == 0 ? p.c2 : lane == 1 ? p.c3 : 0.f);
+                gs[warp][lane] = ll_allreduce_row(p.ll, cta, warp, lane, v, seq, timed_out);
+                if (timed_out) timed_out_s = 1;
+            }
+            __syncthreads();
+            if (threadIdx.x < 8) counts[threadIdx.x] = gs[0][threadIdx.x];
+            nvd = gs[1][0]; nvm = gs[1][1];
+            __syncthreads();
+        }
         if (p.fused) {
             if (threadIdx.x < 4) {
                 const int a = threadIdx.x;
-                const float v = next_velocity(ap.vc[a], __fadd_rn(counts[a], counts[3 - a]), p.c2, __fadd_rn(counts[4 + a], counts[7 - a]), p.c3,
-                                              0.f, ap.mu, ap.lr, 0.f);
-                ap.vc[a] = v;
-                const float cn = __fadd_rn(ap.c[a], v);
-                ap.c[a] = cn;
-                trace_c(ap, a, cn, ap.step_dev ? *ap.step_dev : ap.step);
+                if (timed_out_s) { ap.vc[a] = nan; ap.c[a] = nan; }
+                else {
+                    const float v = next_velocity(ap.vc[a], __fadd_rn(counts[a], counts[3 - a]), nvd, __fadd_rn(counts[4 + a], counts[7 - a]), nvm,
+                                                  0.f, ap.mu, ap.lr, 0.f);
+                    ap.vc[a] = v;
+                    const float cn = __fadd_rn(ap.c[a], v);
+                    ap.c[a] = cn;
+                    trace_c(ap, a, cn, ap.step_dev ? *ap.step_dev : ap.step);
+                }
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
+            if (!ll && threadIdx.x == 0) {
                 if (ap.step_dev) *ap.step_dev += 1ull;
                 if (ap.batch_index_dev) { const int nb = *ap.batch_index_dev + 1; *ap.batch_index_dev = nb >= ap.n_batches ? 0 : nb; }
             }
@@ -404,6 +476,19 @@ __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) 
             if (threadIdx.x == 0) {
                 p.stats[p.lay.n_hidden_data] = p.c0; p.stats[p.lay.n_hidden_model] = p.c1;
                 p.stats[p.lay.n_vis_data] = p.c2; p.stats[p.lay.n_vis_model] = p.c3;
+            }
+        }
+    }
+    if (ll) {
+        // every CTA reads *sequence_dev at its start: the cursors are advanced by the last CTA to finish
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (timed_out_s) *p.ll.error_flag = 1;
+            const unsigned int t = atomicAdd(p.ll.ticket, 1u);
+            if (t == gridDim.x - 1) {
+                *p.ll.ticket = 0u;
+                if (ap.step_dev) *ap.step_dev += 1ull;
+                if (ap.batch_index_dev) { const int nb = *ap.batch_index_dev + 1; *ap.batch_index_dev = nb >= ap.n_batches ? 0 : nb; }
             }
         }
     }
@@ -437,7 +522,7 @@ __global__ void chain_dense_to_lin_kernel(const float *__restrict__ dense, int B
 // ---- one training step on the tcgen05 kernels -----------------------------------------------------------------------------------
 //     h2v_lin -> v2h_train_tc<SAMPLE> [x cd_k, the last one with the model statistics] -> v2h_train_tc<P|Q> (minibatch) -> reduce_tc
 // the same chain of programmatic dependents as the mma.sync path (train.cu), two partial buffers in the workspace.
-static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s, bool p2p, const PackJob *pack = nullptr) {
+static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s, const crbm_p2p_args *p2p, const PackJob *pack = nullptr) {
     const int K = a->K, M = a->M, P = a->pooling, Lh = a->L - M + 1;
     const TtGeom g = tt_geom(K, M, P);
     const int ds = a->doublestranded ? 1 : 0;
@@ -571,8 +656,16 @@ static int train_phases_tc(const crbm_train_args *a, int phases, cudaStream_t s,
         r.cnt_rows[0] = a->data; r.cnt_row_words[0] = a->data_row_words; r.cnt_n[0] = a->n_data; r.cnt_L[0] = a->L;
         r.cnt_rows[1] = a->v_model; r.cnt_row_words[1] = a->v_row_words; r.cnt_n[1] = a->batchsize; r.cnt_L[1] = Lv;
         r.batch_index = a->batch_index_dev;
-        r.fused = ((phases & CRBM_PHASE_APPLY) && !p2p && a->n_data > 0 && fused_update_enabled()) ? 1 : 0;
+        const bool ll = p2p && p2p->peer_ll[0];
+        r.fused = ((phases & CRBM_PHASE_APPLY) && (!p2p || ll) && a->n_data > 0 && fused_update_enabled()) ? 1 : 0;
         if (r.fused) fill_apply_params(a, &r.ap);
+        if (r.fused && ll) {
+            const size_t n_cta = (size_t)g.n_chunks * 4 * M + g.n_chunks + 1;
+            CRBM_CHECK_ARG(p2p->ll_parity_stride >= n_cta * CRBM_MAX_PEERS * LL_ROWS * 32 && p2p->error_flag,
+                           "crbm_train_step_p2p: receive buffer too small (crbm_p2p_ll_elems)");
+            fill_ll_view(a, p2p, &r.ll);
+        }
+        if (p2p && (phases & CRBM_PHASE_APPLY) && !r.fused) { set_error("crbm_train_step_p2p: internal: the fused exchange is not available for this step"); return CRBM_ERR_UNSUPPORTED; }
         CRBM_CHECK_CUDA(launch_chain(reduce_tc_kernel, dim3(g.n_chunks * 4 * M + g.n_chunks + 1), dim3(512), 0, s, r));
         CRBM_CHECK_LAUNCH();
         if (r.fused) return CRBM_OK;

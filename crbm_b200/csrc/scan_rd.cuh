@@ -1,0 +1,276 @@
+// Dense motif scan (getHitProbs / motifHitProbs, reference secomo/convRBM.py:238-257,507-514) with MOTIF = TMEM LANE and rows of
+// the output staged in shared memory and written by the TMA engine.
+//
+// The position-major kernel of scan_tc.cu gives a thread one position and eight motifs: a pool group is P lanes of a warp (shuffles
+// for every value) and a warp's store is 4 * (32 / P) * P bytes of one output row (120 bytes for P = 5: partial 32-byte sectors,
+// measured 19.6 % of the HBM peak). Here the machinery of scan_rt.cuh is used: MMA row r = motif 128 chunk + r (strand-selected
+// W as fp16 hi + lo, A operand), columns = hidden positions (one-hot tile built from the packed words, B operand), a thread of the
+// epilogue owns one motif and 32 consecutive positions: the pooled softmax p = e / (P + sum_group e) (:252) is a run of registers.
+// A CTA follows ONE sequence at a time: a step is four consecutive blocks of VP = (32 / P) * P positions (two units of 64 columns,
+// one per epilogue group), whose 4 VP probabilities per motif are staged in shared memory as one run [motif][4 VP] and stored with
+// one cp.async.bulk per motif row (480 bytes for P = 5, 512 for P = 1, 2, 4: whole sectors when the output rows are padded to
+// multiples of 8 floats, which crbm_b200/convRBM.py does). No per-value store instruction, no shuffle.
+// Bound: HBM write, 4 K bytes per hidden position.
+#pragma once
+#include "train_tc.cuh"
+
+namespace crbm {
+
+constexpr int RD_D1_BUFS = 8;
+constexpr int RD_SROW = 132;                  // floats per staged row: 4 VP (<= 128) + up to 7 pad floats; 132 = 4 mod 32: conflict-free 16-byte stores
+constexpr int RD_XSTAGES = 4;
+
+struct RowDenseParams {
+    const uint32_t *packed;
+    int row_words, n_rows, L, Lh;
+    const float *W, *b;
+    int K, M;
+    int strand_mode, out_kind;
+    int nblk32, nsteps, ksteps, n_atoms, Kdim, xstages;
+    float *out;
+    long long row_stride;          // floats between consecutive (n, k) rows (multiple of 4)
+    int store_len;                 // floats written per row: min(row_stride, Lh rounded up to 8)
+};
+
+__host__ __device__ inline size_t rd_smem_bytes(int n_atoms, int xstages) {
+    return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)xstages * n_atoms * TT_XATOM + (size_t)TT_ROWS * RD_SROW * 4 + 512 + 512;
+}
+
+__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epilogue_bar(int id) { asm volatile("bar.sync %0, 512;" ::"r"(id) : "memory"); }
+
+template <int P>
+__global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const RowDenseParams p) {
+    constexpr int VP = (32 / P) * P, NG = 32 / P;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    unsigned char *smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    const size_t w_bytes = (size_t)p.n_atoms * TT_WATOM, x_bytes = (size_t)p.n_atoms * TT_XATOM;
+    unsigned char *Whi = smem, *Wlo = Whi + w_bytes;
+    unsigned char *X = Wlo + w_bytes;
+    float *stage_s = reinterpret_cast<float *>(X + (size_t)p.xstages * x_bytes);
+    float *bias_s = stage_s + TT_ROWS * RD_SROW;
+    uint64_t *x_full = reinterpret_cast<uint64_t *>(bias_s + TT_ROWS);
+    uint64_t *x_free = x_full + TT_MAX_XSTAGES;
+    uint64_t *d1_full = x_free + TT_MAX_XSTAGES;
+    uint64_t *d1_free = d1_full + RD_D1_BUFS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d1_free + RD_D1_BUFS);
+    const int XS = p.xstages;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int chunk = blockIdx.y, G = gridDim.x;
+    const int Kdim = p.Kdim;
+    const bool prob = p.out_kind == CRBM_OUT_PROBABILITY;
+    // accumulator scale: sigmoid as 1 / (1 + 2^x) needs x = -log2(e) a; the pooled softmax needs 2^x = e^a
+    const float wscale = !prob ? 1.0f : P == 1 ? -1.4426950408889634f : 1.4426950408889634f;
+
+    if (warp == 3) tmem_alloc(tmem_slot, 512u);
+    if (tid == 64) {
+        for (int i = 0; i < TT_MAX_XSTAGES; ++i) { mbar_init(x_full + i, 64); mbar_init(x_free + i, 1); }
+        for (int i = 0; i < RD_D1_BUFS; ++i) { mbar_init(d1_full + i, 1); mbar_init(d1_free + i, 8); }
+    }
+    // ---- A operand: the chunk's rows of W (strand-selected), scaled, fp16 hi / lo, K-major SWIZZLE_128B ---------------------------
+    for (int idx = tid; idx < TT_ROWS * (Kdim >> 3); idx += TT_THREADS) {
+        const int r = idx & (TT_ROWS - 1), ch = idx >> 7;
+        const int k = chunk * TT_ROWS + r;
+        const bool want_f = p.strand_mode != CRBM_STRAND_RC, want_r = p.strand_mode != CRBM_STRAND_FWD;
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int m = 2 * ch + (e >> 2), a = e & 3;
+            float v = 0.f;
+            if (k < p.K && m < p.M) {
+                if (want_f) v += __ldg(p.W + ((size_t)k * 4 + a) * p.M + m);
+                if (want_r) v += __ldg(p.W + ((size_t)k * 4 + (3 - a)) * p.M + (p.M - 1 - m));
+            }
+            w[e] = v * wscale;
+        }
+        uint32_t hh[4], ll[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __half2 h2 = __floats2half2_rn(w[2 * e], w[2 * e + 1]);
+            const float2 back = __half22float2(h2);
+            const __half2 l2 = __floats2half2_rn(w[2 * e] - back.x, w[2 * e + 1] - back.y);
+            hh[e] = *reinterpret_cast<const uint32_t *>(&h2);
+            ll[e] = *reinterpret_cast<const uint32_t *>(&l2);
+        }
+        const uint32_t off = (uint32_t)(ch >> 3) * TT_WATOM + sw128_off(r, ch & 7);
+        *reinterpret_cast<uint4 *>(Whi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+        *reinterpret_cast<uint4 *>(Wlo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+    }
+    for (int r = tid; r < TT_ROWS; r += TT_THREADS) {
+        const int k = chunk * TT_ROWS + r;
+        const float bs = p.strand_mode == CRBM_STRAND_SUM ? 2.f : 1.f;      // both activities carry the bias (:513)
+        bias_s[r] = k < p.K ? bs * wscale * __ldg(p.b + k) : 0.f;
+    }
+    for (int i = tid; i < TT_ROWS * RD_SROW; i += TT_THREADS) stage_s[i] = 0.f;     // the pad columns of a run stay zero
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // work of this CTA: sequences x, x + G, ...; a sequence is nsteps steps of two units (one per epilogue group)
+    const int my_seqs = ((int)blockIdx.x < p.n_rows) ? (p.n_rows - 1 - (int)blockIdx.x) / G + 1 : 0;
+    const int my_units = 2 * my_seqs * p.nsteps;
+
+    if (warp < 2) {
+        // ================================================= producers: one-hot tiles ========================================
+        const int nch = 2 * p.ksteps;
+        // unit t: group t & 1 of step t >> 1 = (sequence iteration, step); tile row rr: block 4 step + 2 (t & 1) + (rr >> 5) of
+        // the sequence, position rr & 31 of the block
+        int qi = 0, st = 0;                                   // of the unit being LOADED (one ahead of the one being built)
+        auto load_row = [&](int t, uint32_t (&w)[4], int &sh, int &mlim) {
+            const int n = (int)blockIdx.x + qi * G, i = tid & 31;
+            const int j = (4 * st + 2 * (t & 1) + (tid >> 5)) * VP + i;
+            mlim = 0; sh = 0;
+            w[0] = w[1] = w[2] = w[3] = 0u;
+            if (i < VP && j < p.Lh) {
+                const int bit = 2 * (j + 16 * FRONT_PAD_WORDS);
+                const uint32_t *src = p.packed + (size_t)n * p.row_words + (bit >> 5);
+                sh = bit & 31;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) w[e] = __ldg(src + e);
+                mlim = p.M;
+            }
+            if (t & 1) { if (++st == p.nsteps) { st = 0; ++qi; } }
+        };
+        uint32_t cw[4], nw[4];
+        int csh = 0, cml = 0, nsh = 0, nml = 0;
+        if (my_units > 0) load_row(0, cw, csh, cml);
+        for (int t = 0; t < my_units; ++t) {
+            const int stage = t % XS, use = t / XS;
+            if (t + 1 < my_units) load_row(t + 1, nw, nsh, nml);
+            if (use > 0) mbar_wait(x_free + stage, (uint32_t)((use - 1) & 1));
+            tt_build_row(X + (size_t)stage * x_bytes, tid, nch, cw, csh, cml);
+            fence_async_smem();
+            mbar_arrive(x_full + stage);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cw[e] = nw[e];
+            csh = nsh; cml = nml;
+        }
+    } else if (warp == 2) {
+        // ================================================= MMA issue (one thread) ==========================================
+        if (lane == 0) {
+            const uint32_t whi = smem_u32(Whi), wlo = smem_u32(Wlo), xa = smem_u32(X);
+            const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TT_UNIT >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
+            for (int t = 0; t < my_units; ++t) {
+                const int stage = t % XS, buf = t & (RD_D1_BUFS - 1);
+                mbar_wait(x_full + stage, (uint32_t)((t / XS) & 1));
+                if (t >= RD_D1_BUFS) mbar_wait(d1_free + buf, (uint32_t)(((t >> 3) - 1) & 1));
+                tc_fence_after();
+                const uint32_t d1 = tmem_base + 64 * buf;
+                const uint32_t xs = xa + (uint32_t)(stage * x_bytes);
+                for (int s = 0; s < p.ksteps; ++s) {
+                    const uint32_t atom = s >> 2, koff = (s & 3) * 32;
+                    const uint64_t bd = umma_desc_sw128(xs + atom * TT_XATOM + koff);
+                    umma_f16(d1, umma_desc_sw128(whi + atom * TT_WATOM + koff), bd, idesc1, s > 0 ? 1u : 0u);
+                    umma_f16(d1, umma_desc_sw128(wlo + atom * TT_WATOM + koff), bd, idesc1, 1u);
+                }
+                umma_commit(d1_full + buf);
+                umma_commit(x_free + stage);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================================= epilogue ========================================================
+        const int ew = warp - 4, q = warp & 3, wg = ew >> 2, pr = wg >> 1, h = wg & 1;
+        const int r = 32 * q + lane;
+        const int k = chunk * TT_ROWS + r;
+        const bool row_ok = k < p.K;
+        const bool issuer = wg == 0;                           // these 128 threads store row r of every step
+        const float bias = bias_s[r];
+        float *my_stage = stage_s + (size_t)r * RD_SROW + (2 * pr + h) * VP;
+        const float *my_row = stage_s + (size_t)r * RD_SROW;
+        int qi = 0, st = 0;
+        for (int t = pr; t < my_units; t += 2) {
+            const int n = (int)blockIdx.x + qi * G;
+            const int blk = 4 * st + 2 * pr + h;
+            int nv = min(VP, p.Lh - blk * VP);
+            nv = nv < 0 ? 0 : nv;
+            const int buf = t & (RD_D1_BUFS - 1);
+            mbar_wait_backoff(d1_full + buf, (uint32_t)((t >> 3) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + 64 * buf + 32 * h;
+            uint32_t va[16], vb[16];
+            tmem_ld16(taddr, va);
+            tmem_ld16(taddr + 16, vb);
+            tmem_ld_wait();
+            tmem_ld_fence16(va);
+            tmem_ld_fence16(vb);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d1_free + buf);          // eight warps per buffer: the four lane quarters of both halves
+            float pv[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { pv[i] = __uint_as_float(va[i]) + bias; pv[16 + i] = __uint_as_float(vb[i]) + bias; }
+            if (prob && P == 1) {
+                // p = 1 / (1 + 2^x), x = -log2(e) a; two values share one reciprocal (x clamped at 60: the product stays finite)
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float e0, e1, rr;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(pv[i], 60.f)));
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(pv[i + 1], 60.f)));
+                    const float a0 = 1.0f + e0, a1 = 1.0f + e1;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rr) : "f"(a0 * a1));
+                    pv[i] = rr * a1;
+                    pv[i + 1] = rr * a0;
+                }
+            } else if (prob) {
+                // pooled probabilities: p = e / (P + sum_group e) (convRBM.py:252); a is clamped at 40 (as in scan_tc.cu)
+                constexpr float fpool = (float)P;
+#pragma unroll
+                for (int i = 0; i < VP; ++i) {
+                    float e;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(pv[i], 57.7f)));
+                    pv[i] = e;
+                }
+                if (nv != VP) {                                 // warp-uniform; whole groups drop out (nv is a multiple of P)
+#pragma unroll
+                    for (int i = 0; i < VP; ++i) pv[i] = i < nv ? pv[i] : 0.f;
+                }
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    float tot = 0.f;
+#pragma unroll
+                    for (int i = 0; i < P; ++i) tot += pv[g * P + i];
+                    float inv;
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fpool + tot));
+#pragma unroll
+                    for (int i = 0; i < P; ++i) pv[g * P + i] *= inv;
+                }
+            }
+            // the staging rows are free again when the bulk copies of the previous step have read them
+            if (issuer) bulk_wait_read();
+            epilogue_bar(2);
+            if (VP == 32) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(my_stage + i) = make_float4(pv[i], pv[i + 1], pv[i + 2], pv[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < VP; i += 2) *reinterpret_cast<float2 *>(my_stage + i) = make_float2(pv[i], pv[i + 1]);
+            }
+            fence_async_smem();
+            epilogue_bar(3);
+            if (issuer && row_ok) {
+                const int start = 4 * VP * st;
+                const int run = st == p.nsteps - 1 ? p.store_len - start : 4 * VP;
+                bulk_store(p.out + ((size_t)n * p.K + k) * (size_t)p.row_stride + start, my_row, (uint32_t)run * 4u);
+                bulk_commit();
+            }
+            if (++st == p.nsteps) { st = 0; ++qi; }
+        }
+        if (issuer) bulk_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 3) tmem_dealloc(tmem_base, 512u);
+}
+
+template <int P> int launch_v2h_rowdense_tc(const RowDenseParams &p, dim3 grid, cudaStream_t stream);
+
+}  // namespace crbm

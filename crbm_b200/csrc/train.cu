@@ -1099,6 +1099,12 @@ int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L, 
         g.mode = GEN_DENSE; g.strand_mode = strand_mode; g.out_kind = out_kind; g.out = out; g.out_row_stride = out_row_stride;
         return launch_gen_v2h(g, (cudaStream_t)stream);
     }
+    if (scan_uses_tcgen05() && pool_uses_mma() && rowdense_wanted(M, pool, out_row_stride, out)) {
+        RowDenseParams r{};
+        r.packed = packed; r.row_words = row_words; r.n_rows = N; r.L = L; r.Lh = Lh; r.W = W; r.b = b; r.K = K; r.M = M;
+        r.strand_mode = strand_mode; r.out_kind = out_kind; r.out = out; r.row_stride = out_row_stride;
+        return launch_rowdense_tc(pool, r, (cudaStream_t)stream);
+    }
     Tiling t = make_tiling(K, M, pool, Lh, N);
     DenseParams p{packed, row_words, N, L, Lh, W, b, K, M, pool, strand_mode, out_kind, t.bv, t.nblk, t.n_items, out};
     if ((pool == 1 || pool_uses_mma()) && scan_uses_tcgen05()) return launch_v2h_dense_tc(p, out_row_stride, (cudaStream_t)stream);

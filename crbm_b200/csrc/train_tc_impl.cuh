@@ -7,6 +7,7 @@
 #pragma once
 #include "train_tc.cuh"
 #include "scan_rt.cuh"
+#include "scan_rd.cuh"
 #include "h2v_tc.cuh"
 
 namespace crbm {
@@ -19,6 +20,10 @@ CRBM_FOR_EACH_TT_P(CRBM_DECLARE_TT)
 #define CRBM_DECLARE_RT(PV) template <> int launch_v2h_rows_tc<PV>(int, const RowsTcParams &, dim3, cudaStream_t);
 CRBM_FOR_EACH_TT_P(CRBM_DECLARE_RT)
 #undef CRBM_DECLARE_RT
+
+#define CRBM_DECLARE_RD(PV) template <> int launch_v2h_rowdense_tc<PV>(const RowDenseParams &, dim3, cudaStream_t);
+CRBM_FOR_EACH_TT_P(CRBM_DECLARE_RD)
+#undef CRBM_DECLARE_RD
 
 static bool tt_pool_built(int P) { return P == 1 || P == 2 || P == 4 || P == 5 || P == 10; }
 // scan reductions / free energy on the tcgen05 rows kernel (scan_rt.cuh): motif_length <= 32, pooling one of the built factors;
@@ -45,6 +50,37 @@ static int launch_rows_tc(int mode, int P, RowsTcParams &p, cudaStream_t s) {
 #undef CRBM_CASE
     }
     set_error("tcgen05 rows kernel: pooling %d not built", P);
+    return CRBM_ERR_UNSUPPORTED;
+}
+// Dense scan with the motif on the TMEM lane and TMA row stores (scan_rd.cuh): pooled probabilities by default (the position-major
+// kernel of scan_tc.cu needs shuffles and writes partial sectors there); CRBM_SCAN_KERNEL=rows also sends the un-pooled scan here,
+// CRBM_POOL_SCAN=pos keeps the pooled scan on scan_tc.cu. Needs output rows that are multiples of 4 floats on a 16-byte base.
+static bool rowdense_wanted(int M, int P, long long row_stride, const void *out) {
+    static int all = -1, pooled = -1;
+    if (all < 0) { const char *e = getenv("CRBM_SCAN_KERNEL"); all = (e && e[0] == 'r') ? 1 : 0; }
+    if (pooled < 0) { const char *e = getenv("CRBM_POOL_SCAN"); pooled = (e && e[0] == 'p') ? 0 : 1; }
+    if (M > 32 || !tt_pool_built(P) || (row_stride & 3) || ((uintptr_t)out & 15)) return false;
+    return P > 1 ? pooled == 1 : all == 1;
+}
+static int launch_rowdense_tc(int P, RowDenseParams &p, cudaStream_t s) {
+    p.Kdim = 16 * ceil_div(4 * p.M, 16);
+    p.ksteps = p.Kdim / 16;
+    p.n_atoms = ceil_div(p.Kdim, 64);
+    const int VP = (32 / P) * P;
+    p.nblk32 = ceil_div(p.Lh, VP);
+    p.nsteps = ceil_div(p.nblk32, 4);
+    p.xstages = RD_XSTAGES;
+    const long long len8 = 8 * (long long)ceil_div(p.Lh, 8);
+    p.store_len = (int)(p.row_stride < len8 ? p.row_stride : len8);
+    const int n_chunks = ceil_div(p.K, TT_ROWS);
+    int gx = num_sms() / n_chunks > 0 ? num_sms() / n_chunks : 1;
+    if (gx > p.n_rows) gx = p.n_rows;
+    switch (P) {
+#define CRBM_CASE(PV) case PV: return launch_v2h_rowdense_tc<PV>(p, dim3(gx, n_chunks), s);
+        CRBM_FOR_EACH_TT_P(CRBM_CASE)
+#undef CRBM_CASE
+    }
+    set_error("tcgen05 row-dense scan kernel: pooling %d not built", P);
     return CRBM_ERR_UNSUPPORTED;
 }
 // The tcgen05 path covers motif_length <= 32 (4 M <= 128 contraction columns, one MMA N) and the pooling factors it is instantiated

@@ -42,7 +42,7 @@ __device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem,
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epilogue_bar(int id) { asm volatile("bar.sync %0, 512;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void quarter_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 template <int P>
 __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const RowDenseParams p) {
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
         const float bs = p.strand_mode == CRBM_STRAND_SUM ? 2.f : 1.f;      // both activities carry the bias (:513)
         bias_s[r] = k < p.K ? bs * wscale * __ldg(p.b + k) : 0.f;
     }
-    for (int i = tid; i < TT_ROWS * RD_SROW; i += TT_THREADS) stage_s[i] = 0.f;     // the pad columns of a run stay zero
+    for (int i = tid; i < TT_ROWS * RD_SROW; i += TT_THREADS) stage_s[i] = 0.f;     // the pad columns behind the last block of a run stay zero
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -180,18 +180,11 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
         // ================================================= epilogue ========================================================
         const int ew = warp - 4, q = warp & 3, wg = ew >> 2, pr = wg >> 1, h = wg & 1;
         const int r = 32 * q + lane;
-        const int k = chunk * TT_ROWS + r;
-        const bool row_ok = k < p.K;
-        const bool issuer = wg == 0;                           // these 128 threads store row r of every step
         const float bias = bias_s[r];
         float *my_stage = stage_s + (size_t)r * RD_SROW + (2 * pr + h) * VP;
-        const float *my_row = stage_s + (size_t)r * RD_SROW;
         int qi = 0, st = 0;
         for (int t = pr; t < my_units; t += 2) {
             const int n = (int)blockIdx.x + qi * G;
-            const int blk = 4 * st + 2 * pr + h;
-            int nv = min(VP, p.Lh - blk * VP);
-            nv = nv < 0 ? 0 : nv;
             const int buf = t & (RD_D1_BUFS - 1);
             mbar_wait_backoff(d1_full + buf, (uint32_t)((t >> 3) & 1));
             tc_fence_after();
@@ -221,32 +214,35 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
                     pv[i + 1] = rr * a0;
                 }
             } else if (prob) {
-                // pooled probabilities: p = e / (P + sum_group e) (convRBM.py:252); a is clamped at 40 (as in scan_tc.cu)
+                // pooled probabilities p = e^a / (P + sum_group e^a) (convRBM.py:252), evaluated as 2^(x - m) / (P 2^-m + sum 2^(x - m))
+                // with m = max(0, max_group x): finite and accurate for any activity (the reference overflows beyond a = 88)
                 constexpr float fpool = (float)P;
 #pragma unroll
-                for (int i = 0; i < VP; ++i) {
-                    float e;
-                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(pv[i], 57.7f)));
-                    pv[i] = e;
-                }
-                if (nv != VP) {                                 // warp-uniform; whole groups drop out (nv is a multiple of P)
-#pragma unroll
-                    for (int i = 0; i < VP; ++i) pv[i] = i < nv ? pv[i] : 0.f;
-                }
-#pragma unroll
                 for (int g = 0; g < NG; ++g) {
-                    float tot = 0.f;
+                    float m = 0.f;
 #pragma unroll
-                    for (int i = 0; i < P; ++i) tot += pv[g * P + i];
+                    for (int i = 0; i < P; ++i) m = fmaxf(m, pv[g * P + i]);
+                    float tot, e0;
+                    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-m));
+                    tot = fpool * e0;
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        float e;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(pv[g * P + i] - m));
+                        pv[g * P + i] = e;
+                        tot += e;
+                    }
                     float inv;
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(fpool + tot));
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(tot));
 #pragma unroll
                     for (int i = 0; i < P; ++i) pv[g * P + i] *= inv;
                 }
             }
-            // the staging rows are free again when the bulk copies of the previous step have read them
-            if (issuer) bulk_wait_read();
-            epilogue_bar(2);
+            // the staging rows of this lane quarter are free again when the bulk copies of the previous step have read them; only the
+            // four warps of a lane quarter (one per block of the step) synchronise, so the quarters drift apart and the exponentials
+            // of one overlap the shared-memory stores and copy issue of another
+            if (lane < 8) bulk_wait_read();
+            quarter_bar(4 + q);
             if (VP == 32) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(my_stage + i) = make_float4(pv[i], pv[i + 1], pv[i + 2], pv[i + 3]);
@@ -255,16 +251,20 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
                 for (int i = 0; i < VP; i += 2) *reinterpret_cast<float2 *>(my_stage + i) = make_float2(pv[i], pv[i + 1]);
             }
             fence_async_smem();
-            epilogue_bar(3);
-            if (issuer && row_ok) {
-                const int start = 4 * VP * st;
-                const int run = st == p.nsteps - 1 ? p.store_len - start : 4 * VP;
-                bulk_store(p.out + ((size_t)n * p.K + k) * (size_t)p.row_stride + start, my_row, (uint32_t)run * 4u);
+            quarter_bar(8 + q);
+            if (lane < 8) {
+                // warp wg of the quarter stores rows 32 q + 8 wg + lane: one bulk copy per motif row and step
+                const int rr = 32 * q + 8 * wg + lane, kk = chunk * TT_ROWS + rr;
+                if (kk < p.K) {
+                    const int start = 4 * VP * st;
+                    const int run = st == p.nsteps - 1 ? p.store_len - start : 4 * VP;
+                    bulk_store(p.out + ((size_t)n * p.K + kk) * (size_t)p.row_stride + start, stage_s + (size_t)rr * RD_SROW, (uint32_t)run * 4u);
+                }
                 bulk_commit();
             }
             if (++st == p.nsteps) { st = 0; ++qi; }
         }
-        if (issuer) bulk_wait_all();
+        if (lane < 8) bulk_wait_all();
     }
     tc_fence_before();
     __syncthreads();

@@ -1,0 +1,5 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_scan_rd.py -x -q 2>&1 | tail -5
+python scratch/scan_ab.py 128 20 5 999 > gpurun_out/plain_rd.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:rowdense -s 2 -c 1 -f -o gpurun_out/r2_rd_c3 python scratch/scan_ab.py 128 20 5 999 > gpurun_out/ncu_rd.log 2>&1
+tail -3 gpurun_out/ncu_rd.log

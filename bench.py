@@ -374,7 +374,7 @@ def bench_scan(ctx, model, K, M, Lt, traffic_key):
         rec = {'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
                'sequences_per_gpu': n, 'n_gpus': world, 'ms': ms, 'output_GB_per_gpu': 4.0 * n * K * Lh / 1e9,
                'roofline': {'bound': 'hbm', 'kernel': ('v2h_dense_tc_kernel<PROB> (tcgen05.mma, TMEM accumulators)' if model.pooling == 1 else
-                                                    'v2h_dense_tc_kernel<PROB, POOL> (tcgen05.mma, TMEM accumulators, pool groups summed by warp shuffles)'),
+                                                    'v2h_rowdense_tc_kernel<P=%d> (tcgen05.mma, motif = TMEM lane, pooled softmax in registers, rows stored by cp.async.bulk)' % model.pooling),
                             'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak,
                             'traffic': ncu_traffic(traffic_key) if (mode == _lib.STRAND_FWD and traffic_key) else None,
                             'algorithmic_bytes': alg, 'peak_source': peak_src, 'bytes_per_nt': alg / (n * Lt)}}
@@ -653,6 +653,9 @@ def main():
                 r2['step_kernels_us'] = k2
                 r2['roofline'] = train_roofline(w2, r2['seq_len'], r2, k2, key + '_positive')
             r2['n_gpus'], r2['scaling'] = world, 'weak'
+            if key == 'c3':
+                # the pooled scan of config 3's model (getHitProbs with pooling 5)
+                r2['scan'] = bench_scan(ctx, m2, w2['K'], w2['M'], r2['seq_len'], 'c3_scan')
             if key == 'c4':
                 # config 5 shares config 4's motif bank: the 512 x 25 scan
                 Lt5 = C5['L']

@@ -10,8 +10,14 @@
 // one per epilogue group), whose 4 VP probabilities per motif are staged in shared memory as one run [motif][4 VP] and stored with
 // one cp.async.bulk per motif row (480 bytes for P = 5, 512 for P = 1, 2, 4: whole sectors when the output rows are padded to
 // multiples of 8 floats, which crbm_b200/convRBM.py does). No per-value store instruction, no shuffle.
+// When VP = 32 (P = 1, 2, 4) a block is a whole 128-byte line of an output row, and the epilogue warps are independent of each other:
+// the CTA's (sequence, block) pairs are dealt out two per unit without regard to sequence boundaries, a warp stages its 32 motifs x
+// 32 positions in its own 4 KB of shared memory (SWIZZLE_128B: conflict-free 16-byte stores) and ONE lane stores the tile with
+// cp.async.bulk.tensor.3d (tensor map over (position, motif, sequence): rows beyond K and positions beyond the row are clipped by
+// the TMA engine). The four warps of an SM sub-partition then drift apart, so the exponentials of one overlap the stores of another.
 // Bound: HBM write, 4 K bytes per hidden position.
 #pragma once
+#include <cuda.h>
 #include "train_tc.cuh"
 
 namespace crbm {
@@ -19,6 +25,9 @@ namespace crbm {
 constexpr int RD_D1_BUFS = 8;
 constexpr int RD_SROW = 132;                  // floats per staged row: 4 VP (<= 128) + up to 7 pad floats; 132 = 4 mod 32: conflict-free 16-byte stores
 constexpr int RD_XSTAGES = 4;
+constexpr int RD_THREADS = 672;               // warps 0-3 build the one-hot tiles (two pairs on alternate units), warp 4 owns TMEM and issues
+                                              // the MMAs, warps 5-20 are the epilogue (warp & 3 = TMEM lane quarter)
+constexpr int RD_LUT_BYTES = 21 * 16;         // one-hot patterns of two bases (16), of one base (4), zero (1)
 
 struct RowDenseParams {
     const uint32_t *packed;
@@ -30,10 +39,12 @@ struct RowDenseParams {
     float *out;
     long long row_stride;          // floats between consecutive (n, k) rows (multiple of 4)
     int store_len;                 // floats written per row: min(row_stride, Lh rounded up to 8)
+    int debug;                     // CRBM_RD_DEBUG bits (timing experiments only): 1 = no stores, 2 = no exponentials
+    int tensor_store;              // VP = 32: per-warp tiles stored through the tensor map (else one bulk copy per motif row and step)
 };
 
 __host__ __device__ inline size_t rd_smem_bytes(int n_atoms, int xstages) {
-    return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)xstages * n_atoms * TT_XATOM + (size_t)TT_ROWS * RD_SROW * 4 + 512 + 512;
+    return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)xstages * n_atoms * TT_XATOM + (size_t)TT_ROWS * RD_SROW * 4 + 512 + 512 + 512;
 }
 
 __device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
@@ -42,11 +53,37 @@ __device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem,
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tensor_store_3d(const CUtensorMap *map, const void *src_smem, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void quarter_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
+// One-hot row of a 64-row tile from a table of the 16-byte patterns of two bases (same chunk layout as tt_build_row: chunk ch = bases
+// 2 ch, 2 ch + 1 as eight fp16): a shift, a mask, a 16-byte table load and a 16-byte store per chunk instead of ~14 ALU instructions.
+// lut: entries 0-15 pattern of (b0 | b1 << 2), 16-19 pattern of b0 alone (last chunk of an odd motif length), 20 zero.
+__device__ __forceinline__ void rd_build_row(unsigned char *X, const unsigned char *lut, int r, int nch, int M, const uint32_t (&w)[4], int sh, bool valid) {
+    uint32_t v[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    const int nfull = M >> 1;
+    unsigned char *row = X + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+        if (ch < nch) {
+            const uint32_t bits = (v[ch >> 3] >> (4 * (ch & 7))) & 15u;
+            uint32_t e = ch < nfull ? bits : (ch == nfull && (M & 1)) ? 16u + (bits & 3u) : 20u;     // (uniform in ch: M is a kernel constant)
+            e = valid ? e : 20u;
+            const uint4 q = *reinterpret_cast<const uint4 *>(lut + e * 16);
+            *reinterpret_cast<uint4 *>(row + (ch >> 3) * TT_XATOM + (((ch ^ r) & 7) << 4)) = q;
+        }
+    }
+}
+
 template <int P>
-__global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const RowDenseParams p) {
+__global__ void __launch_bounds__(RD_THREADS, 1) v2h_rowdense_tc_kernel(const RowDenseParams p, const __grid_constant__ CUtensorMap tmap) {
     constexpr int VP = (32 / P) * P, NG = 32 / P;
+    const bool tensor = VP == 32 && p.tensor_store;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     unsigned char *smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
@@ -60,6 +97,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
     uint64_t *d1_full = x_free + TT_MAX_XSTAGES;
     uint64_t *d1_free = d1_full + RD_D1_BUFS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d1_free + RD_D1_BUFS);
+    unsigned char *lut_s = reinterpret_cast<unsigned char *>(tmem_slot) + 16 + ((16 - ((smem_u32(tmem_slot) + 16) & 15)) & 15);
     const int XS = p.xstages;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -70,13 +108,22 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
     // accumulator scale: sigmoid as 1 / (1 + 2^x) needs x = -log2(e) a; the pooled softmax needs 2^x = e^a
     const float wscale = !prob ? 1.0f : P == 1 ? -1.4426950408889634f : 1.4426950408889634f;
 
-    if (warp == 3) tmem_alloc(tmem_slot, 512u);
+    if (warp == 4) tmem_alloc(tmem_slot, 512u);
     if (tid == 64) {
         for (int i = 0; i < TT_MAX_XSTAGES; ++i) { mbar_init(x_full + i, 64); mbar_init(x_free + i, 1); }
         for (int i = 0; i < RD_D1_BUFS; ++i) { mbar_init(d1_full + i, 1); mbar_init(d1_free + i, 8); }
     }
+    if (tid < 21) {
+        // fp16 1.0 in the half selected by the low bit of the base, in the word selected by its high bit
+        const int b0 = tid & 3, b1 = (tid >> 2) & 3;
+        const uint32_t h0 = tid < 20 ? (0x3C00u << (16 * (b0 & 1))) : 0u, h1 = tid < 16 ? (0x3C00u << (16 * (b1 & 1))) : 0u;
+        uint4 q;
+        q.x = (b0 & 2) ? 0u : h0; q.y = (b0 & 2) ? h0 : 0u;
+        q.z = (b1 & 2) ? 0u : h1; q.w = (b1 & 2) ? h1 : 0u;
+        *reinterpret_cast<uint4 *>(lut_s + tid * 16) = q;
+    }
     // ---- A operand: the chunk's rows of W (strand-selected), scaled, fp16 hi / lo, K-major SWIZZLE_128B ---------------------------
-    for (int idx = tid; idx < TT_ROWS * (Kdim >> 3); idx += TT_THREADS) {
+    for (int idx = tid; idx < TT_ROWS * (Kdim >> 3); idx += RD_THREADS) {
         const int r = idx & (TT_ROWS - 1), ch = idx >> 7;
         const int k = chunk * TT_ROWS + r;
         const bool want_f = p.strand_mode != CRBM_STRAND_RC, want_r = p.strand_mode != CRBM_STRAND_FWD;
@@ -104,12 +151,12 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
         *reinterpret_cast<uint4 *>(Whi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
         *reinterpret_cast<uint4 *>(Wlo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
     }
-    for (int r = tid; r < TT_ROWS; r += TT_THREADS) {
+    for (int r = tid; r < TT_ROWS; r += RD_THREADS) {
         const int k = chunk * TT_ROWS + r;
         const float bs = p.strand_mode == CRBM_STRAND_SUM ? 2.f : 1.f;      // both activities carry the bias (:513)
         bias_s[r] = k < p.K ? bs * wscale * __ldg(p.b + k) : 0.f;
     }
-    for (int i = tid; i < TT_ROWS * RD_SROW; i += TT_THREADS) stage_s[i] = 0.f;     // the pad columns behind the last block of a run stay zero
+    for (int i = tid; i < TT_ROWS * RD_SROW; i += RD_THREADS) stage_s[i] = 0.f;     // the pad columns behind the last block of a run stay zero
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -117,44 +164,55 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
     const uint32_t tmem_base = *tmem_slot;
     // work of this CTA: sequences x, x + G, ...; a sequence is nsteps steps of two units (one per epilogue group)
     const int my_seqs = ((int)blockIdx.x < p.n_rows) ? (p.n_rows - 1 - (int)blockIdx.x) / G + 1 : 0;
-    const int my_units = 2 * my_seqs * p.nsteps;
+    const int my_blocks = my_seqs * p.nblk32;                                       // tensor-store mode: two blocks per unit
+    const int my_units = tensor ? (my_blocks + 1) >> 1 : 2 * my_seqs * p.nsteps;
 
-    if (warp < 2) {
+    if (warp < 4) {
         // ================================================= producers: one-hot tiles ========================================
-        const int nch = 2 * p.ksteps;
-        // unit t: group t & 1 of step t >> 1 = (sequence iteration, step); tile row rr: block 4 step + 2 (t & 1) + (rr >> 5) of
-        // the sequence, position rr & 31 of the block
-        int qi = 0, st = 0;                                   // of the unit being LOADED (one ahead of the one being built)
-        auto load_row = [&](int t, uint32_t (&w)[4], int &sh, int &mlim) {
-            const int n = (int)blockIdx.x + qi * G, i = tid & 31;
-            const int j = (4 * st + 2 * (t & 1) + (tid >> 5)) * VP + i;
-            mlim = 0; sh = 0;
+        // Two pairs of warps on alternate units (pair = warp >> 1): the proxy fence behind a tile waits for the thread's outstanding
+        // global loads (the packed words of its next tile), so one pair delivers a tile per load latency; two pairs hide it.
+        const int nch = 2 * p.ksteps, pair = warp >> 1, ptid = tid & 63;
+        // unit t, tile row rr -> (sequence, position): bulk mode: group t & 1 of step t >> 1, block 4 step + 2 (t & 1) + (rr >> 5) of the
+        // step's sequence; tensor mode: block g = 2 t + (rr >> 5) of the CTA's list, sequence g / nblk
+        auto load_row = [&](int t, uint32_t (&w)[4], int &sh, bool &valid) {
+            const int i = ptid & 31;
+            int n, j;
+            if (tensor) {
+                const int g = 2 * t + (ptid >> 5), si = g / p.nblk32;
+                n = g < my_blocks ? (int)blockIdx.x + si * G : p.n_rows;
+                j = (g - si * p.nblk32) * 32 + i;
+            } else {
+                const int step = t >> 1, si = step / p.nsteps, st = step - si * p.nsteps;
+                n = (int)blockIdx.x + si * G;
+                j = (4 * st + 2 * (t & 1) + (ptid >> 5)) * VP + i;
+            }
+            valid = i < VP && j < p.Lh && n < p.n_rows;
+            sh = 0;
             w[0] = w[1] = w[2] = w[3] = 0u;
-            if (i < VP && j < p.Lh) {
+            if (valid) {
                 const int bit = 2 * (j + 16 * FRONT_PAD_WORDS);
                 const uint32_t *src = p.packed + (size_t)n * p.row_words + (bit >> 5);
                 sh = bit & 31;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) w[e] = __ldg(src + e);
-                mlim = p.M;
             }
-            if (t & 1) { if (++st == p.nsteps) { st = 0; ++qi; } }
         };
         uint32_t cw[4], nw[4];
-        int csh = 0, cml = 0, nsh = 0, nml = 0;
-        if (my_units > 0) load_row(0, cw, csh, cml);
-        for (int t = 0; t < my_units; ++t) {
+        int csh = 0, nsh = 0;
+        bool cv = false, nv = false;
+        if (pair < my_units) load_row(pair, cw, csh, cv);
+        for (int t = pair; t < my_units; t += 2) {
             const int stage = t % XS, use = t / XS;
-            if (t + 1 < my_units) load_row(t + 1, nw, nsh, nml);
+            if (t + 2 < my_units) load_row(t + 2, nw, nsh, nv);
             if (use > 0) mbar_wait(x_free + stage, (uint32_t)((use - 1) & 1));
-            tt_build_row(X + (size_t)stage * x_bytes, tid, nch, cw, csh, cml);
+            rd_build_row(X + (size_t)stage * x_bytes, lut_s, ptid, nch, p.M, cw, csh, cv);
             fence_async_smem();
             mbar_arrive(x_full + stage);
 #pragma unroll
             for (int e = 0; e < 4; ++e) cw[e] = nw[e];
-            csh = nsh; cml = nml;
+            csh = nsh; cv = nv;
         }
-    } else if (warp == 2) {
+    } else if (warp == 4) {
         // ================================================= MMA issue (one thread) ==========================================
         if (lane == 0) {
             const uint32_t whi = smem_u32(Whi), wlo = smem_u32(Wlo), xa = smem_u32(X);
@@ -176,9 +234,10 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
                 umma_commit(x_free + stage);
             }
         }
-    } else if (warp >= 4) {
+    } else {
         // ================================================= epilogue ========================================================
-        const int ew = warp - 4, q = warp & 3, wg = ew >> 2, pr = wg >> 1, h = wg & 1;
+        // (any four consecutive warps cover the four TMEM lane quarters: warp & 3)
+        const int ew = warp - 5, q = warp & 3, wg = ew >> 2, pr = wg >> 1, h = wg & 1;
         const int r = 32 * q + lane;
         const float bias = bias_s[r];
         float *my_stage = stage_s + (size_t)r * RD_SROW + (2 * pr + h) * VP;
@@ -201,7 +260,8 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
             float pv[32];
 #pragma unroll
             for (int i = 0; i < 16; ++i) { pv[i] = __uint_as_float(va[i]) + bias; pv[16 + i] = __uint_as_float(vb[i]) + bias; }
-            if (prob && P == 1) {
+            if (p.debug & 2) {
+            } else if (prob && P == 1) {
                 // p = 1 / (1 + 2^x), x = -log2(e) a; two values share one reciprocal (x clamped at 60: the product stays finite)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
@@ -238,6 +298,23 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
                     for (int i = 0; i < P; ++i) pv[g * P + i] *= inv;
                 }
             }
+            if (tensor) {
+                // this warp's own tile [32 motifs][32 positions], rows of 128 bytes, 16-byte chunks XOR-swizzled with the row (SWIZZLE_128B)
+                const int g = 2 * t + h, si = g / p.nblk32, blk = g - si * p.nblk32;
+                unsigned char *tile = reinterpret_cast<unsigned char *>(stage_s) + (size_t)ew * 4096;
+                if (lane == 0) bulk_wait_read();                // the previous store of this warp has read the tile
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4 *>(tile + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_float4(pv[4 * c], pv[4 * c + 1], pv[4 * c + 2], pv[4 * c + 3]);
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0 && g < my_blocks && !(p.debug & 1)) {
+                    tensor_store_3d(&tmap, tile, blk * 32, chunk * TT_ROWS + 32 * q, (int)blockIdx.x + si * G);
+                    bulk_commit();
+                }
+                continue;
+            }
             // the staging rows of this lane quarter are free again when the bulk copies of the previous step have read them; only the
             // four warps of a lane quarter (one per block of the step) synchronise, so the quarters drift apart and the exponentials
             // of one overlap the shared-memory stores and copy issue of another
@@ -255,7 +332,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
             if (lane < 8) {
                 // warp wg of the quarter stores rows 32 q + 8 wg + lane: one bulk copy per motif row and step
                 const int rr = 32 * q + 8 * wg + lane, kk = chunk * TT_ROWS + rr;
-                if (kk < p.K) {
+                if (kk < p.K && !(p.debug & 1)) {
                     const int start = 4 * VP * st;
                     const int run = st == p.nsteps - 1 ? p.store_len - start : 4 * VP;
                     bulk_store(p.out + ((size_t)n * p.K + kk) * (size_t)p.row_stride + start, stage_s + (size_t)rr * RD_SROW, (uint32_t)run * 4u);
@@ -264,13 +341,13 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
             }
             if (++st == p.nsteps) { st = 0; ++qi; }
         }
-        if (lane < 8) bulk_wait_all();
+        if (lane < 8) bulk_wait_all();                         // (tensor-store mode: lane 0 holds the groups)
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 3) tmem_dealloc(tmem_base, 512u);
+    if (warp == 4) tmem_dealloc(tmem_base, 512u);
 }
 
-template <int P> int launch_v2h_rowdense_tc(const RowDenseParams &p, dim3 grid, cudaStream_t stream);
+template <int P> int launch_v2h_rowdense_tc(const RowDenseParams &p, const CUtensorMap &tmap, dim3 grid, cudaStream_t stream);
 
 }  // namespace crbm

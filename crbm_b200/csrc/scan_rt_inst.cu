@@ -31,7 +31,7 @@ int launch_v2h_rows_tc<CRBM_TT_P>(int mode, const RowsTcParams &p, dim3 grid, cu
 }
 
 template <>
-int launch_v2h_rowdense_tc<CRBM_TT_P>(const RowDenseParams &p, dim3 grid, cudaStream_t stream) {
+int launch_v2h_rowdense_tc<CRBM_TT_P>(const RowDenseParams &p, const CUtensorMap &tmap, dim3 grid, cudaStream_t stream) {
     static size_t configured[64];                         // per device
     int dev = 0;
     CRBM_CHECK_CUDA(cudaGetDevice(&dev));
@@ -41,7 +41,7 @@ int launch_v2h_rowdense_tc<CRBM_TT_P>(const RowDenseParams &p, dim3 grid, cudaSt
         CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_rowdense_tc_kernel<CRBM_TT_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev & 63] = smem;
     }
-    v2h_rowdense_tc_kernel<CRBM_TT_P><<<grid, TT_THREADS, smem, stream>>>(p);
+    v2h_rowdense_tc_kernel<CRBM_TT_P><<<grid, RD_THREADS, smem, stream>>>(p, tmap);
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }

@@ -21,7 +21,7 @@ CRBM_FOR_EACH_TT_P(CRBM_DECLARE_TT)
 CRBM_FOR_EACH_TT_P(CRBM_DECLARE_RT)
 #undef CRBM_DECLARE_RT
 
-#define CRBM_DECLARE_RD(PV) template <> int launch_v2h_rowdense_tc<PV>(const RowDenseParams &, dim3, cudaStream_t);
+#define CRBM_DECLARE_RD(PV) template <> int launch_v2h_rowdense_tc<PV>(const RowDenseParams &, const CUtensorMap &, dim3, cudaStream_t);
 CRBM_FOR_EACH_TT_P(CRBM_DECLARE_RD)
 #undef CRBM_DECLARE_RD
 
@@ -62,6 +62,24 @@ static bool rowdense_wanted(int M, int P, long long row_stride, const void *out)
     if (M > 32 || !tt_pool_built(P) || (row_stride & 3) || ((uintptr_t)out & 15)) return false;
     return P > 1 ? pooled == 1 : all == 1;
 }
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                           const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder() {
+    static TensorMapEncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TensorMapEncodeTiledFn>(ptr);
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
 static int launch_rowdense_tc(int P, RowDenseParams &p, cudaStream_t s) {
     p.Kdim = 16 * ceil_div(4 * p.M, 16);
     p.ksteps = p.Kdim / 16;
@@ -75,8 +93,25 @@ static int launch_rowdense_tc(int P, RowDenseParams &p, cudaStream_t s) {
     const int n_chunks = ceil_div(p.K, TT_ROWS);
     int gx = num_sms() / n_chunks > 0 ? num_sms() / n_chunks : 1;
     if (gx > p.n_rows) gx = p.n_rows;
+    // VP = 32: a warp's tile is stored through a tensor map over (position, motif, sequence) of fp32, box 32 x 32 x 1, SWIZZLE_128B;
+    // CRBM_RD_STORE=bulk keeps the per-row bulk copies
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    static int want_tensor = -1;
+    if (want_tensor < 0) { const char *e = getenv("CRBM_RD_STORE"); want_tensor = (e && e[0] == 'b') ? 0 : 1; }
+    p.tensor_store = 0;
+    { const char *e = getenv("CRBM_RD_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    if (VP == 32 && want_tensor && tensor_map_encoder()) {
+        const cuuint64_t dims[3] = {(cuuint64_t)p.store_len, (cuuint64_t)p.K, (cuuint64_t)p.n_rows};
+        const cuuint64_t strides[2] = {(cuuint64_t)p.row_stride * 4, (cuuint64_t)p.row_stride * 4 * (cuuint64_t)p.K};
+        const cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+        const CUresult r = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out, dims, strides, box, estr,
+                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) p.tensor_store = 1;
+    }
     switch (P) {
-#define CRBM_CASE(PV) case PV: return launch_v2h_rowdense_tc<PV>(p, dim3(gx, n_chunks), s);
+#define CRBM_CASE(PV) case PV: return launch_v2h_rowdense_tc<PV>(p, tmap, dim3(gx, n_chunks), s);
         CRBM_FOR_EACH_TT_P(CRBM_CASE)
 #undef CRBM_CASE
     }

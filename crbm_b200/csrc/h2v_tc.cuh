@@ -220,12 +220,11 @@ __global__ void __launch_bounds__(HT_THREADS, 1) h2v_tc_kernel(const H2VTcParams
                     if (it == 0) HT_MARK(4);
                     if (it == 8) HT_MARK(11);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(ring_a + (size_t)sa_i * 2 * HT_A_BYTES), sb = smem_u32(ring_b + (size_t)sb_i * HT_B_BYTES);
+                    const uint32_t sa = umma_desc_lo(smem_u32(ring_a + (size_t)sa_i * 2 * HT_A_BYTES)), sb = umma_desc_lo(smem_u32(ring_b + (size_t)sb_i * HT_B_BYTES));
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t bd = umma_desc_sw128(sb + 32 * ks);
-                        umma_f16(d, umma_desc_sw128(sa + 32 * ks), bd, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-                        umma_f16(d, umma_desc_sw128(sa + HT_A_BYTES + 32 * ks), bd, idesc, 1u);
+                        umma_f16_lo(d, sa + 2 * ks, sb + 2 * ks, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                        umma_f16_lo(d, sa + (HT_A_BYTES >> 4) + 2 * ks, sb + 2 * ks, idesc, 1u);
                     }
                     umma_commit(empty_b + sb_i);
                     if (cl == 1) umma_commit(empty_a + sa_i);

@@ -27,7 +27,6 @@ constexpr int RD_SROW = 132;                  // floats per staged row: 4 VP (<=
 constexpr int RD_XSTAGES = 4;
 constexpr int RD_THREADS = 672;               // warps 0-3 build the one-hot tiles (two pairs on alternate units), warp 4 owns TMEM and issues
                                               // the MMAs, warps 5-20 are the epilogue (warp & 3 = TMEM lane quarter)
-constexpr int RD_LUT_BYTES = 21 * 16;         // one-hot patterns of two bases (16), of one base (4), zero (1)
 
 struct RowDenseParams {
     const uint32_t *packed;
@@ -58,27 +57,6 @@ __device__ __forceinline__ void tensor_store_3d(const CUtensorMap *map, const vo
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src_smem)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void quarter_bar(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
-
-// One-hot row of a 64-row tile from a table of the 16-byte patterns of two bases (same chunk layout as tt_build_row: chunk ch = bases
-// 2 ch, 2 ch + 1 as eight fp16): a shift, a mask, a 16-byte table load and a 16-byte store per chunk instead of ~14 ALU instructions.
-// lut: entries 0-15 pattern of (b0 | b1 << 2), 16-19 pattern of b0 alone (last chunk of an odd motif length), 20 zero.
-__device__ __forceinline__ void rd_build_row(unsigned char *X, const unsigned char *lut, int r, int nch, int M, const uint32_t (&w)[4], int sh, bool valid) {
-    uint32_t v[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
-    const int nfull = M >> 1;
-    unsigned char *row = X + (r >> 3) * 1024 + (r & 7) * 128;
-#pragma unroll
-    for (int ch = 0; ch < 16; ++ch) {
-        if (ch < nch) {
-            const uint32_t bits = (v[ch >> 3] >> (4 * (ch & 7))) & 15u;
-            uint32_t e = ch < nfull ? bits : (ch == nfull && (M & 1)) ? 16u + (bits & 3u) : 20u;     // (uniform in ch: M is a kernel constant)
-            e = valid ? e : 20u;
-            const uint4 q = *reinterpret_cast<const uint4 *>(lut + e * 16);
-            *reinterpret_cast<uint4 *>(row + (ch >> 3) * TT_XATOM + (((ch ^ r) & 7) << 4)) = q;
-        }
-    }
-}
 
 template <int P>
 __global__ void __launch_bounds__(RD_THREADS, 1) v2h_rowdense_tc_kernel(const RowDenseParams p, const __grid_constant__ CUtensorMap tmap) {
@@ -113,15 +91,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
         for (int i = 0; i < TT_MAX_XSTAGES; ++i) { mbar_init(x_full + i, 64); mbar_init(x_free + i, 1); }
         for (int i = 0; i < RD_D1_BUFS; ++i) { mbar_init(d1_full + i, 1); mbar_init(d1_free + i, 8); }
     }
-    if (tid < 21) {
-        // fp16 1.0 in the half selected by the low bit of the base, in the word selected by its high bit
-        const int b0 = tid & 3, b1 = (tid >> 2) & 3;
-        const uint32_t h0 = tid < 20 ? (0x3C00u << (16 * (b0 & 1))) : 0u, h1 = tid < 16 ? (0x3C00u << (16 * (b1 & 1))) : 0u;
-        uint4 q;
-        q.x = (b0 & 2) ? 0u : h0; q.y = (b0 & 2) ? h0 : 0u;
-        q.z = (b1 & 2) ? 0u : h1; q.w = (b1 & 2) ? h1 : 0u;
-        *reinterpret_cast<uint4 *>(lut_s + tid * 16) = q;
-    }
+    tt_lut_init(lut_s, tid);
     // ---- A operand: the chunk's rows of W (strand-selected), scaled, fp16 hi / lo, K-major SWIZZLE_128B ---------------------------
     for (int idx = tid; idx < TT_ROWS * (Kdim >> 3); idx += RD_THREADS) {
         const int r = idx & (TT_ROWS - 1), ch = idx >> 7;
@@ -205,7 +175,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
             const int stage = t % XS, use = t / XS;
             if (t + 2 < my_units) load_row(t + 2, nw, nsh, nv);
             if (use > 0) mbar_wait(x_free + stage, (uint32_t)((use - 1) & 1));
-            rd_build_row(X + (size_t)stage * x_bytes, lut_s, ptid, nch, p.M, cw, csh, cv);
+            tt_build_row_lut(X + (size_t)stage * x_bytes, lut_s, ptid, nch, p.M, cw, csh, cv);
             fence_async_smem();
             mbar_arrive(x_full + stage);
 #pragma unroll
@@ -215,7 +185,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
     } else if (warp == 4) {
         // ================================================= MMA issue (one thread) ==========================================
         if (lane == 0) {
-            const uint32_t whi = smem_u32(Whi), wlo = smem_u32(Wlo), xa = smem_u32(X);
+            const uint32_t whi_lo = umma_desc_lo(smem_u32(Whi)), wlo_lo = umma_desc_lo(smem_u32(Wlo)), xa = smem_u32(X);
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TT_UNIT >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
             for (int t = 0; t < my_units; ++t) {
                 const int stage = t % XS, buf = t & (RD_D1_BUFS - 1);
@@ -224,11 +194,14 @@ __global__ void __launch_bounds__(RD_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
                 tc_fence_after();
                 const uint32_t d1 = tmem_base + 64 * buf;
                 const uint32_t xs = xa + (uint32_t)(stage * x_bytes);
-                for (int s = 0; s < p.ksteps; ++s) {
-                    const uint32_t atom = s >> 2, koff = (s & 3) * 32;
-                    const uint64_t bd = umma_desc_sw128(xs + atom * TT_XATOM + koff);
-                    umma_f16(d1, umma_desc_sw128(whi + atom * TT_WATOM + koff), bd, idesc1, s > 0 ? 1u : 0u);
-                    umma_f16(d1, umma_desc_sw128(wlo + atom * TT_WATOM + koff), bd, idesc1, 1u);
+                const uint32_t x_lo = umma_desc_lo(xs);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    if (s < p.ksteps) {
+                        const uint32_t oa = (uint32_t)(((s >> 2) * TT_WATOM + (s & 3) * 32) >> 4), ox = (uint32_t)(((s >> 2) * TT_XATOM + (s & 3) * 32) >> 4);
+                        umma_f16_lo(d1, whi_lo + oa, x_lo + ox, idesc1, s > 0 ? 1u : 0u);
+                        umma_f16_lo(d1, wlo_lo + oa, x_lo + ox, idesc1, 1u);
+                    }
                 }
                 umma_commit(d1_full + buf);
                 umma_commit(x_free + stage);

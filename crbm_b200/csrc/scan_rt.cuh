@@ -21,6 +21,8 @@ namespace crbm {
 
 enum : int { RT_REDUCE = 0, RT_FE = 1 };
 constexpr int RT_D1_BUFS = 8;
+constexpr int RT_THREADS = 672;               // warps 0-3 build the one-hot tiles (two pairs on alternate units), warp 4 owns TMEM and issues
+                                              // the MMAs, warps 5-20 are the epilogue (warp & 3 = TMEM lane quarter)
 
 struct RowsTcParams {
     const uint32_t *packed;
@@ -40,7 +42,7 @@ struct RowsTcParams {
 };
 
 __host__ __device__ inline size_t rt_smem_bytes(int n_atoms, int xstages) {
-    return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)xstages * n_atoms * TT_XATOM + 512 + 512;
+    return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)xstages * n_atoms * TT_XATOM + 512 + 512 + 512;
 }
 
 // ln(1 + t) for t = 2^y >= 0 given y (so that huge arguments need no overflow handling): series below 1/16, lg2 above, y ln 2 beyond 2^24
@@ -53,7 +55,7 @@ __device__ __forceinline__ float rt_softplus(float t, float y) {
 }
 
 template <int MODE, int P>
-__global__ void __launch_bounds__(TT_THREADS, 1) v2h_rows_tc_kernel(const RowsTcParams p) {
+__global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTcParams p) {
     constexpr int VP = (32 / P) * P, NG = 32 / P;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -67,6 +69,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
     uint64_t *d1_full = x_free + TT_MAX_XSTAGES;
     uint64_t *d1_free = d1_full + RT_D1_BUFS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d1_free + RT_D1_BUFS);
+    unsigned char *lut_s = reinterpret_cast<unsigned char *>(tmem_slot) + 16 + ((16 - ((smem_u32(tmem_slot) + 16) & 15)) & 15);
     const int XS = p.xstages;
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -77,13 +80,14 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
     // accumulator scale: sigmoid as 1 / (1 + 2^x) needs x = -log2(e) a; the pooled softmax and the free energy need 2^x = e^a
     const float wscale = !prob ? 1.0f : (MODE == RT_REDUCE && P == 1) ? -1.4426950408889634f : 1.4426950408889634f;
 
-    if (warp == 3) tmem_alloc(tmem_slot, 512u);
+    if (warp == 4) tmem_alloc(tmem_slot, 512u);
+    tt_lut_init(lut_s, tid);
     if (tid == 64) {
         for (int i = 0; i < TT_MAX_XSTAGES; ++i) { mbar_init(x_full + i, 64); mbar_init(x_free + i, 1); }
         for (int i = 0; i < RT_D1_BUFS; ++i) { mbar_init(d1_full + i, 1); mbar_init(d1_free + i, 8); }
     }
     // ---- A operand: the chunk's rows of W (strand-selected), scaled, fp16 hi / lo, K-major SWIZZLE_128B ---------------------------
-    for (int idx = tid; idx < TT_ROWS * (Kdim >> 3); idx += TT_THREADS) {
+    for (int idx = tid; idx < TT_ROWS * (Kdim >> 3); idx += RT_THREADS) {
         const int r = idx & (TT_ROWS - 1), ch = idx >> 7;
         int k, want_f, want_r;
         if (MODE == RT_REDUCE) {
@@ -118,7 +122,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
         *reinterpret_cast<uint4 *>(Whi + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
         *reinterpret_cast<uint4 *>(Wlo + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
     }
-    for (int r = tid; r < TT_ROWS; r += TT_THREADS) {
+    for (int r = tid; r < TT_ROWS; r += RT_THREADS) {
         const int k = MODE == RT_REDUCE ? chunk * TT_ROWS + r : chunk * TT_KC + (r & 63);
         const float bs = (MODE == RT_REDUCE && p.strand_mode == CRBM_STRAND_SUM) ? 2.f : 1.f;      // both activities carry the bias (:513)
         bias_s[r] = k < p.K ? bs * wscale * __ldg(p.b + k) : 0.f;
@@ -132,44 +136,47 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
     const int my_quads = ((int)blockIdx.x < p.n_quads) ? (p.n_quads - 1 - (int)blockIdx.x) / G + 1 : 0;
     const int my_units = 2 * my_quads * p.nblk32;
 
-    if (warp < 2) {
+    if (warp < 4) {
         // ================================================= producers: one-hot tiles ========================================
-        const int nch = 2 * p.ksteps;
+        // Two pairs of warps on alternate units (pair = warp >> 1): the proxy fence behind a tile waits for the thread's outstanding
+        // global loads (the packed words of its next tile), so one pair delivers a tile per load latency; two pairs hide it. Rows come
+        // from the pattern table (tt_build_row_lut).
+        const int nch = 2 * p.ksteps, pair = warp >> 1, ptid = tid & 63;
         // unit t: group t & 1, step t >> 1 = (quad iteration, block); tile row rr: stream (group, rr >> 5), position rr & 31 of the block
-        int qi = 0, wb = 0;                                   // of the unit being LOADED (one ahead of the one being built)
-        auto load_row = [&](int t, uint32_t (&w)[4], int &sh, int &mlim) {
-            const int n = 4 * ((int)blockIdx.x + qi * G) + 2 * (t & 1) + (tid >> 5), i = tid & 31;
+        auto load_row = [&](int t, uint32_t (&w)[4], int &sh, bool &valid) {
+            const int step = t >> 1, qi = step / p.nblk32, wb = step - qi * p.nblk32;
+            const int n = 4 * ((int)blockIdx.x + qi * G) + 2 * (t & 1) + (ptid >> 5), i = ptid & 31;
             const int j = wb * VP + i;
-            mlim = 0; sh = 0;
+            valid = n < p.n_rows && i < VP && j < p.Lh;
+            sh = 0;
             w[0] = w[1] = w[2] = w[3] = 0u;
-            if (n < p.n_rows && i < VP && j < p.Lh) {
+            if (valid) {
                 const int bit = 2 * (j + 16 * FRONT_PAD_WORDS);
                 const uint32_t *src = p.packed + (size_t)n * p.row_words + (bit >> 5);
                 sh = bit & 31;
 #pragma unroll
                 for (int e = 0; e < 4; ++e) w[e] = __ldg(src + e);
-                mlim = p.M;
             }
-            if (t & 1) { if (++wb == p.nblk32) { wb = 0; ++qi; } }
         };
         uint32_t cw[4], nw[4];
-        int csh = 0, cml = 0, nsh = 0, nml = 0;
-        if (my_units > 0) load_row(0, cw, csh, cml);
-        for (int t = 0; t < my_units; ++t) {
+        int csh = 0, nsh = 0;
+        bool cv = false, nv = false;
+        if (pair < my_units) load_row(pair, cw, csh, cv);
+        for (int t = pair; t < my_units; t += 2) {
             const int stage = t % XS, use = t / XS;
-            if (t + 1 < my_units) load_row(t + 1, nw, nsh, nml);
+            if (t + 2 < my_units) load_row(t + 2, nw, nsh, nv);
             if (use > 0) mbar_wait(x_free + stage, (uint32_t)((use - 1) & 1));
-            tt_build_row(X + (size_t)stage * x_bytes, tid, nch, cw, csh, cml);
+            tt_build_row_lut(X + (size_t)stage * x_bytes, lut_s, ptid, nch, p.M, cw, csh, cv);
             fence_async_smem();
             mbar_arrive(x_full + stage);
 #pragma unroll
             for (int e = 0; e < 4; ++e) cw[e] = nw[e];
-            csh = nsh; cml = nml;
+            csh = nsh; cv = nv;
         }
-    } else if (warp == 2) {
+    } else if (warp == 4) {
         // ================================================= MMA issue (one thread) ==========================================
         if (lane == 0) {
-            const uint32_t whi = smem_u32(Whi), wlo = smem_u32(Wlo), xa = smem_u32(X);
+            const uint32_t whi_lo = umma_desc_lo(smem_u32(Whi)), wlo_lo = umma_desc_lo(smem_u32(Wlo)), xa = smem_u32(X);
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TT_UNIT >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
             for (int t = 0; t < my_units; ++t) {
                 const int stage = t % XS, buf = t & (RT_D1_BUFS - 1);
@@ -178,19 +185,23 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
                 tc_fence_after();
                 const uint32_t d1 = tmem_base + 64 * buf;
                 const uint32_t xs = xa + (uint32_t)(stage * x_bytes);
-                for (int s = 0; s < p.ksteps; ++s) {
-                    const uint32_t atom = s >> 2, koff = (s & 3) * 32;
-                    const uint64_t bd = umma_desc_sw128(xs + atom * TT_XATOM + koff);
-                    umma_f16(d1, umma_desc_sw128(whi + atom * TT_WATOM + koff), bd, idesc1, s > 0 ? 1u : 0u);
-                    umma_f16(d1, umma_desc_sw128(wlo + atom * TT_WATOM + koff), bd, idesc1, 1u);
+                const uint32_t x_lo = umma_desc_lo(xs);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    if (s < p.ksteps) {
+                        const uint32_t oa = (uint32_t)(((s >> 2) * TT_WATOM + (s & 3) * 32) >> 4), ox = (uint32_t)(((s >> 2) * TT_XATOM + (s & 3) * 32) >> 4);
+                        umma_f16_lo(d1, whi_lo + oa, x_lo + ox, idesc1, s > 0 ? 1u : 0u);
+                        umma_f16_lo(d1, wlo_lo + oa, x_lo + ox, idesc1, 1u);
+                    }
                 }
                 umma_commit(d1_full + buf);
                 umma_commit(x_free + stage);
             }
         }
-    } else if (warp >= 4) {
+    } else {
         // ================================================= epilogue ========================================================
-        const int ew = warp - 4, q = warp & 3, wg = ew >> 2, pr = wg >> 1, h = wg & 1;
+        // (any four consecutive warps cover the four TMEM lane quarters: warp & 3)
+        const int ew = warp - 5, q = warp & 3, wg = ew >> 2, pr = wg >> 1, h = wg & 1;
         const int r = 32 * q + lane;
         const int s = MODE == RT_FE ? (q >> 1) : 0;
         const int k = MODE == RT_REDUCE ? chunk * TT_ROWS + r : chunk * TT_KC + (r & 63);
@@ -409,7 +420,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 3) tmem_dealloc(tmem_base, 512u);
+    if (warp == 4) tmem_dealloc(tmem_base, 512u);
 }
 
 template <int P> int launch_v2h_rows_tc(int mode, const RowsTcParams &p, dim3 grid, cudaStream_t stream);

@@ -20,7 +20,7 @@ static int launch_rt_variant(const RowsTcParams &p, dim3 grid, cudaStream_t stre
         CRBM_CHECK_CUDA(cudaFuncSetAttribute(v2h_rows_tc_kernel<MODE, CRBM_TT_P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev & 63] = smem;
     }
-    v2h_rows_tc_kernel<MODE, CRBM_TT_P><<<grid, TT_THREADS, smem, stream>>>(p);
+    v2h_rows_tc_kernel<MODE, CRBM_TT_P><<<grid, RT_THREADS, smem, stream>>>(p);
     CRBM_CHECK_LAUNCH();
     return CRBM_OK;
 }

@@ -126,12 +126,16 @@ __device__ __forceinline__ void tc_build_row(const TcParams &p, unsigned char *A
 
 __device__ __forceinline__ void tc_issue_mma(const TcParams &p, uint32_t a_addr, uint32_t bhi_addr, uint32_t blo_addr,
                                              uint32_t tmem_d, uint32_t idesc) {
-    const uint32_t b_atom = (uint32_t)p.NT * 128u;
-    for (int s = 0; s < p.ksteps; ++s) {
-        const uint32_t atom = s >> 2, koff = (s & 3) * 32;            // 16 fp16 = 32 bytes per k-step inside the 128-byte row
-        const uint64_t ad = umma_desc_sw128(a_addr + atom * A_ATOM_BYTES + koff);
-        umma_f16(tmem_d, ad, umma_desc_sw128(bhi_addr + atom * b_atom + koff), idesc, s > 0 ? 1u : 0u);
-        umma_f16(tmem_d, ad, umma_desc_sw128(blo_addr + atom * b_atom + koff), idesc, 1u);
+    const uint32_t b_atom = ((uint32_t)p.NT * 128u) >> 4;
+    const uint32_t a_lo = umma_desc_lo(a_addr), bhi_lo = umma_desc_lo(bhi_addr), blo_lo = umma_desc_lo(blo_addr);
+#pragma unroll
+    for (int s = 0; s < 9; ++s) {
+        if (s < p.ksteps) {
+            const uint32_t atom = s >> 2, koff = ((s & 3) * 32) >> 4;     // 16 fp16 = 32 bytes per k-step inside the 128-byte row
+            const uint32_t ad = a_lo + atom * (A_ATOM_BYTES >> 4) + koff;
+            umma_f16_lo(tmem_d, ad, bhi_lo + atom * b_atom + koff, idesc, s > 0 ? 1u : 0u);
+            umma_f16_lo(tmem_d, ad, blo_lo + atom * b_atom + koff, idesc, 1u);
+        }
     }
 }
 __device__ __forceinline__ void producer_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_PRODUCER_WARPS) : "memory"); }

@@ -86,6 +86,40 @@ __device__ __forceinline__ void tt_build_row(unsigned char *X, int r, int nch, c
     }
 }
 
+constexpr int TT_LUT_BYTES = 21 * 16;         // one-hot patterns of two bases (16 entries), of one base (4), zero (1)
+// threads 0-20 of the CTA write the pattern table: fp16 1.0 in the half selected by the low bit of the base, in the word selected by
+// its high bit
+__device__ __forceinline__ void tt_lut_init(unsigned char *lut, int tid) {
+    if (tid < 21) {
+        const int b0 = tid & 3, b1 = (tid >> 2) & 3;
+        const uint32_t h0 = tid < 20 ? (0x3C00u << (16 * (b0 & 1))) : 0u, h1 = tid < 16 ? (0x3C00u << (16 * (b1 & 1))) : 0u;
+        uint4 q;
+        q.x = (b0 & 2) ? 0u : h0; q.y = (b0 & 2) ? h0 : 0u;
+        q.z = (b1 & 2) ? 0u : h1; q.w = (b1 & 2) ? h1 : 0u;
+        *reinterpret_cast<uint4 *>(lut + tid * 16) = q;
+    }
+}
+// One-hot row of a 64-row tile from a table of the 16-byte patterns of two bases (same chunk layout as tt_build_row: chunk ch = bases
+// 2 ch, 2 ch + 1 as eight fp16): a shift, a mask, a 16-byte table load and a 16-byte store per chunk instead of ~14 ALU instructions.
+// lut: entries 0-15 pattern of (b0 | b1 << 2), 16-19 pattern of b0 alone (last chunk of an odd motif length), 20 zero.
+__device__ __forceinline__ void tt_build_row_lut(unsigned char *X, const unsigned char *lut, int r, int nch, int M, const uint32_t (&w)[4], int sh, bool valid) {
+    uint32_t v[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
+    const int nfull = M >> 1;
+    unsigned char *row = X + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+        if (ch < nch) {
+            const uint32_t bits = (v[ch >> 3] >> (4 * (ch & 7))) & 15u;
+            uint32_t e = ch < nfull ? bits : (ch == nfull && (M & 1)) ? 16u + (bits & 3u) : 20u;     // (uniform in ch: M is a kernel constant)
+            e = valid ? e : 20u;
+            const uint4 q = *reinterpret_cast<const uint4 *>(lut + e * 16);
+            *reinterpret_cast<uint4 *>(row + (ch >> 3) * TT_XATOM + (((ch ^ r) & 7) << 4)) = q;
+        }
+    }
+}
+
 __device__ __forceinline__ void tmem_ld_fence16(uint32_t (&v)[16]) {
     asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
                       "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]) :: "memory");
@@ -248,7 +282,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
     } else if (warp == 2) {
         // ================================================= MMA issue (one thread) ==========================================
         if (lane == 0) {
-            const uint32_t whi = smem_u32(Whi), wlo = smem_u32(Wlo), xa = smem_u32(X), pq = smem_u32(PQ);
+            const uint32_t whi_lo = umma_desc_lo(smem_u32(Whi)), wlo_lo = umma_desc_lo(smem_u32(Wlo)), xa = smem_u32(X), pq = smem_u32(PQ);
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TT_UNIT >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (1u << 16) | ((uint32_t)(Kdim >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
             // Polling issue loop: GEMM 2 of the oldest finished unit first (it frees a one-hot stage and an operand set), else the
@@ -263,18 +297,19 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                     if (mbar_test(p_full + set_i, (uint32_t)(use & 1))) {
                         const int t = g2, stage = t % XS;
                         tc_fence_after();
-                        const uint32_t set = pq + set_i * TT_PSET, xs = xa + (uint32_t)(stage * x_bytes);
+                        const uint32_t set_lo = umma_desc_lo(pq + set_i * TT_PSET);
+                        // B = the one-hot tile read MN-major: 16 positions = two 8-row groups (1024 bytes apart), c atoms TT_XATOM apart
+                        const uint32_t xmn_lo = umma_desc_lo(xa + (uint32_t)(stage * x_bytes), TT_XATOM);
 #pragma unroll
                         for (int k2 = 0; k2 < TT_UNIT / 16; ++k2) {
-                            // B = the one-hot tile read MN-major: 16 positions = two 8-row groups (1024 bytes apart), c atoms TT_XATOM apart
-                            const uint64_t bd = umma_desc_sw128_mn(xs + k2 * 2048, TT_XATOM, 1024);
+                            const uint32_t bd = xmn_lo + (uint32_t)(k2 * 2048 >> 4), oa = (uint32_t)(k2 * 32 >> 4);
                             const uint32_t acc = (t > 0 || k2 > 0) ? 1u : 0u;
-                            umma_f16(tmem_base + TT_D2P_COL, umma_desc_sw128(set + TT_PHI + k2 * 32), bd, idesc2, acc);
-                            umma_f16(tmem_base + TT_D2P_COL, umma_desc_sw128(set + TT_PLO + k2 * 32), bd, idesc2, 1u);
+                            umma_f16_lo(tmem_base + TT_D2P_COL, set_lo + (TT_PHI >> 4) + oa, bd, idesc2, acc);
+                            umma_f16_lo(tmem_base + TT_D2P_COL, set_lo + (TT_PLO >> 4) + oa, bd, idesc2, 1u);
                             if (STAT_Q) {
                                 // rows 64-127 of the Q operands alias the buffers that follow them (finite values; those D2 lanes are unused)
-                                umma_f16(tmem_base + TT_D2Q_COL, umma_desc_sw128(set + TT_QHI + k2 * 32), bd, idesc2, acc);
-                                umma_f16(tmem_base + TT_D2Q_COL, umma_desc_sw128(set + TT_QLO + k2 * 32), bd, idesc2, 1u);
+                                umma_f16_lo(tmem_base + TT_D2Q_COL, set_lo + (TT_QHI >> 4) + oa, bd, idesc2, acc);
+                                umma_f16_lo(tmem_base + TT_D2Q_COL, set_lo + (TT_QLO >> 4) + oa, bd, idesc2, 1u);
                             }
                         }
                         umma_commit(x_free + stage);
@@ -293,11 +328,14 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                         tc_fence_after();
                         const uint32_t d1 = tmem_base + TT_D1_COL + 64 * buf;
                         const uint32_t xs = xa + (uint32_t)(stage * x_bytes);
-                        for (int s = 0; s < p.ksteps; ++s) {
-                            const uint32_t atom = s >> 2, koff = (s & 3) * 32;
-                            const uint64_t bd = umma_desc_sw128(xs + atom * TT_XATOM + koff);
-                            umma_f16(d1, umma_desc_sw128(whi + atom * TT_WATOM + koff), bd, idesc1, s > 0 ? 1u : 0u);
-                            umma_f16(d1, umma_desc_sw128(wlo + atom * TT_WATOM + koff), bd, idesc1, 1u);
+                        const uint32_t x_lo = umma_desc_lo(xs);
+#pragma unroll
+                        for (int s = 0; s < 8; ++s) {
+                            if (s < p.ksteps) {
+                                const uint32_t oa = (uint32_t)(((s >> 2) * TT_WATOM + (s & 3) * 32) >> 4), ox = (uint32_t)(((s >> 2) * TT_XATOM + (s & 3) * 32) >> 4);
+                                umma_f16_lo(d1, whi_lo + oa, x_lo + ox, idesc1, s > 0 ? 1u : 0u);
+                                umma_f16_lo(d1, wlo_lo + oa, x_lo + ox, idesc1, 1u);
+                            }
                         }
                         umma_commit(d1_full + buf);
                         if (!STAT) umma_commit(x_free + stage);

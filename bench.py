@@ -373,8 +373,7 @@ def bench_scan(ctx, model, K, M, Lt, traffic_key):
         alg = n * (Lt / 4.0) + 4.0 * n * K * Lh      # per GPU (the roofline is per device)
         rec = {'metric': 'motif-scan nt/s (getHitProbs, fp32 probabilities written)', 'value': nt / (ms * 1e-3), 'unit': 'nt/s',
                'sequences_per_gpu': n, 'n_gpus': world, 'ms': ms, 'output_GB_per_gpu': 4.0 * n * K * Lh / 1e9,
-               'roofline': {'bound': 'hbm', 'kernel': ('v2h_dense_tc_kernel<PROB> (tcgen05.mma, TMEM accumulators)' if model.pooling == 1 else
-                                                    'v2h_rowdense_tc_kernel<P=%d> (tcgen05.mma, motif = TMEM lane, pooled softmax in registers, rows stored by cp.async.bulk)' % model.pooling),
+               'roofline': {'bound': 'hbm', 'kernel': lib.crbm_v2h_dense_kernel_name(K, M, model.pooling, _lib.OUT_PROBABILITY, pitch_fast).decode(),
                             'achieved': alg / (ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': alg / (ms * 1e-3) / 1e9 / hbm_peak,
                             'traffic': ncu_traffic(traffic_key) if (mode == _lib.STRAND_FWD and traffic_key) else None,
                             'algorithmic_bytes': alg, 'peak_source': peak_src, 'bytes_per_nt': alg / (n * Lt)}}

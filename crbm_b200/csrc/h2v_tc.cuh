@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) h2v_tc_kernel(const H2VTcParams
         }
     } else if (warp == 1) {
         // ================================================= MMA issue (one thread) ==========================================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(HT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int it = 0;
             for (int t = 0; t < my_tiles; ++t) {

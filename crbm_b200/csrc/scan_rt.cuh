@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
         }
     } else if (warp == 4) {
         // ================================================= MMA issue (one thread) ==========================================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t whi_lo = umma_desc_lo(smem_u32(Whi)), wlo_lo = umma_desc_lo(smem_u32(Wlo)), xa = smem_u32(X);
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TT_UNIT >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
             for (int t = 0; t < my_units; ++t) {

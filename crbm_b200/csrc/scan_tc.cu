@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) v2h_dense_tc_kernel(const TcPar
             tc_build_row(p, A + (size_t)stage * a_tile_bytes, tid, cur);
             fence_async_smem();
             producer_bar_sync();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 const int buf = i % nbuf, u = i / nbuf;
                 if (u > 0) mbar_wait(empty + buf, (uint32_t)((u - 1) & 1));          // the epilogue has drained this accumulator
                 tc_fence_after();

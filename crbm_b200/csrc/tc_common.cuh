@@ -6,6 +6,16 @@
 namespace crbm {
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------------------
+// true in exactly one lane of a converged warp (elect.sync): ptxas knows that code under this predicate runs in one thread, so a
+// tcgen05.mma there is one UTCHMMA; under `lane == 0` it wraps every MMA in an elect-and-branch loop over the active lanes
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "@p mov.u32 %0, 1;\n\t}" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

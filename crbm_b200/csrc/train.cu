@@ -1099,7 +1099,7 @@ int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L, 
         g.mode = GEN_DENSE; g.strand_mode = strand_mode; g.out_kind = out_kind; g.out = out; g.out_row_stride = out_row_stride;
         return launch_gen_v2h(g, (cudaStream_t)stream);
     }
-    if (scan_uses_tcgen05() && pool_uses_mma() && rowdense_wanted(M, pool, out_row_stride, out)) {
+    if (scan_uses_tcgen05() && pool_uses_mma() && rowdense_wanted(K, M, pool, out_row_stride, out)) {
         RowDenseParams r{};
         r.packed = packed; r.row_words = row_words; r.n_rows = N; r.L = L; r.Lh = Lh; r.W = W; r.b = b; r.K = K; r.M = M;
         r.strand_mode = strand_mode; r.out_kind = out_kind; r.out = out; r.row_stride = out_row_stride;
@@ -1118,6 +1118,17 @@ int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L, 
         return dispatch_dense_mma(ceil_div(M, 4), p, dim3(mtiles, gy), (cudaStream_t)stream);
     }
     return dispatch_dense(t.MW, p, dim3(t.ktiles, t.gy), (cudaStream_t)stream);
+}
+
+const char *crbm_v2h_dense_kernel_name(int K, int M, int pooling, int out_kind, long long out_row_stride) {
+    const int pool = out_kind == CRBM_OUT_PROBABILITY ? pooling : 1;
+    if (K <= 0 || M <= 0 || pool <= 0) return "none";
+    if (shape_is_generic(M, pool)) return "gen_v2h_kernel (shape-generic, CUDA cores)";
+    if (scan_uses_tcgen05() && pool_uses_mma() && rowdense_wanted(K, M, pool, out_row_stride, nullptr))
+        return ((32 / pool) * pool == 32) ? "v2h_rowdense_tc_kernel (tcgen05.mma, motif = TMEM lane, per-warp tiles stored by cp.async.bulk.tensor)"
+                                          : "v2h_rowdense_tc_kernel (tcgen05.mma, motif = TMEM lane, rows stored by cp.async.bulk)";
+    if ((pool == 1 || pool_uses_mma()) && scan_uses_tcgen05()) return "v2h_dense_tc_kernel (tcgen05.mma, position = TMEM lane, 128-byte row stores)";
+    return pool == 1 ? "v2h_dense_mma_kernel (mma.sync)" : "v2h_dense_kernel (CUDA cores)";
 }
 
 int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L, const float *W, const float *b, int K, int M,

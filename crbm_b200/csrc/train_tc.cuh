@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
         }
     } else if (warp == 2) {
         // ================================================= MMA issue (one thread) ==========================================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t whi_lo = umma_desc_lo(smem_u32(Whi)), wlo_lo = umma_desc_lo(smem_u32(Wlo)), xa = smem_u32(X), pq = smem_u32(PQ);
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TT_UNIT >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
             const uint32_t idesc2 = (1u << 4) | (1u << 16) | ((uint32_t)(Kdim >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);

@@ -52,15 +52,21 @@ static int launch_rows_tc(int mode, int P, RowsTcParams &p, cudaStream_t s) {
     set_error("tcgen05 rows kernel: pooling %d not built", P);
     return CRBM_ERR_UNSUPPORTED;
 }
-// Dense scan with the motif on the TMEM lane and TMA row stores (scan_rd.cuh): pooled probabilities by default (the position-major
-// kernel of scan_tc.cu needs shuffles and writes partial sectors there); CRBM_SCAN_KERNEL=rows also sends the un-pooled scan here,
-// CRBM_POOL_SCAN=pos keeps the pooled scan on scan_tc.cu. Needs output rows that are multiples of 4 floats on a 16-byte base.
-static bool rowdense_wanted(int M, int P, long long row_stride, const void *out) {
+// Dense scan with the motif on the TMEM lane and TMA stores (scan_rd.cuh). Pooled probabilities always go there (the position-major
+// kernel of scan_tc.cu needs shuffles and writes partial sectors). Un-pooled scans go there when the 128-row MMA tile is well filled:
+// measured on B200 (% of the HBM copy peak, row-dense against position-major): K=128 93 / 78, K=384 85 / 80, K=512 86 / 81,
+// K=100 77 / 70, but K=200 68 / 80, K=300 72 / 82, K=150 54 / 79 (idle TMEM lanes cost epilogue slots), K=64 52 / 52.
+// CRBM_SCAN_KERNEL=rows | pos forces one of them, CRBM_POOL_SCAN=pos keeps the pooled scan on scan_tc.cu. Needs output rows that are
+// multiples of 4 floats on a 16-byte base.
+static bool rowdense_wanted(int K, int M, int P, long long row_stride, const void *out) {
     static int all = -1, pooled = -1;
-    if (all < 0) { const char *e = getenv("CRBM_SCAN_KERNEL"); all = (e && e[0] == 'r') ? 1 : 0; }
+    if (all < 0) { const char *e = getenv("CRBM_SCAN_KERNEL"); all = !e ? 2 : e[0] == 'r' ? 1 : e[0] == 'p' ? 0 : 2; }
     if (pooled < 0) { const char *e = getenv("CRBM_POOL_SCAN"); pooled = (e && e[0] == 'p') ? 0 : 1; }
     if (M > 32 || !tt_pool_built(P) || (row_stride & 3) || ((uintptr_t)out & 15)) return false;
-    return P > 1 ? pooled == 1 : all == 1;
+    if (P > 1) return pooled == 1;
+    if (all != 2) return all == 1;
+    const int padded = TT_ROWS * ceil_div(K, TT_ROWS);
+    return 10 * K >= 9 * padded || (K <= TT_ROWS && 4 * K >= 3 * padded);
 }
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
 typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,

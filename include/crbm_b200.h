@@ -85,6 +85,9 @@ int crbm_v2h_dense(const uint32_t *packed, int row_words, int N, int L,
 int crbm_v2h_dense_strided(const uint32_t *packed, int row_words, int N, int L,
                            const float *W, const float *b, int K, int M, int pooling,
                            int strand_mode, int out_kind, float *out, long long out_row_stride, void *stream);
+/* Name of the kernel crbm_v2h_dense_strided runs for this model shape and output layout (a 16-byte aligned output is assumed): the
+ * choice depends on the shape (see csrc/train_tc_impl.cuh: rowdense_wanted); reported by bench.py beside the roofline numbers. */
+const char *crbm_v2h_dense_kernel_name(int K, int M, int pooling, int out_kind, long long out_row_stride);
 
 /* ---- A7 with the callers' reductions fused in (reference secomo/utils.py:155,245-247 max over positions, :306 mean) -- */
 /* Per sequence and motif: maximum of the activity / hit probability over positions, the position of the first maximum

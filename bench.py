@@ -182,6 +182,16 @@ class Ctx(object):
             self.dist.barrier()
         torch.cuda.synchronize()
 
+    def gather(self, value):
+        """The value of every rank (list, on every rank), or None on a single GPU."""
+        import torch
+        if self.dist is None:
+            return None
+        t = torch.tensor([float(value)], device=self.dev)
+        ts = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(ts, t)
+        return [float(x.item()) for x in ts]
+
     def max_over_ranks(self, ms):
         import torch
         if self.dist is None:
@@ -233,10 +243,13 @@ def train_workload(ctx, wl, steps, warmup, spg, sampler=None):
         while len(sampler.rows) < 4 and time.time() < t_end:
             run_steps(spg, 0)
             torch.cuda.synchronize()
+    by_rank = ctx.gather(ms / steps)
     ms = ctx.max_over_ranks(ms)
     rec = {'workload': wl['name'], 'value': steps * B * Lt * ctx.world / (ms * 1e-3), 'unit': 'nt/s', 'steps': steps,
            'ms_per_step': ms / steps, 'batch_per_gpu': B, 'seq_len': Lt,
            'gpu_launches': model._engine.get('launches_per_step', 0) * steps}
+    if by_rank is not None:
+        rec['ms_per_step_by_rank'] = by_rank
     return rec, model, data
 
 
@@ -622,6 +635,8 @@ def main():
                        'l2': 'every step reads a new minibatch from a %d-sequence packed dataset (%.0f MB); model state '
                              '(W, persistent chain) is on-chip/L2 resident by design' % (wl['n_seq'], wl['n_seq'] * data.row_words * 4 / 1e6)},
             'gpu_launches': rec['gpu_launches']}
+    if 'ms_per_step_by_rank' in rec:
+        line['ms_per_step_by_rank'] = rec['ms_per_step_by_rank']
 
     # every rank runs every section (the sections synchronise the ranks); rank 0 keeps the records
     if rank == 0:
@@ -647,11 +662,24 @@ def main():
                 continue
             w2 = WORKLOADS[key]
             r2, m2, d2 = train_workload(ctx, w2, w2['sub_steps'], 16, 8)
+            # (at N > 1 every rank times its own phases, without the exchange, so that a slow GPU shows up beside the job time)
+            k2 = phase_times(m2, d2, w2['batch'], dev) if (rank == 0 or world > 1) else None
+            local = ctx.gather(k2['whole_step']) if world > 1 else None
             if rank == 0:
-                k2 = phase_times(m2, d2, w2['batch'], dev)
                 r2['step_kernels_us'] = k2
                 r2['roofline'] = train_roofline(w2, r2['seq_len'], r2, k2, key + '_positive')
+                if local is not None:
+                    r2['single_rank_step_us_by_rank'] = local
             r2['n_gpus'], r2['scaling'] = world, 'weak'
+            if key == 'c3' and world > 1 and w2['batch'] % world == 0:
+                # strong scaling: config 3's global minibatch of 128 sequences split over the ranks
+                ws = dict(w2, batch=w2['batch'] // world, name=w2['name'].replace('batch 128/GPU', 'global batch 128 split over %d GPUs' % world))
+                rs, ms_, ds_ = train_workload(ctx, ws, w2['sub_steps'], 16, 8)
+                rs['n_gpus'], rs['scaling'] = world, 'strong'
+                rs['note'] = 'same optimisation problem as config 3 on one GPU (global batch 128); value = whole-job nt/s'
+                line['c3_strong'] = rs
+                del ms_, ds_
+                torch.cuda.empty_cache()
             if key == 'c3':
                 # the pooled scan of config 3's model (getHitProbs with pooling 5)
                 r2['scan'] = bench_scan(ctx, m2, w2['K'], w2['M'], r2['seq_len'], 'c3_scan')

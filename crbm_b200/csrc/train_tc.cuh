@@ -20,7 +20,9 @@
 // The strand fold (convRBM.py:367) is a row/column permutation of D2 applied by the reduction: VH[k,c] = D2[kl,c] + D2[64+kl,4M-1-c].
 //
 // Warp roles (640 threads, one CTA per SM, persistent over units blockIdx.x, blockIdx.x + gridDim.x, ...):
-//   warps 0-1   build the one-hot tiles (ring of 3), warp 2 issues the MMAs, warp 3 owns the TMEM allocation,
+//   warps 0-1   build the one-hot tiles (ring of up to 8), one lane of warp 2 (elect.sync) issues the MMAs with descriptors advanced by
+//               their low words, warp 3 owns the TMEM allocation (four producer warps with table-built rows, as in scan_rt.cuh, were
+//               measured: no gain, the kernel is not bound by its producers),
 //   warps 4-19  epilogue: two groups of 8 warps work on alternate units; inside a group the two warpgroups take the two
 //               32-position halves. D1 has 4 buffers of 64 columns, the P/Q operands 2 sets (one per group).
 #pragma once

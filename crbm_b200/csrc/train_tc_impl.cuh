@@ -359,6 +359,7 @@ struct TcReduceParams {
 // combined through shared memory in a fixed order — the summation order is part of the contract between the fused and the two-launch
 // path (bit-identical parameters) — and the threads of slice 0 apply the update or write the statistics.
 constexpr int TCR_SLICES = 8;
+constexpr int TCR_BATCH = 5;
 __device__ __forceinline__ float tcr_combine(const float (*sh)[TT_KC], int kl) {
     return ((sh[0][kl] + sh[1][kl]) + (sh[2][kl] + sh[3][kl])) + ((sh[4][kl] + sh[5][kl]) + (sh[6][kl] + sh[7][kl]));
 }
@@ -392,22 +393,42 @@ __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) 
         const int ch = cta / fourM, c = cta - ch * fourM, cr = fourM - 1 - c;
         const int k = ch * TT_KC + kl;
         float df = 0.f, dr = 0.f, qq = 0.f, mf = 0.f, mr = 0.f, hf = 0.f;
+        // The partials of a slice are added in the order x = slice, slice + 8, ... (part of the bit-identity contract); the loads of
+        // TCR_BATCH of them are issued together (a rolled loop paid one L2 round trip per partial: ~10 of them in a row at 74 CTAs per
+        // chunk). A partial beyond the grid contributes +0.f, which leaves every sum as it is.
+        const size_t o_df = (size_t)c * TT_ROWS + kl, o_dr = (size_t)cr * TT_ROWS + TT_KC + kl, o_q = q_off + (size_t)c * TT_KC + kl, o_h = s_off + kl;
         if (p.pos) {
             const float *pos = p.pos + (size_t)ch * p.G_pos * pf;
-            for (int x = slice; x < p.G_pos; x += TCR_SLICES) {
-                const float *b = pos + (size_t)x * pf;
-                df += b[(size_t)c * TT_ROWS + kl];
-                if (p.ds) dr += b[(size_t)cr * TT_ROWS + TT_KC + kl];
-                qq += b[q_off + (size_t)c * TT_KC + kl];
-                hf += b[s_off + kl];
+            for (int x0 = slice; x0 < p.G_pos; x0 += TCR_SLICES * TCR_BATCH) {
+                float a0[TCR_BATCH], a1[TCR_BATCH], a2[TCR_BATCH], a3[TCR_BATCH];
+#pragma unroll
+                for (int u = 0; u < TCR_BATCH; ++u) {
+                    const int x = x0 + TCR_SLICES * u;
+                    const bool ok = x < p.G_pos;
+                    const float *b = pos + (size_t)(ok ? x : slice) * pf;
+                    a0[u] = ok ? b[o_df] : 0.f;
+                    a1[u] = (ok && p.ds) ? b[o_dr] : 0.f;
+                    a2[u] = ok ? b[o_q] : 0.f;
+                    a3[u] = ok ? b[o_h] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < TCR_BATCH; ++u) { df += a0[u]; dr += a1[u]; qq += a2[u]; hf += a3[u]; }
             }
         }
         {
             const float *neg = p.neg + (size_t)ch * p.G_neg * pf;
-            for (int x = slice; x < p.G_neg; x += TCR_SLICES) {
-                const float *b = neg + (size_t)x * pf;
-                mf += b[(size_t)c * TT_ROWS + kl];
-                if (p.ds) mr += b[(size_t)cr * TT_ROWS + TT_KC + kl];
+            for (int x0 = slice; x0 < p.G_neg; x0 += TCR_SLICES * TCR_BATCH) {
+                float a0[TCR_BATCH], a1[TCR_BATCH];
+#pragma unroll
+                for (int u = 0; u < TCR_BATCH; ++u) {
+                    const int x = x0 + TCR_SLICES * u;
+                    const bool ok = x < p.G_neg;
+                    const float *b = neg + (size_t)(ok ? x : slice) * pf;
+                    a0[u] = ok ? b[o_df] : 0.f;
+                    a1[u] = (ok && p.ds) ? b[o_dr] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < TCR_BATCH; ++u) { mf += a0[u]; mr += a1[u]; }
             }
         }
         sh[0][slice][kl] = df; sh[1][slice][kl] = dr; sh[2][slice][kl] = qq;
@@ -456,16 +477,32 @@ __global__ void __launch_bounds__(512) reduce_tc_kernel(const TcReduceParams p) 
         float hf = 0.f, hr = 0.f, hq = 0.f, mf = 0.f, mr = 0.f;
         if (p.pos) {
             const float *pos = p.pos + (size_t)ch * p.G_pos * pf + s_off;
-            for (int x = slice; x < p.G_pos; x += TCR_SLICES) {
-                const float *b = pos + (size_t)x * pf;
-                hf += b[kl]; hr += b[TT_KC + kl]; hq += b[TT_ROWS + kl];
+            for (int x0 = slice; x0 < p.G_pos; x0 += TCR_SLICES * TCR_BATCH) {
+                float a0[TCR_BATCH], a1[TCR_BATCH], a2[TCR_BATCH];
+#pragma unroll
+                for (int u = 0; u < TCR_BATCH; ++u) {
+                    const int x = x0 + TCR_SLICES * u;
+                    const bool ok = x < p.G_pos;
+                    const float *b = pos + (size_t)(ok ? x : slice) * pf;
+                    a0[u] = ok ? b[kl] : 0.f; a1[u] = ok ? b[TT_KC + kl] : 0.f; a2[u] = ok ? b[TT_ROWS + kl] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < TCR_BATCH; ++u) { hf += a0[u]; hr += a1[u]; hq += a2[u]; }
             }
         }
         {
             const float *neg = p.neg + (size_t)ch * p.G_neg * pf + s_off;
-            for (int x = slice; x < p.G_neg; x += TCR_SLICES) {
-                const float *b = neg + (size_t)x * pf;
-                mf += b[kl]; mr += b[TT_KC + kl];
+            for (int x0 = slice; x0 < p.G_neg; x0 += TCR_SLICES * TCR_BATCH) {
+                float a0[TCR_BATCH], a1[TCR_BATCH];
+#pragma unroll
+                for (int u = 0; u < TCR_BATCH; ++u) {
+                    const int x = x0 + TCR_SLICES * u;
+                    const bool ok = x < p.G_neg;
+                    const float *b = neg + (size_t)(ok ? x : slice) * pf;
+                    a0[u] = ok ? b[kl] : 0.f; a1[u] = ok ? b[TT_KC + kl] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < TCR_BATCH; ++u) { mf += a0[u]; mr += a1[u]; }
             }
         }
         sh[0][slice][kl] = hf; sh[1][slice][kl] = hr; sh[2][slice][kl] = hq; sh[3][slice][kl] = mf; sh[4][slice][kl] = mr;

@@ -39,7 +39,10 @@ struct RowsTcParams {
     const float *uniforms;         // RT_FE count: injected uniforms [(n*K+k)*(Lh/P) + group] or null
     uint64_t seed;
     uint32_t ctr_hi;
+    long long *dbg;                // CRBM_RT_DEBUG=1: CTA (0,0) records clock64() per role, unit and stage: [role][RT_DBG_UNITS][4]
 };
+constexpr int RT_DBG_UNITS = 64, RT_DBG_ROLES = 5;
+#define RT_MARK(role, t, i) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (t) < RT_DBG_UNITS) p.dbg[((role) * RT_DBG_UNITS + (t)) * 4 + (i)] = clock64(); } while (0)
 
 __host__ __device__ inline size_t rt_smem_bytes(int n_atoms, int xstages) {
     return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)xstages * n_atoms * TT_XATOM + 512 + 512 + 512;
@@ -165,10 +168,14 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
         for (int t = pair; t < my_units; t += 2) {
             const int stage = t % XS, use = t / XS;
             if (t + 2 < my_units) load_row(t + 2, nw, nsh, nv);
+            if (ptid == 0) RT_MARK(pair, t, 0);
             if (use > 0) mbar_wait(x_free + stage, (uint32_t)((use - 1) & 1));
+            if (ptid == 0) RT_MARK(pair, t, 1);
             tt_build_row_lut(X + (size_t)stage * x_bytes, lut_s, ptid, nch, p.M, cw, csh, cv);
+            if (ptid == 0) RT_MARK(pair, t, 2);
             fence_async_smem();
             mbar_arrive(x_full + stage);
+            if (ptid == 0) RT_MARK(pair, t, 3);
 #pragma unroll
             for (int e = 0; e < 4; ++e) cw[e] = nw[e];
             csh = nsh; cv = nv;
@@ -180,8 +187,11 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
             const uint32_t idesc1 = (1u << 4) | ((uint32_t)(TT_UNIT >> 3) << 17) | ((uint32_t)(TT_ROWS >> 4) << 24);
             for (int t = 0; t < my_units; ++t) {
                 const int stage = t % XS, buf = t & (RT_D1_BUFS - 1);
+                RT_MARK(2, t, 0);
                 mbar_wait(x_full + stage, (uint32_t)((t / XS) & 1));
+                RT_MARK(2, t, 1);
                 if (t >= RT_D1_BUFS) mbar_wait(d1_free + buf, (uint32_t)(((t >> 3) - 1) & 1));
+                RT_MARK(2, t, 2);
                 tc_fence_after();
                 const uint32_t d1 = tmem_base + 64 * buf;
                 const uint32_t xs = xa + (uint32_t)(stage * x_bytes);
@@ -196,6 +206,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
                 }
                 umma_commit(d1_full + buf);
                 umma_commit(x_free + stage);
+                RT_MARK(2, t, 3);
             }
         }
     } else {
@@ -219,7 +230,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
             int nv = n < p.n_rows ? min(VP, p.Lh - wb * VP) : 0;
             nv = nv < 0 ? 0 : nv;
             const int buf = t & (RT_D1_BUFS - 1);
+            if (q == 0 && h == 0 && lane == 0) RT_MARK(3 + pr, t, 0);
             mbar_wait_backoff(d1_full + buf, (uint32_t)((t >> 3) & 1));
+            if (q == 0 && h == 0 && lane == 0) RT_MARK(3 + pr, t, 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + 64 * buf + 32 * h;
             uint32_t va[16], vb[16];
@@ -231,6 +244,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d1_free + buf);          // eight warps per buffer: the four lane quarters of both halves
+            if (q == 0 && h == 0 && lane == 0) RT_MARK(3 + pr, t, 2);
             float pv[32];
 #pragma unroll
             for (int i = 0; i < 16; ++i) { pv[i] = __uint_as_float(va[i]) + bias; pv[16 + i] = __uint_as_float(vb[i]) + bias; }
@@ -415,6 +429,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
                     }
                 }
             }
+            if (q == 0 && h == 0 && lane == 0) RT_MARK(3 + pr, t, 3);
             if (++wb == p.nblk32) { wb = 0; ++qi; }
         }
     }

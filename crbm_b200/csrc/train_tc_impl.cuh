@@ -44,13 +44,40 @@ static int launch_rows_tc(int mode, int P, RowsTcParams &p, cudaStream_t s) {
     const int n_chunks = ceil_div(p.K, mode == RT_REDUCE ? TT_ROWS : TT_KC);
     int gx = num_sms() / n_chunks > 0 ? num_sms() / n_chunks : 1;
     if (gx > p.n_quads) gx = p.n_quads;
+    // CRBM_RT_DEBUG=1 (timing aid, synchronous): clock64() marks of CTA (0,0), printed as cycles since the CTA's first mark
+    static const int rt_debug = [] { const char *e = getenv("CRBM_RT_DEBUG"); return (e && e[0] == '1') ? 1 : 0; }();
+    p.dbg = nullptr;
+    const size_t dbg_n = (size_t)RT_DBG_ROLES * RT_DBG_UNITS * 4;
+    if (rt_debug) {
+        CRBM_CHECK_CUDA(cudaMalloc(&p.dbg, dbg_n * sizeof(long long)));
+        CRBM_CHECK_CUDA(cudaMemsetAsync(p.dbg, 0, dbg_n * sizeof(long long), s));
+    }
+    int rc = CRBM_ERR_UNSUPPORTED;
     switch (P) {
-#define CRBM_CASE(PV) case PV: return launch_v2h_rows_tc<PV>(mode, p, dim3(gx, n_chunks), s);
+#define CRBM_CASE(PV) case PV: rc = launch_v2h_rows_tc<PV>(mode, p, dim3(gx, n_chunks), s); break;
         CRBM_FOR_EACH_TT_P(CRBM_CASE)
 #undef CRBM_CASE
+        default: set_error("tcgen05 rows kernel: pooling %d not built", P);
     }
-    set_error("tcgen05 rows kernel: pooling %d not built", P);
-    return CRBM_ERR_UNSUPPORTED;
+    if (rt_debug && rc == CRBM_OK) {
+        static int printed = 0;
+        long long *h = (long long *)malloc(dbg_n * sizeof(long long));
+        CRBM_CHECK_CUDA(cudaStreamSynchronize(s));
+        CRBM_CHECK_CUDA(cudaMemcpy(h, p.dbg, dbg_n * sizeof(long long), cudaMemcpyDeviceToHost));
+        if (!printed++) {
+            long long t0 = 0;
+            for (size_t i = 0; i < dbg_n; ++i) if (h[i] && (!t0 || h[i] < t0)) t0 = h[i];
+            const char *names[RT_DBG_ROLES] = {"producer0", "producer1", "mma", "epilogue0", "epilogue1"};
+            for (int r = 0; r < RT_DBG_ROLES; ++r)
+                for (int t = 0; t < RT_DBG_UNITS; ++t) {
+                    const long long *e = h + ((size_t)r * RT_DBG_UNITS + t) * 4;
+                    if (e[0]) fprintf(stderr, "RT_DBG %s unit %d: %lld %lld %lld %lld\n", names[r], t, e[0] - t0, e[1] - t0, e[2] - t0, e[3] - t0);
+                }
+        }
+        free(h);
+        cudaFree(p.dbg);
+    }
+    return rc;
 }
 // Dense scan with the motif on the TMEM lane and TMA stores (scan_rd.cuh). Pooled probabilities always go there (the position-major
 // kernel of scan_tc.cu needs shuffles and writes partial sectors). Un-pooled scans go there when the 128-row MMA tile is well filled:

@@ -436,10 +436,12 @@ class CRBM(object):
         mode = _lib.STRAND_FWD if self.doublestranded else _lib.STRAND_SUM
         return self._v2h(data, mode, _lib.OUT_PROBABILITY)
 
-    def motifHitSummary(self, data, chunk_rows=None):
+    def motifHitSummary(self, data, chunk_rows=None, want=('max', 'argmax', 'mean')):
         """Per sequence and motif: max over positions of motifHitProbs, its position and the mean over positions —
         the reductions secomo.utils applies to motifHitProbs (utils.py:155,245-247,306) — computed inside the scan kernel,
         so the (N,K,1,Lh) tensor is never materialised. Returns dict(max=(N,K) float32, argmax=(N,K) int32, mean=(N,K)).
+        `want` selects the results: without 'mean' an un-pooled model is scanned on the activities alone (the maximum of the
+        sigmoid is the sigmoid of the maximum activity: one exponential per sequence and motif instead of one per position).
         Long inputs are scanned in chunks of `chunk_rows` sequences (two sets of device buffers; the device->host copy of a
         chunk into pinned staging memory overlaps the scan of the next one)."""
         lib = self._require_cuda()
@@ -449,7 +451,10 @@ class CRBM(object):
         N = seqs.N
         rows = max(1, min(N, int(chunk_rows or max(1024, (64 << 20) // (4 * K)))))
         nbuf = min(2, -(-N // rows))
-        names = (('max', torch.float32, np.float32), ('argmax', torch.int32, np.int32), ('mean', torch.float32, np.float32))
+        names = tuple(t for t in (('max', torch.float32, np.float32), ('argmax', torch.int32, np.int32), ('mean', torch.float32, np.float32))
+                      if t[0] in want)
+        if not names or any(w not in ('max', 'argmax', 'mean') for w in want):
+            raise ValueError("motifHitSummary: want must be a non-empty subset of ('max', 'argmax', 'mean')")
         out = {nm: np.empty((N, K), dtype=npd) for nm, _, npd in names}
         bufs = [{nm: torch.empty((rows, K), dtype=td, device=self._device) for nm, td, _ in names} for _ in range(nbuf)]
         stage = [{nm: self._staging('sum_%s%d' % (nm, i), (rows, K), td) for nm, td, _ in names} for i in range(nbuf)]
@@ -473,7 +478,7 @@ class CRBM(object):
             b = bufs[j]
             _lib.check(lib.crbm_scan_reduce(_lib.ptr(seqs.words[s:]), seqs.row_words, e - s, seqs.L, _lib.ptr(self._t_W),
                                             _lib.ptr(self._t_bias), K, M, self.pooling, mode, _lib.OUT_PROBABILITY,
-                                            _lib.ptr(b['max']), _lib.ptr(b['argmax']), _lib.ptr(b['mean']), _lib.stream_handle()),
+                                            _lib.ptr(b.get('max')), _lib.ptr(b.get('argmax')), _lib.ptr(b.get('mean')), _lib.stream_handle()),
                        'scan_reduce')
             ready = torch.cuda.Event()
             ready.record(main)

@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
         const int groups_per_seq = p.Lh / P;
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
         const float inv_lh = 1.0f / (float)p.Lh;
+        const bool want_mean = p.out_mean != nullptr;
         // running reductions of the current sequence of this stream
         float best = -INFINITY, sum = 0.f, cnt = 0.f;
         int bpos = 0;
@@ -282,7 +283,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
                         best = key;
                         bpos = wb * VP + at;
                     }
-                    if (prob) {
+                    // the probabilities themselves are only needed for the mean: a caller that asks for the maximum and its position
+                    // alone (utils.py:155,245-247) gets them from the activities, one sigmoid per sequence and motif at the end
+                    if (prob && want_mean) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
                             float e0, e1, rr;
@@ -295,7 +298,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
                         }
                     }
                     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-                    if (fullblk) {
+                    if (!want_mean) {
+                    } else if (fullblk) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) { s0 += pv[i]; s1 += pv[i + 1]; s2 += pv[i + 2]; s3 += pv[i + 3]; }
                     } else {

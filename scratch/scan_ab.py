@@ -22,7 +22,7 @@ if len(sys.argv) > 6 and sys.argv[6] == 'reduce':
     mx = torch.empty((n, K), dtype=torch.float32, device=dev); am = torch.empty((n, K), dtype=torch.int32, device=dev); mean = torch.empty((n, K), dtype=torch.float32, device=dev)
     def call():
         _lib.check(lib.crbm_scan_reduce(_lib.ptr(seqs.words), seqs.row_words, n, L, _lib.ptr(m._t_W), _lib.ptr(m._t_bias), K, M, P,
-                                        mode, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am), _lib.ptr(mean), s), 'scan_reduce')
+                                        mode, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am), None if os.environ.get('NOMEAN') else _lib.ptr(mean), s), 'scan_reduce')
 for _ in range(2): call()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -262,6 +262,15 @@ def test_fused_scan_reductions_match_dense_scan(K, M, L, ds, P):
     at = np.take_along_axis(dense, got['argmax'][:, :, None].astype(np.int64), axis=2)[:, :, 0]
     np.testing.assert_allclose(at, dense.max(axis=2), rtol=4e-6, atol=4e-7)     # near-ties: the reported position is a maximum
     np.testing.assert_allclose(got['mean'], dense.mean(axis=2), rtol=1e-5, atol=1e-7)
+    # maximum and position alone (no mean: the un-pooled kernel then works on the activities only): the same values bit for bit
+    part = m.motifHitSummary(seqs, want=('max', 'argmax'))
+    assert sorted(part) == ['argmax', 'max']
+    np.testing.assert_array_equal(part['max'], got['max'])
+    np.testing.assert_array_equal(part['argmax'], got['argmax'])
+    only = m.motifHitSummary(seqs, want=('mean',))
+    np.testing.assert_array_equal(only['mean'], got['mean'])
+    with pytest.raises(ValueError):
+        m.motifHitSummary(seqs, want=('median',))
 
 
 def test_streamlined_onehot_step_equals_packed_step_and_validates(data):

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(RD_THREADS, 1) v2h_rowdense_tc_kernel(const Ro
             const int stage = t % XS, use = t / XS;
             if (t + 2 < my_units) load_row(t + 2, nw, nsh, nv);
             if (use > 0) mbar_wait(x_free + stage, (uint32_t)((use - 1) & 1));
-            tt_build_row_lut(X + (size_t)stage * x_bytes, lut_s, ptid, nch, p.M, cw, csh, cv);
+            tt_build_row_lut<VP == 32>(X + (size_t)stage * x_bytes, lut_s, ptid, nch, p.M, cw, csh, cv);
             fence_async_smem();
             mbar_arrive(x_full + stage);
 #pragma unroll

@@ -19,7 +19,7 @@
 
 namespace crbm {
 
-enum : int { RT_REDUCE = 0, RT_FE = 1 };
+enum : int { RT_REDUCE = 0, RT_FE = 1, RT_REDUCE_NOMEAN = 2 };      // NOMEAN: maximum and position only (out_mean == null)
 constexpr int RT_D1_BUFS = 8;
 constexpr int RT_THREADS = 672;               // warps 0-3 build the one-hot tiles (two pairs on alternate units), warp 4 owns TMEM and issues
                                               // the MMAs, warps 5-20 are the epilogue (warp & 3 = TMEM lane quarter)
@@ -42,7 +42,11 @@ struct RowsTcParams {
     long long *dbg;                // CRBM_RT_DEBUG=1: CTA (0,0) records clock64() per role, unit and stage: [role][RT_DBG_UNITS][4]
 };
 constexpr int RT_DBG_UNITS = 64, RT_DBG_ROLES = 5;
+#ifdef CRBM_RT_TIMELINE          // (the marks cost the reduction kernels ~5 %: compiled in only with -DCRBM_RT_TIMELINE)
 #define RT_MARK(role, t, i) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (t) < RT_DBG_UNITS) p.dbg[((role) * RT_DBG_UNITS + (t)) * 4 + (i)] = clock64(); } while (0)
+#else
+#define RT_MARK(role, t, i) do { } while (0)
+#endif
 
 __host__ __device__ inline size_t rt_smem_bytes(int n_atoms, int xstages) {
     return 1024 + 2 * (size_t)n_atoms * TT_WATOM + (size_t)xstages * n_atoms * TT_XATOM + 512 + 512 + 512;
@@ -57,8 +61,10 @@ __device__ __forceinline__ float rt_softplus(float t, float y) {
     return y > 24.f ? y * 0.6931471805599453f : (t < 0.0625f ? small : mid);
 }
 
-template <int MODE, int P>
+template <int MODE_T, int P>
 __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTcParams p) {
+    constexpr int MODE = MODE_T == RT_FE ? RT_FE : RT_REDUCE;
+    constexpr bool want_mean = MODE_T != RT_REDUCE_NOMEAN;
     constexpr int VP = (32 / P) * P, NG = 32 / P;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
             if (ptid == 0) RT_MARK(pair, t, 0);
             if (use > 0) mbar_wait(x_free + stage, (uint32_t)((use - 1) & 1));
             if (ptid == 0) RT_MARK(pair, t, 1);
-            tt_build_row_lut(X + (size_t)stage * x_bytes, lut_s, ptid, nch, p.M, cw, csh, cv);
+            tt_build_row_lut<false>(X + (size_t)stage * x_bytes, lut_s, ptid, nch, p.M, cw, csh, cv);
             if (ptid == 0) RT_MARK(pair, t, 2);
             fence_async_smem();
             mbar_arrive(x_full + stage);
@@ -221,7 +227,6 @@ __global__ void __launch_bounds__(RT_THREADS, 1) v2h_rows_tc_kernel(const RowsTc
         const int groups_per_seq = p.Lh / P;
         const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
         const float inv_lh = 1.0f / (float)p.Lh;
-        const bool want_mean = p.out_mean != nullptr;
         // running reductions of the current sequence of this stream
         float best = -INFINITY, sum = 0.f, cnt = 0.f;
         int bpos = 0;

@@ -27,7 +27,12 @@ static int launch_rt_variant(const RowsTcParams &p, dim3 grid, cudaStream_t stre
 
 template <>
 int launch_v2h_rows_tc<CRBM_TT_P>(int mode, const RowsTcParams &p, dim3 grid, cudaStream_t stream) {
-    return mode == RT_REDUCE ? launch_rt_variant<RT_REDUCE>(p, grid, stream) : launch_rt_variant<RT_FE>(p, grid, stream);
+    if (mode == RT_FE) return launch_rt_variant<RT_FE>(p, grid, stream);
+    // un-pooled scans that do not ask for the mean run on the activities alone (the pooled maximum needs the probabilities anyway)
+#if CRBM_TT_P == 1
+    if (!p.out_mean) return launch_rt_variant<RT_REDUCE_NOMEAN>(p, grid, stream);
+#endif
+    return launch_rt_variant<RT_REDUCE>(p, grid, stream);
 }
 
 template <>

@@ -104,20 +104,46 @@ __device__ __forceinline__ void tt_lut_init(unsigned char *lut, int tid) {
 // One-hot row of a 64-row tile from a table of the 16-byte patterns of two bases (same chunk layout as tt_build_row: chunk ch = bases
 // 2 ch, 2 ch + 1 as eight fp16): a shift, a mask, a 16-byte table load and a 16-byte store per chunk instead of ~14 ALU instructions.
 // lut: entries 0-15 pattern of (b0 | b1 << 2), 16-19 pattern of b0 alone (last chunk of an odd motif length), 20 zero.
+// BATCH: one 64-column atom (eight chunks) at a time, the eight table loads issued together, then the eight stores; chunks beyond nch
+// inside an atom that exists are stored as zeros. Written as one load and one store per chunk (!BATCH) the compiler reuses a single
+// register quad and the row becomes a chain of 2 x nch shared-memory round trips (1600-2000 cycles per tile, measured): that is the
+// better schedule for the kernels bound by their epilogue (fused reductions with the mean, pooled scans: the bursts of the batched
+// builder cost them 5-7 %), while the kernels bound by the tile supply gain from the batch (un-pooled dense scan: +5 % of the HBM peak).
+template <bool BATCH>
 __device__ __forceinline__ void tt_build_row_lut(unsigned char *X, const unsigned char *lut, int r, int nch, int M, const uint32_t (&w)[4], int sh, bool valid) {
     uint32_t v[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) v[i] = __funnelshift_r(w[i], w[i + 1], sh);
     const int nfull = M >> 1;
     unsigned char *row = X + (r >> 3) * 1024 + (r & 7) * 128;
+    if (BATCH) {
 #pragma unroll
-    for (int ch = 0; ch < 16; ++ch) {
-        if (ch < nch) {
-            const uint32_t bits = (v[ch >> 3] >> (4 * (ch & 7))) & 15u;
-            uint32_t e = ch < nfull ? bits : (ch == nfull && (M & 1)) ? 16u + (bits & 3u) : 20u;     // (uniform in ch: M is a kernel constant)
-            e = valid ? e : 20u;
-            const uint4 q = *reinterpret_cast<const uint4 *>(lut + e * 16);
-            *reinterpret_cast<uint4 *>(row + (ch >> 3) * TT_XATOM + (((ch ^ r) & 7) << 4)) = q;
+        for (int half = 0; half < 2; ++half) {
+            if (8 * half < nch) {
+                uint4 q[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int ch = 8 * half + c;
+                    const uint32_t bits = (v[ch >> 3] >> (4 * (ch & 7))) & 15u;
+                    uint32_t e = ch < nfull ? bits : (ch == nfull && (M & 1)) ? 16u + (bits & 3u) : 20u;     // (uniform in ch: M is a kernel constant)
+                    e = valid ? e : 20u;
+                    q[c] = *reinterpret_cast<const uint4 *>(lut + e * 16);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<uint4 *>(row + half * TT_XATOM + (((c ^ r) & 7) << 4)) = q[c];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < 16; ++ch) {
+            if (ch < nch) {
+                const uint32_t bits = (v[ch >> 3] >> (4 * (ch & 7))) & 15u;
+                uint32_t e = ch < nfull ? bits : (ch == nfull && (M & 1)) ? 16u + (bits & 3u) : 20u;
+                e = valid ? e : 20u;
+                const uint4 q = *reinterpret_cast<const uint4 *>(lut + e * 16);
+                *reinterpret_cast<uint4 *>(row + (ch >> 3) * TT_XATOM + (((ch ^ r) & 7) << 4)) = q;
+            }
         }
     }
 }

@@ -405,6 +405,11 @@ def bench_scan(ctx, model, K, M, Lt, traffic_key):
         out_rec[mode_name]['fused_reductions'] = {
             'metric': 'motif-scan nt/s, max/argmax/mean over positions fused (no dense output)',
             'value': n * Lt * world / (ms_red * 1e-3), 'unit': 'nt/s', 'ms': ms_red}
+        # maximum and its position alone (motifHitSummary(want=('max', 'argmax')); utils.py:155,245-247 use nothing else)
+        ms_mx = timed_calls(ctx, lambda: _lib.check(lib.crbm_scan_reduce(
+            _lib.ptr(seqs.words), seqs.row_words, n, Lt, _lib.ptr(model._t_W), _lib.ptr(model._t_bias), K, M, model.pooling,
+            mode, _lib.OUT_PROBABILITY, _lib.ptr(mx), _lib.ptr(am), None, s), 'scan_reduce'), reps=3, warm=1)
+        out_rec[mode_name]['fused_reductions']['max_argmax_only'] = {'value': n * Lt * world / (ms_mx * 1e-3), 'unit': 'nt/s', 'ms': ms_mx}
     out_rec['sharding'] = 'sequences sharded across ranks, weights replicated, no collective on the data path'
     return out_rec
 
@@ -421,13 +426,14 @@ def bench_scan_job(ctx, model, K, M, Lt, total_nt):
     warm = seqs.rows(0, min(n, 40000))          # (more than one chunk: the call's pinned staging buffers take their final shape)
     rec = {'metric': 'motif-scan nt/s, CRBM.motifHitSummary over the whole job (max/argmax/mean per sequence and motif)',
            'total_nt': float(n) * Lt * ctx.world, 'sequences_per_gpu': n, 'unit': 'nt/s'}
-    for name, ds in (('forward', True), ('both_strands_summed', False)):
+    for name, ds, want in (('forward', True, ('max', 'argmax', 'mean')), ('both_strands_summed', False, ('max', 'argmax', 'mean')),
+                           ('forward_max_argmax_only', True, ('max', 'argmax'))):
         model.doublestranded = ds
-        model.motifHitSummary(warm)
+        model.motifHitSummary(warm, want=want)
         ctx.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = model.motifHitSummary(seqs)          # includes the device->host copy of the three (N,K) results
+        res = model.motifHitSummary(seqs, want=want)          # includes the device->host copy of the (N,K) results
         e1.record()
         torch.cuda.synchronize()
         ms = ctx.max_over_ranks(e0.elapsed_time(e1))

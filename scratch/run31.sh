@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/r2u_dp2_20.json 2> gpurun_out/r2u_dp2_20.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --impl reference --steps 5 --warmup 3 > gpurun_out/r2u_ref2.json 2> gpurun_out/r2u_ref2.err

@@ -776,6 +776,7 @@ class CRBM(object):
             torch.cuda.synchronize(self._device)
             for t, v in zip(tensors, saved):
                 t.copy_(v)
+            eng['cursor'] = None                      # (the warm-up ran on the cursors and restored them: be explicit)
             g = torch.cuda.CUDAGraph()
             c0 = _lib.load().crbm_launch_count()
             with torch.cuda.graph(g):
@@ -812,8 +813,11 @@ class CRBM(object):
             eager(min(count, (self._dp_seq & 1) + (0 if ('p2p_warm' in eng) else 2)))
             eng['p2p_warm'] = True
             if spg >= 2 and count - done >= 2:
-                eng['step_dev'].fill_(self._dp_seq)
-                eng['batch_dev'].fill_(first_batch + done)
+                # the device cursors are only written when they do not already stand where this call starts (a caller that continues
+                # where the previous call ended launches nothing but the graphs)
+                if eng.get('cursor') != ('p2p', self._dp_seq, (first_batch + done) % eng['n_full']):
+                    eng['step_dev'].fill_(self._dp_seq)
+                    eng['batch_dev'].fill_(first_batch + done)
                 while count - done >= 2:
                     # graphs of spg steps, then ONE graph of the remaining even number of steps (cached per length); only a last
                     # odd step runs eagerly
@@ -824,11 +828,14 @@ class CRBM(object):
                         g.replay()
                     self._dp_seq += nrep * n
                     done += nrep * n
+                eng['cursor'] = ('p2p', self._dp_seq, (first_batch + done) % eng['n_full'])
             eager(count - done)
             self._step += count
             return
-        eng['step_dev'].fill_(self._step)
-        eng['batch_dev'].fill_(first_batch)
+        if eng.get('cursor') != ('local', self._step, first_batch % eng['n_full']):
+            eng['step_dev'].fill_(self._step)
+            eng['batch_dev'].fill_(first_batch)
+        eng['cursor'] = ('local', self._step + count, (first_batch + count) % eng['n_full'])
         if self._world > 1:
             import torch.distributed as dist
             ga, gb = self._graph_for(eng, 1, 'accumulate'), self._graph_for(eng, 1, 'apply')

@@ -6,15 +6,17 @@
 // measured 19.6 % of the HBM peak). Here the machinery of scan_rt.cuh is used: MMA row r = motif 128 chunk + r (strand-selected
 // W as fp16 hi + lo, A operand), columns = hidden positions (one-hot tile built from the packed words, B operand), a thread of the
 // epilogue owns one motif and 32 consecutive positions: the pooled softmax p = e / (P + sum_group e) (:252) is a run of registers.
-// A CTA follows ONE sequence at a time: a step is four consecutive blocks of VP = (32 / P) * P positions (two units of 64 columns,
-// one per epilogue group), whose 4 VP probabilities per motif are staged in shared memory as one run [motif][4 VP] and stored with
-// one cp.async.bulk per motif row (480 bytes for P = 5, 512 for P = 1, 2, 4: whole sectors when the output rows are padded to
-// multiples of 8 floats, which crbm_b200/convRBM.py does). No per-value store instruction, no shuffle.
-// When VP = 32 (P = 1, 2, 4) a block is a whole 128-byte line of an output row, and the epilogue warps are independent of each other:
-// the CTA's (sequence, block) pairs are dealt out two per unit without regard to sequence boundaries, a warp stages its 32 motifs x
-// 32 positions in its own 4 KB of shared memory (SWIZZLE_128B: conflict-free 16-byte stores) and ONE lane stores the tile with
-// cp.async.bulk.tensor.3d (tensor map over (position, motif, sequence): rows beyond K and positions beyond the row are clipped by
-// the TMA engine). The four warps of an SM sub-partition then drift apart, so the exponentials of one overlap the stores of another.
+// Two store paths, by the block width VP = (32 / P) * P:
+//   VP = 32 (P = 1, 2, 4): a block is a whole 128-byte line of an output row and the epilogue warps are independent of each other:
+//     the CTA's (sequence, block) pairs are dealt out two per unit without regard to sequence boundaries, a warp stages its 32 motifs x
+//     32 positions in its own 4 KB of shared memory (SWIZZLE_128B: conflict-free 16-byte stores) and ONE lane stores the tile with
+//     cp.async.bulk.tensor.3d (tensor map over (position, motif, sequence): rows beyond K and positions beyond the row are clipped by
+//     the TMA engine). The four warps of an SM sub-partition drift apart, so the exponentials of one overlap the stores of another.
+//   VP = 30 (P = 5, 10): 120 bytes are no legal TMA box. A CTA follows ONE sequence at a time: a step is four consecutive blocks (two
+//     units of 64 columns, one per epilogue group) whose 4 VP probabilities per motif are staged as one run [motif][4 VP] by the four
+//     warps of a lane quarter (named barriers of 128 threads) and stored with one cp.async.bulk of 480 bytes per motif row.
+// Whole 32-byte sectors are written when the output rows are padded to multiples of 8 floats, which crbm_b200/convRBM.py does.
+// No per-value store instruction, no shuffle. Tile supply: scan_rt.cuh (four producer warps, rows from the pattern table).
 // Bound: HBM write, 4 K bytes per hidden position.
 #pragma once
 #include <cuda.h>

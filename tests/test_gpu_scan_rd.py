@@ -71,14 +71,18 @@ def test_pooled_many_sequences_same_window_property():
     np.testing.assert_allclose(got[:1], O.hit_probs(crbm_b200.codesToOneHot(base).astype(np.float64), W, b, P, True), **TOL)
 
 
-@pytest.mark.parametrize('kernel', ['rows', 'pos'])
+@pytest.mark.parametrize('kernel', ['rows', 'pos', 'rows-bulk'])
 def test_unpooled_scan_suite_on_either_kernel(kernel):
     """The un-pooled scan picks the row-dense or the position-major kernel by the model shape (train_tc_impl.cuh: rowdense_wanted);
     CRBM_SCAN_KERNEL=rows | pos (read once per process: subprocess) forces one of them for every shape, and the scan suite of
     test_gpu_scan_tc.py (activities and probabilities, all strand modes) must pass on both."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CRBM_SCAN_KERNEL=kernel)
+    # 'rows-bulk': the row-dense kernel without the tensor map (per-row bulk copies, the path taken when cuTensorMapEncodeTiled is
+    # not available)
+    env = dict(os.environ, CRBM_SCAN_KERNEL=kernel.split('-')[0])
+    if kernel.endswith('-bulk'):
+        env['CRBM_RD_STORE'] = 'bulk'
     r = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x', '-m', 'gpu', os.path.join(root, 'tests', 'test_gpu_scan_tc.py')],
                        capture_output=True, text=True, timeout=900, cwd=root, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

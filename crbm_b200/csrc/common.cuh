@@ -113,6 +113,15 @@ __device__ __forceinline__ uint32_t window_bits(const uint32_t (&a)[NW], int t) 
     return v & ((1u << (2 * NB)) - 1u);
 }
 
+// floor(t) of 0 <= t < 2^23 in the low 23 bits of a float's pattern: t + 2^23 rounded toward zero has an ulp of one. A Bernoulli
+// decision "floor(65536 p) > 16-bit uniform" is then one fma and one integer compare against (0x4B000000 | uniform) — no float-to-int
+// conversion (F2I runs on the XU pipe, beside the exponentials), and the same decision bit for bit.
+__device__ __forceinline__ uint32_t floor_bits(float v, float scale) {
+    float x;
+    asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(x) : "f"(v), "f"(scale));
+    return __float_as_uint(x);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -505,9 +505,11 @@ __global__ void __launch_bounds__(TT_THREADS, 1) v2h_train_tc_kernel(const Train
                             const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const int ti = (int)(pv[8 * c4 + i] * 4.f), u16 = (int)((rw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-                                word |= (ti > u16 ? 1u : 0u) << (8 * c4 + i);
-                                ambw |= (ti == u16 ? 1u : 0u) << (8 * c4 + i);
+                                // floor(65536 p) against the 16 bits, both in the pattern of a float near 2^23 (floor_bits, common.cuh)
+                                const uint32_t tb = floor_bits(pv[8 * c4 + i], 4.f);
+                                const uint32_t ub = 0x4B000000u | ((rw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                                word |= (tb > ub ? 1u : 0u) << (8 * c4 + i);
+                                ambw |= (tb == ub ? 1u : 0u) << (8 * c4 + i);
                             }
                         }
                         if (__any_sync(0xffffffffu, ambw != 0u)) {

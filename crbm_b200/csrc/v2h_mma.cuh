@@ -457,22 +457,24 @@ __device__ __forceinline__ void v2h_mma_body(const V2HParams &p, unsigned char *
                     const uint4 ctr = make_uint4((uint32_t)(n * p.K + mtile * MTILE + g), (uint32_t)(jb * 4 + q), ctr_hi, tag);
                     const uint4 rnd = philox4x32(ctr, key);
                     const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
-                    float fr[8];
-                    bool amb = false;
+                    uint32_t ambm = 0u;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const float t = d1[s][(i >> 1) & 1][2 * (i >> 2) + (i & 1)] * 65536.f;
-                        const int ti = (int)t, u16 = (int)((rw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-                        fr[i] = ti == u16 ? t - (float)ti : -1.f;
-                        hit[i] = ti > u16;
-                        amb = amb || ti == u16;
+                        // floor(65536 p) against the 16 bits, both carried in the pattern of a float near 2^23 (floor_bits, common.cuh)
+                        const uint32_t tb = floor_bits(d1[s][(i >> 1) & 1][2 * (i >> 2) + (i & 1)], 65536.f);
+                        const uint32_t ub = 0x4B000000u | ((rw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                        hit[i] = tb > ub;
+                        ambm |= (tb == ub ? 1u : 0u) << i;
                     }
-                    if (__any_sync(0xffffffffu, amb)) {          // rare: ~1 % of the blocks
+                    if (__any_sync(0xffffffffu, ambm != 0u)) {          // rare: ~1 % of the blocks
                         const uint4 r2 = philox4x32_call(make_uint4(ctr.x, ctr.y, ctr.z, tag + 16u), key);
                         const uint32_t r2w[4] = {r2.x, r2.y, r2.z, r2.w};
 #pragma unroll
                         for (int i = 0; i < 8; ++i)
-                            if (fr[i] >= 0.f) hit[i] = fr[i] * 65536.f > (float)((r2w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                            if ((ambm >> i) & 1u) {
+                                const float t = d1[s][(i >> 1) & 1][2 * (i >> 2) + (i & 1)] * 65536.f;
+                                hit[i] = (t - floorf(t)) * 65536.f > (float)((r2w[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+                            }
                     }
                 }
 #pragma unroll

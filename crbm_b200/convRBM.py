@@ -313,13 +313,40 @@ class CRBM(object):
         if Lh <= 0:
             raise ValueError("sequences of length %d are shorter than the motif (%d)" % (seqs.L, M))
         torch = _torch()
-        out = np.empty((seqs.N, K, 1, Lh), dtype=np.float32)
         rows = max(1, min(seqs.N, int(max_chunk_bytes // (4 * K * Lh))))
         nbuf = min(2, -(-seqs.N // rows))
         pitch = self._scan_pitch(Lh, out_kind)
         main = torch.cuda.current_stream(self._device)
         side = torch.cuda.Stream(device=self._device)
         bufs = [torch.empty((rows, K, 1, pitch), dtype=torch.float32, device=self._device) for _ in range(nbuf)]
+        # Results up to CRBM_PINNED_RESULT_MAX bytes (default 4 GB) are returned in page-locked memory: the chunks are copied device ->
+        # result directly (no staging buffer, no host memcpy into freshly faulted pageable pages, which was the slowest stage: ~5 GB/s),
+        # and torch's caching host allocator hands the pages out again once the caller has dropped the previous result.
+        nbytes = 4 * seqs.N * K * Lh
+        out_t = None
+        if nbytes <= int(os.environ.get('CRBM_PINNED_RESULT_MAX', str(4 << 30))):
+            try:
+                out_t = torch.empty((seqs.N, K, 1, Lh), dtype=torch.float32, pin_memory=True)
+            except RuntimeError:
+                out_t = None
+        if out_t is not None:
+            done = [None] * nbuf                                # per device buffer: its last copy has read it
+            for i, s in enumerate(range(0, seqs.N, rows)):
+                e, j = min(seqs.N, s + rows), i % nbuf
+                if done[j] is not None:
+                    main.wait_event(done[j])                    # the scan into this buffer follows the copy that read it last
+                view = self._v2h_device(seqs, strand_mode, out_kind, s, e, buf=bufs[j])
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    out_t[s:e].copy_(view, non_blocking=True)
+                    done[j] = torch.cuda.Event()
+                    done[j].record(side)
+            side.synchronize()
+            main.wait_stream(side)
+            return out_t.numpy()
+        out = np.empty((seqs.N, K, 1, Lh), dtype=np.float32)
         stage = [self._staging('scan%d' % i, (rows, K, 1, Lh), torch.float32) for i in range(nbuf)]
         copied = [None, None]
         pending = []                                            # (chunk start, end, staging index) whose copies are in flight

@@ -482,12 +482,45 @@ class CRBM(object):
                       if t[0] in want)
         if not names or any(w not in ('max', 'argmax', 'mean') for w in want):
             raise ValueError("motifHitSummary: want must be a non-empty subset of ('max', 'argmax', 'mean')")
-        out = {nm: np.empty((N, K), dtype=npd) for nm, _, npd in names}
         bufs = [{nm: torch.empty((rows, K), dtype=td, device=self._device) for nm, td, _ in names} for _ in range(nbuf)]
-        stage = [{nm: self._staging('sum_%s%d' % (nm, i), (rows, K), td) for nm, td, _ in names} for i in range(nbuf)]
         mode = _lib.STRAND_FWD if self.doublestranded else _lib.STRAND_SUM
         main = torch.cuda.current_stream(self._device)
         side = torch.cuda.Stream(device=self._device)
+
+        def scan(s, e, b):
+            _lib.check(lib.crbm_scan_reduce(_lib.ptr(seqs.words[s:]), seqs.row_words, e - s, seqs.L, _lib.ptr(self._t_W),
+                                            _lib.ptr(self._t_bias), K, M, self.pooling, mode, _lib.OUT_PROBABILITY,
+                                            _lib.ptr(b.get('max')), _lib.ptr(b.get('argmax')), _lib.ptr(b.get('mean')), _lib.stream_handle()),
+                       'scan_reduce')
+
+        # results up to CRBM_PINNED_RESULT_MAX bytes (default 4 GB) are returned in page-locked memory, the chunks copied device ->
+        # result directly (see _v2h)
+        out_t = None
+        if 4 * N * K * len(names) <= int(os.environ.get('CRBM_PINNED_RESULT_MAX', str(4 << 30))):
+            try:
+                out_t = {nm: torch.empty((N, K), dtype=td, pin_memory=True) for nm, td, _ in names}
+            except RuntimeError:
+                out_t = None
+        if out_t is not None:
+            done = [None] * nbuf
+            for i, s in enumerate(range(0, N, rows)):
+                e, j = min(N, s + rows), i % nbuf
+                if done[j] is not None:
+                    main.wait_event(done[j])                    # the scan into these buffers follows the copies that read them last
+                scan(s, e, bufs[j])
+                ready = torch.cuda.Event()
+                ready.record(main)
+                side.wait_event(ready)
+                with torch.cuda.stream(side):
+                    for nm, _, _ in names:
+                        out_t[nm][s:e].copy_(bufs[j][nm][:e - s], non_blocking=True)
+                    done[j] = torch.cuda.Event()
+                    done[j].record(side)
+            side.synchronize()
+            main.wait_stream(side)
+            return {nm: t.numpy() for nm, t in out_t.items()}
+        out = {nm: np.empty((N, K), dtype=npd) for nm, _, npd in names}
+        stage = [{nm: self._staging('sum_%s%d' % (nm, i), (rows, K), td) for nm, td, _ in names} for i in range(nbuf)]
         copied = [None, None]
         pending = []
 
@@ -503,10 +536,7 @@ class CRBM(object):
             j = i % nbuf
             drain(nbuf - 1)
             b = bufs[j]
-            _lib.check(lib.crbm_scan_reduce(_lib.ptr(seqs.words[s:]), seqs.row_words, e - s, seqs.L, _lib.ptr(self._t_W),
-                                            _lib.ptr(self._t_bias), K, M, self.pooling, mode, _lib.OUT_PROBABILITY,
-                                            _lib.ptr(b.get('max')), _lib.ptr(b.get('argmax')), _lib.ptr(b.get('mean')), _lib.stream_handle()),
-                       'scan_reduce')
+            scan(s, e, b)
             ready = torch.cuda.Event()
             ready.record(main)
             side.wait_event(ready)

@@ -106,6 +106,8 @@ SIGNATURES = {
     'crbm_chain_from_dense': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'crbm_fasta_parse_block_host': (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_longlong),
                                             ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_int)]),
+    'crbm_fasta_pack_block_host': (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_size_t, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_longlong),
+                                           ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_int), c_int]),
     'crbm_v2h_dense_kernel_name': (ctypes.c_char_p, [c_int, c_int, c_int, c_int, ctypes.c_longlong]),
     'crbm_launch_count': (ctypes.c_ulonglong, []),
 }

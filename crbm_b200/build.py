@@ -37,7 +37,7 @@ def _newest_header():
 
 def _jobs():
     jobs = []
-    for src in ('api.cu', 'ops.cu', 'train.cu', 'scan_tc.cu'):
+    for src in ('api.cu', 'ingest.cu', 'ops.cu', 'train.cu', 'scan_tc.cu'):
         jobs.append((os.path.join(CSRC, src), os.path.join(OBJ, src[:-3] + '.o'), []))
     for mw in MWS:
         jobs.append((os.path.join(CSRC, 'v2h_inst.cu'), os.path.join(OBJ, 'v2h_inst_%d.o' % mw), ['-DCRBM_MW=%d' % mw]))

@@ -1,0 +1,221 @@
+// Host side of the streaming ingest (secomo/sequences.py:33-52 readSeqsFromFasta, :20-31 the base table, :101-117
+// seqToOneHot): a block of complete multi-FASTA records -> rows of 2-bit bases in the device layout (common.cuh), written where the
+// caller says — a page-locked staging buffer, so that one cudaMemcpyAsync of 0.25 byte per base is all that crosses PCIe and no packing
+// kernel runs. No device code in this file.
+//
+// The block is cut into segments at record starts, one host thread per segment:
+//   pass 1  every thread counts the headers of its segment (memchr): an upper bound on the rows it will write, hence its first row;
+//   pass 2  every thread parses its records: a sequence line is found with memchr, translated 16 bytes at a time
+//           (code = ((c >> 1) ^ (c >> 2)) & 3 maps A/a C/c G/g T/t to 0 1 2 3; (c | 0x20) is compared with the four letters
+//           for validity, both loops auto-vectorised), a line holding anything else goes through the byte-wise table of
+//           crbm_fasta_parse_block_host (N: record skipped, blank / CR: dropped, other letters: error), and a complete record of L
+//           codes is packed 8 bases per 64-bit word operation into its row;
+//   pass 3  rows of segments behind a segment that dropped records (N, or a header without sequence) are moved down.
+// The first error in file order is the one reported, as the one-pass parser does.
+#include <string.h>
+#include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+#include <vector>
+#include "common.cuh"
+
+namespace {
+
+struct Lut {
+    unsigned char v[256];
+    Lut() {
+        for (int i = 0; i < 256; ++i) v[i] = 255;
+        v[(int)'A'] = v[(int)'a'] = 0; v[(int)'C'] = v[(int)'c'] = 1; v[(int)'G'] = v[(int)'g'] = 2; v[(int)'T'] = v[(int)'t'] = 3;
+        v[(int)'N'] = v[(int)'n'] = 4;
+        v[10] = v[13] = v[32] = v[9] = 254;                   // line ends and blanks inside a record are dropped
+    }
+};
+const Lut g_lut;
+
+inline bool header_at(const unsigned char *buf, size_t i) { return buf[i] == '>' && (i == 0 || buf[i - 1] == 10); }
+
+// first header at or after `from` (n if none)
+size_t next_header(const unsigned char *buf, size_t n, size_t from) {
+    size_t i = from;
+    while (i < n) {
+        const void *p = memchr(buf + i, '>', n - i);
+        if (!p) return n;
+        i = (const unsigned char *)p - buf;
+        if (header_at(buf, i)) return i;
+        ++i;
+    }
+    return n;
+}
+
+long long count_headers(const unsigned char *buf, size_t begin, size_t end) {
+    long long c = 0;
+    for (size_t i = next_header(buf, end, begin); i < end; i = next_header(buf, end, i + 1)) ++c;
+    return c;
+}
+
+// 8 base codes (one per byte, little endian) -> 16 bits
+inline uint32_t pack8(uint64_t x) {
+    x = (x | (x >> 6)) & 0x000F000F000F000FULL;
+    x = (x | (x >> 12)) & 0x000000FF000000FFULL;
+    x = (x | (x >> 24)) & 0xFFFFULL;
+    return (uint32_t)x;
+}
+
+struct alignas(64) Segment {
+    size_t begin = 0, end = 0;          // [begin, end) of the block; begin is at a header
+    long long first_row = 0;            // row index of this segment's first record (from the header counts)
+    long long headers = 0, n_out = 0, n_skip = 0;
+    int rc = CRBM_OK, bad = 0;
+};
+
+// translate a sequence line; returns false if it holds anything but ACGT / acgt
+inline bool translate_line(const unsigned char *src, size_t len, unsigned char *dst) {
+#if defined(__SSE2__)
+    if (len >= 16) {
+        const __m128i x20 = _mm_set1_epi8(0x20), three = _mm_set1_epi8(3);
+        const __m128i la = _mm_set1_epi8('a'), lc = _mm_set1_epi8('c'), lg = _mm_set1_epi8('g'), lt = _mm_set1_epi8('t');
+        __m128i ok = _mm_set1_epi8((char)0xff);
+        auto step = [&](size_t j) {
+            const __m128i c = _mm_loadu_si128((const __m128i *)(src + j));
+            const __m128i u = _mm_or_si128(c, x20);
+            ok = _mm_and_si128(ok, _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(u, la), _mm_cmpeq_epi8(u, lc)),
+                                                _mm_or_si128(_mm_cmpeq_epi8(u, lg), _mm_cmpeq_epi8(u, lt))));
+            _mm_storeu_si128((__m128i *)(dst + j), _mm_and_si128(_mm_xor_si128(_mm_srli_epi16(c, 1), _mm_srli_epi16(c, 2)), three));
+        };
+        size_t j = 0;
+        for (; j + 16 <= len; j += 16) step(j);
+        if (j < len) step(len - 16);                              // the last 16 bytes again (same values)
+        return _mm_movemask_epi8(ok) == 0xffff;
+    }
+#endif
+    unsigned char bad = 0;
+    for (size_t j = 0; j < len; ++j) {
+        const unsigned char c = src[j], u = c | 0x20;
+        bad |= (unsigned char)!((u == 'a') | (u == 'c') | (u == 'g') | (u == 't'));
+        dst[j] = ((c >> 1) ^ (c >> 2)) & 3;
+    }
+    return !bad;
+}
+
+void parse_segment(const unsigned char *buf, Segment &sg, long long L, uint32_t *rows, int row_words, size_t capacity_rows) {
+    const int nw = (int)((L + 15) / 16);
+    std::vector<unsigned char> tmp((size_t)nw * 16 + 16, 0);      // codes of the record being read; the tail beyond L stays zero
+    size_t i = sg.begin;
+    const size_t end = sg.end;
+    while (i < end) {
+        const void *p = memchr(buf + i, 10, end - i);              // header line
+        i = p ? (size_t)((const unsigned char *)p - buf) + 1 : end;
+        long long len = 0;
+        bool has_n = false;
+        while (i < end && buf[i] != '>') {                         // sequence lines (i is at a line start)
+            p = memchr(buf + i, 10, end - i);
+            const size_t e = p ? (size_t)((const unsigned char *)p - buf) : end;
+            size_t line = e - i;
+            if (line && buf[e - 1] == 13) --line;                  // CRLF file: the CR is dropped, as the table does
+                        if (len + (long long)line <= L && translate_line(buf + i, line, tmp.data() + len)) {
+                len += (long long)line;
+            } else {
+                for (size_t j = i; j < e; ++j) {
+                    const unsigned char v = g_lut.v[buf[j]];
+                    if (v <= 4) {
+                        if (len >= L) { sg.rc = -11; return; }     // ragged: longer than the first record
+                        tmp[len++] = v & 3;
+                        has_n |= v == 4;
+                    } else if (v == 255) { sg.bad = buf[j]; sg.rc = -12; return; }
+                }
+            }
+            i = p ? e + 1 : end;
+        }
+        if (len == 0) continue;                                    // a header without sequence: dropped
+        if (len != L) { sg.rc = -11; return; }
+        if (has_n) { ++sg.n_skip; continue; }
+        const size_t r = (size_t)(sg.first_row + sg.n_out);
+        if (r >= capacity_rows) { sg.rc = -13; return; }
+        uint32_t *row = rows + r * (size_t)row_words;
+        for (int w = 0; w < crbm::FRONT_PAD_WORDS; ++w) row[w] = 0;
+        for (int w = 0; w < nw; ++w) {
+            uint64_t a, b;
+            memcpy(&a, tmp.data() + 16 * w, 8);
+            memcpy(&b, tmp.data() + 16 * w + 8, 8);
+            row[crbm::FRONT_PAD_WORDS + w] = pack8(a) | (pack8(b) << 16);
+        }
+        for (int w = crbm::FRONT_PAD_WORDS + nw; w < row_words; ++w) row[w] = 0;
+        ++sg.n_out;
+    }
+}
+
+}  // namespace
+
+extern "C" int crbm_fasta_pack_block_host(const unsigned char *buf, size_t n, uint32_t *rows, int row_words, size_t capacity_rows, int *L_io,
+                                          long long *n_records, long long *n_skipped, int *bad_char, int n_threads) {
+    if (!buf || !L_io || !n_records || !n_skipped || !bad_char) { crbm::set_error("crbm_fasta_pack_block_host: null argument"); return CRBM_ERR_ARG; }
+    *n_records = 0; *n_skipped = 0;
+    long long L = *L_io;
+    const size_t first = next_header(buf, n, 0);                   // anything before the first header is not a record
+    if (L <= 0) {                                                  // record length = that of the first record that has bases
+        for (size_t i = first; i < n && L <= 0;) {
+            const void *p = memchr(buf + i, 10, n - i);
+            i = p ? (size_t)((const unsigned char *)p - buf) + 1 : n;
+            const size_t e = next_header(buf, n, i);
+            long long len = 0;
+            for (size_t j = i; j < e; ++j) len += g_lut.v[buf[j]] <= 4;
+            if (len > 0) L = len;
+            i = e;
+        }
+        if (L <= 0) return CRBM_OK;                                // no record with bases in this block
+        if (L > 0x7fffffff) { crbm::set_error("crbm_fasta_pack_block_host: record longer than 2^31 bases"); return CRBM_ERR_ARG; }
+        *L_io = (int)L;
+    }
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 64) T = 64;
+    const size_t min_segment = 1 << 20;                            // a thread is not worth starting for less
+    if ((size_t)T > (n - first) / min_segment + 1) T = (int)((n - first) / min_segment + 1);
+
+    std::vector<Segment> seg((size_t)T);
+    size_t at = first;
+    for (int t = 0; t < T; ++t) {
+        seg[t].begin = at;
+        at = t + 1 == T ? n : next_header(buf, n, first + (n - first) / T * (size_t)(t + 1));
+        if (at < seg[t].begin) at = seg[t].begin;
+        seg[t].end = at;
+    }
+    auto run = [&](auto fn) {
+        if (T == 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; ++t) th.emplace_back(fn, t);
+        fn(0);
+        for (auto &x : th) x.join();
+    };
+    // (one thread: no first rows to find; the headers are counted only if the parser runs out of rows)
+    const bool counted = T > 1 || !rows || capacity_rows == 0;
+    if (counted) run([&](int t) { seg[t].headers = count_headers(buf, seg[t].begin, seg[t].end); });
+    long long need = 0;
+    for (int t = 0; t < T; ++t) { seg[t].first_row = need; need += seg[t].headers; }
+    if (counted && ((size_t)need > capacity_rows || !rows)) {      // the caller sizes its buffer from this and calls again
+        *n_records = need;
+        crbm::set_error("crbm_fasta_pack_block_host: %lld rows needed, %zu given", need, capacity_rows);
+        return -13;
+    }
+    if (row_words < crbm::packed_row_words((int)L)) { crbm::set_error("crbm_fasta_pack_block_host: row_words %d < %d", row_words, crbm::packed_row_words((int)L)); return CRBM_ERR_ARG; }
+    run([&](int t) { parse_segment(buf, seg[t], L, rows, row_words, capacity_rows); });
+    long long out = 0, skipped = 0;
+    for (int t = 0; t < T; ++t) {
+        if (seg[t].rc == -13) {                                    // (single thread) out of rows: now count
+            *n_records = count_headers(buf, first, n);
+            crbm::set_error("crbm_fasta_pack_block_host: %lld rows needed, %zu given", *n_records, capacity_rows);
+            return -13;
+        }
+        if (seg[t].rc != CRBM_OK) {                                // first error in file order
+            if (seg[t].rc == -12) *bad_char = seg[t].bad;
+            return seg[t].rc;
+        }
+        if (seg[t].first_row != out && seg[t].n_out)
+            memmove(rows + (size_t)out * row_words, rows + (size_t)seg[t].first_row * row_words, (size_t)seg[t].n_out * row_words * sizeof(uint32_t));
+        out += seg[t].n_out;
+        skipped += seg[t].n_skip;
+    }
+    *n_records = out; *n_skipped = skipped;
+    return CRBM_OK;
+}

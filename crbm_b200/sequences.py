@@ -57,7 +57,7 @@ def _parse_fasta(handle):
             name = desc.split()[0] if desc.split() else ''
             chunks = []
         else:
-            chunks.append(line)
+            chunks.append(line.replace(' ', '').replace('\t', ''))     # (Biopython's reader drops blanks inside a record too)
     if name is not None:
         yield SeqRecord(''.join(chunks), id=name, description=desc)
 
@@ -221,6 +221,68 @@ def iterFastaCodes(filename, chunk_bytes=32 << 20, quiet=False):
                     yield np.ascontiguousarray(codes)
             if last:
                 return
+
+
+def iterFastaPacked(filename, chunk_bytes=32 << 20, quiet=False, threads=0, get_buffer=None):
+    """Streams a multi-FASTA file as rows of 2-bit bases in the device layout (packedRowWords(L) uint32 words per record): yields
+    (rows, L) with rows an (n, row_words) uint32 array per block of about `chunk_bytes` of file. Same record semantics as
+    iterFastaCodes (reference secomo/sequences.py:33-52, 20-31: N records skipped, case folded, KeyError on other letters, equal
+    lengths). The file is memory-mapped and cut into blocks at record starts; a block is parsed and packed by the host threads of
+    crbm_fasta_pack_block_host (csrc/ingest.cu) straight into the array `get_buffer(rows_needed, row_words)` returns (default: a
+    fresh NumPy array; PackedSequences.from_fasta hands out page-locked staging buffers). Needs the built library."""
+    import ctypes
+    import mmap
+    from . import _lib
+    lib = _lib.load()
+    size = os.path.getsize(filename)
+    if size == 0:
+        return
+    if get_buffer is None:
+        get_buffer = lambda rows, rw: np.empty((rows, rw), dtype=np.uint32)
+    L0 = ctypes.c_int(0)
+    nrec, nskip, bad = ctypes.c_longlong(0), ctypes.c_longlong(0), ctypes.c_int(0)
+    chunk_bytes = max(1, int(chunk_bytes))
+    with open(filename, 'rb') as f:
+        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+    view = np.frombuffer(mm, dtype=np.uint8)
+    try:
+        addr = view.ctypes.data
+        lo = 0
+        while lo < size:
+            hi = min(size, lo + chunk_bytes)
+            if hi < size:                                   # a block ends where a record starts
+                cut = mm.rfind(b'\n>', lo, hi + 1)
+                if cut < 0:
+                    cut = mm.find(b'\n>', hi)
+                hi = size if cut < 0 else cut + 1
+            n = hi - lo
+            rows, rw = None, 0
+            if L0.value > 0:
+                rw = packedRowWords(L0.value)
+                rows = get_buffer(n // (L0.value + 2) + 1, rw)
+            for attempt in range(2):
+                rc = lib.crbm_fasta_pack_block_host(ctypes.c_void_p(addr + lo), n, None if rows is None else rows.ctypes.data_as(ctypes.c_void_p),
+                                                    rw, 0 if rows is None else rows.shape[0], ctypes.byref(L0), ctypes.byref(nrec),
+                                                    ctypes.byref(nskip), ctypes.byref(bad), int(threads))
+                if rc != -13:
+                    break
+                rw = packedRowWords(L0.value)                # the block may need more rows than its size suggests (or L was unknown)
+                rows = get_buffer(int(nrec.value), rw)
+            if rc == -11:
+                raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
+            if rc == -12:
+                raise KeyError(chr(bad.value))
+            if rc != 0:
+                raise RuntimeError("crbm_fasta_pack_block_host failed (%d): %s" % (rc, lib.crbm_last_error().decode()))
+            if not quiet:
+                for _ in range(int(nskip.value)):
+                    print("skip sequence containing N")
+            if nrec.value:
+                yield rows[:int(nrec.value)], int(L0.value)
+            lo = hi
+    finally:
+        del view
+        mm.close()
 
 
 def codesToOneHot(codes):
@@ -407,56 +469,55 @@ class PackedSequences(object):
         return cls(torch.from_numpy(words.view(np.int32)).to(device), words.shape[0], L)
 
     @classmethod
-    def from_fasta(cls, filename, device='cuda', chunk_bytes=32 << 20, quiet=True):
+    def from_fasta(cls, filename, device='cuda', chunk_bytes=32 << 20, quiet=True, threads=0):
         """FASTA file -> packed sequences on the device, streamed (semantics of readSeqsFromFasta + seqToOneHot,
         reference sequences.py:33-52,101-117: N records skipped, case folded, KeyError on other letters).
 
-        The file is read in blocks of `chunk_bytes` (iterFastaCodes); the base codes of a block (1 byte per base) go through one of
-        two pinned staging buffers, one asynchronous host->device copy per block on a side stream, and are packed to 2 bits per base
-        on the device (crbm_pack_codes) while the host parses the next block. Neither the file nor a one-hot array is ever held in
-        host memory; the device tensor is sized from the file size (an upper bound: header bytes count as bases)."""
+        The file is memory-mapped and cut into blocks of about `chunk_bytes` at record starts (iterFastaPacked). The host threads of
+        crbm_fasta_pack_block_host (`threads`; 0 = one per core) parse a block and write its rows, already packed to 2 bits per base,
+        into one of two page-locked staging buffers; one asynchronous host->device copy per block (0.25 byte per base, on a side
+        stream) puts them in place while the host parses the next block. No packing kernel runs, and neither the file nor a one-hot
+        array is ever held in host memory; the device tensor is sized from the file size (an upper bound on the record count)."""
         import torch
-        from . import _lib
-        lib = _lib.load()
         dev = torch.device(device)
         size = os.path.getsize(filename)
-        words, rw, Ln, n_done = None, 0, None, 0
         main = torch.cuda.current_stream(dev)
         side = torch.cuda.Stream(device=dev)
-        side.wait_stream(main)
-        stage, dbuf, done = [None, None], [None, None], [None, None]
-        bad = torch.zeros(1, dtype=torch.int32, device=dev)
-        for i, codes in enumerate(iterFastaCodes(filename, chunk_bytes, quiet)):
-            n, j = codes.shape[0], i & 1
+        stage, done = [None, None], [None, None]
+        state = {'j': 0}
+
+        def get_buffer(rows, rw):
+            j = state['j']
+            if done[j] is not None:
+                done[j].synchronize()                           # the copy that read this staging buffer two blocks ago has finished
+                done[j] = None
+            if stage[j] is None or stage[j].shape[0] < rows or stage[j].shape[1] != rw:
+                stage[j] = torch.empty((max(rows, 1), rw), dtype=torch.int32, pin_memory=True)
+            return stage[j].numpy().view(np.uint32)
+
+        words, Ln, n_done = None, None, 0
+        for rows, L in iterFastaPacked(filename, chunk_bytes, quiet, threads, get_buffer):
+            n, j = rows.shape[0], state['j']
             if words is None:
-                Ln = codes.shape[1]
-                cap = size // (Ln + 2) + 1
-                words, rw = cls._alloc(cap, Ln, dev)
+                Ln = L
+                words = torch.empty((size // (Ln + 2) + 1, rows.shape[1]), dtype=torch.int32, device=dev)
                 side.wait_stream(main)
-            if n_done + n > words.shape[0]:                  # (cannot happen for a well-formed file; keep the bound honest)
-                grown = torch.zeros((max(2 * words.shape[0], n_done + n), rw), dtype=torch.int32, device=dev)
+            if n_done + n > words.shape[0]:                  # (cannot happen: a record takes at least L + 2 bytes of file)
+                grown = torch.empty((max(2 * words.shape[0], n_done + n), words.shape[1]), dtype=torch.int32, device=dev)
                 side.synchronize()
                 grown[:n_done] = words[:n_done]
                 words = grown
                 side.wait_stream(main)
-            if stage[j] is None or stage[j].shape[0] < n:
-                if done[j] is not None:
-                    done[j].synchronize()
-                stage[j] = torch.empty((max(n, 1), Ln), dtype=torch.uint8, pin_memory=True)
-                dbuf[j] = torch.empty((max(n, 1), Ln), dtype=torch.uint8, device=dev)
-            if done[j] is not None:
-                done[j].synchronize()                           # the copy that read this staging buffer two blocks ago has finished
-            np.copyto(stage[j].numpy()[:n], codes)
             with torch.cuda.stream(side):
-                dbuf[j][:n].copy_(stage[j][:n], non_blocking=True)
-                _lib.check(lib.crbm_pack_codes(_lib.ptr(dbuf[j]), n, Ln, _lib.ptr(words[n_done:]), rw, _lib.ptr(bad),
-                                               ctypes_stream(side)), 'pack_codes')
+                words[n_done:n_done + n].copy_(stage[j][:n], non_blocking=True)
                 done[j] = torch.cuda.Event()
                 done[j].record(side)
             n_done += n
+            state['j'] = j ^ 1
         if words is None:
             raise ValueError("no usable record in %s" % filename)
         main.wait_stream(side)
+        words.record_stream(side)
         return cls(words[:n_done], n_done, Ln)
 
     @classmethod

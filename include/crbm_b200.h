@@ -292,6 +292,14 @@ int    crbm_chain_from_dense(const float *dense, int B, int K, int M, int poolin
 int crbm_fasta_parse_block_host(const unsigned char *buf_host, size_t n, unsigned char *codes_host, size_t capacity_records,
                                 int *L_io, long long *n_records, long long *n_skipped, int *bad_char);
 
+/* The same pass, multi-threaded, writing rows of 2-bit bases in the device layout (row_words >= crbm_packed_row_words(L) words per
+ * record, pad words zeroed) — into page-locked memory, one cudaMemcpyAsync away from a PackedSequences tensor: readSeqsFromFasta +
+ * seqToOneHot (secomo/sequences.py:33-52, 101-117) without the one-hot array and without a packing kernel. `n_threads` <= 0: one per
+ * host core (at most one per MiB of input). Returns CRBM_OK, -11 / -12 as above, or -13 if `rows_host` is NULL or holds fewer than the
+ * *n_records rows the block may need (an upper bound: its number of headers; *L_io is set) — size the buffer and call again. */
+int crbm_fasta_pack_block_host(const unsigned char *buf_host, size_t n, uint32_t *rows_host, int row_words, size_t capacity_rows,
+                               int *L_io, long long *n_records, long long *n_skipped, int *bad_char, int n_threads);
+
 /* launch counter: number of kernels this library has launched since load (bench.py's `gpu_launches`) */
 unsigned long long crbm_launch_count(void);
 

@@ -586,6 +586,7 @@ def bench_e2e_scan(ctx, model, K, M, Lt):
     region); `motifHitSummary` the three (N,K) reductions."""
     import numpy as np
     import torch
+    import crbm_b200
     Lh = Lt - M + 1
     n = max(256, min(20000, int(1.5e9 // (4 * K * Lh))))
     rs = np.random.RandomState(3 + ctx.rank)
@@ -608,8 +609,9 @@ def bench_e2e_scan(ctx, model, K, M, Lt):
             del res
         ms = ctx.max_over_ranks(best * 1e3)
         rec[name] = {'value': n * Lt * ctx.world / (ms * 1e-3), 'unit': 'nt/s', 'ms': ms, 'sequences_per_gpu': n,
-                     'h2d_bytes': int(D.nbytes), 'd2h_bytes': int(out_bytes)}
-    rec['call'] = 'host one-hot fp32 (N,1,4,L) in, NumPy result out; wall clock around the call (it returns host data), best of 3'
+                     'host_input_bytes': int(D.nbytes), 'h2d_bytes': int(n * 4 * crbm_b200.packedRowWords(Lt)), 'd2h_bytes': int(out_bytes)}
+    rec['call'] = ('host one-hot fp32 (N,1,4,L) in, NumPy result out; wall clock around the call (it returns host data), best of 3; the '
+                   'one-hot array is packed to 2-bit rows by the host threads (crbm_pack_onehot_host), the rows are what crosses PCIe')
     return rec
 
 

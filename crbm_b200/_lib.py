@@ -108,6 +108,8 @@ SIGNATURES = {
                                             ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_int)]),
     'crbm_fasta_pack_block_host': (c_int, [c_void_p, c_size_t, c_void_p, c_int, c_size_t, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_longlong),
                                            ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(c_int), c_int]),
+    'crbm_pack_onehot_host': (c_int, [c_void_p, ctypes.c_longlong, c_int, ctypes.c_longlong, ctypes.c_longlong, c_void_p, c_int,
+                                      ctypes.POINTER(ctypes.c_longlong), c_int]),
     'crbm_v2h_dense_kernel_name': (ctypes.c_char_p, [c_int, c_int, c_int, c_int, ctypes.c_longlong]),
     'crbm_launch_count': (ctypes.c_ulonglong, []),
 }

@@ -62,6 +62,18 @@ inline uint32_t pack8(uint64_t x) {
     return (uint32_t)x;
 }
 
+// nw * 16 base codes (one per byte, zero beyond the record) -> one row in the device layout, pad words zeroed
+inline void pack_row(const unsigned char *codes, int nw, uint32_t *row, int row_words) {
+    for (int w = 0; w < crbm::FRONT_PAD_WORDS; ++w) row[w] = 0;
+    for (int w = 0; w < nw; ++w) {
+        uint64_t a, b;
+        memcpy(&a, codes + 16 * w, 8);
+        memcpy(&b, codes + 16 * w + 8, 8);
+        row[crbm::FRONT_PAD_WORDS + w] = pack8(a) | (pack8(b) << 16);
+    }
+    for (int w = crbm::FRONT_PAD_WORDS + nw; w < row_words; ++w) row[w] = 0;
+}
+
 struct alignas(64) Segment {
     size_t begin = 0, end = 0;          // [begin, end) of the block; begin is at a header
     long long first_row = 0;            // row index of this segment's first record (from the header counts)
@@ -132,20 +144,84 @@ void parse_segment(const unsigned char *buf, Segment &sg, long long L, uint32_t 
         if (has_n) { ++sg.n_skip; continue; }
         const size_t r = (size_t)(sg.first_row + sg.n_out);
         if (r >= capacity_rows) { sg.rc = -13; return; }
-        uint32_t *row = rows + r * (size_t)row_words;
-        for (int w = 0; w < crbm::FRONT_PAD_WORDS; ++w) row[w] = 0;
-        for (int w = 0; w < nw; ++w) {
-            uint64_t a, b;
-            memcpy(&a, tmp.data() + 16 * w, 8);
-            memcpy(&b, tmp.data() + 16 * w + 8, 8);
-            row[crbm::FRONT_PAD_WORDS + w] = pack8(a) | (pack8(b) << 16);
-        }
-        for (int w = crbm::FRONT_PAD_WORDS + nw; w < row_words; ++w) row[w] = 0;
+        pack_row(tmp.data(), nw, rows + r * (size_t)row_words, row_words);
         ++sg.n_out;
     }
 }
 
+// ---- one-hot (N,1,4,L) float32 in host memory -> packed rows (A0: the layout secomo/sequences.py:20-31 builds, read back) -------------
+// Same rule as pack_onehot_kernel (ops.cu): a position is valid iff exactly one of its four values == 1.0f and the other three
+// == 0.0f; the base is the plane holding the one. Returns the number of invalid positions of sequences [n0, n1).
+long long pack_onehot_range(const float *oh, long long n0, long long n1, int L, long long seq_stride, long long plane_stride,
+                            uint32_t *rows, int row_words) {
+    const int nw = (L + 15) / 16;
+    std::vector<unsigned char> tmp((size_t)nw * 16 + 16, 0);
+    long long bad = 0;
+    for (long long n = n0; n < n1; ++n) {
+        const float *pa = oh + n * seq_stride, *pc = pa + plane_stride, *pg = pc + plane_stride, *pt = pg + plane_stride;
+        int i = 0;
+#if defined(__SSE2__)
+        const __m128 one = _mm_set1_ps(1.f), zero = _mm_setzero_ps();
+        const __m128i i1 = _mm_set1_epi32(1), i2 = _mm_set1_epi32(2), m1 = _mm_set1_epi32(-1), m3 = _mm_set1_epi32(-3);
+        __m128i badv = _mm_setzero_si128();
+        for (; i + 4 <= L; i += 4) {
+            const __m128 a = _mm_loadu_ps(pa + i), c = _mm_loadu_ps(pc + i), g = _mm_loadu_ps(pg + i), t = _mm_loadu_ps(pt + i);
+            const __m128i ea = _mm_castps_si128(_mm_cmpeq_ps(a, one)), ec = _mm_castps_si128(_mm_cmpeq_ps(c, one));
+            const __m128i eg = _mm_castps_si128(_mm_cmpeq_ps(g, one)), et = _mm_castps_si128(_mm_cmpeq_ps(t, one));
+            const __m128i za = _mm_castps_si128(_mm_cmpeq_ps(a, zero)), zc = _mm_castps_si128(_mm_cmpeq_ps(c, zero));
+            const __m128i zg = _mm_castps_si128(_mm_cmpeq_ps(g, zero)), zt = _mm_castps_si128(_mm_cmpeq_ps(t, zero));
+            const __m128i ones = _mm_add_epi32(_mm_add_epi32(ea, ec), _mm_add_epi32(eg, et));           // -(number of ones)
+            const __m128i zeros = _mm_add_epi32(_mm_add_epi32(za, zc), _mm_add_epi32(zg, zt));          // -(number of zeros)
+            const __m128i ok = _mm_and_si128(_mm_cmpeq_epi32(ones, m1), _mm_cmpeq_epi32(zeros, m3));
+            badv = _mm_add_epi32(badv, _mm_add_epi32(ok, i1));                                          // + (ok ? 0 : 1)
+            const __m128i code = _mm_or_si128(_mm_and_si128(_mm_or_si128(ec, et), i1), _mm_and_si128(_mm_or_si128(eg, et), i2));
+            const __m128i b16 = _mm_packs_epi32(code, code);
+            const int four = _mm_cvtsi128_si32(_mm_packus_epi16(b16, b16));
+            memcpy(tmp.data() + i, &four, 4);
+        }
+        {
+            int lanes[4];
+            _mm_storeu_si128((__m128i *)lanes, badv);
+            bad += (long long)lanes[0] + lanes[1] + lanes[2] + lanes[3];
+        }
+#endif
+        for (; i < L; ++i) {
+            const float a = pa[i], c = pc[i], g = pg[i], t = pt[i];
+            const int ones = (a == 1.f) + (c == 1.f) + (g == 1.f) + (t == 1.f);
+            const int zeros = (a == 0.f) + (c == 0.f) + (g == 0.f) + (t == 0.f);
+            bad += ones != 1 || zeros != 3;
+            tmp[i] = (unsigned char)(((c == 1.f) | (t == 1.f)) | (((g == 1.f) | (t == 1.f)) << 1));
+        }
+        pack_row(tmp.data(), nw, rows + (size_t)n * row_words, row_words);
+    }
+    return bad;
+}
+
 }  // namespace
+
+extern "C" int crbm_pack_onehot_host(const float *onehot, long long N, int L, long long seq_stride, long long plane_stride,
+                                     uint32_t *rows, int row_words, long long *bad_count, int n_threads) {
+    if (!onehot || !rows || !bad_count || N <= 0 || L <= 0) { crbm::set_error("crbm_pack_onehot_host: bad arguments"); return CRBM_ERR_ARG; }
+    if (row_words < crbm::packed_row_words(L)) { crbm::set_error("crbm_pack_onehot_host: row_words %d < %d", row_words, crbm::packed_row_words(L)); return CRBM_ERR_ARG; }
+    int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (T < 1) T = 1;
+    if (T > 64) T = 64;
+    const long long min_positions = 1 << 16;                       // a thread is not worth starting for less
+    if ((long long)T > N * L / min_positions + 1) T = (int)(N * L / min_positions + 1);
+    if ((long long)T > N) T = (int)N;
+    std::vector<long long> bad((size_t)T * 8, 0);                  // (one cache line per thread)
+    auto work = [&](int t) {
+        bad[(size_t)t * 8] = pack_onehot_range(onehot, N * t / T, N * (t + 1) / T, L, seq_stride, plane_stride, rows, row_words);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    long long total = 0;
+    for (int t = 0; t < T; ++t) total += bad[(size_t)t * 8];
+    *bad_count = total;
+    return CRBM_OK;
+}
 
 extern "C" int crbm_fasta_pack_block_host(const unsigned char *buf, size_t n, uint32_t *rows, int row_words, size_t capacity_rows, int *L_io,
                                           long long *n_records, long long *n_skipped, int *bad_char, int n_threads) {

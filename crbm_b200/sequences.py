@@ -377,6 +377,31 @@ def packCodesHost(codes):
     return out
 
 
+def packOneHotHost(data, out=None, threads=0):
+    """(N,1,4,L) float32 one-hot in host memory -> ((N, packedRowWords(L)) uint32 rows in the device layout, number of positions
+    that are not one-hot), on the host threads of the library (crbm_pack_onehot_host; no GPU). `data` may be a view whose positions
+    are contiguous (fit()'s truncation `data[:, :, :, :n]`); `out` an array to fill (a page-locked staging buffer)."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    if data.ndim != 4 or data.shape[1] != 1 or data.shape[2] != 4:
+        raise ValueError("expected one-hot data of shape (N,1,4,L), got %r" % (data.shape,))
+    N, Ln = data.shape[0], data.shape[3]
+    if data.dtype != np.float32 or (Ln > 1 and data.strides[3] != 4) or data.strides[0] % 4 or data.strides[2] % 4 \
+            or data.strides[0] < 0 or data.strides[2] < 0:
+        data = np.ascontiguousarray(data, dtype=np.float32)
+    rw = packedRowWords(Ln)
+    if out is None:
+        out = np.empty((N, rw), dtype=np.uint32)
+    if out.shape[0] < N or out.shape[1] != rw or out.dtype != np.uint32 or not out.flags.c_contiguous:
+        raise ValueError("packOneHotHost: `out` must be a C-contiguous (>= %d, %d) uint32 array" % (N, rw))
+    bad = ctypes.c_longlong(0)
+    if N:
+        _lib.check(lib.crbm_pack_onehot_host(data.ctypes.data_as(ctypes.c_void_p), N, Ln, data.strides[0] // 4, data.strides[2] // 4,
+                                             out.ctypes.data_as(ctypes.c_void_p), rw, ctypes.byref(bad), int(threads)), 'pack_onehot_host')
+    return out[:N], int(bad.value)
+
+
 def unpackCodesHost(words, L):
     """Inverse of packCodesHost: (N, row_words) uint32 rows -> (N,L) uint8 base codes."""
     words = np.asarray(words, dtype=np.uint32)
@@ -413,8 +438,13 @@ class PackedSequences(object):
         return torch.zeros((int(N), rw), dtype=torch.int32, device=device), rw
 
     @classmethod
-    def from_onehot(cls, data, device='cuda', chunk_rows=None):
-        """(N,1,4,L) one-hot (NumPy or torch) -> packed, validated on the GPU (non-one-hot input is rejected)."""
+    def from_onehot(cls, data, device='cuda', chunk_rows=None, threads=0):
+        """(N,1,4,L) one-hot (NumPy or torch) -> packed and validated (non-one-hot input is rejected).
+
+        A NumPy array (what seqToOneHot returns, 16 bytes per base) is packed where it lies by the host threads of the library
+        (packOneHotHost -> crbm_pack_onehot_host) into two page-locked staging buffers in turn, and each chunk of rows goes to the
+        device as one asynchronous copy of 0.25 byte per base while the next chunk is packed. A torch tensor (on any device) is
+        packed by crbm_pack_onehot on the GPU."""
         import torch
         from . import _lib
         lib = _lib.load()
@@ -422,22 +452,45 @@ class PackedSequences(object):
             if data.ndim != 4 or data.shape[1] != 1 or data.shape[2] != 4:
                 raise ValueError("expected one-hot data of shape (N,1,4,L), got %r" % (data.shape,))
             N, Ln = data.shape[0], data.shape[3]
-        else:
-            N, Ln = data.shape[0], data.shape[3]
+            dev = torch.device(device)
+            rw = lib.crbm_packed_row_words(int(Ln))
+            words = torch.empty((int(N), rw), dtype=torch.int32, device=dev)
+            chunk_rows = max(1, min(max(N, 1), chunk_rows or (256 << 20) // (16 * Ln)))
+            main = torch.cuda.current_stream(dev)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(main)
+            nbuf = min(2, -(-N // chunk_rows))
+            stage = [torch.empty((chunk_rows, rw), dtype=torch.int32, pin_memory=True) for _ in range(nbuf)]
+            done = [None] * nbuf
+            total_bad = 0
+            for i, s in enumerate(range(0, N, chunk_rows)):
+                e, j = min(N, s + chunk_rows), i % nbuf
+                if done[j] is not None:
+                    done[j].synchronize()                       # the copy that read this staging buffer has finished
+                _, bad = packOneHotHost(data[s:e], out=stage[j].numpy().view(np.uint32), threads=threads)
+                total_bad += bad
+                with torch.cuda.stream(side):
+                    words[s:e].copy_(stage[j][:e - s], non_blocking=True)
+                    done[j] = torch.cuda.Event()
+                    done[j].record(side)
+            main.wait_stream(side)
+            if N:
+                words.record_stream(side)
+            if total_bad:
+                raise ValueError("input is not one-hot at %d positions (expected exactly one 1 among A,C,G,T)" % total_bad)
+            return cls(words, N, Ln)
+        N, Ln = data.shape[0], data.shape[3]
         words, rw = cls._alloc(N, Ln, device)
         bad = torch.zeros(1, dtype=torch.int32, device=device)
         chunk_rows = chunk_rows or max(1, (64 << 20) // (16 * Ln))
         total_bad = 0
         for s in range(0, N, chunk_rows):
             e = min(N, s + chunk_rows)
-            if isinstance(data, np.ndarray):
-                host = torch.from_numpy(np.ascontiguousarray(data[s:e], dtype=np.float32))
-                dev = host.to(device, non_blocking=False)
-            else:
-                dev = data[s:e].to(device=device, dtype=torch.float32).contiguous()
+            dev = data[s:e].to(device=device, dtype=torch.float32).contiguous()
             _lib.check(lib.crbm_pack_onehot(_lib.ptr(dev), e - s, Ln, _lib.ptr(words[s:]), rw, _lib.ptr(bad),
                                             _lib.stream_handle()), 'pack_onehot')
             total_bad += int(bad.item())
+            bad.zero_()
         if total_bad:
             raise ValueError("input is not one-hot at %d positions (expected exactly one 1 among A,C,G,T)" % total_bad)
         return cls(words, N, Ln)

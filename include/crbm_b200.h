@@ -300,6 +300,13 @@ int crbm_fasta_parse_block_host(const unsigned char *buf_host, size_t n, unsigne
 int crbm_fasta_pack_block_host(const unsigned char *buf_host, size_t n, uint32_t *rows_host, int row_words, size_t capacity_rows,
                                int *L_io, long long *n_records, long long *n_skipped, int *bad_char, int n_threads);
 
+/* A0 on the host threads: one-hot float32 (N,1,4,L) in HOST memory (sequence / plane strides in floats, positions contiguous) ->
+ * packed rows in HOST memory (page-locked: one cudaMemcpyAsync of 0.25 byte per base follows), with the validity rule of
+ * crbm_pack_onehot; *bad_count = number of positions that are not one-hot. The reference-facing calls take NumPy one-hot arrays
+ * (secomo/sequences.py:101-117 builds them, 16 bytes per base): packing them where they lie saves 63/64 of the PCIe traffic. */
+int crbm_pack_onehot_host(const float *onehot_host, long long N, int L, long long seq_stride, long long plane_stride,
+                          uint32_t *rows_host, int row_words, long long *bad_count, int n_threads);
+
 /* launch counter: number of kernels this library has launched since load (bench.py's `gpu_launches`) */
 unsigned long long crbm_launch_count(void);
 

@@ -51,6 +51,14 @@ def test_pack_roundtrip_bit_exact(crbm, N, L):
         ref[:, 1 + i // 16] |= codes[:, i].astype(np.uint32) << np.uint32(2 * (i % 16))
     np.testing.assert_array_equal(w1, ref)
     np.testing.assert_array_equal(p1.to_onehot(), D)
+    # a NumPy array is packed by the host threads (crbm_pack_onehot_host), a torch tensor by crbm_pack_onehot on the device
+    import torch
+    for t in (torch.from_numpy(D), torch.from_numpy(D).cuda()):
+        np.testing.assert_array_equal(crbm.PackedSequences.from_onehot(t).words.cpu().numpy().view(np.uint32), ref)
+    # strided view (fit()'s truncation) and several staging chunks
+    if L > 3:
+        p3 = crbm.PackedSequences.from_onehot(D[:, :, :, :L - 3], chunk_rows=2)
+        np.testing.assert_array_equal(p3.to_onehot(), D[:, :, :, :L - 3])
 
 
 def test_pack_rejects_non_onehot(crbm):
@@ -61,6 +69,9 @@ def test_pack_rejects_non_onehot(crbm):
     D[1, 0, :, 5] = 0.0
     with pytest.raises(ValueError):
         crbm.PackedSequences.from_onehot(D)
+    import torch
+    with pytest.raises(ValueError):
+        crbm.PackedSequences.from_onehot(torch.from_numpy(D))
 
 
 def test_random_bases_uniform_and_padded(crbm):

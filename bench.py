@@ -580,6 +580,34 @@ def bench_e2e_train(ctx, model, B, Lt, steps):
                     'step before issuing the next)' % ring}
 
 
+def bench_fit(ctx, wl, n=200000):
+    """The whole user call: CRBM(...).fit(one-hot NumPy array), one epoch — packing of the host array, every training step of the
+    epoch, the evaluation pass over the (same) data and the parameter metrics, wall clock around the call."""
+    import contextlib
+    import numpy as np
+    import torch
+    import crbm_b200
+    K, M, P, B, L = wl['K'], wl['M'], wl['P'], wl['batch'], wl['L']
+    rs = np.random.RandomState(11)
+    D = crbm_b200.codesToOneHot(rs.randint(0, 4, size=(n, L)).astype(np.uint8))
+    np.random.seed(0)
+    best = None
+    model = crbm_b200.CRBM(K, M, epochs=1, batchsize=B, pooling=P, cd_k=wl['cd_k'], seed=99, device=ctx.dev)
+    for _ in range(3):                                      # (the first call loads the kernels and pins the staging buffers)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(sys.stderr):
+            model.fit(D)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        assert np.all(np.isfinite(model.motifs.get_value()))
+    del model
+    Lt = int((L - M + 1) / P) * P + M - 1
+    return {'metric': 'CRBM.fit(one-hot NumPy array), 1 epoch: packing + %d training steps + evaluation pass, nt/s' % (n // B),
+            'value': n * Lt / best, 'unit': 'nt/s', 'seconds': best, 'sequences': n, 'host_input_bytes': int(D.nbytes)}
+
+
 def bench_e2e_scan(ctx, model, K, M, Lt):
     """The scan through the reference-facing calls with HOST buffers: `motifHitProbs(one-hot NumPy array)` returns the (N,K,1,Lh)
     NumPy array (host->device copy of the one-hot input, packing, scan, device->host copy of the probabilities inside the timed
@@ -748,6 +776,12 @@ def main():
             del mb, db
         except Exception as ex:
             line['c3']['global_batch_1024_on_one_gpu'] = {'error': str(ex)[:300]}
+
+    if world == 1 and not args.only_headline:
+        try:
+            line['fit'] = bench_fit(ctx, wl)
+        except Exception as ex:                               # (an extra record must not cost the line)
+            line['fit'] = {'error': str(ex)[:300]}
 
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:

@@ -580,6 +580,8 @@ class CRBM(object):
         fe_seq = torch.empty(seqs.N, dtype=torch.float32, device=self._device) if want_seq else None
         fe_mot = torch.empty((seqs.N, K), dtype=torch.float32, device=self._device) if want_motif else None
         cnt = torch.empty(seqs.N, dtype=torch.float32, device=self._device) if want_count else None
+        if seqs.N == 0:                                           # no sequence: empty results, nothing to launch
+            return fe_seq, fe_mot, cnt
         u = None if uniforms is None else torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float32)).to(self._device)
         self._step += 1
         _lib.check(lib.crbm_free_energy(_lib.ptr(seqs.words), seqs.row_words, seqs.N, seqs.L, _lib.ptr(self._t_W),

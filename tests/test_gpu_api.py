@@ -380,3 +380,15 @@ def test_streamed_fasta_ingest_matches_host_packing(tmp_path):
         got = crbm_b200.PackedSequences.from_fasta(p, chunk_bytes=cb)
         assert (got.N, got.L) == codes.shape
         np.testing.assert_array_equal(got.words.cpu().numpy(), want)
+
+
+def test_empty_input_gives_empty_results(data):
+    """No sequence in: arrays of the reference's shapes with a zero first axis out (nothing is launched)."""
+    from crbm_b200 import CRBM
+    m = CRBM(num_motifs=5, motif_length=7, epochs=1, seed=1)
+    D = data[:0]
+    assert m.motifHitProbs(D).shape == (0, 5, 1, 194)
+    assert m.freeEnergy(D).shape == (0,) and m.freeEnergy(D, permotif=True).shape == (0, 5)
+    s = m.motifHitSummary(D)
+    assert s['max'].shape == (0, 5) and s['argmax'].shape == (0, 5) and s['mean'].shape == (0, 5)
+    assert m.motifHitProbs(data[:3]).shape == (3, 5, 1, 194)

@@ -141,18 +141,21 @@ def _iter_fasta_codes_native(lib, filename, chunk_bytes, quiet):
                 return
 
 
-def iterFastaCodes(filename, chunk_bytes=32 << 20, quiet=False):
+def iterFastaCodes(filename, chunk_bytes=32 << 20, quiet=False, native=None):
     """Streams a multi-FASTA file as (n, L) uint8 base-code arrays (A0 C1 G2 T3, case-insensitive), one per `chunk_bytes` of file,
     without ever holding the file or a per-record Python object: a block of bytes is split into records with NumPy (header lines
     and line ends removed by masks, record lengths by a segmented count), so multi-line records and CRLF files are handled.
     Semantics of the reference reader (secomo/sequences.py:33-52, 20-31): records containing N/n are skipped ("skip sequence
     containing N" is printed once per skipped record unless `quiet`), any other non-ACGT letter raises KeyError, and all records
     must have the same length (the reference's one-hot array cannot be built otherwise)."""
-    try:
-        from . import _lib
-        lib = _lib.load()
-    except Exception:                                        # library not built: the NumPy parser below does the same job
-        lib = None
+    lib = None
+    if native is None or native:                             # native=False: the NumPy parser below (same results, tested against it)
+        try:
+            from . import _lib
+            lib = _lib.load()
+        except Exception:                                    # library not built: host-side parsing needs no GPU, NumPy does the same job
+            if native:
+                raise
     if lib is not None:
         for codes in _iter_fasta_codes_native(lib, filename, chunk_bytes, quiet):
             yield codes

@@ -15,6 +15,8 @@ GPU. Weak scaling: every rank trains `batch` sequences per step, one exchange of
                callers' reductions fused over the whole 3e9-nt job (sharded over the ranks)
   scan         getHitProbs at the headline shape (dense, fused reductions, and end to end with host buffers)
   eval         the per-epoch evaluation pass (free energy + sampled hidden mean, convRBM.py:466-472,616-624)
+  ingest       FASTA file -> packed sequences resident in HBM (threaded host parser, all host threads and one)
+  fit          N = 1: the whole `CRBM.fit(one-hot NumPy array)` call of one epoch (packing, steps, evaluation pass)
   cpu_baseline the reference's train step restated with torch-CPU ops, on the host cores (N = 1 only)
 `--impl reference` times that CPU restatement (oracle/crbm_torch_cpu.py; Theano itself is not installable offline) with
 the same metric/config.

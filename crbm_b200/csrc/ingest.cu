@@ -74,6 +74,20 @@ inline void pack_row(const unsigned char *codes, int nw, uint32_t *row, int row_
     for (int w = crbm::FRONT_PAD_WORDS + nw; w < row_words; ++w) row[w] = 0;
 }
 
+// fn(0) here, fn(1..T-1) on threads of their own; a thread that cannot be started (process limit) has its share run here instead
+template <typename F>
+void run_segments(int T, F fn) {
+    std::vector<std::thread> th;
+    int started = 1;
+    try {
+        for (int t = 1; t < T; ++t) { th.emplace_back(fn, t); ++started; }
+    } catch (...) {
+    }
+    fn(0);
+    for (int t = started; t < T; ++t) fn(t);
+    for (auto &x : th) x.join();
+}
+
 struct alignas(64) Segment {
     size_t begin = 0, end = 0;          // [begin, end) of the block; begin is at a header
     long long first_row = 0;            // row index of this segment's first record (from the header counts)
@@ -213,10 +227,7 @@ extern "C" int crbm_pack_onehot_host(const float *onehot, long long N, int L, lo
     auto work = [&](int t) {
         bad[(size_t)t * 8] = pack_onehot_range(onehot, N * t / T, N * (t + 1) / T, L, seq_stride, plane_stride, rows, row_words);
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto &x : th) x.join();
+    run_segments(T, work);
     long long total = 0;
     for (int t = 0; t < T; ++t) total += bad[(size_t)t * 8];
     *bad_count = total;
@@ -257,13 +268,7 @@ extern "C" int crbm_fasta_pack_block_host(const unsigned char *buf, size_t n, ui
         if (at < seg[t].begin) at = seg[t].begin;
         seg[t].end = at;
     }
-    auto run = [&](auto fn) {
-        if (T == 1) { fn(0); return; }
-        std::vector<std::thread> th;
-        for (int t = 1; t < T; ++t) th.emplace_back(fn, t);
-        fn(0);
-        for (auto &x : th) x.join();
-    };
+    auto run = [&](auto fn) { run_segments(T, fn); };
     // (one thread: no first rows to find; the headers are counted only if the parser runs out of rows)
     const bool counted = T > 1 || !rows || capacity_rows == 0;
     if (counted) run([&](int t) { seg[t].headers = count_headers(buf, seg[t].begin, seg[t].end); });

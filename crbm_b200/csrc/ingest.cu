@@ -12,6 +12,7 @@
 //           codes is packed 8 bases per 64-bit word operation into its row;
 //   pass 3  rows of segments behind a segment that dropped records (N, or a header without sequence) are moved down.
 // The first error in file order is the one reported, as the one-pass parser does.
+#include <stdlib.h>
 #include <string.h>
 #include <thread>
 #if defined(__SSE2__)
@@ -124,7 +125,12 @@ inline bool translate_line(const unsigned char *src, size_t len, unsigned char *
     return !bad;
 }
 
-void parse_segment(const unsigned char *buf, Segment &sg, long long L, uint32_t *rows, int row_words, size_t capacity_rows) {
+// One segment of complete records. A record's length is the number of its non-blank characters (the reference: len(record.seq));
+// records without any are dropped; a record containing N / n is skipped whatever else it holds (the reference drops it before it
+// looks at anything else, sequences.py:47-50); then another letter outside ACGT is error -12 (KeyError of sequences.py:30) and a
+// length other than L error -11 (the one-hot arrays cannot be concatenated). Output: packed rows (`rows`) or L base codes (`codes`).
+void parse_segment(const unsigned char *buf, Segment &sg, long long L, uint32_t *rows, int row_words, unsigned char *codes,
+                   size_t capacity_rows) {
     const int nw = (int)((L + 15) / 16);
     std::vector<unsigned char> tmp((size_t)nw * 16 + 16, 0);      // codes of the record being read; the tail beyond L stays zero
     size_t i = sg.begin;
@@ -134,31 +140,34 @@ void parse_segment(const unsigned char *buf, Segment &sg, long long L, uint32_t 
         i = p ? (size_t)((const unsigned char *)p - buf) + 1 : end;
         long long len = 0;
         bool has_n = false;
+        int badc = 0;
         while (i < end && buf[i] != '>') {                         // sequence lines (i is at a line start)
             p = memchr(buf + i, 10, end - i);
             const size_t e = p ? (size_t)((const unsigned char *)p - buf) : end;
             size_t line = e - i;
             if (line && buf[e - 1] == 13) --line;                  // CRLF file: the CR is dropped, as the table does
-                        if (len + (long long)line <= L && translate_line(buf + i, line, tmp.data() + len)) {
+            if (len + (long long)line <= L && translate_line(buf + i, line, tmp.data() + len)) {
                 len += (long long)line;
             } else {
                 for (size_t j = i; j < e; ++j) {
                     const unsigned char v = g_lut.v[buf[j]];
-                    if (v <= 4) {
-                        if (len >= L) { sg.rc = -11; return; }     // ragged: longer than the first record
-                        tmp[len++] = v & 3;
-                        has_n |= v == 4;
-                    } else if (v == 255) { sg.bad = buf[j]; sg.rc = -12; return; }
+                    if (v == 254) continue;
+                    if (v <= 3) { if (len < L) tmp[len] = v; }
+                    else if (v == 4) has_n = true;
+                    else if (!badc) badc = buf[j];
+                    ++len;
                 }
             }
             i = p ? e + 1 : end;
         }
         if (len == 0) continue;                                    // a header without sequence: dropped
-        if (len != L) { sg.rc = -11; return; }
         if (has_n) { ++sg.n_skip; continue; }
+        if (badc) { sg.bad = badc; sg.rc = -12; return; }
+        if (len != L) { sg.rc = -11; return; }
         const size_t r = (size_t)(sg.first_row + sg.n_out);
         if (r >= capacity_rows) { sg.rc = -13; return; }
-        pack_row(tmp.data(), nw, rows + r * (size_t)row_words, row_words);
+        if (codes) memcpy(codes + r * (size_t)L, tmp.data(), (size_t)L);
+        else pack_row(tmp.data(), nw, rows + r * (size_t)row_words, row_words);
         ++sg.n_out;
     }
 }
@@ -234,30 +243,36 @@ extern "C" int crbm_pack_onehot_host(const float *onehot, long long N, int L, lo
     return CRBM_OK;
 }
 
-extern "C" int crbm_fasta_pack_block_host(const unsigned char *buf, size_t n, uint32_t *rows, int row_words, size_t capacity_rows, int *L_io,
-                                          long long *n_records, long long *n_skipped, int *bad_char, int n_threads) {
-    if (!buf || !L_io || !n_records || !n_skipped || !bad_char) { crbm::set_error("crbm_fasta_pack_block_host: null argument"); return CRBM_ERR_ARG; }
+static int fasta_block(const unsigned char *buf, size_t n, uint32_t *rows, int row_words, unsigned char *codes, size_t capacity_rows, int *L_io,
+                       long long *n_records, long long *n_skipped, int *bad_char, int n_threads) {
     *n_records = 0; *n_skipped = 0;
     long long L = *L_io;
     const size_t first = next_header(buf, n, 0);                   // anything before the first header is not a record
-    if (L <= 0) {                                                  // record length = that of the first record that has bases
+    if (L <= 0) {                          // record length = that of the first record that has bases and no N (N records are skipped)
+        long long skipped = 0;
         for (size_t i = first; i < n && L <= 0;) {
             const void *p = memchr(buf + i, 10, n - i);
             i = p ? (size_t)((const unsigned char *)p - buf) + 1 : n;
             const size_t e = next_header(buf, n, i);
             long long len = 0;
-            for (size_t j = i; j < e; ++j) len += g_lut.v[buf[j]] <= 4;
-            if (len > 0) L = len;
+            bool has_n = false;
+            for (size_t j = i; j < e; ++j) { const unsigned char v = g_lut.v[buf[j]]; len += v != 254; has_n |= v == 4; }
+            if (len > 0 && !has_n) L = len;
+            else if (len > 0) ++skipped;
             i = e;
         }
-        if (L <= 0) return CRBM_OK;                                // no record with bases in this block
+        if (L <= 0) { *n_skipped = skipped; return CRBM_OK; }      // nothing but N records / empty records in this block
         if (L > 0x7fffffff) { crbm::set_error("crbm_fasta_pack_block_host: record longer than 2^31 bases"); return CRBM_ERR_ARG; }
         *L_io = (int)L;
     }
     int T = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
     if (T < 1) T = 1;
     if (T > 64) T = 64;
-    const size_t min_segment = 1 << 20;                            // a thread is not worth starting for less
+    size_t min_segment = 1 << 20;                                  // a thread is not worth starting for less
+    if (const char *e = getenv("CRBM_INGEST_MIN_SEGMENT")) {       // (tests: many segments in a small file)
+        const long long v = atoll(e);
+        if (v > 0) min_segment = (size_t)v;
+    }
     if ((size_t)T > (n - first) / min_segment + 1) T = (int)((n - first) / min_segment + 1);
 
     std::vector<Segment> seg((size_t)T);
@@ -270,17 +285,18 @@ extern "C" int crbm_fasta_pack_block_host(const unsigned char *buf, size_t n, ui
     }
     auto run = [&](auto fn) { run_segments(T, fn); };
     // (one thread: no first rows to find; the headers are counted only if the parser runs out of rows)
-    const bool counted = T > 1 || !rows || capacity_rows == 0;
+    const bool have_out = rows || codes;
+    const bool counted = T > 1 || !have_out || capacity_rows == 0;
     if (counted) run([&](int t) { seg[t].headers = count_headers(buf, seg[t].begin, seg[t].end); });
     long long need = 0;
     for (int t = 0; t < T; ++t) { seg[t].first_row = need; need += seg[t].headers; }
-    if (counted && ((size_t)need > capacity_rows || !rows)) {      // the caller sizes its buffer from this and calls again
+    if (counted && ((size_t)need > capacity_rows || !have_out)) {      // the caller sizes its buffer from this and calls again
         *n_records = need;
         crbm::set_error("crbm_fasta_pack_block_host: %lld rows needed, %zu given", need, capacity_rows);
         return -13;
     }
-    if (row_words < crbm::packed_row_words((int)L)) { crbm::set_error("crbm_fasta_pack_block_host: row_words %d < %d", row_words, crbm::packed_row_words((int)L)); return CRBM_ERR_ARG; }
-    run([&](int t) { parse_segment(buf, seg[t], L, rows, row_words, capacity_rows); });
+    if (rows && row_words < crbm::packed_row_words((int)L)) { crbm::set_error("crbm_fasta_pack_block_host: row_words %d < %d", row_words, crbm::packed_row_words((int)L)); return CRBM_ERR_ARG; }
+    run([&](int t) { parse_segment(buf, seg[t], L, rows, row_words, codes, capacity_rows); });
     long long out = 0, skipped = 0;
     for (int t = 0; t < T; ++t) {
         if (seg[t].rc == -13) {                                    // (single thread) out of rows: now count
@@ -292,11 +308,28 @@ extern "C" int crbm_fasta_pack_block_host(const unsigned char *buf, size_t n, ui
             if (seg[t].rc == -12) *bad_char = seg[t].bad;
             return seg[t].rc;
         }
-        if (seg[t].first_row != out && seg[t].n_out)
-            memmove(rows + (size_t)out * row_words, rows + (size_t)seg[t].first_row * row_words, (size_t)seg[t].n_out * row_words * sizeof(uint32_t));
+        if (seg[t].first_row != out && seg[t].n_out) {
+            if (codes) memmove(codes + (size_t)out * L, codes + (size_t)seg[t].first_row * L, (size_t)seg[t].n_out * L);
+            else memmove(rows + (size_t)out * row_words, rows + (size_t)seg[t].first_row * row_words, (size_t)seg[t].n_out * row_words * sizeof(uint32_t));
+        }
         out += seg[t].n_out;
         skipped += seg[t].n_skip;
     }
     *n_records = out; *n_skipped = skipped;
     return CRBM_OK;
+}
+
+extern "C" int crbm_fasta_pack_block_host(const unsigned char *buf, size_t n, uint32_t *rows, int row_words, size_t capacity_rows, int *L_io,
+                                          long long *n_records, long long *n_skipped, int *bad_char, int n_threads) {
+    if (!buf || !L_io || !n_records || !n_skipped || !bad_char) { crbm::set_error("crbm_fasta_pack_block_host: null argument"); return CRBM_ERR_ARG; }
+    return fasta_block(buf, n, rows, row_words, nullptr, capacity_rows, L_io, n_records, n_skipped, bad_char, n_threads);
+}
+
+// the same pass with one byte per base as its output (iterFastaCodes)
+extern "C" int crbm_fasta_parse_block_host(const unsigned char *buf, size_t n, unsigned char *codes, size_t capacity_records, int *L_io,
+                                           long long *n_records, long long *n_skipped, int *bad_char) {
+    if (!buf || !codes || !L_io || !n_records || !n_skipped || !bad_char) { crbm::set_error("crbm_fasta_parse_block_host: null argument"); return CRBM_ERR_ARG; }
+    const int rc = fasta_block(buf, n, nullptr, 0, codes, capacity_records, L_io, n_records, n_skipped, bad_char, 1);
+    if (rc == -13) { crbm::set_error("crbm_fasta_parse_block_host: more records than the output holds"); return CRBM_ERR_ARG; }
+    return rc;
 }

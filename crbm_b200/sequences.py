@@ -200,28 +200,33 @@ def iterFastaCodes(filename, chunk_bytes=32 << 20, quiet=False, native=None):
             keep[:hdr_start[0]] = False                      # anything before the first header is not a record
             rec_of_byte = np.cumsum(start & (a == ord('>'))) - 1
             lengths = np.bincount(rec_of_byte[keep], minlength=hdr_start.size)
-            seq = _STREAM_LUT[a[keep]]
-            nz = lengths > 0
-            if not np.all(nz):                               # header without sequence lines: an empty record, dropped like an N record
-                lengths = lengths[nz]
+            raw = a[keep]
+            seq = _STREAM_LUT[raw]
+            lengths = lengths[lengths > 0]                   # header without sequence lines: an empty record, dropped
             if lengths.size:
-                if L0 is None:
-                    L0 = int(lengths[0])
-                if np.any(lengths != L0):
-                    raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
-                codes = seq.reshape(-1, L0)
-                bad = codes == 255
-                if bad.any():
-                    r, c = np.argwhere(bad)[0]
-                    raise KeyError(chr(int(a[keep].reshape(-1, L0)[r, c])))
-                has_n = (codes == _N_CODE).any(axis=1)
-                if has_n.any():
-                    if not quiet:
-                        for _ in range(int(has_n.sum())):
-                            print("skip sequence containing N")
-                    codes = codes[~has_n]
-                if codes.shape[0]:
-                    yield np.ascontiguousarray(codes)
+                starts = np.concatenate(([0], np.cumsum(lengths)[:-1]))
+                # a record containing N is skipped whatever else it holds (the reference drops it before it looks at anything else)
+                has_n = np.add.reduceat((seq == _N_CODE).astype(np.int64), starts) > 0
+                if not quiet:
+                    for _ in range(int(has_n.sum())):
+                        print("skip sequence containing N")
+                good = ~has_n
+                if good.any():
+                    bad_rec = (np.add.reduceat((seq == 255).astype(np.int64), starts) > 0)[good]
+                    glen = lengths[good]
+                    if L0 is None:
+                        L0 = int(glen[0])
+                    off = bad_rec | (glen != L0)
+                    if off.any():                           # the first offending record in file order
+                        k = int(np.argmax(off))
+                        if bad_rec[k]:
+                            g = int(np.flatnonzero(good)[k])
+                            rec = slice(int(starts[g]), int(starts[g] + lengths[g]))
+                            raise KeyError(chr(int(raw[rec][np.argmax(seq[rec] == 255)])))
+                        raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
+                    codes = seq[np.repeat(good, lengths)].reshape(-1, L0)
+                    if codes.shape[0]:
+                        yield np.ascontiguousarray(codes)
             if last:
                 return
 

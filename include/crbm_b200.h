@@ -288,7 +288,9 @@ int    crbm_chain_from_dense(const float *dense, int B, int K, int M, int poolin
  * record dropped, letters mapped A0 C1 G2 T3 case-insensitively into codes[record][L]; records containing N/n are skipped and
  * counted in *n_skipped (the reference prints "skip sequence containing N" for each). *L_io is the record length (0 = not yet
  * known: taken from the first record). Returns CRBM_OK, -11 if a record's length differs (the reference's one-hot array cannot be
- * built), -12 for any other letter (*bad_char = the letter; the reference raises KeyError). */
+ * built), -12 for any other letter (*bad_char = the letter; the reference raises KeyError). As in the reference, a record
+ * containing N is skipped before its other letters or its length matter, and the record length is that of the first record
+ * without N; records without any sequence character are dropped; the first defect in file order is the one reported. */
 int crbm_fasta_parse_block_host(const unsigned char *buf_host, size_t n, unsigned char *codes_host, size_t capacity_records,
                                 int *L_io, long long *n_records, long long *n_skipped, int *bad_char);
 
